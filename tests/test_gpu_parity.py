@@ -1,0 +1,279 @@
+"""GPU parity tests proper: libvkrt_cuda (through the C ABI) against the CPU oracle on identical
+scene, camera and RNG seed.  Bar: primary hit ids bit-exact; linear radiance bit-exact where the
+arithmetic contract promises it (this is stricter than BASELINE.json's 1e-3 / 99.9 % / RMSE 1e-4,
+which is asserted as well)."""
+import numpy as np
+import pytest
+
+from helpers import apply_scene, bits_equal, mismatch_report, radiance_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _render_gpu(V, scene, w, h, fd, spp, depth, integrator, bvh, seed=7, frame_index=0, variant=0, flags=0, default=None):
+    r = V.Renderer(w, h, spp=spp, max_depth=depth, integrator=integrator, variant=variant,
+                   flags=V.FLAG_HIT_IDS | flags)
+    if default is not None:
+        r.use_default_scene(default)
+    else:
+        r.set_scene(scene)
+    if bvh:
+        r.build_bvh()
+    r.set_seed(seed)
+    r.set_frame_index(frame_index)
+    r.draw(fd)
+    out = (r.read_accum(), r.read_hit_ids(), r.read_rgba8(), r.counters())
+    return r, out
+
+
+def test_whitted_default_scene_bit_exact(vk, oracle):
+    """BASELINE config 1: Raytracer.comp scene, 640x480, whitted; fully deterministic."""
+    V = vk
+    w, h = 640, 480
+    fd = V.default_frame_data(aspect_ratio=w / h)
+    r, (acc, ids, rgba, cnt) = _render_gpu(V, None, w, h, fd, 1, 2, V.INTEGRATOR_WHITTED, False, default=V.SCENE_RAYTRACER)
+    sc = oracle.Scene().use_default(oracle.SCENE_RAYTRACER)
+    oacc, oids, orgba, ocnt = sc.render(fd, w, h, spp=1, max_depth=2, integrator=oracle.WHITTED)
+    assert np.array_equal(ids, oids)
+    assert bits_equal(acc, oacc), mismatch_report(acc, oacc)
+    assert np.array_equal(rgba, orgba)
+    assert (cnt.closest_rays, cnt.shadow_rays) == (ocnt.closest_rays, ocnt.shadow_rays)
+    r.close()
+
+
+@pytest.mark.parametrize("variant", [0])
+def test_path_default_scene_bit_exact(vk, oracle, variant):
+    """Tracer.comp scene at the reference's SAMPLES = DEPTH = 4, literal primitive order."""
+    V = vk
+    w, h = 320, 240
+    fd = V.default_frame_data(aspect_ratio=1024 / 768, seed=0.25)
+    r, (acc, ids, rgba, cnt) = _render_gpu(V, None, w, h, fd, 4, 4, V.INTEGRATOR_PATH, False, variant=variant, default=V.SCENE_TRACER)
+    sc = oracle.Scene().use_default(oracle.SCENE_TRACER)
+    oacc, oids, orgba, ocnt = sc.render(fd, w, h, spp=4, max_depth=4, integrator=oracle.PATH, seed=7)
+    assert np.array_equal(ids, oids)
+    assert bits_equal(acc, oacc), mismatch_report(acc, oacc)
+    frac, rmse = radiance_parity(acc, oacc)
+    assert frac >= 0.999 and rmse <= 1e-4
+    assert np.array_equal(rgba, orgba)
+    assert (cnt.closest_rays, cnt.shadow_rays, cnt.paths) == (ocnt.closest_rays, ocnt.shadow_rays, ocnt.paths)
+    r.close()
+
+
+def test_path_config2_full_size_subrect(vk, oracle):
+    """BASELINE config 2 at full size (1920x1080, 16 spp, depth 8) on the GPU; the oracle renders two
+    sub-rectangles of the same frame and those must match bit for bit."""
+    V = vk
+    w, h = 1920, 1080
+    fd = V.default_frame_data(aspect_ratio=w / h, seed=0.5)
+    r, (acc, ids, rgba, cnt) = _render_gpu(V, None, w, h, fd, 16, 8, V.INTEGRATOR_PATH, False, default=V.SCENE_TRACER)
+    sc = oracle.Scene().use_default(oracle.SCENE_TRACER)
+    for rect in ((0, 0, 64, 48), (900, 500, 1000, 560), (1856, 1040, 1920, 1080)):
+        oacc, oids, _, _ = sc.render(fd, w, h, spp=16, max_depth=8, integrator=oracle.PATH, seed=7, rect=rect, want_rgba=False)
+        x0, y0, x1, y1 = rect
+        assert np.array_equal(ids[y0:y1, x0:x1], oids[y0:y1, x0:x1])
+        assert bits_equal(acc[y0:y1, x0:x1], oacc[y0:y1, x0:x1]), mismatch_report(acc[y0:y1, x0:x1], oacc[y0:y1, x0:x1])
+    # size-independent properties at full size
+    assert np.all(acc[..., 3] == 16.0)
+    assert cnt.paths == w * h * 16
+    assert cnt.closest_rays >= cnt.paths and cnt.shadow_rays <= cnt.closest_rays
+    r.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 1024])
+def test_bvh_tree_matches_oracle_tree(vk, oracle, n):
+    V = vk
+    scene = V.scenes.random_spheres(n)
+    scene.spheres, scene.sphere_mat = scene.spheres[1:], scene.sphere_mat[1:]     # drop the light: exactly n spheres
+    r = V.Renderer(64, 64)
+    r.set_scene(scene)
+    info = r.build_bvh()
+    assert info.n_nodes == max(n - 1, 1)
+    gpu_nodes = r.bvh_nodes()
+    sc = apply_scene(oracle, scene).build_bvh()
+    assert bits_equal(gpu_nodes, sc.bvh_nodes())
+    r.close()
+
+
+def test_bvh_duplicate_centres(vk, oracle):
+    """Many identical Morton codes (coincident centres) exercise the index tie-break of the hierarchy."""
+    V = vk
+    scene = V.scenes.random_spheres(64)
+    scene.spheres = np.repeat(scene.spheres[:8], 8, axis=0).copy()
+    scene.spheres[:, 3] = np.linspace(0.5, 3.0, 64, dtype=np.float32)
+    scene.sphere_mat = np.arange(8, 8 + 64, dtype=np.uint32)
+    r = V.Renderer(64, 64)
+    r.set_scene(scene)
+    r.build_bvh()
+    sc = apply_scene(oracle, scene).build_bvh()
+    assert bits_equal(r.bvh_nodes(), sc.bvh_nodes())
+    r.close()
+
+
+def test_path_random_spheres_bvh_bit_exact(vk, oracle):
+    """BASELINE config 3's scene (1,024 random spheres, device LBVH) at a size the oracle finishes in
+    seconds: the GPU's LBVH traversal must equal both the oracle's own BVH traversal and the oracle's
+    LINEAR scan under rule S; the count of primary rays on which the literal chain rule of
+    Tracer.comp:398-412 disagrees with rule S (the "epsilon band of grazing ties") is reported."""
+    V = vk
+    w, h = 320, 180
+    scene = V.scenes.random_spheres(1024)
+    fd = V.default_frame_data(aspect_ratio=w / h, seed=0.75)
+    r, (acc, ids, rgba, cnt) = _render_gpu(V, scene, w, h, fd, 4, 8, V.INTEGRATOR_PATH, True, flags=V.FLAG_STATS)
+    sc = apply_scene(oracle, scene).build_bvh()
+    oacc, oids, orgba, ocnt = sc.render(fd, w, h, spp=4, max_depth=8, integrator=oracle.PATH, sphere_mode=oracle.S_BVH, seed=7)
+    lacc, lids, _, lcnt = sc.render(fd, w, h, spp=4, max_depth=8, integrator=oracle.PATH, sphere_mode=oracle.S_LINEAR, seed=7)
+    assert np.array_equal(ids, oids) and np.array_equal(ids, lids)
+    assert bits_equal(acc, oacc), mismatch_report(acc, oacc)
+    assert bits_equal(acc, lacc), mismatch_report(acc, lacc)
+    assert np.array_equal(rgba, orgba)
+    assert (cnt.closest_rays, cnt.shadow_rays) == (ocnt.closest_rays, ocnt.shadow_rays)
+    band = ocnt.literal_vs_s_mismatch
+    print("tie band: %d of %d primary rays differ between the literal chain rule and rule S" % (band, w * h))
+    assert band <= w * h * 1e-3
+    # literal-order brute force on the GPU agrees with the oracle's literal loop, too
+    r.clear_bvh(); r.reset_counters(); r.set_frame_index(0)
+    r.draw(fd)
+    bacc, bids = r.read_accum(), r.read_hit_ids()
+    oacc2, oids2, _, _ = sc.render(fd, w, h, spp=4, max_depth=8, integrator=oracle.PATH, sphere_mode=oracle.LITERAL, seed=7)
+    assert np.array_equal(bids, oids2)
+    assert bits_equal(bacc, oacc2), mismatch_report(bacc, oacc2)
+    assert int((bids != ids).sum()) == band
+    r.close()
+
+
+def test_path_grid_100k_bvh_bit_exact(vk, oracle):
+    """BASELINE config 4's scene (100,000 procedural spheres) against the oracle's BVH traversal."""
+    V = vk
+    w, h = 192, 108
+    scene = V.scenes.grid_spheres()
+    assert scene.spheres.shape[0] == 100001
+    fd = V.default_frame_data(aspect_ratio=w / h, seed=0.125)
+    r, (acc, ids, rgba, cnt) = _render_gpu(V, scene, w, h, fd, 4, 8, V.INTEGRATOR_PATH, True)
+    assert r.bvh_info().n_nodes == 100000
+    sc = apply_scene(oracle, scene, fast=True).build_bvh()
+    oacc, oids, orgba, ocnt = sc.render(fd, w, h, spp=4, max_depth=8, integrator=oracle.PATH, sphere_mode=oracle.S_BVH, seed=7)
+    assert np.array_equal(ids, oids)
+    assert bits_equal(acc, oacc), mismatch_report(acc, oacc)
+    assert (cnt.closest_rays, cnt.shadow_rays) == (ocnt.closest_rays, ocnt.shadow_rays)
+    r.close()
+
+
+def test_whitted_with_bvh(vk, oracle):
+    V = vk
+    w, h = 256, 192
+    scene = V.scenes.random_spheres(300)
+    scene.materials[8::3, 7] = 1.0          # make a third of the spheres reflective
+    fd = V.default_frame_data(aspect_ratio=w / h)
+    r, (acc, ids, rgba, cnt) = _render_gpu(V, scene, w, h, fd, 1, 2, V.INTEGRATOR_WHITTED, True)
+    sc = apply_scene(oracle, scene).build_bvh()
+    oacc, oids, orgba, ocnt = sc.render(fd, w, h, spp=1, max_depth=2, integrator=oracle.WHITTED, sphere_mode=oracle.S_LINEAR)
+    assert np.array_equal(ids, oids)
+    assert bits_equal(acc, oacc), mismatch_report(acc, oacc)
+    assert np.array_equal(rgba, orgba)
+    r.close()
+
+
+def test_progressive_accumulation(vk, oracle):
+    """Three accumulated frames == the oracle accumulating the same three frame keys."""
+    V = vk
+    w, h = 160, 120
+    fd = V.default_frame_data(aspect_ratio=w / h, seed=0.5)
+    r = V.Renderer(w, h, spp=4, max_depth=4, flags=V.FLAG_PROGRESSIVE)
+    r.use_default_scene(V.SCENE_TRACER)
+    r.set_seed(3)
+    sc = oracle.Scene().use_default(oracle.SCENE_TRACER)
+    oacc = None
+    for f in range(3):
+        r.draw(fd)
+        oacc, _, orgba, _ = sc.render(fd, w, h, spp=4, max_depth=4, seed=3, frame_index=f, accum=oacc)
+    acc = r.read_accum()
+    assert np.all(acc[..., 3] == 12.0)
+    assert bits_equal(acc, oacc), mismatch_report(acc, oacc)
+    assert np.array_equal(r.read_rgba8(), orgba)
+    r.reset_accum()
+    r.set_frame_index(0)
+    r.draw(fd)
+    first, _, _, _ = sc.render(fd, w, h, spp=4, max_depth=4, seed=3, frame_index=0)
+    assert bits_equal(r.read_accum(), first)
+    r.close()
+
+
+def test_tile_and_sample_shards_recombine(vk, oracle):
+    """tile shards are disjoint pixels -> recombination is bit-identical to one GPU;
+    sample shards change the summation order -> equal to the oracle's per-range sums added in order."""
+    V = vk
+    w, h = 200, 150      # not a multiple of the 32-px tile
+    scene = V.scenes.random_spheres(256)
+    fd = V.default_frame_data(aspect_ratio=w / h, seed=0.3)
+
+    def make(tile=(0, 1), samp=(0, 1)):
+        r = V.Renderer(w, h, spp=8, max_depth=6, tile_shard=tile, sample_shard=samp, flags=V.FLAG_NO_RESOLVE)
+        r.set_scene(scene); r.build_bvh(); r.set_seed(11)
+        return r
+
+    full = make(); full.draw(fd); ref = full.read_accum()
+    gather = make()
+    for rank in range(3):
+        part = make(tile=(rank, 3)); part.draw(fd)
+        ptr, n = part.pack_shard()
+        part.wait_idle()
+        gather.unpack_shard(ptr, rank, 3, add=False)
+        gather.wait_idle()
+        part.close()
+    assert bits_equal(gather.read_accum(), ref), mismatch_report(gather.read_accum(), ref)
+
+    sc = apply_scene(oracle, scene).build_bvh()
+    gather.reset_accum()
+    expect = None
+    for srank in range(2):
+        part = make(samp=(srank, 2)); part.draw(fd)
+        ptr, n = part.pack_shard(); part.wait_idle()
+        gather.unpack_shard(ptr, 0, 1, add=(srank > 0)); gather.wait_idle()
+        part.close()
+        expect, _, _, _ = sc.render(fd, w, h, spp=8, max_depth=6, sphere_mode=oracle.S_BVH, seed=11,
+                                    samples=(srank * 4, srank * 4 + 4), accum=expect, want_ids=False, want_rgba=False)
+    got = gather.read_accum()
+    assert bits_equal(got, expect), mismatch_report(got, expect)
+    frac, rmse = radiance_parity(got, ref)
+    assert frac >= 0.999 and rmse <= 1e-4
+    full.close(); gather.close()
+
+
+def test_error_behaviour(vk):
+    V = vk
+    with pytest.raises(V.VkrtError) as e:
+        V.Renderer(0, 10)
+    assert e.value.code == V._lib.BAD_ARG and "[app] - err ::" in str(e.value)
+    with pytest.raises(V.VkrtError):
+        V.Renderer(16, 16, device_id=99)
+    r = V.Renderer(16, 16)
+    with pytest.raises(V.VkrtError):
+        r.read_hit_ids()                      # created without FLAG_HIT_IDS
+    with pytest.raises(V.VkrtError):
+        r.set_sampling(0, 4)
+    scene = V.scenes.tracer_default()
+    scene.sphere_mat = scene.sphere_mat + 100
+    r.set_scene(scene)
+    with pytest.raises(V.VkrtError):
+        r.draw(V.default_frame_data())
+    r.close()
+
+
+def test_graphics_device_mirror(vk):
+    """The reference's call pattern (Main.cpp:105-196): Construct -> Draw per frame -> WaitIdle -> Destruct."""
+    V = vk
+    dev = V.GraphicsDevice()
+    info = V.GraphicsDevice.CreateInfo(None, 3, 2, 256, False)
+    assert dev.Construct(info) == V.GraphicsDevice.Error.SUCCESS
+    cam = V.default_camera()
+    fd = V.default_frame_data(camera=cam)
+    for _ in range(3):
+        cam.move_forward(1.0)
+        fd.camera = cam.data
+        dev.Draw(fd)
+    dev.WaitIdle()
+    img = dev.renderer.read_rgba8()
+    assert img.shape == (256, 256, 4) and img[..., 3].min() == 255 and img[..., :3].max() > 0
+    assert dev.Destruct() == V.GraphicsDevice.Error.SUCCESS
+    bad = V.GraphicsDevice.CreateInfo(None, 3, 2, 256, False, device_id=77)
+    assert V.GraphicsDevice().Construct(bad) == V.GraphicsDevice.Error.NO_SUITABLE_GPU

@@ -1,0 +1,58 @@
+"""Build recipe of libvkrt_cuda.so (nvcc, sm_100a only, in-tree so the .so travels with gpurun).
+
+The vkrt-f32 arithmetic contract needs -fmad=false -prec-div=true -prec-sqrt=true -ftz=false
+(csrc/vkrt_arith.cuh refuses to compile without -DVKRT_FMAD_OFF, which is set next to them).
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libvkrt_cuda.so")
+OBJ = os.path.join(HERE, "..", "build")
+SOURCES = ["vkrt_render.cu", "vkrt_wavefront.cu", "vkrt_bvh.cu", "vkrt_api.cu", "vkrt_micro.cu"]
+NVCC_FLAGS = [
+    "-std=c++17", "-O3", "-lineinfo",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false", "-DVKRT_FMAD_OFF",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden",
+]
+
+
+def _newer(src, dst):
+    return not os.path.exists(dst) or os.path.getmtime(src) > os.path.getmtime(dst)
+
+
+def build(force=False, verbose=False):
+    nvcc = os.environ.get("NVCC", "nvcc")
+    os.makedirs(OBJ, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(HERE, "..", "include", "vkrt.h"))
+    hdr_time = max(os.path.getmtime(h) for h in headers)
+    objs, rebuilt = [], False
+    procs = []
+    for s in SOURCES:
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(OBJ, s[:-3] + ".o")
+        objs.append(obj)
+        if force or _newer(src, obj) or hdr_time > os.path.getmtime(obj):
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+            rebuilt = True
+    for s, p in procs:
+        out, _ = p.communicate()
+        if verbose and out:
+            sys.stderr.write(out)
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s" % (s, out))
+    if rebuilt or not os.path.exists(OUT):
+        cmd = [nvcc, "-shared", "-cudart", "static", "-Wno-deprecated-gpu-targets", "-o", OUT] + objs
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n" + r.stdout)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,613 @@
+// C ABI of libvkrt_cuda (include/vkrt.h): context, scene upload, per-frame draw, outputs.
+//
+// Mirrors the ownership model of the reference's GraphicsDevice (Source/GraphicsDevice.cpp:40-43:
+// the library owns every GPU object; the caller owns FrameData, copied inside Draw at :1258).
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "vkrt_device.cuh"
+#include "vkrt_internal.h"
+
+using namespace vkrt;
+
+static_assert(sizeof(vkrt_camera_data) == 64, "CameraData must be 64 B (ref: Include/Camera.h:5-12)");
+static_assert(sizeof(vkrt_frame_data) == 96, "FrameData must be 96 B (ref: Include/GraphicsDevice.h:20-29)");
+static_assert(offsetof(vkrt_frame_data, aspect_ratio) == 0 && offsetof(vkrt_frame_data, seed) == 4 &&
+              offsetof(vkrt_frame_data, light_pos) == 16 && offsetof(vkrt_frame_data, camera) == 32,
+              "FrameData offsets (Tracer.comp.spv Offset decorations 0/4/16/32)");
+static_assert(offsetof(vkrt_camera_data, dir) == 16 && offsetof(vkrt_camera_data, right) == 32 &&
+              offsetof(vkrt_camera_data, up) == 48, "Camera offsets 0/16/32/48");
+static_assert(sizeof(vkrt_triangle) == 48, "Triangle must be 48 B (ref: Include/GraphicsDevice.h:13-18)");
+static_assert(sizeof(vkrt_material) == 48 && sizeof(vkrt_sphere) == 16 && sizeof(vkrt_plane) == 16, "scene records");
+static_assert(sizeof(DevScene) <= 1024 && sizeof(RenderParams) <= 512, "kernel parameter budget");
+
+static thread_local std::string g_create_error;
+
+struct vkrt_ctx {
+    vkrt_create_info info{};
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+
+    // scene (host mirrors + device buffers)
+    std::vector<vkrt_material> mats;
+    std::vector<vkrt_sphere> spheres;
+    std::vector<uint32_t> sphere_mat;
+    std::vector<vkrt_plane> planes;
+    std::vector<uint32_t> plane_mat;
+    std::vector<vkrt_triangle> tris;
+    uint32_t tri_mat = 0;
+    bool scene_dirty = true;
+    float4 *d_spheres = nullptr, *d_mats = nullptr, *d_tris = nullptr;
+    uint32_t *d_sphere_mat = nullptr;
+    BvhBuild bvh;
+    bool use_bvh = false;
+    DevScene dev{};
+
+    // frame state
+    uint32_t spp = 4, max_depth = 4;
+    uint64_t seed = 0;
+    uint32_t frame_index = 0;
+    uint32_t last_fkey = 0;
+    vkrt_frame_data last_fd{};
+    uint32_t frames_drawn = 0;
+    uint32_t n_tiles = 0, owned_tiles = 0;
+    bool accum_valid = false;
+
+    float4 *d_accum = nullptr;
+    uint32_t *d_hit_ids = nullptr;
+    std::vector<uchar4 *> d_rgba;
+    uint32_t cur_target = 0;
+    unsigned long long *d_counters = nullptr;
+    uint32_t *d_work_head = nullptr;
+    float4 *d_packed = nullptr;
+    uint64_t frames = 0;
+    WaveBuffers wave{};
+    bool wave_ready = false;
+
+    cudaEvent_t ev_begin = nullptr, ev_trace0 = nullptr, ev_trace1 = nullptr, ev_end = nullptr;
+    bool timing_valid = false;
+    uint32_t last_launches = 0;
+};
+
+namespace {
+
+vkrt_error fail(vkrt_ctx *c, vkrt_error code, const std::string &msg)
+{
+    // same prefix as the reference's diagnostics (Source/GraphicsDevice.cpp:25)
+    const std::string full = "[app] - err :: " + msg;
+    if (c) c->err = full; else g_create_error = full;
+    return code;
+}
+vkrt_error cuda_fail(vkrt_ctx *c, cudaError_t e, const char *what)
+{
+    return fail(c, VKRT_CUDA_ERROR, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(c, call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return cuda_fail((c), _e, #call); } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+vkrt_material make_mat(float r, float g, float b, float e, float rough, float metal, uint32_t type)
+{
+    vkrt_material m{};
+    m.albedo[0] = r; m.albedo[1] = g; m.albedo[2] = b;
+    m.emissive[0] = m.emissive[1] = m.emissive[2] = e;
+    m.roughness = rough; m.metalness = metal; m.type = type;
+    return m;
+}
+
+vkrt_error upload_scene(vkrt_ctx *c)
+{
+    if (!c->scene_dirty) return VKRT_SUCCESS;
+    for (uint32_t m : c->sphere_mat) if (m >= c->mats.size()) return fail(c, VKRT_BAD_ARG, "sphere material id out of range");
+    for (uint32_t m : c->plane_mat) if (m >= c->mats.size()) return fail(c, VKRT_BAD_ARG, "plane material id out of range");
+    if (!c->tris.empty() && c->tri_mat >= c->mats.size()) return fail(c, VKRT_BAD_ARG, "triangle material id out of range");
+    for (const vkrt_material &m : c->mats) if (m.type > 1u) return fail(c, VKRT_BAD_ARG, "unknown material type");
+
+    // the emissive-sphere list of Tracer.comp:458-462, in sphere order
+    std::vector<uint32_t> lights;
+    for (size_t i = 0; i < c->spheres.size(); ++i) {
+        const vkrt_material &m = c->mats[c->sphere_mat[i]];
+        if (!(m.emissive[0] == 0.0f && m.emissive[1] == 0.0f && m.emissive[2] == 0.0f)) lights.push_back((uint32_t)i);
+    }
+    if (lights.size() > MAX_LIGHTS) return fail(c, VKRT_BAD_ARG, "more than 14 emissive spheres");
+
+    auto up = [&](auto **dptr, const void *src, size_t bytes) -> cudaError_t {
+        if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
+        if (bytes == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc((void **)dptr, bytes);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpyAsync(*dptr, src, bytes, cudaMemcpyHostToDevice, c->stream);
+    };
+    CU(c, up(&c->d_spheres, c->spheres.data(), c->spheres.size() * sizeof(vkrt_sphere)));
+    CU(c, up(&c->d_sphere_mat, c->sphere_mat.data(), c->sphere_mat.size() * sizeof(uint32_t)));
+    CU(c, up(&c->d_mats, c->mats.data(), c->mats.size() * sizeof(vkrt_material)));
+    CU(c, up(&c->d_tris, c->tris.data(), c->tris.size() * sizeof(vkrt_triangle)));
+    CU(c, cudaStreamSynchronize(c->stream));
+
+    DevScene &d = c->dev;
+    std::memset(&d, 0, sizeof(d));
+    d.spheres = c->d_spheres; d.sphere_mat = c->d_sphere_mat; d.mats = c->d_mats; d.tris = c->d_tris;
+    d.bvh = c->use_bvh ? c->bvh.nodes : nullptr;
+    d.n_nodes = c->use_bvh ? c->bvh.n_nodes : 0;
+    d.n_spheres = (uint32_t)c->spheres.size(); d.n_tris = (uint32_t)c->tris.size(); d.tri_mat = c->tri_mat;
+    d.n_planes = (uint32_t)c->planes.size(); d.n_mats = (uint32_t)c->mats.size();
+    for (size_t i = 0; i < c->planes.size(); ++i) {
+        d.planes[i] = make_float4(c->planes[i].nx, c->planes[i].ny, c->planes[i].nz, c->planes[i].len);
+        d.plane_mat[i] = c->plane_mat[i];
+    }
+    d.n_lights = (uint32_t)lights.size();
+    for (size_t i = 0; i < lights.size(); ++i) d.lights[i] = lights[i];
+    c->scene_dirty = false;
+    return VKRT_SUCCESS;
+}
+
+void fill_params(vkrt_ctx *c, RenderParams &rp)
+{
+    std::memset(&rp, 0, sizeof(rp));
+    rp.fd = c->last_fd;
+    rp.width = c->info.width; rp.height = c->info.height;
+    rp.tiles_x = (rp.width + TILE - 1) / TILE; rp.tiles_y = (rp.height + TILE - 1) / TILE;
+    rp.tile_rank = c->info.tile_shard_rank; rp.tile_count = c->info.tile_shard_count;
+    rp.n_work = c->owned_tiles * TILE_PX;
+    rp.max_depth = c->max_depth;
+    rp.fkey = c->last_fkey;
+    const uint32_t sc = c->info.sample_shard_count, sr = c->info.sample_shard_rank;
+    rp.s_begin = (uint32_t)((uint64_t)sr * c->spp / sc);
+    rp.s_end = (uint32_t)((uint64_t)(sr + 1) * c->spp / sc);
+    rp.accum = c->d_accum; rp.hit_ids = c->d_hit_ids; rp.counters = c->d_counters; rp.work_head = c->d_work_head;
+}
+
+} // namespace
+
+extern "C" {
+
+VKRT_API const char *vkrt_version(void) { return "libvkrt_cuda 0.1 (sm_100a)"; }
+
+VKRT_API const char *vkrt_last_error_string(vkrt_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+VKRT_API vkrt_error vkrt_create(const vkrt_create_info *info, vkrt_ctx **out_ctx)
+{
+    if (!info || !out_ctx) return fail(nullptr, VKRT_BAD_ARG, "null argument");
+    *out_ctx = nullptr;
+    if (info->struct_size != sizeof(vkrt_create_info)) return fail(nullptr, VKRT_BAD_ARG, "vkrt_create_info.struct_size mismatch");
+    if (info->width == 0 || info->height == 0 || info->width > 65536 || info->height > 65536)
+        return fail(nullptr, VKRT_BAD_ARG, "bad resolution");
+    if (info->integrator > VKRT_INTEGRATOR_PATH || info->variant > VKRT_VARIANT_WAVEFRONT)
+        return fail(nullptr, VKRT_BAD_ARG, "bad integrator / variant");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, VKRT_NO_SUITABLE_GPU, "no CUDA device (libvkrt_cuda has no CPU fallback)");
+    }
+    if (info->device_id < 0 || info->device_id >= n_dev) return fail(nullptr, VKRT_NO_SUITABLE_GPU, "device_id out of range");
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, info->device_id) != cudaSuccess || prop.major < 10)
+        return fail(nullptr, VKRT_NO_SUITABLE_GPU, "device is not sm_100-class (this library ships sm_100a code only)");
+
+    vkrt_ctx *c = new (std::nothrow) vkrt_ctx();
+    if (!c) return fail(nullptr, VKRT_UNKNOWN, "out of host memory");
+    c->info = *info;
+    if (c->info.tile_shard_count == 0) c->info.tile_shard_count = 1;
+    if (c->info.sample_shard_count == 0) c->info.sample_shard_count = 1;
+    if (c->info.frames_in_flight == 0) c->info.frames_in_flight = 2;
+    if (c->info.tile_shard_rank >= c->info.tile_shard_count || c->info.sample_shard_rank >= c->info.sample_shard_count ||
+        c->info.frames_in_flight > 8) {
+        delete c;
+        return fail(nullptr, VKRT_BAD_ARG, "bad shard rank / frames_in_flight");
+    }
+    c->spp = info->spp ? info->spp : 4;                 // SAMPLES (Tracer.comp:180)
+    c->max_depth = info->max_depth ? info->max_depth : (info->integrator == VKRT_INTEGRATOR_PATH ? 4 : 2);
+    c->sm_count = prop.multiProcessorCount;
+    DeviceGuard g(info->device_id);
+#define CC(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { vkrt_error r = cuda_fail(nullptr, _e, #call); vkrt_destroy(c); return r; } } while (0)
+    if (info->stream) c->stream = (cudaStream_t)info->stream;
+    else { CC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    const size_t n_px = (size_t)info->width * info->height;
+    const uint32_t tiles_x = (info->width + TILE - 1) / TILE, tiles_y = (info->height + TILE - 1) / TILE;
+    c->n_tiles = tiles_x * tiles_y;
+    c->owned_tiles = c->info.tile_shard_rank < c->n_tiles
+                         ? (c->n_tiles - c->info.tile_shard_rank + c->info.tile_shard_count - 1) / c->info.tile_shard_count : 0;
+    CC(cudaMalloc(&c->d_accum, n_px * sizeof(float4)));
+    CC(cudaMemsetAsync(c->d_accum, 0, n_px * sizeof(float4), c->stream));
+    if (info->flags & VKRT_FLAG_HIT_IDS) {
+        CC(cudaMalloc(&c->d_hit_ids, n_px * sizeof(uint32_t)));
+        CC(cudaMemsetAsync(c->d_hit_ids, 0, n_px * sizeof(uint32_t), c->stream));
+    }
+    c->d_rgba.assign(c->info.frames_in_flight, nullptr);
+    for (auto &p : c->d_rgba) { CC(cudaMalloc(&p, n_px * sizeof(uchar4))); CC(cudaMemsetAsync(p, 0, n_px * sizeof(uchar4), c->stream)); }
+    CC(cudaMalloc(&c->d_counters, CNT_N * sizeof(unsigned long long)));
+    CC(cudaMemsetAsync(c->d_counters, 0, CNT_N * sizeof(unsigned long long), c->stream));
+    CC(cudaMalloc(&c->d_work_head, 64));
+    CC(cudaMemsetAsync(c->d_work_head, 0, 64, c->stream));
+    CC(cudaEventCreate(&c->ev_begin)); CC(cudaEventCreate(&c->ev_trace0));
+    CC(cudaEventCreate(&c->ev_trace1)); CC(cudaEventCreate(&c->ev_end));
+    CC(cudaStreamSynchronize(c->stream));
+#undef CC
+    *out_ctx = c;
+    return VKRT_SUCCESS;
+}
+
+VKRT_API vkrt_error vkrt_destroy(vkrt_ctx *c)
+{
+    if (!c) return VKRT_BAD_ARG;
+    DeviceGuard g(c->info.device_id);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_spheres); cudaFree(c->d_sphere_mat); cudaFree(c->d_mats); cudaFree(c->d_tris);
+    cudaFree(c->bvh.nodes); cudaFree(c->d_accum); cudaFree(c->d_hit_ids);
+    for (auto p : c->d_rgba) cudaFree(p);
+    cudaFree(c->d_counters); cudaFree(c->d_work_head); cudaFree(c->d_packed);
+    if (c->wave_ready) wave_free(c->wave);
+    if (c->ev_begin) cudaEventDestroy(c->ev_begin);
+    if (c->ev_trace0) cudaEventDestroy(c->ev_trace0);
+    if (c->ev_trace1) cudaEventDestroy(c->ev_trace1);
+    if (c->ev_end) cudaEventDestroy(c->ev_end);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return VKRT_SUCCESS;
+}
+
+VKRT_API vkrt_error vkrt_set_sampling(vkrt_ctx *c, uint32_t spp, uint32_t max_depth)
+{
+    if (!c) return VKRT_BAD_ARG;
+    if (spp == 0 || max_depth == 0 || spp > (1u << 24) || max_depth > 255) return fail(c, VKRT_BAD_ARG, "spp / max_depth out of range");
+    c->spp = spp; c->max_depth = max_depth;
+    return VKRT_SUCCESS;
+}
+VKRT_API vkrt_error vkrt_set_seed(vkrt_ctx *c, uint64_t seed) { if (!c) return VKRT_BAD_ARG; c->seed = seed; return VKRT_SUCCESS; }
+VKRT_API vkrt_error vkrt_set_frame_index(vkrt_ctx *c, uint32_t i) { if (!c) return VKRT_BAD_ARG; c->frame_index = i; return VKRT_SUCCESS; }
+VKRT_API vkrt_error vkrt_reset_accum(vkrt_ctx *c)
+{
+    if (!c) return VKRT_BAD_ARG;
+    DeviceGuard g(c->info.device_id);
+    CU(c, launch_clear_accum(c->d_accum, (size_t)c->info.width * c->info.height, c->stream));
+    c->accum_valid = false;
+    return VKRT_SUCCESS;
+}
+
+// ---- scene --------------------------------------------------------------------------------------
+VKRT_API vkrt_error vkrt_set_triangles(vkrt_ctx *c, const vkrt_triangle *t, uint32_t n)
+{
+    if (!c || (n && !t)) return VKRT_BAD_ARG;
+    c->tris.assign(t, t + n); c->scene_dirty = true;
+    return VKRT_SUCCESS;
+}
+VKRT_API vkrt_error vkrt_set_triangle_material(vkrt_ctx *c, uint32_t mat_id)
+{
+    if (!c) return VKRT_BAD_ARG;
+    c->tri_mat = mat_id; c->scene_dirty = true;
+    return VKRT_SUCCESS;
+}
+VKRT_API vkrt_error vkrt_set_materials(vkrt_ctx *c, const vkrt_material *m, uint32_t n)
+{
+    if (!c || (n && !m)) return VKRT_BAD_ARG;
+    for (uint32_t i = 0; i < n; ++i) if (m[i].type > 1u) return fail(c, VKRT_BAD_ARG, "unknown material type");
+    c->mats.assign(m, m + n); c->scene_dirty = true;
+    return VKRT_SUCCESS;
+}
+VKRT_API vkrt_error vkrt_set_spheres(vkrt_ctx *c, const vkrt_sphere *s, const uint32_t *mat_id, uint32_t n)
+{
+    if (!c || (n && (!s || !mat_id))) return VKRT_BAD_ARG;
+    c->spheres.assign(s, s + n); c->sphere_mat.assign(mat_id, mat_id + n);
+    c->use_bvh = false;                       // a new sphere list invalidates the tree
+    c->scene_dirty = true;
+    return VKRT_SUCCESS;
+}
+VKRT_API vkrt_error vkrt_set_planes(vkrt_ctx *c, const vkrt_plane *p, const uint32_t *mat_id, uint32_t n)
+{
+    if (!c || (n && (!p || !mat_id))) return VKRT_BAD_ARG;
+    if (n > MAX_PLANES) return fail(c, VKRT_BAD_ARG, "more than 16 planes");
+    c->planes.assign(p, p + n); c->plane_mat.assign(mat_id, mat_id + n); c->scene_dirty = true;
+    return VKRT_SUCCESS;
+}
+
+VKRT_API vkrt_error vkrt_use_default_scene(vkrt_ctx *c, uint32_t which)
+{
+    if (!c) return VKRT_BAD_ARG;
+    // the one triangle the host uploads, Source/GraphicsDevice.cpp:798-803 (== Raytracer.comp:116)
+    vkrt_triangle tri{};
+    tri.v0 = {10.0f, 10.0f, 0.0f, 0.0f}; tri.v1 = {0.0f, 20.0f, 0.0f, 0.0f}; tri.v2 = {-10.0f, 10.0f, 0.0f, 0.0f};
+    if (which == VKRT_SCENE_TRACER) {
+        const vkrt_material mats[8] = {                                   // Tracer.comp:186-194
+            make_mat(1.0f, 1.0f, 1.0f, 0.0f, 0.3f, 0.7f, VKRT_MAT_DIFFUSE),      // 0 matte_white
+            make_mat(0.75f, 0.25f, 0.25f, 0.0f, 0.4f, 0.0f, VKRT_MAT_DIFFUSE),   // 1 matte_red
+            make_mat(0.25f, 0.75f, 0.25f, 0.0f, 0.4f, 0.0f, VKRT_MAT_DIFFUSE),   // 2 matte_green
+            make_mat(0.25f, 0.25f, 0.75f, 0.0f, 0.4f, 0.0f, VKRT_MAT_DIFFUSE),   // 3 matte_blue
+            make_mat(0.25f, 0.25f, 0.75f, 0.0f, 0.3f, 0.6f, VKRT_MAT_DIFFUSE),   // 4 plastic
+            make_mat(1.0f, 0.5f, 0.5f, 0.0f, 0.0f, 1.0f, VKRT_MAT_DIFFUSE),      // 5 mirror
+            make_mat(1.0f, 1.0f, 1.0f, 0.0f, 0.42f, 0.0f, VKRT_MAT_DIELECTRIC),  // 6 glass
+            make_mat(1.0f, 1.0f, 1.0f, 128.0f, 0.6f, 0.0f, VKRT_MAT_DIFFUSE)};   // 7 light
+        const vkrt_sphere sp[4] = {{42.0f, 16.0f, 12.0f, 16.0f}, {0.0f, 96.0f, 0.0f, 12.0f},   // Tracer.comp:196-202
+                                   {-32.0f, 24.0f, 24.0f, 24.0f}, {-24.0f, 11.0f, -48.0f, 11.0f}};
+        const uint32_t spm[4] = {6, 7, 5, 4};
+        const vkrt_plane pl[5] = {{0.0f, 1.0f, 0.0f, 0.0f}, {0.0f, -1.0f, 0.0f, 128.0f}, {1.0f, 0.0f, 0.0f, 64.0f}, // :204-211
+                                  {0.0f, 0.0f, -1.0f, 64.0f}, {-1.0f, 0.0f, 0.0f, 64.0f}};
+        const uint32_t plm[5] = {0, 0, 1, 2, 3};
+        vkrt_set_materials(c, mats, 8); vkrt_set_spheres(c, sp, spm, 4); vkrt_set_planes(c, pl, plm, 5);
+        vkrt_set_triangles(c, &tri, 1); vkrt_set_triangle_material(c, 5);     // every triangle is `mirror` (:386)
+        return VKRT_SUCCESS;
+    }
+    if (which == VKRT_SCENE_RAYTRACER) {
+        auto R = [](bool refl, float r, float g, float b) {
+            return make_mat(r, g, b, 0.0f, refl ? 0.0f : 0.4f, refl ? 1.0f : 0.0f, VKRT_MAT_DIFFUSE);
+        };
+        const vkrt_material mats[6] = {R(true, 1, 1, 1), R(false, 1, 0, 0), R(true, 0, 1, 0),      // Raytracer.comp:119-127
+                                       R(false, 0, 0, 1), R(false, 1, 1, 0), R(false, 1, 0, 1)};
+        const vkrt_sphere sp[2] = {{-14.0f, 12.0f, 32.0f, 5.0f}, {32.0f, 24.0f, 25.0f, 12.0f}};   // :98-102
+        const uint32_t spm[2] = {5, 4};
+        const vkrt_plane pl[5] = {{0.0f, 1.0f, 0.0f, 0.0f}, {0.0f, -1.0f, 0.0f, 128.0f}, {0.0f, 0.0f, -1.0f, 64.0f}, // :104-112
+                                  {1.0f, 0.0f, 0.0f, 64.0f}, {-1.0f, 0.0f, 0.0f, 64.0f}};
+        const uint32_t plm[5] = {0, 0, 2, 1, 3};
+        vkrt_set_materials(c, mats, 6); vkrt_set_spheres(c, sp, spm, 2); vkrt_set_planes(c, pl, plm, 5);
+        vkrt_set_triangles(c, &tri, 1); vkrt_set_triangle_material(c, 1);     // Raytracer.comp:116
+        return VKRT_SUCCESS;
+    }
+    return fail(c, VKRT_BAD_ARG, "unknown default scene");
+}
+
+VKRT_API vkrt_error vkrt_build_bvh(vkrt_ctx *c)
+{
+    if (!c) return VKRT_BAD_ARG;
+    DeviceGuard g(c->info.device_id);
+    c->scene_dirty = true;
+    c->use_bvh = false;
+    vkrt_error r = upload_scene(c);
+    if (r != VKRT_SUCCESS) return r;
+    CU(c, build_lbvh(c->d_spheres, (uint32_t)c->spheres.size(), c->bvh, c->stream));
+    c->use_bvh = true;
+    c->scene_dirty = true;
+    return VKRT_SUCCESS;
+}
+VKRT_API vkrt_error vkrt_clear_bvh(vkrt_ctx *c)
+{
+    if (!c) return VKRT_BAD_ARG;
+    c->use_bvh = false; c->scene_dirty = true;
+    return VKRT_SUCCESS;
+}
+VKRT_API vkrt_error vkrt_get_bvh_info(vkrt_ctx *c, vkrt_bvh_info *out)
+{
+    if (!c || !out) return VKRT_BAD_ARG;
+    out->n_spheres = (uint32_t)c->spheres.size();
+    out->n_nodes = c->use_bvh ? c->bvh.n_nodes : 0;
+    out->node_bytes = 64;
+    out->build_ms = c->bvh.build_ms;
+    out->build_launches = c->bvh.launches;
+    return VKRT_SUCCESS;
+}
+VKRT_API vkrt_error vkrt_read_bvh_nodes(vkrt_ctx *c, float *host, size_t bytes)
+{
+    if (!c || !host) return VKRT_BAD_ARG;
+    if (!c->use_bvh) return fail(c, VKRT_BAD_ARG, "no BVH built");
+    if (bytes < (size_t)c->bvh.n_nodes * 64) return fail(c, VKRT_BAD_ARG, "buffer too small");
+    DeviceGuard g(c->info.device_id);
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaMemcpy(host, c->bvh.nodes, (size_t)c->bvh.n_nodes * 64, cudaMemcpyDeviceToHost));
+    return VKRT_SUCCESS;
+}
+
+// ---- per-frame ----------------------------------------------------------------------------------
+VKRT_API vkrt_error vkrt_draw(vkrt_ctx *c, const vkrt_frame_data *frame)
+{
+    if (!c || !frame) return VKRT_BAD_ARG;
+    DeviceGuard g(c->info.device_id);
+    vkrt_error r = upload_scene(c);
+    if (r != VKRT_SUCCESS) return r;
+
+    c->last_fd = *frame;                                            // "FrameData frame_data_real = frame_data" (:1258)
+    uint32_t seed_bits; std::memcpy(&seed_bits, &frame->seed, 4);
+    c->last_fkey = frame_key(c->seed, seed_bits, c->frame_index);
+    RenderParams rp;
+    fill_params(c, rp);
+    const bool progressive = (c->info.flags & VKRT_FLAG_PROGRESSIVE) != 0 && c->info.integrator == VKRT_INTEGRATOR_PATH;
+    rp.accumulate = (progressive && c->accum_valid) ? 1u : 0u;
+    const bool stats = (c->info.flags & VKRT_FLAG_STATS) != 0;
+    uint32_t launches = 0;
+
+    CU(c, cudaEventRecord(c->ev_begin, c->stream));
+    CU(c, cudaMemsetAsync(c->d_work_head, 0, 64, c->stream));
+    CU(c, cudaEventRecord(c->ev_trace0, c->stream));
+    if (rp.n_work > 0 && rp.s_end > rp.s_begin) {
+        if (c->info.integrator == VKRT_INTEGRATOR_WHITTED) {
+            CU(c, launch_whitted(c->dev, rp, c->use_bvh, stats, c->stream)); ++launches;
+        } else if (c->info.variant == VKRT_VARIANT_WAVEFRONT) {
+            if (!c->wave_ready) {
+                size_t cap = (size_t)c->owned_tiles * TILE_PX * 16;        // 16 samples of every owned pixel per wave
+                const size_t cap_max = (size_t)64 << 20;
+                if (cap > cap_max) cap = cap_max - cap_max % ((size_t)c->owned_tiles * TILE_PX ? 1 : 1);
+                CU(c, wave_alloc(c->wave, cap));
+                c->wave_ready = true;
+            }
+            uint32_t nl = 0;
+            CU(c, launch_path_wavefront(c->dev, rp, c->wave, c->use_bvh, stats, c->sm_count, c->stream, &nl));
+            launches += nl;
+        } else {
+            CU(c, launch_path_mega(c->dev, rp, c->use_bvh, stats, c->sm_count, c->stream)); ++launches;
+        }
+    }
+    CU(c, cudaEventRecord(c->ev_trace1, c->stream));
+    c->cur_target = (c->cur_target + 1) % (uint32_t)c->d_rgba.size();   // currentFrame = (currentFrame + 1) % FRAMES_IN_FLIGHT (:1341)
+    if (!(c->info.flags & VKRT_FLAG_NO_RESOLVE)) {
+        CU(c, launch_resolve(rp, c->info.integrator, c->d_rgba[c->cur_target], c->stream)); ++launches;
+    }
+    CU(c, cudaEventRecord(c->ev_end, c->stream));
+    c->timing_valid = true;
+    c->last_launches = launches;
+    c->accum_valid = true;
+    ++c->frame_index;
+    ++c->frames;
+    return VKRT_SUCCESS;
+}
+
+VKRT_API vkrt_error vkrt_resolve(vkrt_ctx *c)
+{
+    if (!c) return VKRT_BAD_ARG;
+    DeviceGuard g(c->info.device_id);
+    RenderParams rp;
+    fill_params(c, rp);
+    CU(c, launch_resolve(rp, c->info.integrator, c->d_rgba[c->cur_target], c->stream));
+    return VKRT_SUCCESS;
+}
+
+VKRT_API vkrt_error vkrt_wait_idle(vkrt_ctx *c)
+{
+    if (!c) return VKRT_BAD_ARG;
+    DeviceGuard g(c->info.device_id);
+    CU(c, cudaStreamSynchronize(c->stream));
+    return VKRT_SUCCESS;
+}
+
+// ---- outputs --------------------------------------------------------------------------------------
+VKRT_API vkrt_error vkrt_get_rgba8(vkrt_ctx *c, void **dev_ptr, size_t *pitch)
+{
+    if (!c || !dev_ptr) return VKRT_BAD_ARG;
+    *dev_ptr = c->d_rgba[c->cur_target];
+    if (pitch) *pitch = (size_t)c->info.width * 4;
+    return VKRT_SUCCESS;
+}
+VKRT_API vkrt_error vkrt_get_accum(vkrt_ctx *c, float **dev_ptr)
+{
+    if (!c || !dev_ptr) return VKRT_BAD_ARG;
+    *dev_ptr = (float *)c->d_accum;
+    return VKRT_SUCCESS;
+}
+VKRT_API vkrt_error vkrt_get_hit_ids(vkrt_ctx *c, uint32_t **dev_ptr)
+{
+    if (!c || !dev_ptr) return VKRT_BAD_ARG;
+    if (!c->d_hit_ids) return fail(c, VKRT_BAD_ARG, "context created without VKRT_FLAG_HIT_IDS");
+    *dev_ptr = c->d_hit_ids;
+    return VKRT_SUCCESS;
+}
+VKRT_API vkrt_error vkrt_get_stream(vkrt_ctx *c, void **stream)
+{
+    if (!c || !stream) return VKRT_BAD_ARG;
+    *stream = (void *)c->stream;
+    return VKRT_SUCCESS;
+}
+
+static vkrt_error read_back(vkrt_ctx *c, void *host, const void *dev, size_t have, size_t bytes)
+{
+    if (!host || !dev) return fail(c, VKRT_BAD_ARG, "null buffer");
+    if (bytes < have) return fail(c, VKRT_BAD_ARG, "host buffer too small");
+    DeviceGuard g(c->info.device_id);
+    CU(c, cudaMemcpyAsync(host, dev, have, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return VKRT_SUCCESS;
+}
+VKRT_API vkrt_error vkrt_read_rgba8(vkrt_ctx *c, void *host, size_t bytes)
+{
+    if (!c) return VKRT_BAD_ARG;
+    return read_back(c, host, c->d_rgba[c->cur_target], (size_t)c->info.width * c->info.height * 4, bytes);
+}
+VKRT_API vkrt_error vkrt_read_rgba8_async(vkrt_ctx *c, void *host, size_t bytes)
+{
+    if (!c || !host) return VKRT_BAD_ARG;
+    const size_t have = (size_t)c->info.width * c->info.height * 4;
+    if (bytes < have) return fail(c, VKRT_BAD_ARG, "host buffer too small");
+    DeviceGuard g(c->info.device_id);
+    CU(c, cudaMemcpyAsync(host, c->d_rgba[c->cur_target], have, cudaMemcpyDeviceToHost, c->stream));
+    return VKRT_SUCCESS;
+}
+VKRT_API vkrt_error vkrt_read_accum(vkrt_ctx *c, float *host, size_t bytes)
+{
+    if (!c) return VKRT_BAD_ARG;
+    return read_back(c, host, c->d_accum, (size_t)c->info.width * c->info.height * 16, bytes);
+}
+VKRT_API vkrt_error vkrt_read_hit_ids(vkrt_ctx *c, uint32_t *host, size_t bytes)
+{
+    if (!c) return VKRT_BAD_ARG;
+    if (!c->d_hit_ids) return fail(c, VKRT_BAD_ARG, "context created without VKRT_FLAG_HIT_IDS");
+    return read_back(c, host, c->d_hit_ids, (size_t)c->info.width * c->info.height * 4, bytes);
+}
+
+VKRT_API vkrt_error vkrt_get_counters(vkrt_ctx *c, vkrt_counters *out)
+{
+    if (!c || !out) return VKRT_BAD_ARG;
+    DeviceGuard g(c->info.device_id);
+    unsigned long long h[CNT_N];
+    CU(c, cudaMemcpyAsync(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    out->closest_rays = h[CNT_CLOSEST]; out->shadow_rays = h[CNT_SHADOW]; out->node_visits = h[CNT_NODES];
+    out->leaf_tests = h[CNT_LEAVES]; out->paths = h[CNT_PATHS]; out->frames = c->frames;
+    return VKRT_SUCCESS;
+}
+VKRT_API vkrt_error vkrt_reset_counters(vkrt_ctx *c)
+{
+    if (!c) return VKRT_BAD_ARG;
+    DeviceGuard g(c->info.device_id);
+    CU(c, cudaMemsetAsync(c->d_counters, 0, CNT_N * sizeof(unsigned long long), c->stream));
+    c->frames = 0;
+    return VKRT_SUCCESS;
+}
+VKRT_API vkrt_error vkrt_last_frame_timing(vkrt_ctx *c, float *trace_ms, float *total_ms, uint32_t *n_launches)
+{
+    if (!c) return VKRT_BAD_ARG;
+    if (!c->timing_valid) return fail(c, VKRT_BAD_ARG, "no frame drawn yet");
+    DeviceGuard g(c->info.device_id);
+    CU(c, cudaEventSynchronize(c->ev_end));
+    float a = 0.f, b = 0.f;
+    CU(c, cudaEventElapsedTime(&a, c->ev_trace0, c->ev_trace1));
+    CU(c, cudaEventElapsedTime(&b, c->ev_begin, c->ev_end));
+    if (trace_ms) *trace_ms = a;
+    if (total_ms) *total_ms = b;
+    if (n_launches) *n_launches = c->last_launches;
+    return VKRT_SUCCESS;
+}
+
+// ---- sharding -------------------------------------------------------------------------------------
+VKRT_API vkrt_error vkrt_shard_floats(vkrt_ctx *c, uint32_t tile_rank, size_t *n_floats)
+{
+    if (!c || !n_floats) return VKRT_BAD_ARG;
+    const uint32_t cnt = c->info.tile_shard_count;
+    const uint32_t owned = tile_rank < c->n_tiles ? (c->n_tiles - tile_rank + cnt - 1) / cnt : 0;
+    *n_floats = (size_t)owned * TILE_PX * 4;
+    return VKRT_SUCCESS;
+}
+VKRT_API vkrt_error vkrt_pack_shard(vkrt_ctx *c, float **dev_ptr, size_t *n_floats)
+{
+    if (!c || !dev_ptr) return VKRT_BAD_ARG;
+    DeviceGuard g(c->info.device_id);
+    // every rank packs the size of rank 0 (the largest shard) so that a plain gather works
+    const uint32_t cnt = c->info.tile_shard_count;
+    const size_t max_slots = (size_t)((c->n_tiles + cnt - 1) / cnt) * TILE_PX;
+    if (!c->d_packed) {
+        CU(c, cudaMalloc(&c->d_packed, max_slots * sizeof(float4)));
+        CU(c, cudaMemsetAsync(c->d_packed, 0, max_slots * sizeof(float4), c->stream));
+    }
+    RenderParams rp;
+    fill_params(c, rp);
+    if (rp.n_work) CU(c, launch_pack(rp, c->d_packed, c->stream));
+    *dev_ptr = (float *)c->d_packed;
+    if (n_floats) *n_floats = max_slots * 4;
+    return VKRT_SUCCESS;
+}
+VKRT_API vkrt_error vkrt_unpack_shard(vkrt_ctx *c, const float *dev_packed, uint32_t tile_rank, uint32_t tile_count, int add)
+{
+    if (!c || !dev_packed || tile_count == 0 || tile_rank >= tile_count) return VKRT_BAD_ARG;
+    DeviceGuard g(c->info.device_id);
+    CU(c, launch_unpack(c->d_accum, (const float4 *)dev_packed, c->info.width, c->info.height, tile_rank, tile_count, add, c->stream));
+    c->accum_valid = true;
+    return VKRT_SUCCESS;
+}
+
+VKRT_API vkrt_error vkrt_measure_fp32_peak(int device_id, float *tflops)
+{
+    if (!tflops) return VKRT_BAD_ARG;
+    DeviceGuard g(device_id);
+    return measure_fp32_peak(tflops) == cudaSuccess ? VKRT_SUCCESS : VKRT_CUDA_ERROR;
+}
+VKRT_API vkrt_error vkrt_measure_l2_bandwidth(int device_id, float *gbs)
+{
+    if (!gbs) return VKRT_BAD_ARG;
+    DeviceGuard g(device_id);
+    return measure_l2_bandwidth(gbs) == cudaSuccess ? VKRT_SUCCESS : VKRT_CUDA_ERROR;
+}
+
+} // extern "C"

@@ -1,0 +1,329 @@
+// Device LBVH build over the sphere list: centroid bounds -> 30-bit Morton codes -> LSD radix
+// sort (4 x 8 bit, stable) -> Karras 2012 hierarchy -> bottom-up refit with per-node arrival
+// counters -> packed 64-byte nodes (vkrt_device.cuh "HBM layout").
+//
+// New functionality: the reference brute-forces every primitive (Tracer.comp:378-428); what it
+// pins is only the nearest-hit semantics the tree has to reproduce (DESIGN.md "Rule S").
+// The tree is a pure function of the sphere array (stable sort by (code, index), exact min/max),
+// so every GPU that builds it gets the identical tree.
+#include "vkrt_device.cuh"
+#include "vkrt_internal.h"
+
+namespace vkrt {
+
+// float <-> order-preserving int, for atomicMin/atomicMax on floats
+__device__ __forceinline__ int f2ord(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void k_bounds_init(int *b)
+{
+    if (threadIdx.x < 3) b[threadIdx.x] = 0x7fffffff;          // min
+    else if (threadIdx.x < 6) b[threadIdx.x] = (int)0x80000000; // max
+}
+
+__global__ void __launch_bounds__(256) k_bounds(const float4 *__restrict__ sph, uint32_t n, int *b)
+{
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 s = sph[i];
+        lo[0] = fminf(lo[0], s.x); lo[1] = fminf(lo[1], s.y); lo[2] = fminf(lo[2], s.z);
+        hi[0] = fmaxf(hi[0], s.x); hi[1] = fmaxf(hi[1], s.y); hi[2] = fmaxf(hi[2], s.z);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int l = f2ord(lo[k]), h = f2ord(hi[k]);
+        l = __reduce_min_sync(0xffffffffu, l);
+        h = __reduce_max_sync(0xffffffffu, h);
+        if ((threadIdx.x & 31) == 0) { atomicMin(b + k, l); atomicMax(b + 3 + k, h); }
+    }
+}
+
+__device__ __forceinline__ uint32_t expand_bits(uint32_t v)
+{
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__device__ __forceinline__ uint32_t quant10(float c, float cmin, float scale)
+{
+    float q = (c - cmin) * scale;
+    q = fminf(fmaxf(q, 0.0f), 1023.0f);
+    return (uint32_t)q;
+}
+
+__global__ void __launch_bounds__(256) k_morton(const float4 *__restrict__ sph, uint32_t n, const int *__restrict__ b,
+                                                 uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float cminx = ord2f(b[0]), cminy = ord2f(b[1]), cminz = ord2f(b[2]);
+    const float ex = ord2f(b[3]) - cminx, ey = ord2f(b[4]) - cminy, ez = ord2f(b[5]) - cminz;
+    const float sx = ex > 0.0f ? 1024.0f / ex : 0.0f, sy = ey > 0.0f ? 1024.0f / ey : 0.0f, sz = ez > 0.0f ? 1024.0f / ez : 0.0f;
+    const float4 s = sph[i];
+    keys[i] = (expand_bits(quant10(s.x, cminx, sx)) << 2) | (expand_bits(quant10(s.y, cminy, sy)) << 1) |
+              expand_bits(quant10(s.z, cminz, sz));
+    vals[i] = i;
+}
+
+// ---- LSD radix sort, 8 bits per pass, stable --------------------------------------------------
+enum { RS_THREADS = 256, RS_ROUNDS = 4, RS_TILE = RS_THREADS * RS_ROUNDS, RS_DIGITS = 256 };
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint32_t *__restrict__ keys, uint32_t n, int shift,
+                                                         uint32_t *__restrict__ hist, uint32_t n_blocks)
+{
+    __shared__ uint32_t h[RS_DIGITS];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * RS_TILE;
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        const uint32_t i = base + r * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[threadIdx.x * n_blocks + blockIdx.x] = h[threadIdx.x];   // digit-major
+}
+
+// exclusive scan of hist[0 .. m) by one block (m = 256 * n_blocks); fine for a one-off build
+__global__ void __launch_bounds__(1024) k_rs_scan(uint32_t *__restrict__ hist, uint32_t m)
+{
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < m; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < m ? hist[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = warp_sums[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (threadIdx.x >= o) w += y; }
+            warp_sums[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const uint32_t warp_off = (threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0u;
+        const uint32_t c = carry;
+        if (i < m) hist[i] = c + warp_off + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = c + warp_off + x;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                                                            uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
+                                                            uint32_t n, int shift, const uint32_t *__restrict__ hist,
+                                                            uint32_t n_blocks)
+{
+    __shared__ uint32_t warp_cnt[RS_THREADS / 32][RS_DIGITS];
+    __shared__ uint32_t running[RS_DIGITS];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    running[threadIdx.x] = hist[threadIdx.x * n_blocks + blockIdx.x];
+    const uint32_t base = blockIdx.x * RS_TILE;
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+#pragma unroll
+        for (int w = 0; w < RS_THREADS / 32; ++w) warp_cnt[w][threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t i = base + r * RS_THREADS + threadIdx.x;
+        const bool valid = i < n;
+        const uint32_t key = valid ? keys_in[i] : 0xffffffffu;
+        const uint32_t dig = valid ? ((key >> shift) & 255u) : 256u;     // 256 = "no digit"
+        const unsigned peers = __match_any_sync(0xffffffffu, dig);
+        const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+        if (valid && rank_in_warp == 0) warp_cnt[warp][dig] = __popc(peers);
+        __syncthreads();
+        if (valid) {
+            uint32_t off = running[dig] + rank_in_warp;
+            for (unsigned w = 0; w < warp; ++w) off += warp_cnt[w][dig];
+            keys_out[off] = key;
+            vals_out[off] = vals_in[i];
+        }
+        __syncthreads();
+        uint32_t tot = 0;
+#pragma unroll
+        for (int w = 0; w < RS_THREADS / 32; ++w) tot += warp_cnt[w][threadIdx.x];
+        running[threadIdx.x] += tot;
+        __syncthreads();
+    }
+}
+
+// ---- Karras 2012: one thread per inner node ---------------------------------------------------
+__device__ __forceinline__ int delta(const uint32_t *__restrict__ codes, int n, int i, int j)
+{
+    if (j < 0 || j >= n) return -1;
+    const uint32_t a = codes[i], b = codes[j];
+    if (a == b) return 32 + __clz((uint32_t)i ^ (uint32_t)j);
+    return __clz(a ^ b);
+}
+
+// child encoding in the temporary arrays: >= 0 inner node, < 0 leaf ~sorted_position
+__global__ void __launch_bounds__(256) k_karras(const uint32_t *__restrict__ codes, int n, int2 *__restrict__ children,
+                                                 int *__restrict__ parent_inner, int *__restrict__ parent_leaf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = (delta(codes, n, i, i + 1) - delta(codes, n, i, i - 1)) > 0 ? 1 : -1;
+    const int dmin = delta(codes, n, i, i - d);
+    int lmax = 2;
+    while (delta(codes, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (delta(codes, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta(codes, n, i, j);
+    int s = 0;
+    for (int t = (l + 1) / 2;; t = (t + 1) / 2) {
+        if (delta(codes, n, i, i + (s + t) * d) > dnode) s += t;
+        if (t == 1) break;
+    }
+    const int gamma = i + s * d + min(d, 0);
+    const int first = min(i, j), last = max(i, j);
+    int2 c;
+    if (first == gamma) { c.x = ~gamma; parent_leaf[gamma] = i; } else { c.x = gamma; parent_inner[gamma] = i; }
+    if (last == gamma + 1) { c.y = ~(gamma + 1); parent_leaf[gamma + 1] = i; } else { c.y = gamma + 1; parent_inner[gamma + 1] = i; }
+    children[i] = c;
+    if (i == 0) parent_inner[0] = -1;
+}
+
+// ---- refit + pack: one thread per leaf walks up; the second arrival at a node owns it ---------
+__device__ __forceinline__ void write_child(float4 *node, int k, bool leaf, float4 sphere, int index, const float *lo, const float *hi)
+{
+    if (leaf) {
+        node[2 * k] = sphere;
+        node[2 * k + 1] = make_float4(sphere_pad_radius(sphere.w), 0.0f, __int_as_float(index), __int_as_float(1));
+    } else {
+        node[2 * k] = make_float4(lo[0], lo[1], lo[2], hi[0]);
+        node[2 * k + 1] = make_float4(hi[1], hi[2], __int_as_float(index), __int_as_float(0));
+    }
+}
+__device__ __forceinline__ void leaf_box(float4 s, float *lo, float *hi)
+{
+    const float rp = sphere_pad_radius(s.w);
+    lo[0] = s.x - rp; lo[1] = s.y - rp; lo[2] = s.z - rp;
+    hi[0] = s.x + rp; hi[1] = s.y + rp; hi[2] = s.z + rp;
+}
+
+__global__ void __launch_bounds__(256) k_refit(const float4 *__restrict__ sph, const uint32_t *__restrict__ sorted_idx, int n,
+                                                const int2 *__restrict__ children, const int *__restrict__ parent_inner,
+                                                const int *__restrict__ parent_leaf, int *__restrict__ arrivals,
+                                                float4 *__restrict__ box_lo, float4 *__restrict__ box_hi,
+                                                float4 *__restrict__ nodes)
+{
+    const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+    if (leaf >= n) return;
+    int node = parent_leaf[leaf];
+    while (node >= 0) {
+        __threadfence();
+        if (atomicAdd(arrivals + node, 1) == 0) return;      // the sibling subtree is not done yet
+        __threadfence();
+        const int2 c = children[node];
+        float lo[2][3], hi[2][3];
+        float4 sp[2];
+        int idx[2];
+        bool is_leaf[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int ch = k == 0 ? c.x : c.y;
+            is_leaf[k] = ch < 0;
+            if (is_leaf[k]) {
+                idx[k] = (int)sorted_idx[~ch];
+                sp[k] = sph[idx[k]];
+                leaf_box(sp[k], lo[k], hi[k]);
+            } else {
+                idx[k] = ch;
+                const volatile float4 *pl = box_lo + ch, *ph = box_hi + ch;
+                lo[k][0] = pl->x; lo[k][1] = pl->y; lo[k][2] = pl->z;
+                hi[k][0] = ph->x; hi[k][1] = ph->y; hi[k][2] = ph->z;
+                sp[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            write_child(nodes + 4 * (size_t)node, k, is_leaf[k], sp[k], idx[k], lo[k], hi[k]);
+        }
+        box_lo[node] = make_float4(fminf(lo[0][0], lo[1][0]), fminf(lo[0][1], lo[1][1]), fminf(lo[0][2], lo[1][2]), 0.f);
+        box_hi[node] = make_float4(fmaxf(hi[0][0], hi[1][0]), fmaxf(hi[0][1], hi[1][1]), fmaxf(hi[0][2], hi[1][2]), 0.f);
+        node = parent_inner[node];
+    }
+}
+
+__global__ void k_single_leaf(const float4 *__restrict__ sph, float4 *__restrict__ nodes)
+{
+    const float4 s = sph[0];
+    write_child(nodes, 0, true, s, 0, nullptr, nullptr);
+    write_child(nodes, 1, true, s, 0, nullptr, nullptr);
+}
+
+#define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { err = _e; goto done; } } while (0)
+
+cudaError_t build_lbvh(const float4 *d_spheres, uint32_t n, BvhBuild &out, cudaStream_t st)
+{
+    cudaError_t err = cudaSuccess;
+    if (out.nodes) { cudaFree(out.nodes); out.nodes = nullptr; }
+    out.n_nodes = 0; out.build_ms = 0.f; out.launches = 0;
+    if (n == 0) return cudaSuccess;
+
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int *bounds = nullptr, *parent_inner = nullptr, *parent_leaf = nullptr, *arrivals = nullptr;
+    uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr}, *hist = nullptr;
+    int2 *children = nullptr;
+    float4 *box_lo = nullptr, *box_hi = nullptr;
+    const uint32_t n_inner = n > 1 ? n - 1 : 1;
+    const uint32_t n_blocks = (n + RS_TILE - 1) / RS_TILE;
+    uint32_t launches = 0;
+
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaMalloc(&out.nodes, (size_t)n_inner * 64));
+    CK(cudaEventRecord(e0, st));
+    if (n == 1) {
+        k_single_leaf<<<1, 1, 0, st>>>(d_spheres, out.nodes); ++launches;
+        CK(cudaGetLastError());
+    } else {
+        CK(cudaMalloc(&bounds, 6 * sizeof(int)));
+        for (int k = 0; k < 2; ++k) { CK(cudaMalloc(&keys[k], n * sizeof(uint32_t))); CK(cudaMalloc(&vals[k], n * sizeof(uint32_t))); }
+        CK(cudaMalloc(&hist, (size_t)RS_DIGITS * n_blocks * sizeof(uint32_t)));
+        CK(cudaMalloc(&children, (size_t)(n - 1) * sizeof(int2)));
+        CK(cudaMalloc(&parent_inner, (size_t)(n - 1) * sizeof(int)));
+        CK(cudaMalloc(&parent_leaf, (size_t)n * sizeof(int)));
+        CK(cudaMalloc(&arrivals, (size_t)(n - 1) * sizeof(int)));
+        CK(cudaMalloc(&box_lo, (size_t)(n - 1) * sizeof(float4)));
+        CK(cudaMalloc(&box_hi, (size_t)(n - 1) * sizeof(float4)));
+        CK(cudaMemsetAsync(arrivals, 0, (size_t)(n - 1) * sizeof(int), st));
+
+        k_bounds_init<<<1, 32, 0, st>>>(bounds); ++launches;
+        {
+            unsigned g = (n + 255u) / 256u; if (g > 592u) g = 592u;   // 4 x 148 SMs
+            k_bounds<<<g, 256, 0, st>>>(d_spheres, n, bounds); ++launches;
+        }
+        k_morton<<<(n + 255u) / 256u, 256, 0, st>>>(d_spheres, n, bounds, keys[0], vals[0]); ++launches;
+        int cur = 0;
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = pass * 8;
+            k_rs_hist<<<n_blocks, RS_THREADS, 0, st>>>(keys[cur], n, shift, hist, n_blocks); ++launches;
+            k_rs_scan<<<1, 1024, 0, st>>>(hist, RS_DIGITS * n_blocks); ++launches;
+            k_rs_scatter<<<n_blocks, RS_THREADS, 0, st>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, hist, n_blocks); ++launches;
+            cur ^= 1;
+        }
+        k_karras<<<(n - 1 + 255u) / 256u, 256, 0, st>>>(keys[cur], (int)n, children, parent_inner, parent_leaf); ++launches;
+        k_refit<<<(n + 255u) / 256u, 256, 0, st>>>(d_spheres, vals[cur], (int)n, children, parent_inner, parent_leaf, arrivals,
+                                                   box_lo, box_hi, out.nodes); ++launches;
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(e1, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&out.build_ms, e0, e1));
+    out.n_nodes = n_inner;
+    out.launches = launches;
+done:
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(bounds); cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); cudaFree(hist);
+    cudaFree(children); cudaFree(parent_inner); cudaFree(parent_leaf); cudaFree(arrivals); cudaFree(box_lo); cudaFree(box_hi);
+    if (err != cudaSuccess && out.nodes) { cudaFree(out.nodes); out.nodes = nullptr; }
+    return err;
+}
+
+} // namespace vkrt

@@ -1,0 +1,454 @@
+// Device-side scene layout, intersection routines, LBVH traversal and the two integrators'
+// per-bounce bodies.  Shared by the megakernel and the wavefront kernels.
+//
+// Reference semantics restated here (paths relative to the reference root):
+//   Assets/Tracer.comp:314-431    calc_*_intersect, trace_ray   (path integrator)
+//   Assets/Tracer.comp:256-312    jitter, schlick, GGX, Smith
+//   Assets/Tracer.comp:433-553    radiance
+//   Assets/Raytracer.comp:129-355 calc_*_intersect, trace_ray, render_scene (whitted)
+#pragma once
+#include "vkrt_arith.cuh"
+#include "../../include/vkrt.h"
+
+namespace vkrt {
+
+enum { MAX_PLANES = 16, BVH_STACK = 64 };
+enum { KIND_TRI = 1, KIND_SPHERE = 2, KIND_PLANE = 3 };
+
+// ---- HBM layout (DESIGN.md "Data layout") ----------------------------------------------------
+// spheres : float4 {cx,cy,cz,r}             16 B, original order (shading fetch: normal)
+// mats    : 3 x float4 per material         48 B {albedo.rgb, roughness | emissive.rgb, metalness | type,-,-,-}
+// tris    : 3 x float4 per triangle         48 B, the reference's SSBO layout verbatim
+// bvh     : 4 x float4 per inner node       64 B = two 32 B child records:
+//             inner child: {lo.x lo.y lo.z hi.x | hi.y hi.z  idx  kind=0}
+//             leaf  child: {cx   cy   cz   r    | rp   0     sphere kind=1}   (the sphere itself:
+//             a leaf costs no second dependent fetch)
+struct DevScene {
+    const float4 *spheres;
+    const uint32_t *sphere_mat;
+    const float4 *bvh;
+    const float4 *tris;
+    const float4 *mats;
+    uint32_t n_spheres, n_tris, tri_mat, n_planes, n_lights, n_nodes, n_mats, _pad;
+    float4 planes[MAX_PLANES];
+    uint32_t plane_mat[MAX_PLANES];
+    uint32_t lights[MAX_LIGHTS];
+    uint32_t _pad2[2];
+};
+
+struct Material { V3 albedo; float roughness; V3 emissive; float metalness; uint32_t type; };
+
+struct Stats { uint32_t closest, shadow, nodes, leaves, paths; };
+VKRT_DEV void stats_zero(Stats &s) { s.closest = s.shadow = s.nodes = s.leaves = s.paths = 0; }
+
+struct Hit { float t; uint32_t kind, index; };
+
+VKRT_DEV Material load_material(const DevScene &sc, uint32_t id)
+{
+    const float4 a = __ldg(sc.mats + 3 * id), b = __ldg(sc.mats + 3 * id + 1);
+    const uint32_t type = __float_as_uint(__ldg(&sc.mats[3 * id + 2].x));
+    return Material{{a.x, a.y, a.z}, a.w, {b.x, b.y, b.z}, b.w, type};
+}
+
+// ---- Tracer.comp:314-329 / Raytracer.comp:163-178 ---------------------------------------------
+VKRT_DEV float sphere_intersect(V3 o, V3 d, float4 s)
+{
+    const V3 oc = o - xyz(s);
+    const float b = 2.0f * dot3(oc, d);
+    const float c = fma_(-s.w, s.w, dot3(oc, oc));
+    const float h = fma_(b, b, -(4.0f * c));
+    if (h < 0.0f) return -1.0f;
+    return (-b - sqrtf(h)) * 0.5f;
+}
+// ---- Tracer.comp:331-338 ----------------------------------------------------------------------
+VKRT_DEV float plane_intersect_tracer(V3 o, V3 d, float4 p)
+{
+    const V3 N = xyz(p);
+    const float dn = dot3(d, N);
+    const float dist = -(p.w + dot3(o, N)) / dn;
+    const float when_neq = gl_abs(gl_sign(dn - 0.0f));
+    return when_neq * gl_max(dist, 0.0f);
+}
+// ---- Raytracer.comp:180-192 -------------------------------------------------------------------
+VKRT_DEV float plane_intersect_raytracer(V3 o, V3 d, float4 p)
+{
+    const V3 N = xyz(p);
+    const float dn = dot3(d, N);
+    if (dn == 0.0f) return 0.0f;
+    const float dist = -(p.w + dot3(o, N)) / dn;
+    return gl_max(dist, 0.0f);
+}
+// ---- Tracer.comp:340-372 / Raytracer.comp:129-161 ---------------------------------------------
+VKRT_DEV float tri_intersect(V3 o, V3 d, V3 v0, V3 v1, V3 v2, float eps)
+{
+    const V3 v0v1 = v1 - v0, v0v2 = v2 - v0;
+    const V3 pvec = cross3(d, v0v2);
+    const float det = dot3(v0v1, pvec);
+    if (det < eps) return -1.0f;
+    const float inv_det = 1.0f / det;
+    const V3 tvec = o - v0;
+    const float u = dot3(tvec, pvec) * inv_det;
+    if (u < 0.0f || u > 1.0f) return -1.0f;
+    const V3 qvec = cross3(tvec, v0v1);
+    const float v = dot3(d, qvec) * inv_det;
+    if (v < 0.0f || u + v > 1.0f) return -1.0f;
+    return dot3(v0v2, qvec) * inv_det;
+}
+
+// ---- rule S: order-independent nearest sphere through the LBVH (DESIGN.md "Rule S") ------------
+VKRT_DEV float safe_inv(float d)
+{
+    const float dd = gl_abs(d) > 1e-20f ? d : copysignf(1e-20f, d);
+    return 1.0f / dd;
+}
+struct SlabRay { V3 inv, oinv; };
+VKRT_DEV SlabRay slab_setup(V3 o, V3 d)
+{
+    SlabRay s;
+    s.inv = {safe_inv(d.x), safe_inv(d.y), safe_inv(d.z)};
+    s.oinv = o * s.inv;
+    return s;
+}
+VKRT_DEV bool slab_test(const SlabRay &s, V3 lo, V3 hi, float &tn, float &tf)
+{
+    const float t0x = fma_(lo.x, s.inv.x, -s.oinv.x), t1x = fma_(hi.x, s.inv.x, -s.oinv.x);
+    const float t0y = fma_(lo.y, s.inv.y, -s.oinv.y), t1y = fma_(hi.y, s.inv.y, -s.oinv.y);
+    const float t0z = fma_(lo.z, s.inv.z, -s.oinv.z), t1z = fma_(hi.z, s.inv.z, -s.oinv.z);
+    tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+    tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+    return tn <= tf && tf >= 0.0f;
+}
+VKRT_DEV float sphere_pad_radius(float r) { return r * 1.001f + 0.001f; }
+
+struct SBest { float t; int idx; };
+
+VKRT_DEV void s_consider(V3 o, V3 d, float4 sph, int i, float tn, float eps, float B, SBest &best)
+{
+    const float t = sphere_intersect(o, d, sph);
+    if (!(t > eps) || !(tn <= t)) return;
+    if (best.idx < 0) { if (t < B) { best.t = t; best.idx = i; } }
+    else if (t < best.t || (t == best.t && i < best.idx)) { best.t = t; best.idx = i; }
+}
+
+template <bool ANY, bool STATS>
+VKRT_DEV SBest bvh_query(const DevScene &sc, V3 o, V3 d, float eps, float B, Stats &st)
+{
+    SBest best{B, -1};
+    if (sc.n_nodes == 0) return best;
+    const SlabRay sr = slab_setup(o, d);
+    int stack[BVH_STACK];
+    int sp = 0, node = 0;
+    for (;;) {
+        const float4 *np = sc.bvh + 4 * (size_t)node;
+        const float4 a0 = __ldg(np), b0 = __ldg(np + 1), a1 = __ldg(np + 2), b1 = __ldg(np + 3);
+        if (STATS) ++st.nodes;
+        int nxt0 = -1, nxt1 = -1;
+        float tn0, tn1, tf;
+        {
+            const bool leaf = __float_as_int(b0.w) == 1;
+            const V3 lo = leaf ? v3(a0.x - b0.x, a0.y - b0.x, a0.z - b0.x) : v3(a0.x, a0.y, a0.z);
+            const V3 hi = leaf ? v3(a0.x + b0.x, a0.y + b0.x, a0.z + b0.x) : v3(a0.w, b0.x, b0.y);
+            const bool hit = slab_test(sr, lo, hi, tn0, tf) && tn0 <= best.t;
+            if (hit) {
+                if (leaf) {
+                    if (STATS) ++st.leaves;
+                    s_consider(o, d, a0, __float_as_int(b0.z), tn0, eps, B, best);
+                    if (ANY && best.idx >= 0) return best;
+                } else nxt0 = __float_as_int(b0.z);
+            }
+        }
+        {
+            const bool leaf = __float_as_int(b1.w) == 1;
+            const V3 lo = leaf ? v3(a1.x - b1.x, a1.y - b1.x, a1.z - b1.x) : v3(a1.x, a1.y, a1.z);
+            const V3 hi = leaf ? v3(a1.x + b1.x, a1.y + b1.x, a1.z + b1.x) : v3(a1.w, b1.x, b1.y);
+            const bool hit = slab_test(sr, lo, hi, tn1, tf) && tn1 <= best.t;
+            if (hit) {
+                if (leaf) {
+                    if (STATS) ++st.leaves;
+                    s_consider(o, d, a1, __float_as_int(b1.z), tn1, eps, B, best);
+                    if (ANY && best.idx >= 0) return best;
+                } else nxt1 = __float_as_int(b1.z);
+            }
+        }
+        if (nxt0 >= 0 && nxt1 >= 0) {
+            const bool swap = tn1 < tn0;
+            stack[sp++] = swap ? nxt0 : nxt1;
+            node = swap ? nxt1 : nxt0;
+        } else if (nxt0 >= 0) node = nxt0;
+        else if (nxt1 >= 0) node = nxt1;
+        else { if (sp == 0) break; node = stack[--sp]; }
+    }
+    return best;
+}
+
+// ---- trace_ray: Tracer.comp:374-431 (TRACER = true) / Raytracer.comp:224-278 (false) ----------
+// SHADOW queries only need the boolean, so they may leave early.
+template <bool TRACER, bool BVH, bool SHADOW, bool STATS>
+VKRT_DEV bool trace_ray(const DevScene &sc, V3 o, V3 d, Hit &hit, Stats &st)
+{
+    const float EPS = TRACER ? 1e-3f : 0.01f;
+    if (SHADOW) ++st.shadow; else ++st.closest;
+    bool found = false;
+    float cur = hit.t;
+    for (uint32_t i = 0; i < sc.n_tris; ++i) {
+        const V3 v0 = xyz(__ldg(sc.tris + 3 * i)), v1 = xyz(__ldg(sc.tris + 3 * i + 1)), v2 = xyz(__ldg(sc.tris + 3 * i + 2));
+        const float t = tri_intersect(o, d, v0, v1, v2, EPS);
+        const bool acc = TRACER ? ((t > EPS) && (t < cur + EPS)) : (t > EPS && t < cur);
+        if (acc) { cur = t; hit.kind = KIND_TRI; hit.index = i; found = true; }
+    }
+    if (SHADOW && found) return true;
+    if (BVH) {
+        const float B = TRACER ? cur + EPS : cur;
+        const SBest b = bvh_query<SHADOW, STATS>(sc, o, d, EPS, B, st);
+        if (b.idx >= 0) { cur = b.t; hit.kind = KIND_SPHERE; hit.index = (uint32_t)b.idx; found = true; }
+    } else {
+        for (uint32_t i = 0; i < sc.n_spheres; ++i) {
+            const float t = sphere_intersect(o, d, __ldg(sc.spheres + i));
+            const bool acc = TRACER ? ((t > EPS) && (t < cur + EPS)) : (t > EPS && t < cur);
+            if (acc) { cur = t; hit.kind = KIND_SPHERE; hit.index = i; found = true; }
+        }
+    }
+    if (SHADOW && found) return true;
+    for (uint32_t i = 0; i < sc.n_planes; ++i) {
+        const float t = TRACER ? plane_intersect_tracer(o, d, sc.planes[i]) : plane_intersect_raytracer(o, d, sc.planes[i]);
+        const bool acc = TRACER ? ((t > EPS) && (t < cur - EPS)) : (t > EPS && t < cur);
+        if (acc) { cur = t; hit.kind = KIND_PLANE; hit.index = i; found = true; }
+    }
+    hit.t = cur;
+    return found;
+}
+
+struct Surface { V3 P, N; uint32_t mat; };
+
+VKRT_DEV Surface surface_of(const DevScene &sc, V3 o, V3 d, const Hit &hit)
+{
+    Surface s;
+    s.P = madd3(hit.t, d, o);
+    if (hit.kind == KIND_TRI) {
+        const V3 v0 = xyz(__ldg(sc.tris + 3 * hit.index)), v1 = xyz(__ldg(sc.tris + 3 * hit.index + 1)),
+                 v2 = xyz(__ldg(sc.tris + 3 * hit.index + 2));
+        s.N = cross3(v1 - v0, v2 - v0);      // unnormalised (Tracer.comp:389-392)
+        s.mat = sc.tri_mat;
+    } else if (hit.kind == KIND_SPHERE) {
+        const float4 sp = __ldg(sc.spheres + hit.index);
+        s.N = (s.P - xyz(sp)) / sp.w;         // Tracer.comp:408
+        s.mat = __ldg(sc.sphere_mat + hit.index);
+    } else {
+        s.N = xyz(sc.planes[hit.index]);
+        s.mat = sc.plane_mat[hit.index];
+    }
+    return s;
+}
+
+// ---- Tracer.comp:256-312 ----------------------------------------------------------------------
+VKRT_DEV V3 jitter(V3 d, float phi, float sina, float cosa)
+{
+    const V3 w = normalize3(d);
+    const V3 u = normalize3(cross3(v3(w.y, w.z, w.x), w));
+    const V3 v = cross3(w, u);
+    float s, c;
+    sincos_(phi, s, c);
+    return (u * c + v * s) * sina + w * cosa;
+}
+VKRT_DEV float schlick(float cosine, float ior)
+{
+    float r0 = (1.0f - ior) / (1.0f + ior);
+    r0 = r0 * r0;
+    return r0 + (1.0f - r0) * pow_(1.0f - cosine, 5.0f);
+}
+VKRT_DEV V3 fresnel_schlick(float cosTheta, V3 F0)
+{
+    const float p = pow_(1.0f - cosTheta, 5.0f);
+    return F0 + (v3(1.0f) - F0) * p;
+}
+VKRT_DEV float distribution_ggx(V3 N, V3 H, float roughness)
+{
+    const float a = roughness * roughness;
+    const float a2 = a * a;
+    const float NdotH = gl_max(dot3(N, H), 0.0f);
+    const float NdotH2 = NdotH * NdotH;
+    float denom = (NdotH2 * (a2 - 1.0f) + 1.0f);
+    denom = VKRT_PI * denom * denom;
+    return a2 / denom;
+}
+VKRT_DEV float geometry_schlick_ggx(float NdotV, float roughness)
+{
+    const float r = (roughness + 1.0f);
+    const float k = (r * r) / 8.0f;
+    return NdotV / (NdotV * (1.0f - k) + k);
+}
+VKRT_DEV float geometry_smith(V3 N, V3 V, V3 L, float roughness)
+{
+    const float NdotV = gl_max(dot3(N, V), 0.0f);
+    const float NdotL = gl_max(dot3(N, L), 0.0f);
+    const float ggx2 = geometry_schlick_ggx(NdotV, roughness);
+    const float ggx1 = geometry_schlick_ggx(NdotL, roughness);
+    return ggx1 * ggx2;
+}
+VKRT_DEV float max3(V3 e) { return gl_max(gl_max(e.x, e.y), e.z); }
+
+// ---- one iteration of radiance()'s depth loop, Tracer.comp:438-550 ----------------------------
+struct PathState { V3 o, d, acc, mask; uint32_t depth; };
+
+VKRT_DEV void path_begin(PathState &ps, V3 o, V3 d)
+{
+    ps.o = o; ps.d = d; ps.acc = v3(0.0f); ps.mask = v3(1.0f); ps.depth = 0;
+}
+VKRT_DEV float path_tmax(uint32_t depth) { return 3000.0f / pow_((float)(depth + 1u), 2.0f); }   // :444
+
+// Shades the hit (incl. the shadow rays of the light loop) and rolls Russian roulette.
+// Returns true when the path continues into the next depth iteration.
+template <bool BVH, bool STATS>
+VKRT_DEV bool path_shade(const DevScene &sc, V3 cam_pos, uint32_t max_depth, uint32_t skey, PathState &ps,
+                         const Hit &hit, Stats &st)
+{
+    const uint32_t dim0 = ps.depth * DIMS_PER_BOUNCE;
+    const Surface sf = surface_of(sc, ps.o, ps.d, hit);
+    const Material mat = load_material(sc, sf.mat);
+    if (mat.type == 0u) {                                                            // MAT_TYPE_DIFFUSE
+        const float r2 = u01(skey, dim0 + SLOT_R2);
+        const V3 dj = jitter(sf.N, VKRT_TWO_PI * u01(skey, dim0 + SLOT_PHI), sqrtf(r2), sqrtf(1.0f - r2)) *
+                      (1.0f - mat.metalness);
+        V3 e = v3(0.0f);
+        for (uint32_t l = 0; l < sc.n_lights; ++l) {
+            const uint32_t li = sc.lights[l];
+            const float4 s = __ldg(sc.spheres + li);
+            const V3 sP = xyz(s);
+            const float t = length3(sP - sf.P) - s.w;
+            const V3 l0 = sP - sf.P;
+            const float cos_a_max = sqrtf(1.0f - gl_clamp(s.w * s.w / dot3(l0, l0), 0.0f, 1.0f));
+            const float cosa = gl_mix(cos_a_max, 1.0f, u01(skey, dim0 + SLOT_LIGHT + 2 * l));
+            const V3 L = jitter(l0, VKRT_TWO_PI * u01(skey, dim0 + SLOT_LIGHT + 2 * l + 1),
+                                sqrtf(1.0f - cosa * cosa), cosa);
+            Hit sh{t, 0, 0};
+            if (!trace_ray<true, BVH, true, STATS>(sc, sf.P, L, sh, st)) {
+                const V3 semis = xyz(__ldg(sc.mats + 3 * __ldg(sc.sphere_mat + li) + 1));
+                V3 attenuation = semis * 1.0f / pow_(t / s.w + 1.0f, 2.0f);
+                attenuation = (attenuation - v3(0.001f)) / (1.0f - 0.001f);
+                attenuation = v3(gl_max(attenuation.x, 0.0f), gl_max(attenuation.y, 0.0f), gl_max(attenuation.z, 0.0f));
+                V3 F0 = v3(0.04f);
+                F0 = mix3(F0, mat.albedo, mat.metalness);
+                const V3 V = normalize3(cam_pos - sf.P);
+                const V3 H = normalize3(V + L);
+                const float NDF = distribution_ggx(sf.N, H, mat.roughness);
+                const float G = geometry_smith(sf.N, V, L, mat.roughness);
+                const V3 F = fresnel_schlick(gl_max(dot3(H, V), 0.0f), F0);
+                V3 kD = v3(1.0f) - F;
+                kD = kD * (1.0f - mat.metalness);
+                const V3 numerator = (NDF * G) * F;
+                const float denominator = 4.0f * gl_max(dot3(sf.N, V), 0.0f) * gl_max(dot3(sf.N, L), 0.0f);
+                const V3 specular = numerator / gl_max(denominator, 0.001f);
+                const float NdotL = gl_max(dot3(sf.N, L), 0.0f);
+                e = e + (kD * mat.albedo / VKRT_PI + specular) * attenuation * NdotL;
+            }
+        }
+        const bool all_pos = mat.emissive.x > 0.0f && mat.emissive.y > 0.0f && mat.emissive.z > 0.0f;
+        const V3 emissive = all_pos ? normalize3(mat.emissive) : v3(0.0f);
+        ps.acc = ps.acc + ps.mask * (emissive + e);
+        ps.mask = ps.mask * mat.albedo;
+        const V3 nd = normalize3(reflect3(ps.d, sf.N) + dj);
+        ps.o = sf.P; ps.d = nd;
+    } else {                                                                         // MAT_TYPE_DIELECTRIC
+        ps.acc = ps.acc + mat.emissive * ps.mask;
+        ps.mask = ps.mask * mat.albedo;
+        const float cosine = -dot3(ps.d, sf.N) / length3(ps.d);
+        const V3 reflected = reflect3(ps.d, sf.N);
+        const V3 refracted = refract3(ps.d, sf.N, mat.roughness);
+        const bool is_zero = refracted.x == 0.0f && refracted.y == 0.0f && refracted.z == 0.0f;
+        const float p_reflect = is_zero ? 1.0f : schlick(cosine, mat.roughness);
+        const V3 nd = normalize3(u01(skey, dim0 + SLOT_R2) < p_reflect ? reflected : refracted);
+        ps.o = sf.P; ps.d = nd;
+    }
+    const float p = max3(ps.mask);
+    if (u01(skey, dim0 + SLOT_RR) > p) return false;
+    ps.mask = ps.mask * (1.0f / p);
+    ++ps.depth;
+    return ps.depth < max_depth;
+}
+
+// full bounce = firefly clamp + closest hit + shade.  Returns true while the path is alive.
+template <bool BVH, bool STATS>
+VKRT_DEV bool path_bounce(const DevScene &sc, V3 cam_pos, uint32_t max_depth, uint32_t skey, PathState &ps,
+                          Stats &st, uint32_t *primary_id)
+{
+    ps.acc = clamp3(ps.acc, 0.0f, 1.0f);                                             // :441
+    Hit hit{path_tmax(ps.depth), 0, 0};
+    const bool found = trace_ray<true, BVH, false, STATS>(sc, ps.o, ps.d, hit, st);
+    if (primary_id) *primary_id = found ? ((hit.kind << 28) | hit.index) : 0u;
+    if (!found) return false;
+    return path_shade<BVH, STATS>(sc, cam_pos, max_depth, skey, ps, hit, st);
+}
+
+// ---- primary ray: Tracer.comp:561-574 == Raytracer.comp:361-376 -------------------------------
+VKRT_DEV void primary_ray(const vkrt_frame_data &fd, uint32_t w, uint32_t h, uint32_t x, uint32_t y, V3 &o, V3 &d)
+{
+    const float u = (float)x / (float)w, v = (float)y / (float)h;
+    const float tx = 2.0f * u - 1.0f, ty = 2.0f * v - 1.0f;
+    const V3 cd = v3(fd.camera.dir.x, fd.camera.dir.y, fd.camera.dir.z);
+    const V3 cr = v3(fd.camera.right.x, fd.camera.right.y, fd.camera.right.z);
+    const V3 cu = v3(fd.camera.up.x, fd.camera.up.y, fd.camera.up.z);
+    V3 dir = cd + cr * tx + cu * ty;
+    dir = dir * v3(fd.aspect_ratio, 1.0f, fd.aspect_ratio);
+    o = v3(fd.camera.pos.x, fd.camera.pos.y, fd.camera.pos.z);
+    d = normalize3(dir);
+}
+
+// ---- whitted: render_scene + main, Raytracer.comp:280-399 -------------------------------------
+template <bool BVH, bool STATS>
+VKRT_DEV V3 whitted_render_scene(const DevScene &sc, V3 &ro, V3 &rd, uint32_t &bounce_depth, uint32_t bounces,
+                                 V3 light_pos, V3 cam_pos, Stats &st, uint32_t *primary_id)
+{
+    V3 color = v3(0.0f);
+    Hit hit{1000.0f, 0, 0};
+    const bool found = trace_ray<false, BVH, false, STATS>(sc, ro, rd, hit, st);
+    if (primary_id) *primary_id = found ? ((hit.kind << 28) | hit.index) : 0u;
+    if (!found) return color;
+    const Surface sf = surface_of(sc, ro, rd, hit);
+    const Material mat = load_material(sc, sf.mat);
+    const V3 light_vec = normalize3(light_pos - sf.P);
+    const float dist_to_light = length3(light_pos - sf.P);
+    {
+        const float li = 540.0f / ((4.0f * 3.14159268f) * dist_to_light);
+        const V3 light_intensity = v3(li);
+        const V3 diffuse = light_intensity * mat.albedo * gl_max(dot3(sf.N, light_vec), 0.0f);
+        const V3 half_vec = normalize3(light_vec + normalize3(cam_pos));
+        const V3 specular = light_intensity * pow_(gl_clamp(dot3(sf.N, half_vec), 0.0f, 1.0f), 16.0f);
+        color = diffuse + specular;
+    }
+    {
+        Hit sh{dist_to_light, 0, 0};
+        if (trace_ray<false, BVH, true, STATS>(sc, sf.P, light_vec, sh, st)) {
+            color = color * 0.5f;
+            bounce_depth = bounces + 1;
+        }
+    }
+    if (mat.metalness >= 0.5f) { rd = reflect3(rd, sf.N); ro = sf.P; }
+    else bounce_depth = bounces + 1;
+    return color;
+}
+
+template <bool BVH, bool STATS>
+VKRT_DEV V3 whitted_pixel(const DevScene &sc, const vkrt_frame_data &fd, V3 ro, V3 rd, uint32_t bounces, Stats &st,
+                          uint32_t *primary_id)
+{
+    const V3 light_pos = v3(fd.light_pos.x, fd.light_pos.y, fd.light_pos.z);
+    const V3 cam_pos = v3(fd.camera.pos.x, fd.camera.pos.y, fd.camera.pos.z);
+    uint32_t bounce = 0;
+    V3 fin = whitted_render_scene<BVH, STATS>(sc, ro, rd, bounce, bounces, light_pos, cam_pos, st, primary_id);
+    float strength = 0.4f;
+    while (++bounce <= bounces) {
+        const V3 refl = whitted_render_scene<BVH, STATS>(sc, ro, rd, bounce, bounces, light_pos, cam_pos, st, nullptr);
+        fin = (1.0f - strength) * fin + strength * mix3(refl, fin, 1.0f - strength);
+        strength *= 0.5f;
+    }
+    return fin;
+}
+
+VKRT_DEV uint8_t unorm8(float x)
+{
+    if (!(x == x)) return 0;
+    const float c = gl_clamp(x, 0.0f, 1.0f);
+    return (uint8_t)(int)floorf(c * 255.0f + 0.5f);
+}
+
+} // namespace vkrt

@@ -1,0 +1,71 @@
+// Host-side declarations shared by the translation units of libvkrt_cuda (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/vkrt.h"
+
+namespace vkrt {
+
+struct DevScene;   // vkrt_device.cuh
+
+// per-draw parameters: the "push constants" of the CUDA path (passed by value as kernel arguments,
+// like vkCmdPushConstants at Source/GraphicsDevice.cpp:1264 -- no per-frame H2D copy is needed)
+struct RenderParams {
+    vkrt_frame_data fd;
+    uint32_t width, height;
+    uint32_t s_begin, s_end;      // sample range of this frame rendered by this context
+    uint32_t max_depth;           // DEPTH (path) / BOUNCES (whitted)
+    uint32_t fkey;                // frame key of the integer RNG
+    uint32_t tile_rank, tile_count, tiles_x, tiles_y;
+    uint32_t n_work;              // owned tiles * 1024 pixel slots
+    uint32_t accumulate;
+    float4 *accum;
+    uint32_t *hit_ids;            // may be null
+    unsigned long long *counters; // closest, shadow, nodes, leaves, paths
+    uint32_t *work_head;
+};
+
+enum { TILE = 32, TILE_PX = TILE * TILE };
+enum { CNT_CLOSEST = 0, CNT_SHADOW = 1, CNT_NODES = 2, CNT_LEAVES = 3, CNT_PATHS = 4, CNT_N = 8 };
+
+struct LaunchCfg { int sm_count; };
+
+// vkrt_render.cu
+cudaError_t launch_path_mega(const DevScene &sc, const RenderParams &rp, bool bvh, bool stats, int sm_count,
+                             cudaStream_t st);
+cudaError_t launch_whitted(const DevScene &sc, const RenderParams &rp, bool bvh, bool stats, cudaStream_t st);
+cudaError_t launch_resolve(const RenderParams &rp, uint32_t integrator, uchar4 *rgba8, cudaStream_t st);
+cudaError_t launch_pack(const RenderParams &rp, float4 *packed, cudaStream_t st);
+cudaError_t launch_unpack(float4 *accum, const float4 *packed, uint32_t width, uint32_t height, uint32_t tile_rank,
+                          uint32_t tile_count, int add, cudaStream_t st);
+cudaError_t launch_clear_accum(float4 *accum, size_t n, cudaStream_t st);
+
+// vkrt_wavefront.cu
+struct WaveBuffers {
+    size_t capacity;              // paths per wave
+    float4 *ray_o, *ray_d;        // origin.xyz + t_hit ; dir.xyz + hit id bits
+    float4 *acc, *mask;           // acc.xyz + pixel bits ; mask.xyz + (sample | depth << 24) bits
+    uint32_t *queue[2];           // active path indices (ping-pong)
+    uint32_t *queue_mat[2];       // per-material-type bins of the shade stage
+    uint32_t *counts;             // [0]=n_active(next) [1]=n_diffuse [2]=n_dielectric [3]=extend head [4]=shade head...
+    float4 *sample_rad;           // per (pixel-slot, sample-in-wave) finished radiance, reduced in sample order
+};
+cudaError_t wave_alloc(WaveBuffers &wb, size_t capacity);
+void wave_free(WaveBuffers &wb);
+cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, WaveBuffers &wb, bool bvh, bool stats,
+                                  int sm_count, cudaStream_t st, uint32_t *n_launches);
+
+// vkrt_bvh.cu
+struct BvhBuild {
+    float4 *nodes = nullptr;      // 4 float4 per inner node
+    uint32_t n_nodes = 0;
+    float build_ms = 0.f;
+    uint32_t launches = 0;
+};
+cudaError_t build_lbvh(const float4 *d_spheres, uint32_t n, BvhBuild &out, cudaStream_t st);
+
+// vkrt_micro.cu
+cudaError_t measure_fp32_peak(float *tflops);
+cudaError_t measure_l2_bandwidth(float *gbs);
+
+} // namespace vkrt
