@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Headline benchmark of the ray-tracing hot path (BASELINE.json: Mrays/s over all bounces, and
+ms/frame at 1080p / 16 spp / depth 8).
+
+  python bench.py [--gpus N --steps K --warmup W] [--workload cfg4|cfg2|cfg3] [--variant mega|wavefront]
+  python bench.py --impl reference ...      # the CPU restatement of the reference shaders (oracle)
+
+A "step" is one frame: one pass of the path tracer over every pixel of the workload, rendered from
+scratch like the reference does every Draw (Source/GraphicsDevice.cpp:1215).  Default workload =
+BASELINE.json configs[3], the configuration the north_star's target is quoted on: the synthetic
+100,000-sphere scene at 1920x1080, 16 spp, depth 8, device LBVH.
+
+Mrays/s counts trace_ray invocations of the reference algorithm (Tracer.comp:374): nearest-hit +
+shadow queries, counted on the device by the kernels themselves.
+N > 1 (torchrun, one rank per GPU): the frame is sharded by interleaved 32x32 screen tiles (fixed
+total work => "scaling": "strong"); every step ends with the NCCL gather of the owned accumulator
+tiles to rank 0 and the resolve there.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (description, width, height, spp, depth)
+    "cfg4": ("synthetic 100k procedural spheres (jittered 50x40x50 grid + light + 5 planes), 1920x1080, 16 spp, depth 8, device LBVH",
+             1920, 1080, 16, 8),
+    "cfg3": ("synthetic 1,024 random spheres (mixed lambertian/metal/dielectric + light + 5 planes), 3840x2160, 64 spp, depth 8, device LBVH",
+             3840, 2160, 64, 8),
+    "cfg2": ("reference default scene (Tracer.comp:186-211), 1920x1080, 16 spp, depth 8, literal primitive loop",
+             1920, 1080, 16, 8),
+}
+SEED = 2026
+
+
+def make_scene(V, workload):
+    if workload == "cfg4":
+        return V.scenes.grid_spheres(), True
+    if workload == "cfg3":
+        return V.scenes.random_spheres(1024), True
+    return V.scenes.tracer_default(), False
+
+
+def frame_data_for(V, w, h, step):
+    # the reference passes a fresh seed = rand()/RAND_MAX every Draw (GraphicsDevice.cpp:1262); here a fixed sequence
+    return V.default_frame_data(aspect_ratio=float(w) / float(h), seed=float((step * 0.61803398875) % 1.0))
+
+
+class ClockSampler:
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if there is one."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle (a port of the reference shaders; lavapipe / the shaders themselves cannot run
+# in this image).  TEST INFRASTRUCTURE used here only as the reported baseline.
+# ---------------------------------------------------------------------------------------------
+def cpu_render(workload, target_seconds, steps=1, warmup=0):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    import vk_renderer_b200.scenes as scenes   # scene generator only (numpy); no CUDA involved
+    from vk_renderer_b200.device import default_frame_data
+    O.build()
+    desc, w, h, spp, depth = WORKLOADS[workload]
+    scene = {"cfg4": scenes.grid_spheres, "cfg3": lambda: scenes.random_spheres(1024), "cfg2": scenes.tracer_default}[workload]()
+    use_bvh = workload != "cfg2"
+    sc = O.Scene(fast=True)
+    sc.set_materials(scene.materials); sc.set_spheres(scene.spheres, scene.sphere_mat)
+    sc.set_planes(scene.planes, scene.plane_mat); sc.set_triangles(scene.triangles, scene.tri_mat)
+    if use_bvh:
+        sc.build_bvh()
+    mode = O.S_BVH if use_bvh else O.LITERAL
+    cores = os.cpu_count() or 1
+
+    def run(rect, step):
+        fd = default_frame_data(aspect_ratio=float(w) / float(h), seed=float((step * 0.61803398875) % 1.0))
+        t0 = time.perf_counter()
+        _, _, _, cnt = sc.render(fd, w, h, spp=spp, max_depth=depth, integrator=O.PATH, sphere_mode=mode, seed=SEED,
+                                 frame_index=step, rect=rect, want_ids=False, want_rgba=False)
+        dt = time.perf_counter() - t0
+        return cnt.closest_rays + cnt.shadow_rays, dt
+
+    # probe a centred 1/64-area window to size the bounded sample
+    pw, ph = max(w // 8, 8), max(h // 8, 8)
+    px, py = (w - pw) // 2, (h - ph) // 2
+    rays, dt = run((px, py, px + pw, py + ph), 0)
+    rate = rays / dt
+    frac = min(1.0, max(1.0 / 64.0, target_seconds * rate / (rays * 64.0)))
+    sw, sh = max(int(w * frac ** 0.5) // 8 * 8, 8), max(int(h * frac ** 0.5) // 8 * 8, 8)
+    sx, sy = (w - sw) // 2, (h - sh) // 2
+    rect = (sx, sy, sx + sw, sy + sh)
+    times, total_rays = [], 0
+    for s in range(warmup + steps):
+        rays, dt = run(rect, s)
+        if s >= warmup:
+            times.append(dt); total_rays += rays
+    mrays = total_rays / sum(times) / 1e6
+    sample = ("centred %dx%d window (%.1f%% of the pixels) of the %dx%d frame, same scene/spp/depth, %d step(s)"
+              % (sw, sh, 100.0 * sw * sh / (w * h), w, h, steps))
+    return {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample,
+            "ms_per_sample_step": 1e3 * sum(times) / len(times),
+            "note": "CPU restatement of the reference shaders (oracle, -O3, std::thread over rows); lavapipe unavailable in image"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    desc, w, h, spp, depth = WORKLOADS[args.workload]
+    per_step = max(2.0, min(20.0, 120.0 / max(args.steps + args.warmup, 1)))
+    r = cpu_render(args.workload, per_step, steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": "Mrays/s (all bounces)", "value": r["value"], "unit": "Mrays/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_sample_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "width": w, "height": h, "spp": spp, "max_depth": depth},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": r["note"]}
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import vk_renderer_b200 as V
+    from vk_renderer_b200.sharding import FrameGather, shard_layout
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- libvkrt_cuda has no CPU fallback (use --impl reference for the CPU arm)")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+
+    desc, w, h, spp, depth = WORKLOADS[args.workload]
+    scene, use_bvh = make_scene(V, args.workload)
+    variant = V.VARIANT_WAVEFRONT if args.variant == "wavefront" else V.VARIANT_MEGAKERNEL
+    tile_shard, sample_shard = shard_layout(rank, world, 1)
+    stream = torch.cuda.Stream(device=device)
+
+    def make_renderer(flags):
+        r = V.Renderer(w, h, spp=spp, max_depth=depth, integrator=V.INTEGRATOR_PATH, variant=variant, flags=flags,
+                       device_id=local, tile_shard=tile_shard, sample_shard=sample_shard, stream=stream.cuda_stream)
+        r.set_scene(scene)
+        if use_bvh:
+            r.build_bvh()
+        r.set_seed(SEED)
+        return r
+
+    r = make_renderer(V.FLAG_NO_RESOLVE if world > 1 else 0)
+    bvh = r.bvh_info()
+    gather = FrameGather(r, rank, world, 1, stream, device) if world > 1 else None
+    n_px = w * h
+    pinned = torch.empty(2, n_px * 4, dtype=torch.uint8).pin_memory() if rank == 0 else None
+
+    def step(i, e2e=False):
+        fd = frame_data_for(V, w, h, i)
+        r.set_frame_index(i)
+        r.draw(fd)
+        if gather is not None:
+            gather.gather()
+            if rank == 0:
+                r.resolve()
+        if e2e and rank == 0:
+            r.read_rgba8_async(pinned[i % 2].data_ptr(), n_px * 4)
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    # -------- device-resident timing ("value") ------------------------------------------------
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    r.reset_counters()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    trace_ms = []
+    barrier()
+    ev0.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + i)
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    cnt = r.counters()
+    launches_per_step = r.last_frame_timing()[2] + (1 if world > 1 else 0) + ((world + 1) if (world > 1 and rank == 0) else 0)
+    rays = torch.tensor([cnt.closest_rays + cnt.shadow_rays, cnt.closest_rays, cnt.shadow_rays, cnt.paths], dtype=torch.float64, device=device)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(rays, op=dist.ReduceOp.SUM)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    total_rays = float(rays[0].item())
+    value = total_rays / (ms_total * 1e-3) / 1e6
+
+    # per-launch duration of the dominant kernel, live, on its own stream (library-side CUDA events)
+    for i in range(min(args.steps, 5)):
+        step(args.warmup + i)
+        trace_ms.append(r.last_frame_timing()[0])
+    barrier()
+    kernel_ms = statistics.mean(trace_ms)
+
+    # -------- end-to-end through the public API with host buffers ("e2e") -----------------------
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(args.warmup + i, e2e=True)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = total_rays / float(e2e_t.item()) / 1e6
+
+    # -------- algorithmic bytes of the dominant kernel (stats build, untimed) --------------------
+    rs = make_renderer(V.FLAG_NO_RESOLVE | V.FLAG_STATS)
+    n_stat = min(args.steps, 3)
+    for i in range(n_stat):
+        rs.set_frame_index(args.warmup + i)
+        rs.draw(frame_data_for(V, w, h, args.warmup + i))
+    sc = rs.counters()
+    rs.close()
+    owned_px = n_px / world
+    # per launch: 64 B per BVH node fetched (leaf spheres are embedded in the node: no extra bytes), per nearest hit
+    # 16 B sphere + 4 B material id + 36 B material, per shadow ray 16 B light sphere + 12 B emissive, 16 B accumulator store
+    alg_bytes = (sc.node_visits * 64 + sc.closest_rays * (16 + 4 + 36) + sc.shadow_rays * (16 + 12)) / n_stat + owned_px * 16
+    hbm_peak, peak_src = measured_peaks()
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_path_mega" if variant == V.VARIANT_MEGAKERNEL else "wavefront extend+shade",
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
+                "nodes_per_ray": sc.node_visits / max(sc.closest_rays + sc.shadow_rays, 1),
+                "leaf_tests_per_ray": sc.leaf_tests / max(sc.closest_rays + sc.shadow_rays, 1),
+                "note": "scene + BVH (%.1f MB) is L2-resident on B200: the bytes are served by L1/L2, so frac is vs HBM only "
+                        "for reference; the kernel is latency/divergence-bound (DESIGN.md)" % (bvh.n_nodes * 64 / 1e6)}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_render(args.workload, 15.0)
+        line = {"metric": "Mrays/s (all bounces)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": desc, "width": w, "height": h, "spp": spp, "max_depth": depth,
+                           "variant": args.variant, "scene_sha": scene.digest(), "bvh_nodes": bvh.n_nodes,
+                           "bvh_build_ms": bvh.build_ms, "parallelism": "tile-shard x%d" % world,
+                           "l2_policy": "every step renders a new frame (new RNG keys); accumulator (%.0f MB) + rgba8 are rewritten each step; "
+                                        "scene is L2-resident by design, no flush" % (n_px * 16 / 1e6)},
+                "ms_per_frame": ms_total / args.steps,
+                "rays_per_frame": total_rays / args.steps, "closest_rays": float(rays[1].item()) / args.steps,
+                "shadow_rays": float(rays[2].item()) / args.steps, "paths_per_frame": float(rays[3].item()) / args.steps,
+                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 96 * world, "d2h_bytes_per_step": n_px * 4,
+                        "ms_per_step": 1e3 * float(e2e_t.item()) / args.steps,
+                        "note": "vkrt_draw(host FrameData) + resolve + rgba8 D2H into pinned memory each step, wall clock"},
+                "gpu_launches": int(launches_per_step * args.steps),
+                "clocks": clocks, "roofline": roofline}
+        if cpu is not None:
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if args.micro:
+            line["fp32_peak_tflops_measured"] = V.measure_fp32_peak(local)
+            line["l2_read_gbs_measured"] = V.measure_l2_bandwidth(local)
+        print(json.dumps(line))
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--variant", default="mega", choices=["mega", "wavefront"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--micro", action="store_true", help="also run the FP32 / L2 microbenchmarks")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

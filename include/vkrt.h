@@ -237,6 +237,9 @@ VKRT_API vkrt_error vkrt_read_bvh_nodes(vkrt_ctx *ctx, float *host, size_t bytes
 /* Packs the accumulator of the tiles this context owns into a compact buffer
  * (n_owned_tiles * 1024 float4) and returns it. */
 VKRT_API vkrt_error vkrt_pack_shard(vkrt_ctx *ctx, float **dev_ptr, size_t *n_floats);
+/* Same, into a caller-owned device buffer (e.g. a torch tensor that NCCL will send);
+ * n_floats must be at least what vkrt_shard_floats(ctx, 0, ..) reports (the largest shard). */
+VKRT_API vkrt_error vkrt_pack_shard_into(vkrt_ctx *ctx, float *dev_dst, size_t n_floats);
 /* Number of floats vkrt_pack_shard produces for shard `tile_rank` of this image. */
 VKRT_API vkrt_error vkrt_shard_floats(vkrt_ctx *ctx, uint32_t tile_rank, size_t *n_floats);
 /* On the gathering context: scatters the packed buffer of (tile_rank, sample_rank) into the

@@ -275,6 +275,8 @@ inline float tri_intersect(const Ray &ray, const orc_triangle &tri, float eps)
 // rule "skip a box whose tn > current best", returns exactly this result.
 // ------------------------------------------------------------------------------------------
 struct SlabRay { V3 inv, oinv; };
+inline float mn(float a, float b) { return a < b ? a : b; }
+inline float mx(float a, float b) { return a > b ? a : b; }
 inline float safe_inv(float d)
 {
     const float ad = gl_abs(d);
@@ -293,8 +295,9 @@ inline bool slab_test(const SlabRay &s, V3 lo, V3 hi, float &tn, float &tf)
     const float t0x = fma_(lo.x, s.inv.x, -s.oinv.x), t1x = fma_(hi.x, s.inv.x, -s.oinv.x);
     const float t0y = fma_(lo.y, s.inv.y, -s.oinv.y), t1y = fma_(hi.y, s.inv.y, -s.oinv.y);
     const float t0z = fma_(lo.z, s.inv.z, -s.oinv.z), t1z = fma_(hi.z, s.inv.z, -s.oinv.z);
-    tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
-    tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+    // all six values are finite by construction (safe_inv), so plain compares == fminf/fmaxf
+    tn = mx(mx(mn(t0x, t1x), mn(t0y, t1y)), mn(t0z, t1z));
+    tf = mn(mn(mx(t0x, t1x), mx(t0y, t1y)), mx(t0z, t1z));
     return tn <= tf && tf >= 0.0f;
 }
 inline float sphere_pad_radius(float r) { return r * 1.001f + 0.001f; }
@@ -891,7 +894,7 @@ int orc_render(const orc_scene *sc, const orc_params *pp, const orc_frame_data *
     std::atomic<uint32_t> next_row{y0};
     std::vector<Stats> stats(nt);
     auto worker = [&](unsigned tid) {
-        Stats &st = stats[tid];
+        Stats st;                       // thread-local (no false sharing); published at the end
         for (;;) {
             const uint32_t y = next_row.fetch_add(1);
             if (y >= y1) break;
@@ -938,6 +941,7 @@ int orc_render(const orc_scene *sc, const orc_params *pp, const orc_frame_data *
                 }
             }
         }
+        stats[tid] = st;
     };
     std::vector<std::thread> th;
     for (unsigned t = 1; t < nt; ++t) th.emplace_back(worker, t);

@@ -41,7 +41,7 @@ def test_whitted_default_scene_bit_exact(vk, oracle):
     r.close()
 
 
-@pytest.mark.parametrize("variant", [0])
+@pytest.mark.parametrize("variant", [0, 1])
 def test_path_default_scene_bit_exact(vk, oracle, variant):
     """Tracer.comp scene at the reference's SAMPLES = DEPTH = 4, literal primitive order."""
     V = vk
@@ -109,7 +109,8 @@ def test_bvh_duplicate_centres(vk, oracle):
     r.close()
 
 
-def test_path_random_spheres_bvh_bit_exact(vk, oracle):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_path_random_spheres_bvh_bit_exact(vk, oracle, variant):
     """BASELINE config 3's scene (1,024 random spheres, device LBVH) at a size the oracle finishes in
     seconds: the GPU's LBVH traversal must equal both the oracle's own BVH traversal and the oracle's
     LINEAR scan under rule S; the count of primary rays on which the literal chain rule of
@@ -118,7 +119,7 @@ def test_path_random_spheres_bvh_bit_exact(vk, oracle):
     w, h = 320, 180
     scene = V.scenes.random_spheres(1024)
     fd = V.default_frame_data(aspect_ratio=w / h, seed=0.75)
-    r, (acc, ids, rgba, cnt) = _render_gpu(V, scene, w, h, fd, 4, 8, V.INTEGRATOR_PATH, True, flags=V.FLAG_STATS)
+    r, (acc, ids, rgba, cnt) = _render_gpu(V, scene, w, h, fd, 4, 8, V.INTEGRATOR_PATH, True, flags=V.FLAG_STATS, variant=variant)
     sc = apply_scene(oracle, scene).build_bvh()
     oacc, oids, orgba, ocnt = sc.render(fd, w, h, spp=4, max_depth=8, integrator=oracle.PATH, sphere_mode=oracle.S_BVH, seed=7)
     lacc, lids, _, lcnt = sc.render(fd, w, h, spp=4, max_depth=8, integrator=oracle.PATH, sphere_mode=oracle.S_LINEAR, seed=7)
@@ -141,14 +142,15 @@ def test_path_random_spheres_bvh_bit_exact(vk, oracle):
     r.close()
 
 
-def test_path_grid_100k_bvh_bit_exact(vk, oracle):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_path_grid_100k_bvh_bit_exact(vk, oracle, variant):
     """BASELINE config 4's scene (100,000 procedural spheres) against the oracle's BVH traversal."""
     V = vk
     w, h = 192, 108
     scene = V.scenes.grid_spheres()
     assert scene.spheres.shape[0] == 100001
     fd = V.default_frame_data(aspect_ratio=w / h, seed=0.125)
-    r, (acc, ids, rgba, cnt) = _render_gpu(V, scene, w, h, fd, 4, 8, V.INTEGRATOR_PATH, True)
+    r, (acc, ids, rgba, cnt) = _render_gpu(V, scene, w, h, fd, 4, 8, V.INTEGRATOR_PATH, True, variant=variant)
     assert r.bvh_info().n_nodes == 100000
     sc = apply_scene(oracle, scene, fast=True).build_bvh()
     oacc, oids, orgba, ocnt = sc.render(fd, w, h, spp=4, max_depth=8, integrator=oracle.PATH, sphere_mode=oracle.S_BVH, seed=7)
@@ -196,6 +198,29 @@ def test_progressive_accumulation(vk, oracle):
     first, _, _, _ = sc.render(fd, w, h, spp=4, max_depth=4, seed=3, frame_index=0)
     assert bits_equal(r.read_accum(), first)
     r.close()
+
+
+def test_wavefront_multi_wave_equals_megakernel(vk):
+    """40 spp needs three waves of <= 16 samples: the running per-pixel sum must still be formed in
+    sample order, i.e. be bit-identical to the megakernel; also with tile + sample shards and with
+    progressive accumulation."""
+    V = vk
+    w, h = 96, 72
+    scene = V.scenes.random_spheres(200)
+    fd = V.default_frame_data(aspect_ratio=w / h, seed=0.9)
+    outs = []
+    for variant in (0, 1):
+        r = V.Renderer(w, h, spp=40, max_depth=5, variant=variant, flags=V.FLAG_PROGRESSIVE | V.FLAG_HIT_IDS,
+                       tile_shard=(1, 2), sample_shard=(1, 3))
+        r.set_scene(scene); r.build_bvh(); r.set_seed(5)
+        r.draw(fd); r.draw(fd)
+        c = r.counters()
+        outs.append((r.read_accum(), r.read_hit_ids(), (c.closest_rays, c.shadow_rays, c.paths)))
+        r.close()
+    assert bits_equal(outs[0][0], outs[1][0]), mismatch_report(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert outs[0][2] == outs[1][2]
+    assert outs[0][0][..., 3].max() == 2 * (40 * 2 // 3 - 40 // 3)
 
 
 def test_tile_and_sample_shards_recombine(vk, oracle):

@@ -101,6 +101,7 @@ SIGNATURES = {
     "vkrt_get_bvh_info": ([_vp, _P(BvhInfo)], C.c_int8),
     "vkrt_read_bvh_nodes": ([_vp, _vp, _sz], C.c_int8),
     "vkrt_pack_shard": ([_vp, _P(_vp), _P(_sz)], C.c_int8),
+    "vkrt_pack_shard_into": ([_vp, _vp, _sz], C.c_int8),
     "vkrt_shard_floats": ([_vp, _u32, _P(_sz)], C.c_int8),
     "vkrt_unpack_shard": ([_vp, _vp, _u32, _u32, _i32], C.c_int8),
     "vkrt_measure_fp32_peak": ([_i32, _P(C.c_float)], C.c_int8),

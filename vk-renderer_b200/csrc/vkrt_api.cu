@@ -419,10 +419,11 @@ VKRT_API vkrt_error vkrt_draw(vkrt_ctx *c, const vkrt_frame_data *frame)
             CU(c, launch_whitted(c->dev, rp, c->use_bvh, stats, c->stream)); ++launches;
         } else if (c->info.variant == VKRT_VARIANT_WAVEFRONT) {
             if (!c->wave_ready) {
-                size_t cap = (size_t)c->owned_tiles * TILE_PX * 16;        // 16 samples of every owned pixel per wave
-                const size_t cap_max = (size_t)64 << 20;
-                if (cap > cap_max) cap = cap_max - cap_max % ((size_t)c->owned_tiles * TILE_PX ? 1 : 1);
-                CU(c, wave_alloc(c->wave, cap));
+                // up to 16 samples of every owned pixel per wave, at most 64 Mi path records (~7 GB of HBM)
+                const size_t slots = (size_t)c->owned_tiles * TILE_PX;
+                size_t per_wave = c->spp < 16 ? c->spp : 16;
+                while (per_wave > 1 && slots * per_wave > ((size_t)64 << 20)) --per_wave;
+                CU(c, wave_alloc(c->wave, slots * per_wave));
                 c->wave_ready = true;
             }
             uint32_t nl = 0;
@@ -586,6 +587,16 @@ VKRT_API vkrt_error vkrt_pack_shard(vkrt_ctx *c, float **dev_ptr, size_t *n_floa
     if (rp.n_work) CU(c, launch_pack(rp, c->d_packed, c->stream));
     *dev_ptr = (float *)c->d_packed;
     if (n_floats) *n_floats = max_slots * 4;
+    return VKRT_SUCCESS;
+}
+VKRT_API vkrt_error vkrt_pack_shard_into(vkrt_ctx *c, float *dev_dst, size_t n_floats)
+{
+    if (!c || !dev_dst) return VKRT_BAD_ARG;
+    DeviceGuard g(c->info.device_id);
+    RenderParams rp;
+    fill_params(c, rp);
+    if (n_floats < (size_t)rp.n_work * 4) return fail(c, VKRT_BAD_ARG, "shard buffer too small");
+    if (rp.n_work) CU(c, launch_pack(rp, (float4 *)dev_dst, c->stream));
     return VKRT_SUCCESS;
 }
 VKRT_API vkrt_error vkrt_unpack_shard(vkrt_ctx *c, const float *dev_packed, uint32_t tile_rank, uint32_t tile_count, int add)

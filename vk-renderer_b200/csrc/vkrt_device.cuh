@@ -130,76 +130,115 @@ VKRT_DEV void s_consider(V3 o, V3 d, float4 sph, int i, float tn, float eps, flo
     else if (t < best.t || (t == best.t && i < best.idx)) { best.t = t; best.idx = i; }
 }
 
+// Resumable traversal state: one call of trav_step visits one inner node (both child records).
+// node < 0 means the traversal is finished.  The stack lives in local memory (L1-resident).
+struct Trav {
+    SlabRay sr;
+    SBest best;
+    float eps, B;
+    int node, sp;
+    int stack[BVH_STACK];
+};
+VKRT_DEV void trav_init(Trav &tv, const DevScene &sc, V3 o, V3 d, float eps, float B)
+{
+    tv.sr = slab_setup(o, d);
+    tv.best.t = B; tv.best.idx = -1;
+    tv.eps = eps; tv.B = B;
+    tv.sp = 0;
+    tv.node = sc.n_nodes ? 0 : -1;
+}
+template <bool ANY, bool STATS>
+VKRT_DEV void trav_step(Trav &tv, const DevScene &sc, V3 o, V3 d, Stats &st)
+{
+    const float4 *np = sc.bvh + 4 * (size_t)tv.node;
+    const float4 a0 = __ldg(np), b0 = __ldg(np + 1), a1 = __ldg(np + 2), b1 = __ldg(np + 3);
+    if (STATS) ++st.nodes;
+    int nxt0 = -1, nxt1 = -1;
+    float tn0, tn1, tf;
+    {
+        const bool leaf = __float_as_int(b0.w) == 1;
+        const V3 lo = leaf ? v3(a0.x - b0.x, a0.y - b0.x, a0.z - b0.x) : v3(a0.x, a0.y, a0.z);
+        const V3 hi = leaf ? v3(a0.x + b0.x, a0.y + b0.x, a0.z + b0.x) : v3(a0.w, b0.x, b0.y);
+        const bool hit = slab_test(tv.sr, lo, hi, tn0, tf) && tn0 <= tv.best.t;
+        if (hit) {
+            if (leaf) {
+                if (STATS) ++st.leaves;
+                s_consider(o, d, a0, __float_as_int(b0.z), tn0, tv.eps, tv.B, tv.best);
+            } else nxt0 = __float_as_int(b0.z);
+        }
+    }
+    {
+        const bool leaf = __float_as_int(b1.w) == 1;
+        const V3 lo = leaf ? v3(a1.x - b1.x, a1.y - b1.x, a1.z - b1.x) : v3(a1.x, a1.y, a1.z);
+        const V3 hi = leaf ? v3(a1.x + b1.x, a1.y + b1.x, a1.z + b1.x) : v3(a1.w, b1.x, b1.y);
+        const bool hit = slab_test(tv.sr, lo, hi, tn1, tf) && tn1 <= tv.best.t;
+        if (hit) {
+            if (leaf) {
+                if (STATS) ++st.leaves;
+                s_consider(o, d, a1, __float_as_int(b1.z), tn1, tv.eps, tv.B, tv.best);
+            } else nxt1 = __float_as_int(b1.z);
+        }
+    }
+    if (ANY && tv.best.idx >= 0) { tv.node = -1; return; }
+    if (nxt0 >= 0 && nxt1 >= 0) {
+        const bool swap = tn1 < tn0;
+        tv.stack[tv.sp++] = swap ? nxt0 : nxt1;
+        tv.node = swap ? nxt1 : nxt0;
+    } else if (nxt0 >= 0) tv.node = nxt0;
+    else if (nxt1 >= 0) tv.node = nxt1;
+    else tv.node = tv.sp ? tv.stack[--tv.sp] : -1;
+}
+
 template <bool ANY, bool STATS>
 VKRT_DEV SBest bvh_query(const DevScene &sc, V3 o, V3 d, float eps, float B, Stats &st)
 {
-    SBest best{B, -1};
-    if (sc.n_nodes == 0) return best;
-    const SlabRay sr = slab_setup(o, d);
-    int stack[BVH_STACK];
-    int sp = 0, node = 0;
-    for (;;) {
-        const float4 *np = sc.bvh + 4 * (size_t)node;
-        const float4 a0 = __ldg(np), b0 = __ldg(np + 1), a1 = __ldg(np + 2), b1 = __ldg(np + 3);
-        if (STATS) ++st.nodes;
-        int nxt0 = -1, nxt1 = -1;
-        float tn0, tn1, tf;
-        {
-            const bool leaf = __float_as_int(b0.w) == 1;
-            const V3 lo = leaf ? v3(a0.x - b0.x, a0.y - b0.x, a0.z - b0.x) : v3(a0.x, a0.y, a0.z);
-            const V3 hi = leaf ? v3(a0.x + b0.x, a0.y + b0.x, a0.z + b0.x) : v3(a0.w, b0.x, b0.y);
-            const bool hit = slab_test(sr, lo, hi, tn0, tf) && tn0 <= best.t;
-            if (hit) {
-                if (leaf) {
-                    if (STATS) ++st.leaves;
-                    s_consider(o, d, a0, __float_as_int(b0.z), tn0, eps, B, best);
-                    if (ANY && best.idx >= 0) return best;
-                } else nxt0 = __float_as_int(b0.z);
-            }
-        }
-        {
-            const bool leaf = __float_as_int(b1.w) == 1;
-            const V3 lo = leaf ? v3(a1.x - b1.x, a1.y - b1.x, a1.z - b1.x) : v3(a1.x, a1.y, a1.z);
-            const V3 hi = leaf ? v3(a1.x + b1.x, a1.y + b1.x, a1.z + b1.x) : v3(a1.w, b1.x, b1.y);
-            const bool hit = slab_test(sr, lo, hi, tn1, tf) && tn1 <= best.t;
-            if (hit) {
-                if (leaf) {
-                    if (STATS) ++st.leaves;
-                    s_consider(o, d, a1, __float_as_int(b1.z), tn1, eps, B, best);
-                    if (ANY && best.idx >= 0) return best;
-                } else nxt1 = __float_as_int(b1.z);
-            }
-        }
-        if (nxt0 >= 0 && nxt1 >= 0) {
-            const bool swap = tn1 < tn0;
-            stack[sp++] = swap ? nxt0 : nxt1;
-            node = swap ? nxt1 : nxt0;
-        } else if (nxt0 >= 0) node = nxt0;
-        else if (nxt1 >= 0) node = nxt1;
-        else { if (sp == 0) break; node = stack[--sp]; }
-    }
-    return best;
+    Trav tv;
+    trav_init(tv, sc, o, d, eps, B);
+    while (tv.node >= 0) trav_step<ANY, STATS>(tv, sc, o, d, st);
+    return tv.best;
 }
 
 // ---- trace_ray: Tracer.comp:374-431 (TRACER = true) / Raytracer.comp:224-278 (false) ----------
 // SHADOW queries only need the boolean, so they may leave early.
-template <bool TRACER, bool BVH, bool SHADOW, bool STATS>
-VKRT_DEV bool trace_ray(const DevScene &sc, V3 o, V3 d, Hit &hit, Stats &st)
+template <bool TRACER>
+VKRT_DEV bool trace_tris(const DevScene &sc, V3 o, V3 d, float &cur, Hit &hit)
 {
     const float EPS = TRACER ? 1e-3f : 0.01f;
-    if (SHADOW) ++st.shadow; else ++st.closest;
     bool found = false;
-    float cur = hit.t;
     for (uint32_t i = 0; i < sc.n_tris; ++i) {
         const V3 v0 = xyz(__ldg(sc.tris + 3 * i)), v1 = xyz(__ldg(sc.tris + 3 * i + 1)), v2 = xyz(__ldg(sc.tris + 3 * i + 2));
         const float t = tri_intersect(o, d, v0, v1, v2, EPS);
         const bool acc = TRACER ? ((t > EPS) && (t < cur + EPS)) : (t > EPS && t < cur);
         if (acc) { cur = t; hit.kind = KIND_TRI; hit.index = i; found = true; }
     }
+    return found;
+}
+template <bool TRACER>
+VKRT_DEV bool trace_planes(const DevScene &sc, V3 o, V3 d, float &cur, Hit &hit)
+{
+    const float EPS = TRACER ? 1e-3f : 0.01f;
+    bool found = false;
+    for (uint32_t i = 0; i < sc.n_planes; ++i) {
+        const float t = TRACER ? plane_intersect_tracer(o, d, sc.planes[i]) : plane_intersect_raytracer(o, d, sc.planes[i]);
+        const bool acc = TRACER ? ((t > EPS) && (t < cur - EPS)) : (t > EPS && t < cur);
+        if (acc) { cur = t; hit.kind = KIND_PLANE; hit.index = i; found = true; }
+    }
+    return found;
+}
+// upper bound handed to the sphere query after the triangle loop (rule S: exclusive)
+template <bool TRACER> VKRT_DEV float sphere_bound(float cur) { return TRACER ? cur + 1e-3f : cur; }
+template <bool TRACER> VKRT_DEV float trace_eps() { return TRACER ? 1e-3f : 0.01f; }
+
+template <bool TRACER, bool BVH, bool SHADOW, bool STATS>
+VKRT_DEV bool trace_ray(const DevScene &sc, V3 o, V3 d, Hit &hit, Stats &st)
+{
+    const float EPS = trace_eps<TRACER>();
+    if (SHADOW) ++st.shadow; else ++st.closest;
+    float cur = hit.t;
+    bool found = trace_tris<TRACER>(sc, o, d, cur, hit);
     if (SHADOW && found) return true;
     if (BVH) {
-        const float B = TRACER ? cur + EPS : cur;
-        const SBest b = bvh_query<SHADOW, STATS>(sc, o, d, EPS, B, st);
+        const SBest b = bvh_query<SHADOW, STATS>(sc, o, d, EPS, sphere_bound<TRACER>(cur), st);
         if (b.idx >= 0) { cur = b.t; hit.kind = KIND_SPHERE; hit.index = (uint32_t)b.idx; found = true; }
     } else {
         for (uint32_t i = 0; i < sc.n_spheres; ++i) {
@@ -209,11 +248,7 @@ VKRT_DEV bool trace_ray(const DevScene &sc, V3 o, V3 d, Hit &hit, Stats &st)
         }
     }
     if (SHADOW && found) return true;
-    for (uint32_t i = 0; i < sc.n_planes; ++i) {
-        const float t = TRACER ? plane_intersect_tracer(o, d, sc.planes[i]) : plane_intersect_raytracer(o, d, sc.planes[i]);
-        const bool acc = TRACER ? ((t > EPS) && (t < cur - EPS)) : (t > EPS && t < cur);
-        if (acc) { cur = t; hit.kind = KIND_PLANE; hit.index = i; found = true; }
-    }
+    found = trace_planes<TRACER>(sc, o, d, cur, hit) || found;
     hit.t = cur;
     return found;
 }
@@ -296,11 +331,34 @@ VKRT_DEV void path_begin(PathState &ps, V3 o, V3 d)
 }
 VKRT_DEV float path_tmax(uint32_t depth) { return 3000.0f / pow_((float)(depth + 1u), 2.0f); }   // :444
 
-// Shades the hit (incl. the shadow rays of the light loop) and rolls Russian roulette.
-// Returns true when the path continues into the next depth iteration.
+// the cone sample towards emissive sphere l (Tracer.comp:464-469): direction L and distance bound t
+VKRT_DEV void nee_sample(const DevScene &sc, V3 P, uint32_t l, uint32_t skey, uint32_t dim0, V3 &L, float &t)
+{
+    const float4 s = __ldg(sc.spheres + sc.lights[l]);
+    const V3 sP = xyz(s);
+    t = length3(sP - P) - s.w;
+    const V3 l0 = sP - P;
+    const float cos_a_max = sqrtf(1.0f - gl_clamp(s.w * s.w / dot3(l0, l0), 0.0f, 1.0f));
+    const float cosa = gl_mix(cos_a_max, 1.0f, u01(skey, dim0 + SLOT_LIGHT + 2 * l));
+    L = jitter(l0, VKRT_TWO_PI * u01(skey, dim0 + SLOT_LIGHT + 2 * l + 1), sqrtf(1.0f - cosa * cosa), cosa);
+}
+
+// occlusion query used by the megakernel: trace the shadow ray in place (Tracer.comp:471-473)
 template <bool BVH, bool STATS>
+struct OccTrace {
+    const DevScene &sc; Stats &st;
+    VKRT_DEV bool operator()(uint32_t, V3 P, V3 L, float t) const
+    {
+        Hit sh{t, 0, 0};
+        return trace_ray<true, BVH, true, STATS>(sc, P, L, sh, st);
+    }
+};
+
+// Shades the hit (the light loop asks `occluded(l, P, L, t)` for every emissive sphere) and rolls
+// Russian roulette.  Returns true when the path continues into the next depth iteration.
+template <class Occ>
 VKRT_DEV bool path_shade(const DevScene &sc, V3 cam_pos, uint32_t max_depth, uint32_t skey, PathState &ps,
-                         const Hit &hit, Stats &st)
+                         const Hit &hit, const Occ &occluded)
 {
     const uint32_t dim0 = ps.depth * DIMS_PER_BOUNCE;
     const Surface sf = surface_of(sc, ps.o, ps.d, hit);
@@ -311,19 +369,13 @@ VKRT_DEV bool path_shade(const DevScene &sc, V3 cam_pos, uint32_t max_depth, uin
                       (1.0f - mat.metalness);
         V3 e = v3(0.0f);
         for (uint32_t l = 0; l < sc.n_lights; ++l) {
-            const uint32_t li = sc.lights[l];
-            const float4 s = __ldg(sc.spheres + li);
-            const V3 sP = xyz(s);
-            const float t = length3(sP - sf.P) - s.w;
-            const V3 l0 = sP - sf.P;
-            const float cos_a_max = sqrtf(1.0f - gl_clamp(s.w * s.w / dot3(l0, l0), 0.0f, 1.0f));
-            const float cosa = gl_mix(cos_a_max, 1.0f, u01(skey, dim0 + SLOT_LIGHT + 2 * l));
-            const V3 L = jitter(l0, VKRT_TWO_PI * u01(skey, dim0 + SLOT_LIGHT + 2 * l + 1),
-                                sqrtf(1.0f - cosa * cosa), cosa);
-            Hit sh{t, 0, 0};
-            if (!trace_ray<true, BVH, true, STATS>(sc, sf.P, L, sh, st)) {
+            V3 L; float t;
+            nee_sample(sc, sf.P, l, skey, dim0, L, t);
+            if (!occluded(l, sf.P, L, t)) {
+                const uint32_t li = sc.lights[l];
+                const float sr = __ldg(&sc.spheres[li].w);
                 const V3 semis = xyz(__ldg(sc.mats + 3 * __ldg(sc.sphere_mat + li) + 1));
-                V3 attenuation = semis * 1.0f / pow_(t / s.w + 1.0f, 2.0f);
+                V3 attenuation = semis * 1.0f / pow_(t / sr + 1.0f, 2.0f);
                 attenuation = (attenuation - v3(0.001f)) / (1.0f - 0.001f);
                 attenuation = v3(gl_max(attenuation.x, 0.0f), gl_max(attenuation.y, 0.0f), gl_max(attenuation.z, 0.0f));
                 V3 F0 = v3(0.04f);
@@ -376,7 +428,8 @@ VKRT_DEV bool path_bounce(const DevScene &sc, V3 cam_pos, uint32_t max_depth, ui
     const bool found = trace_ray<true, BVH, false, STATS>(sc, ps.o, ps.d, hit, st);
     if (primary_id) *primary_id = found ? ((hit.kind << 28) | hit.index) : 0u;
     if (!found) return false;
-    return path_shade<BVH, STATS>(sc, cam_pos, max_depth, skey, ps, hit, st);
+    const OccTrace<BVH, STATS> occ{sc, st};
+    return path_shade(sc, cam_pos, max_depth, skey, ps, hit, occ);
 }
 
 // ---- primary ray: Tracer.comp:561-574 == Raytracer.comp:361-376 -------------------------------

@@ -42,13 +42,17 @@ cudaError_t launch_clear_accum(float4 *accum, size_t n, cudaStream_t st);
 
 // vkrt_wavefront.cu
 struct WaveBuffers {
-    size_t capacity;              // paths per wave
+    size_t capacity;              // path records per wave
     float4 *ray_o, *ray_d;        // origin.xyz + t_hit ; dir.xyz + hit id bits
-    float4 *acc, *mask;           // acc.xyz + pixel bits ; mask.xyz + (sample | depth << 24) bits
-    uint32_t *queue[2];           // active path indices (ping-pong)
-    uint32_t *queue_mat[2];       // per-material-type bins of the shade stage
-    uint32_t *counts;             // [0]=n_active(next) [1]=n_diffuse [2]=n_dielectric [3]=extend head [4]=shade head...
-    float4 *sample_rad;           // per (pixel-slot, sample-in-wave) finished radiance, reduced in sample order
+    float4 *acc, *mask;           // acc.xyz + pixel bits ; mask.xyz + (sample_in_wave << 8 | depth) bits
+    uint32_t *queue[2];           // active path indices (ping-pong over depth iterations)
+    uint32_t *queue_mat[2];       // material bins of the shade stage: [0] dielectric, [1] diffuse
+    uint32_t *counts;             // queue counters and work-fetch heads
+    float4 *sample_rad;           // finished radiance per (pixel slot, sample in wave); reduced in sample order
+    float4 *shadow;               // light-sample shadow rays {L.xyz, t_light}, n_lights per path
+    uint8_t *occ;                 // their any-hit results
+    float4 *frame_sum;            // running per-slot sum when a frame needs more than one wave
+    uint32_t shadow_lights;
 };
 cudaError_t wave_alloc(WaveBuffers &wb, size_t capacity);
 void wave_free(WaveBuffers &wb);

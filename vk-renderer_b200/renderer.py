@@ -184,6 +184,14 @@ class Renderer:
         self._ck(self.lib.vkrt_pack_shard(self.ctx, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    def pack_shard_into(self, dev_ptr, n_floats):
+        self._ck(self.lib.vkrt_pack_shard_into(self.ctx, C.c_void_p(dev_ptr), n_floats))
+
+    def shard_floats(self, tile_rank=0):
+        n = C.c_size_t()
+        self._ck(self.lib.vkrt_shard_floats(self.ctx, tile_rank, C.byref(n)))
+        return n.value
+
     def unpack_shard(self, dev_ptr, tile_rank, tile_count, add=False):
         self._ck(self.lib.vkrt_unpack_shard(self.ctx, C.c_void_p(dev_ptr), tile_rank, tile_count, 1 if add else 0))
 
