@@ -1,0 +1,11 @@
+#!/bin/bash
+# usage: tools/bench_brief.sh <label> [bench.py args...]  -> one short line per run
+label=$1; shift
+python bench.py --no-cpu-baseline "$@" 2>gpurun_out/err_$label.txt | tail -1 | python -c "
+import sys, json
+try:
+    d = json.loads(sys.stdin.read())
+    print('$label', 'Mrays/s %.1f' % d['value'], 'ms/frame %.2f' % d['ms_per_step'], 'e2e %.1f' % d['e2e']['value'], 'launches', d['gpu_launches'], 'clk', d['clocks']['sm_mhz'])
+except Exception as e:
+    print('$label FAILED', e); print(open('gpurun_out/err_$label.txt').read()[-800:])
+"

@@ -118,9 +118,12 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("VKRT_LIB") or LIB_PATH      # VKRT_LIB: a tuning build of the same library
+    if not os.path.exists(path):
+        if path != LIB_PATH:
+            raise OSError("VKRT_LIB=%s does not exist" % path)
         _build.build()
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (args, res) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
         fn.argtypes = args

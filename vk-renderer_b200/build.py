@@ -24,8 +24,15 @@ def _newer(src, dst):
     return not os.path.exists(dst) or os.path.getmtime(src) > os.path.getmtime(dst)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines / out: tuning builds (e.g. defines=["VKRT_REFILL=24"], out="vk-renderer_b200/libvkrt_r24.so",
+    selected at run time with the VKRT_LIB environment variable); the default build has neither."""
+    global OBJ
     nvcc = os.environ.get("NVCC", "nvcc")
+    out = out or OUT
+    if defines:
+        OBJ = os.path.join(HERE, "..", "build", "_".join(d.replace("=", "") for d in defines))
+        force = True
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "vkrt.h"))
@@ -37,22 +44,24 @@ def build(force=False, verbose=False):
         obj = os.path.join(OBJ, s[:-3] + ".o")
         objs.append(obj)
         if force or _newer(src, obj) or hdr_time > os.path.getmtime(obj):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
             rebuilt = True
     for s, p in procs:
-        out, _ = p.communicate()
-        if verbose and out:
-            sys.stderr.write(out)
+        log, _ = p.communicate()
+        if verbose and log:
+            sys.stderr.write(log)
         if p.returncode != 0:
-            raise RuntimeError("nvcc failed for %s:\n%s" % (s, out))
-    if rebuilt or not os.path.exists(OUT):
-        cmd = [nvcc, "-shared", "-cudart", "static", "-Wno-deprecated-gpu-targets", "-o", OUT] + objs
+            raise RuntimeError("nvcc failed for %s:\n%s" % (s, log))
+    if rebuilt or not os.path.exists(out):
+        cmd = [nvcc, "-shared", "-cudart", "static", "-Wno-deprecated-gpu-targets", "-o", out] + objs
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

@@ -130,14 +130,22 @@ VKRT_DEV void s_consider(V3 o, V3 d, float4 sph, int i, float tn, float eps, flo
     else if (t < best.t || (t == best.t && i < best.idx)) { best.t = t; best.idx = i; }
 }
 
+VKRT_DEV void ldg256(const float4 *p, float4 &a, float4 &b)
+{
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+
 // Resumable traversal state: one call of trav_step visits one inner node (both child records).
-// node < 0 means the traversal is finished.  The stack lives in local memory (L1-resident).
+// node < 0 means the traversal is finished.  The stack is a separate local-memory array (L1-resident)
+// so that the scalar state below stays in registers (an array member would drag the whole struct
+// into local memory).
 struct Trav {
     SlabRay sr;
     SBest best;
     float eps, B;
     int node, sp;
-    int stack[BVH_STACK];
 };
 VKRT_DEV void trav_init(Trav &tv, const DevScene &sc, V3 o, V3 d, float eps, float B)
 {
@@ -148,10 +156,14 @@ VKRT_DEV void trav_init(Trav &tv, const DevScene &sc, V3 o, V3 d, float eps, flo
     tv.node = sc.n_nodes ? 0 : -1;
 }
 template <bool ANY, bool STATS>
-VKRT_DEV void trav_step(Trav &tv, const DevScene &sc, V3 o, V3 d, Stats &st)
+VKRT_DEV void trav_step(Trav &tv, int *__restrict__ stack, const DevScene &sc, V3 o, V3 d, Stats &st)
 {
+    // one 64-byte node = two 256-bit loads (LDG.E.256, sm_100): the traversal is bound by L1TEX request
+    // throughput (scattered lines), so halving the number of load instructions per node matters
     const float4 *np = sc.bvh + 4 * (size_t)tv.node;
-    const float4 a0 = __ldg(np), b0 = __ldg(np + 1), a1 = __ldg(np + 2), b1 = __ldg(np + 3);
+    float4 a0, b0, a1, b1;
+    ldg256(np, a0, b0);
+    ldg256(np + 2, a1, b1);
     if (STATS) ++st.nodes;
     int nxt0 = -1, nxt1 = -1;
     float tn0, tn1, tf;
@@ -182,19 +194,20 @@ VKRT_DEV void trav_step(Trav &tv, const DevScene &sc, V3 o, V3 d, Stats &st)
     if (ANY && tv.best.idx >= 0) { tv.node = -1; return; }
     if (nxt0 >= 0 && nxt1 >= 0) {
         const bool swap = tn1 < tn0;
-        tv.stack[tv.sp++] = swap ? nxt0 : nxt1;
+        stack[tv.sp++] = swap ? nxt0 : nxt1;
         tv.node = swap ? nxt1 : nxt0;
     } else if (nxt0 >= 0) tv.node = nxt0;
     else if (nxt1 >= 0) tv.node = nxt1;
-    else tv.node = tv.sp ? tv.stack[--tv.sp] : -1;
+    else tv.node = tv.sp ? stack[--tv.sp] : -1;
 }
 
 template <bool ANY, bool STATS>
 VKRT_DEV SBest bvh_query(const DevScene &sc, V3 o, V3 d, float eps, float B, Stats &st)
 {
     Trav tv;
+    int stack[BVH_STACK];
     trav_init(tv, sc, o, d, eps, B);
-    while (tv.node >= 0) trav_step<ANY, STATS>(tv, sc, o, d, st);
+    while (tv.node >= 0) trav_step<ANY, STATS>(tv, stack, sc, o, d, st);
     return tv.best;
 }
 

@@ -51,6 +51,7 @@ struct WaveBuffers {
     float4 *sample_rad;           // finished radiance per (pixel slot, sample in wave); reduced in sample order
     float4 *shadow;               // light-sample shadow rays {L.xyz, t_light}, n_lights per path
     uint8_t *occ;                 // their any-hit results
+    uint32_t *queue_shadow;       // (path << 4 | light) items that still need the sphere any-hit query
     float4 *frame_sum;            // running per-slot sum when a frame needs more than one wave
     uint32_t shadow_lights;
 };

@@ -1,17 +1,20 @@
 // Wavefront variant of the path integrator (Assets/Tracer.comp::radiance, :433-553).
 //
-// One "wave" holds S samples of every owned pixel as path records in HBM (SoA float4s).  Per depth
-// iteration the queues are processed by small kernels:
+// One "wave" holds S samples of every owned pixel as path records in HBM (SoA float4s, sample-major:
+// path = sample_in_wave * n_slots + pixel_slot, so every kernel reads and writes them coalesced).
+// Per depth iteration the queues are processed by small kernels:
 //
 //   extend   persistent warps pull rays from the active queue (one atomicAdd per warp for all lanes
 //            that need a ray, found with __ballot_sync, base broadcast with __shfl_sync); a lane whose
-//            traversal ends is refilled as soon as fewer than REFILL lanes are still traversing, so
-//            the heavy-tailed LBVH traversal keeps the warp full
-//   classify firefly clamp (:441); misses end the path; hits are binned by material type into the
-//            dielectric queue and the diffuse queue (warp-aggregated pushes)
+//            traversal ends is refilled as soon as fewer than REFILL lanes are still traversing, so the
+//            heavy-tailed LBVH traversal keeps the warp full.  Triangles + spheres only.
+//   classify firefly clamp (:441), the plane loop of trace_ray (:414-428) on top of extend's result,
+//            misses end the path, hits are binned by material type into the dielectric queue and the
+//            diffuse queue (warp-aggregated pushes)
 //   dielectric  shades the dielectric bin (:514-542) + Russian roulette, pushes survivors
-//   nee      writes the light-sample shadow rays of the diffuse bin (:464-469)
-//   shadow   the same persistent traversal kernel in any-hit mode
+//   nee      light-sample shadow rays of the diffuse bin (:464-469); triangle / plane occluders are
+//            resolved here, only rays that still need the sphere any-hit query are queued
+//   shadow   the same persistent traversal kernel in any-hit mode (spheres only)
 //   diffuse  shades the diffuse bin (:451-513) with the occlusion flags + Russian roulette
 //
 // and a wave ends with `reduce`, which adds the per-sample radiances of every pixel IN SAMPLE ORDER,
@@ -19,18 +22,25 @@
 #include "vkrt_device.cuh"
 #include "vkrt_internal.h"
 
+#ifndef VKRT_REFILL
+#define VKRT_REFILL 20      // refill the warp when fewer than this many lanes are still traversing
+#endif
+#ifndef VKRT_TRACE_BLOCK
+#define VKRT_TRACE_BLOCK 128
+#endif
+
 namespace vkrt {
 
-enum { C_ACTIVE0 = 0, C_ACTIVE1 = 1, C_DIEL = 2, C_DIFF = 3, C_HEAD_EXTEND = 4, C_HEAD_SHADOW = 5, C_N = 8 };
-enum { REFILL = 20 };   // refill the warp when fewer than this many lanes are still traversing
+enum { C_ACTIVE0 = 0, C_ACTIVE1 = 1, C_DIEL = 2, C_DIFF = 3, C_SHADOW = 4, C_HEAD_EXTEND = 5, C_HEAD_SHADOW = 6, C_N = 8 };
 
 struct WaveParams {
     float4 *po, *pd, *pacc, *pmask, *sh, *rad;
-    uint32_t *q_active[2], *q_diel, *q_diff;
+    uint32_t *q_active[2], *q_diel, *q_diff, *q_shadow;
     uint8_t *occ;
     uint32_t *cnt;
     uint32_t s0, S;          // first sample of the wave, samples per pixel in the wave
-    uint32_t n_paths;        // n_work * S
+    uint32_t n_slots;        // = RenderParams.n_work
+    uint32_t n_lights;
 };
 
 VKRT_DEV bool slot_to_pixel_w(const RenderParams &rp, uint32_t w, uint32_t &px, uint32_t &py)
@@ -77,48 +87,52 @@ VKRT_DEV void wf_flush(const Stats &st, unsigned long long *counters, bool stats
 __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ RenderParams rp, const __grid_constant__ WaveParams wp)
 {
     Stats st; stats_zero(st);
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = false;
-    if (p < wp.n_paths) {
-        const uint32_t slot = p / wp.S, sl = p % wp.S;
-        uint32_t px, py;
-        if (slot_to_pixel_w(rp, slot, px, py)) {
-            V3 o, d;
-            primary_ray(rp.fd, rp.width, rp.height, px, py, o, d);
-            wp.po[p] = make_float4(o.x, o.y, o.z, 0.f);
-            wp.pd[p] = make_float4(d.x, d.y, d.z, 0.f);
-            wp.pacc[p] = make_float4(0.f, 0.f, 0.f, __uint_as_float(py * rp.width + px));
-            wp.pmask[p] = make_float4(1.f, 1.f, 1.f, __uint_as_float(sl << 8));
-            valid = true;
-            ++st.paths;
-        } else {
-            wp.rad[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t px = 0, py = 0;
+    const bool valid = slot < wp.n_slots && slot_to_pixel_w(rp, slot, px, py);
+    float4 fo = make_float4(0.f, 0.f, 0.f, 0.f), fd = fo;
+    uint32_t pix = 0;
+    if (valid) {
+        V3 o, d;
+        primary_ray(rp.fd, rp.width, rp.height, px, py, o, d);
+        fo = make_float4(o.x, o.y, o.z, 0.f); fd = make_float4(d.x, d.y, d.z, 0.f);
+        pix = py * rp.width + px;
     }
-    push(wp.q_active[0], wp.cnt + C_ACTIVE0, valid, p);
+    for (uint32_t sl = 0; sl < wp.S; ++sl) {
+        const uint32_t p = sl * wp.n_slots + slot;
+        if (valid) {
+            wp.po[p] = fo; wp.pd[p] = fd;
+            wp.pacc[p] = make_float4(0.f, 0.f, 0.f, __uint_as_float(pix));
+            wp.pmask[p] = make_float4(1.f, 1.f, 1.f, __uint_as_float(sl << 8));
+            ++st.paths;
+        }
+        push(wp.q_active[0], wp.cnt + C_ACTIVE0, valid, p);
+    }
     wf_flush(st, rp.counters, false);
 }
 
 // ---- persistent trace kernel (nearest-hit for `extend`, any-hit for `shadow`) --------------------
-// ANY = false: item i -> path q[i]; ray = (po, pd), bound = 3000/(depth+1)^2; result -> po.w (t), pd.w (id)
-// ANY = true : item i -> path q[i / n_lights], light i % n_lights; ray = (P, sh.xyz), bound sh.w; result -> occ
+// ANY = false: item i -> path queue[i]; ray (po, pd), bound 3000/(depth+1)^2; triangles, then spheres;
+//              result -> po.w (t so far), pd.w (id so far); the plane loop follows in classify
+// ANY = true : item i -> queue[i] = path * 16 + light; ray (P, sh.xyz), bound sh.w; spheres only; -> occ
 template <bool ANY, bool BVH, bool STATS>
-__global__ void __launch_bounds__(128) k_wf_trace(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
-                                                   const __grid_constant__ WaveParams wp, const uint32_t *__restrict__ queue,
-                                                   const uint32_t *__restrict__ n_items_ptr, uint32_t *head)
+__global__ void __launch_bounds__(VKRT_TRACE_BLOCK) k_wf_trace(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
+                                                                const __grid_constant__ WaveParams wp, const uint32_t *__restrict__ queue,
+                                                                const uint32_t *__restrict__ n_items_ptr, uint32_t *head)
 {
     const unsigned full = 0xffffffffu, lane = threadIdx.x & 31u;
     Stats st; stats_zero(st);
-    const uint32_t nl = ANY ? sc.n_lights : 1u;
-    const uint32_t n_items = *n_items_ptr * nl;
+    const uint32_t n_items = *n_items_ptr;
+    const float EPS = 1e-3f;
 
     bool has = false, drained = false;
-    uint32_t item = 0, path = 0;
+    uint32_t path = 0, light = 0;
     V3 o = v3(0.f), d = v3(0.f);
     Hit hit{0.f, 0, 0};
     bool found = false;
     float cur = 0.f;
     Trav tv; tv.node = -1; tv.sp = 0;
+    int stack[BVH_STACK];
 
     for (;;) {
         // ---- refill the lanes that have no ray -------------------------------------------------
@@ -130,26 +144,27 @@ __global__ void __launch_bounds__(128) k_wf_trace(const __grid_constant__ DevSce
             if ((int)lane == leader) base = atomicAdd(head, (uint32_t)__popc(m));
             base = __shfl_sync(full, base, leader);
             if (need) {
-                item = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                const uint32_t item = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
                 if (item >= n_items) drained = true;
                 else {
                     has = true;
-                    path = queue[item / nl];
+                    const uint32_t q = queue[item];
+                    path = ANY ? (q >> 4) : q;
+                    light = ANY ? (q & 15u) : 0u;
                     const float4 fo = wp.po[path], fd = wp.pd[path];
+                    found = false; hit.kind = 0; hit.index = 0;
                     if (ANY) {
-                        const float4 s = wp.sh[(size_t)path * nl + item % nl];
+                        const float4 s = wp.sh[(size_t)path * wp.n_lights + light];
                         o = madd3(fo.w, xyz(fd), xyz(fo));           // the hit point P (== surface_of's P)
                         d = xyz(s); cur = s.w;
-                        ++st.shadow;
                     } else {
                         o = xyz(fo); d = xyz(fd);
                         const uint32_t depth = __float_as_uint(wp.pmask[path].w) & 255u;
                         cur = path_tmax(depth);
                         ++st.closest;
+                        found = trace_tris<true>(sc, o, d, cur, hit);
                     }
-                    hit.kind = 0; hit.index = 0;
-                    found = trace_tris<true>(sc, o, d, cur, hit);
-                    if (BVH && !(ANY && found)) trav_init(tv, sc, o, d, trace_eps<true>(), sphere_bound<true>(cur));
+                    if (BVH) trav_init(tv, sc, o, d, EPS, sphere_bound<true>(cur));
                     else tv.node = -1;
                 }
             }
@@ -162,24 +177,22 @@ __global__ void __launch_bounds__(128) k_wf_trace(const __grid_constant__ DevSce
                 const bool trav = has && tv.node >= 0;
                 const unsigned tm = __ballot_sync(full, trav);
                 if (tm == 0) break;
-                if (__popc(tm) < REFILL && __any_sync(full, !drained && !trav)) break;
-                if (trav) trav_step<ANY, STATS>(tv, sc, o, d, st);
+                if (__popc(tm) < VKRT_REFILL && __any_sync(full, !drained && !trav)) break;
+                if (trav) trav_step<ANY, STATS>(tv, stack, sc, o, d, st);
             }
         }
 
         // ---- finish the lanes whose traversal is over ---------------------------------------------
         if (has && tv.node < 0) {
             if (BVH) {
-                if (tv.best.idx >= 0 && !(ANY && found)) { cur = tv.best.t; hit.kind = KIND_SPHERE; hit.index = (uint32_t)tv.best.idx; found = true; }
-            } else if (!(ANY && found)) {
-                const float EPS = 1e-3f;
+                if (tv.best.idx >= 0) { cur = tv.best.t; hit.kind = KIND_SPHERE; hit.index = (uint32_t)tv.best.idx; found = true; }
+            } else {
                 for (uint32_t i = 0; i < sc.n_spheres; ++i) {                     // literal loop, Tracer.comp:398-412
                     const float t = sphere_intersect(o, d, __ldg(sc.spheres + i));
                     if ((t > EPS) && (t < cur + EPS)) { cur = t; hit.kind = KIND_SPHERE; hit.index = i; found = true; }
                 }
             }
-            if (!(ANY && found)) found = trace_planes<true>(sc, o, d, cur, hit) || found;
-            if (ANY) wp.occ[(size_t)path * nl + item % nl] = found ? 1 : 0;
+            if (ANY) wp.occ[(size_t)path * wp.n_lights + light] = found ? 1 : 0;
             else {
                 wp.po[path].w = cur;
                 wp.pd[path].w = __uint_as_float(found ? ((hit.kind << 28) | hit.index) : 0u);
@@ -190,7 +203,7 @@ __global__ void __launch_bounds__(128) k_wf_trace(const __grid_constant__ DevSce
     wf_flush(st, rp.counters, STATS);
 }
 
-// ---- classify: clamp, end missed paths, bin hits by material type ---------------------------------
+// ---- classify: clamp, plane loop, end missed paths, bin hits by material type ---------------------
 __global__ void __launch_bounds__(256) k_wf_classify(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
                                                       const __grid_constant__ WaveParams wp, const uint32_t *__restrict__ queue,
                                                       const uint32_t *__restrict__ n_ptr)
@@ -202,16 +215,22 @@ __global__ void __launch_bounds__(256) k_wf_classify(const __grid_constant__ Dev
         uint32_t path = 0;
         if (i < n) {
             path = queue[i];
-            float4 a = wp.pacc[path];
-            a.x = gl_clamp(a.x, 0.0f, 1.0f); a.y = gl_clamp(a.y, 0.0f, 1.0f); a.z = gl_clamp(a.z, 0.0f, 1.0f);   // :441
-            wp.pacc[path] = a;
-            const uint32_t id = __float_as_uint(wp.pd[path].w);
+            const float4 a = wp.pacc[path];
+            const float4 c = make_float4(gl_clamp(a.x, 0.0f, 1.0f), gl_clamp(a.y, 0.0f, 1.0f), gl_clamp(a.z, 0.0f, 1.0f), a.w);   // :441
+            if (__float_as_uint(c.x) != __float_as_uint(a.x) || __float_as_uint(c.y) != __float_as_uint(a.y) ||
+                __float_as_uint(c.z) != __float_as_uint(a.z)) wp.pacc[path] = c;
+            const float4 fo = wp.po[path], fd = wp.pd[path];
+            const uint32_t id0 = __float_as_uint(fd.w);
+            Hit hit{fo.w, id0 >> 28, id0 & 0x0fffffffu};
+            float cur = fo.w;
+            const bool found = trace_planes<true>(sc, xyz(fo), xyz(fd), cur, hit) || id0 != 0u;     // :414-428
+            const uint32_t id = found ? ((hit.kind << 28) | hit.index) : 0u;
+            if (id != id0) { wp.po[path].w = cur; wp.pd[path].w = __uint_as_float(id); }
             const uint32_t sd = __float_as_uint(wp.pmask[path].w);
-            if (rp.hit_ids && (sd & 255u) == 0u && (sd >> 8) == 0u && wp.s0 == rp.s_begin) rp.hit_ids[__float_as_uint(a.w)] = id;
-            if (id == 0u) wp.rad[path] = make_float4(a.x, a.y, a.z, 0.f);           // miss: break (:445)
+            if (rp.hit_ids && sd == 0u && wp.s0 == rp.s_begin) rp.hit_ids[__float_as_uint(a.w)] = id;
+            if (id == 0u) wp.rad[path] = make_float4(c.x, c.y, c.z, 0.f);           // miss: break (:445)
             else {
-                const uint32_t kind = id >> 28, index = id & 0x0fffffffu;
-                const uint32_t mat = kind == KIND_TRI ? sc.tri_mat : kind == KIND_SPHERE ? __ldg(sc.sphere_mat + index) : sc.plane_mat[index];
+                const uint32_t mat = hit.kind == KIND_TRI ? sc.tri_mat : hit.kind == KIND_SPHERE ? __ldg(sc.sphere_mat + hit.index) : sc.plane_mat[hit.index];
                 const uint32_t type = __float_as_uint(__ldg(&sc.mats[3 * mat + 2].x));
                 diel = type != 0u; diff = type == 0u;
             }
@@ -231,34 +250,52 @@ VKRT_DEV void load_path(const WaveParams &wp, uint32_t path, PathState &ps, Hit 
     const uint32_t id = __float_as_uint(fd.w);
     hit.t = fo.w; hit.kind = id >> 28; hit.index = id & 0x0fffffffu;
 }
-VKRT_DEV void store_path(const WaveParams &wp, uint32_t path, const PathState &ps, uint32_t pix, uint32_t sl, bool alive, uint32_t *q_next, uint32_t *c_next)
+VKRT_DEV void store_path(const WaveParams &wp, uint32_t path, const PathState &ps, uint32_t pix, uint32_t sl)
 {
-    if (alive) {
-        wp.po[path] = make_float4(ps.o.x, ps.o.y, ps.o.z, 0.f);
-        wp.pd[path] = make_float4(ps.d.x, ps.d.y, ps.d.z, 0.f);
-        wp.pacc[path] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, __uint_as_float(pix));
-        wp.pmask[path] = make_float4(ps.mask.x, ps.mask.y, ps.mask.z, __uint_as_float((sl << 8) | ps.depth));
-    }
+    wp.po[path] = make_float4(ps.o.x, ps.o.y, ps.o.z, 0.f);
+    wp.pd[path] = make_float4(ps.d.x, ps.d.y, ps.d.z, 0.f);
+    wp.pacc[path] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, __uint_as_float(pix));
+    wp.pmask[path] = make_float4(ps.mask.x, ps.mask.y, ps.mask.z, __uint_as_float((sl << 8) | ps.depth));
 }
 
 // ---- nee: shadow rays of the diffuse bin ----------------------------------------------------------
 __global__ void __launch_bounds__(256) k_wf_nee(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
                                                  const __grid_constant__ WaveParams wp)
 {
+    Stats st; stats_zero(st);
     const uint32_t n = wp.cnt[C_DIFF];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t path = wp.q_diff[i];
-        const float4 fo = wp.po[path], fd = wp.pd[path], fa = wp.pacc[path], fm = wp.pmask[path];
-        const V3 P = madd3(fo.w, xyz(fd), xyz(fo));
-        const uint32_t sd = __float_as_uint(fm.w);
-        const uint32_t skey = sample_key(rp.fkey, __float_as_uint(fa.w), wp.s0 + (sd >> 8));
-        const uint32_t dim0 = (sd & 255u) * DIMS_PER_BOUNCE;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t path = 0, skey = 0, dim0 = 0;
+        V3 P = v3(0.f);
+        if (i < n) {
+            path = wp.q_diff[i];
+            const float4 fo = wp.po[path], fd = wp.pd[path], fa = wp.pacc[path], fm = wp.pmask[path];
+            P = madd3(fo.w, xyz(fd), xyz(fo));
+            const uint32_t sd = __float_as_uint(fm.w);
+            skey = sample_key(rp.fkey, __float_as_uint(fa.w), wp.s0 + (sd >> 8));
+            dim0 = (sd & 255u) * DIMS_PER_BOUNCE;
+        }
         for (uint32_t l = 0; l < sc.n_lights; ++l) {
-            V3 L; float t;
-            nee_sample(sc, P, l, skey, dim0, L, t);
-            wp.sh[(size_t)path * sc.n_lights + l] = make_float4(L.x, L.y, L.z, t);
+            bool queue_it = false;
+            if (i < n) {
+                V3 L; float t;
+                nee_sample(sc, P, l, skey, dim0, L, t);
+                ++st.shadow;
+                // any-hit is a plain OR over the primitive classes: triangles and planes here,
+                // spheres (bound t + EPSILON, unchanged because nothing was accepted before them) in `shadow`
+                Hit h{t, 0, 0};
+                float cur = t;
+                bool occluded = trace_tris<true>(sc, P, L, cur, h);
+                if (!occluded) { cur = t; occluded = trace_planes<true>(sc, P, L, cur, h); }
+                wp.sh[(size_t)path * sc.n_lights + l] = make_float4(L.x, L.y, L.z, t);
+                if (occluded) wp.occ[(size_t)path * sc.n_lights + l] = 1;
+                queue_it = !occluded;
+            }
+            push(wp.q_shadow, wp.cnt + C_SHADOW, queue_it, (path << 4) | l);
         }
     }
+    wf_flush(st, rp.counters, false);
 }
 
 struct OccFlags {
@@ -271,8 +308,8 @@ struct OccNever {
 
 // ---- shade one material bin + Russian roulette -----------------------------------------------------
 template <bool DIFFUSE>
-__global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
-                                                   const __grid_constant__ WaveParams wp, uint32_t next)
+__global__ void __launch_bounds__(256, 3) k_wf_shade(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
+                                                      const __grid_constant__ WaveParams wp, uint32_t next)
 {
     const uint32_t *queue = DIFFUSE ? wp.q_diff : wp.q_diel;
     const uint32_t n = wp.cnt[DIFFUSE ? C_DIFF : C_DIEL];
@@ -292,7 +329,7 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ DevSce
             } else {
                 alive = path_shade(sc, cam_pos, rp.max_depth, skey, ps, hit, OccNever{});
             }
-            if (alive) store_path(wp, path, ps, pix, sl, true, nullptr, nullptr);
+            if (alive) store_path(wp, path, ps, pix, sl);
             else wp.rad[path] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, 0.f);
         }
         push(wp.q_active[next], wp.cnt + (next ? C_ACTIVE1 : C_ACTIVE0), alive, path);
@@ -302,7 +339,7 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ DevSce
 // resets the per-iteration counters (one tiny launch instead of several memsets)
 __global__ void k_wf_reset(uint32_t *cnt, uint32_t clear_active)
 {
-    cnt[C_DIEL] = 0; cnt[C_DIFF] = 0; cnt[C_HEAD_EXTEND] = 0; cnt[C_HEAD_SHADOW] = 0;
+    cnt[C_DIEL] = 0; cnt[C_DIFF] = 0; cnt[C_SHADOW] = 0; cnt[C_HEAD_EXTEND] = 0; cnt[C_HEAD_SHADOW] = 0;
     cnt[clear_active ? C_ACTIVE1 : C_ACTIVE0] = 0;
 }
 
@@ -311,11 +348,11 @@ __global__ void __launch_bounds__(256) k_wf_reduce(const __grid_constant__ Rende
                                                     float4 *__restrict__ frame_sum, uint32_t first_wave, uint32_t last_wave)
 {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= rp.n_work) return;
+    if (slot >= wp.n_slots) return;
     uint32_t px, py;
     if (!slot_to_pixel_w(rp, slot, px, py)) return;
     V3 sum = first_wave ? v3(0.0f) : xyz(frame_sum[slot]);
-    for (uint32_t s = 0; s < wp.S; ++s) sum = sum + xyz(wp.rad[(size_t)slot * wp.S + s]);      // Tracer.comp:580
+    for (uint32_t s = 0; s < wp.S; ++s) sum = sum + xyz(wp.rad[(size_t)s * wp.n_slots + slot]);      // Tracer.comp:580
     if (!last_wave) { frame_sum[slot] = make_float4(sum.x, sum.y, sum.z, 0.f); return; }
     const uint32_t pix = py * rp.width + px;
     float4 a = make_float4(sum.x, sum.y, sum.z, (float)(rp.s_end - rp.s_begin));
@@ -348,7 +385,7 @@ void wave_free(WaveBuffers &wb)
 {
     cudaFree(wb.ray_o); cudaFree(wb.ray_d); cudaFree(wb.acc); cudaFree(wb.mask); cudaFree(wb.sample_rad);
     cudaFree(wb.queue[0]); cudaFree(wb.queue[1]); cudaFree(wb.queue_mat[0]); cudaFree(wb.queue_mat[1]); cudaFree(wb.counts);
-    cudaFree(wb.shadow); cudaFree(wb.occ); cudaFree(wb.frame_sum);
+    cudaFree(wb.shadow); cudaFree(wb.occ); cudaFree(wb.frame_sum); cudaFree(wb.queue_shadow);
     wb = WaveBuffers{};
 }
 
@@ -361,13 +398,15 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
     const uint32_t nl = sc.n_lights ? sc.n_lights : 1;
     // samples per wave: as many as fit the path capacity
     uint32_t S = (uint32_t)(wb.capacity / rp.n_work);
-    if (S == 0) return cudaErrorMemoryAllocation;
+    if (S == 0 || wb.capacity >= ((size_t)1 << 28)) return cudaErrorMemoryAllocation;   // shadow items pack path << 4
     if (S > spp) S = spp;
     // shadow-ray storage depends on the light count of the scene: (re)allocate lazily
     if (wb.shadow_lights < nl) {
-        cudaFree(wb.shadow); cudaFree(wb.occ); wb.shadow = nullptr; wb.occ = nullptr;
+        cudaFree(wb.shadow); cudaFree(wb.occ); cudaFree(wb.queue_shadow);
+        wb.shadow = nullptr; wb.occ = nullptr; wb.queue_shadow = nullptr;
         if ((e = cudaMalloc((void **)&wb.shadow, wb.capacity * nl * sizeof(float4))) != cudaSuccess) return e;
         if ((e = cudaMalloc((void **)&wb.occ, wb.capacity * nl)) != cudaSuccess) return e;
+        if ((e = cudaMalloc((void **)&wb.queue_shadow, wb.capacity * nl * sizeof(uint32_t))) != cudaSuccess) return e;
         wb.shadow_lights = nl;
     }
     const uint32_t n_waves = (spp + S - 1) / S;
@@ -383,8 +422,8 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
     };
     auto k_extend = pick_trace(false), k_shadow = pick_trace(true);
     int occ_e = 0, occ_s = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_extend, 128, 0)) != cudaSuccess) return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_shadow, 128, 0)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_extend, VKRT_TRACE_BLOCK, 0)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_shadow, VKRT_TRACE_BLOCK, 0)) != cudaSuccess) return e;
     const unsigned grid_e = (unsigned)(sm_count * (occ_e > 0 ? occ_e : 1)), grid_s = (unsigned)(sm_count * (occ_s > 0 ? occ_s : 1));
     const unsigned grid_shade = (unsigned)sm_count * 8u;
 
@@ -392,26 +431,28 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
         WaveParams wp{};
         wp.po = wb.ray_o; wp.pd = wb.ray_d; wp.pacc = wb.acc; wp.pmask = wb.mask; wp.sh = wb.shadow; wp.rad = wb.sample_rad;
         wp.q_active[0] = wb.queue[0]; wp.q_active[1] = wb.queue[1]; wp.q_diel = wb.queue_mat[0]; wp.q_diff = wb.queue_mat[1];
+        wp.q_shadow = wb.queue_shadow;
         wp.occ = wb.occ; wp.cnt = wb.counts;
         wp.s0 = rp.s_begin + wv * S;
         wp.S = (wp.s0 + S <= rp.s_end) ? S : (rp.s_end - wp.s0);
-        wp.n_paths = rp.n_work * wp.S;
+        wp.n_slots = rp.n_work;
+        wp.n_lights = sc.n_lights;
         if ((e = cudaMemsetAsync(wb.counts, 0, 64 * sizeof(uint32_t), st)) != cudaSuccess) return e;
-        k_wf_generate<<<(wp.n_paths + 255u) / 256u, 256, 0, st>>>(rp, wp); ++launches;
+        k_wf_generate<<<(wp.n_slots + 255u) / 256u, 256, 0, st>>>(rp, wp); ++launches;
         for (uint32_t depth = 0; depth < rp.max_depth; ++depth) {
             const uint32_t cur = depth & 1u, nxt = cur ^ 1u;
             const uint32_t *n_active = wb.counts + (cur ? C_ACTIVE1 : C_ACTIVE0);
             k_wf_reset<<<1, 1, 0, st>>>(wb.counts, nxt); ++launches;
-            k_extend<<<grid_e, 128, 0, st>>>(sc, rp, wp, wp.q_active[cur], n_active, wb.counts + C_HEAD_EXTEND); ++launches;
+            k_extend<<<grid_e, VKRT_TRACE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_active[cur], n_active, wb.counts + C_HEAD_EXTEND); ++launches;
             k_wf_classify<<<grid_shade, 256, 0, st>>>(sc, rp, wp, wp.q_active[cur], n_active); ++launches;
             k_wf_shade<false><<<grid_shade, 256, 0, st>>>(sc, rp, wp, nxt); ++launches;
             if (sc.n_lights) {
                 k_wf_nee<<<grid_shade, 256, 0, st>>>(sc, rp, wp); ++launches;
-                k_shadow<<<grid_s, 128, 0, st>>>(sc, rp, wp, wp.q_diff, wb.counts + C_DIFF, wb.counts + C_HEAD_SHADOW); ++launches;
+                k_shadow<<<grid_s, VKRT_TRACE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_shadow, wb.counts + C_SHADOW, wb.counts + C_HEAD_SHADOW); ++launches;
             }
             k_wf_shade<true><<<grid_shade, 256, 0, st>>>(sc, rp, wp, nxt); ++launches;
         }
-        k_wf_reduce<<<(rp.n_work + 255u) / 256u, 256, 0, st>>>(rp, wp, wb.frame_sum, wv == 0, wv + 1 == n_waves); ++launches;
+        k_wf_reduce<<<(wp.n_slots + 255u) / 256u, 256, 0, st>>>(rp, wp, wb.frame_sum, wv == 0, wv + 1 == n_waves); ++launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     if (n_launches) *n_launches = launches;
