@@ -1,0 +1,186 @@
+"""CPU tests of the boundary and the host logic: the C-ABI library loads and exports exactly what
+include/vkrt.h declares (no compute calls here), error behaviour without a GPU, scene generators,
+the shard layout, and the N>1 gather path with world_size 2 on gloo."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, has_gpu
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "vkrt.h")).read()
+    return sorted(set(re.findall(r"VKRT_API\s+[\w\s\*]+?\b(vkrt_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(vk):
+    names = declared_functions()
+    assert len(names) >= 35 and "vkrt_draw" in names and "vkrt_create" in names
+    lib = C.CDLL(vk._lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), "libvkrt_cuda.so does not export %s" % n
+    assert sorted(vk._lib.SIGNATURES) == names                   # the binding covers the header, nothing else
+    out = subprocess.run(["nm", "-D", "--defined-only", vk._lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r" T (vkrt_\w+)", out)))
+    assert exported == names                                      # and nothing undeclared leaks out
+    assert vk._lib.load().vkrt_version().startswith(b"libvkrt_cuda")
+
+
+def test_library_is_sm100a_only(vk):
+    out = subprocess.run(["cuobjdump", "-lelf", vk._lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert "sm_100a" in archs and not (archs - {"sm_100a", "sm_52"}), archs   # sm_52: cudart's own static stub
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under vk-renderer_b200/ may import, link or open it."""
+    pkg = os.path.join(ROOT, "vk-renderer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                for pat in (r"^\s*(import|from)\s+oracle\b", r"vkrt_oracle", r"\borc_\w+\s*\(", r"#include.*oracle", r"_ref/libref"):
+                    assert not re.search(pat, text, re.M), "%s matches %s" % (f, pat)
+
+
+@pytest.mark.skipif(has_gpu(), reason="exercises the no-GPU failure path")
+def test_create_fails_loudly_without_gpu(vk):
+    with pytest.raises(vk.VkrtError) as e:
+        vk.Renderer(64, 64)
+    assert e.value.code == vk._lib.NO_SUITABLE_GPU
+    assert "[app] - err ::" in str(e.value) and "no CPU fallback" in str(e.value)
+    dev = vk.GraphicsDevice()
+    assert dev.Construct(vk.GraphicsDevice.CreateInfo(None, 3, 2, 64, False)) == vk.GraphicsDevice.Error.NO_SUITABLE_GPU
+    assert dev.Destruct() == vk.GraphicsDevice.Error.UNKNOWN
+
+
+def test_error_enum_matches_reference(vk):
+    E = vk.GraphicsDevice.Error                                    # Include/GraphicsDevice.h:46-52
+    assert (E.SUCCESS, E.NO_SUITABLE_GPU, E.NO_SUITABLE_SURFACE, E.UNKNOWN) == (0, 1, 2, 3)
+    info = vk.GraphicsDevice.CreateInfo(None, 3, 2, 1024, False)   # Main.cpp:105-115
+    assert (info.swapchainSize, info.framesInFlight, info.raytrace_resolution, info.debug) == (3, 2, 1024, False)
+    assert (info.width, info.height) == (1024, 1024) and info.swapchain_extent == (1024, 768)
+
+
+def test_scene_generators_are_deterministic(vk):
+    s = vk.scenes
+    assert s.tracer_default().digest() == s.tracer_default().digest()
+    a, b = s.random_spheres(1024), s.random_spheres(1024)
+    assert a.digest() == b.digest() == "ed102bc746ea584f"
+    assert a.spheres.shape == (1025, 4) and a.materials.shape == (8 + 1024, 12)
+    assert a.spheres[1:, 3].min() >= 0.5 and a.spheres[1:, 3].max() <= 3.0
+    kinds = a.materials[8:].view(np.uint32)[:, 8]
+    frac_diel = (kinds == 1).mean()
+    metal = (a.materials[8:, 7] == 1.0).mean()
+    assert 0.05 < frac_diel < 0.16 and 0.22 < metal < 0.38            # ~10 % dielectric, ~30 % metal, rest lambertian
+    g = s.grid_spheres()
+    assert g.spheres.shape == (100001, 4) and g.digest() == "d78035e0463ed3f3"
+    c, r = g.spheres[1:, :3], g.spheres[1:, 3]
+    assert c[:, 0].min() - r[0] >= -60 and c[:, 0].max() + r[0] <= 60 and c[:, 1].min() - r[0] >= 2 and c[:, 1].max() + r[0] <= 120
+    assert s.random_spheres(64, seed=1).digest() != s.random_spheres(64, seed=2).digest()
+
+
+def test_default_scenes_match_the_oracles_builtin_copy(vk, oracle):
+    """scenes.py, libvkrt_cuda's vkrt_use_default_scene and the oracle each restate the shader constants;
+    the python and oracle copies must render identically."""
+    from helpers import apply_scene, bits_equal
+    fd = vk.default_frame_data(aspect_ratio=4 / 3, seed=0.5)
+    for scene, which, integ, depth in ((vk.scenes.tracer_default(), oracle.SCENE_TRACER, oracle.PATH, 4),
+                                       (vk.scenes.raytracer_default(), oracle.SCENE_RAYTRACER, oracle.WHITTED, 2)):
+        a, ia, _, _ = apply_scene(oracle, scene).render(fd, 48, 36, spp=2, max_depth=depth, integrator=integ, seed=3)
+        b, ib, _, _ = oracle.Scene().use_default(which).render(fd, 48, 36, spp=2, max_depth=depth, integrator=integ, seed=3)
+        assert bits_equal(a, b) and np.array_equal(ia, ib)
+
+
+def test_shard_layout(vk):
+    from vk_renderer_b200.sharding import owned_pixels, shard_layout
+    assert shard_layout(0, 1) == ((0, 1), (0, 1))
+    assert shard_layout(5, 8) == ((5, 8), (0, 1))
+    assert shard_layout(5, 8, sample_shards=2) == ((1, 4), (1, 2))
+    w, h = 200, 150
+    seen = np.zeros(w * h, dtype=np.int32)
+    for rank in range(3):
+        pix = owned_pixels(w, h, rank, 3)
+        valid = pix[pix >= 0]
+        seen[valid] += 1
+        assert pix.shape[0] % 1024 == 0
+    assert np.all(seen == 1)                                       # tile shards partition the image exactly
+    # the first 32 slots of a tile are an 8x4 pixel block
+    p = owned_pixels(w, h, 0, 1)[:32]
+    assert sorted((p % w).tolist()) == sorted(list(range(8)) * 4) and sorted((p // w).tolist()) == sorted(list(range(4)) * 8)
+
+
+GLOO_WORKER = r"""
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "oracle")); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import vk_renderer_b200 as V
+import oracle as O
+from vk_renderer_b200.sharding import owned_pixels, shard_layout, gather_packed
+from helpers import bits_equal
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+w, h, spp = 100, 70, 4
+fd = V.default_frame_data(aspect_ratio=w / h, seed=0.5)
+sc = O.Scene().use_default(O.SCENE_TRACER)
+# tile x sample layout: 2 ranks = 2 tile shards here; then 2 sample shards
+for sample_shards in (1, 2):
+    (tr, tc), (sr, scount) = shard_layout(rank, world, sample_shards)
+    s0, s1 = sr * spp // scount, (sr + 1) * spp // scount
+    full, _, _, _ = sc.render(fd, w, h, spp=spp, max_depth=4, seed=9, samples=(s0, s1), want_ids=False, want_rgba=False)
+    pix = owned_pixels(w, h, tr, tc)
+    n_floats = owned_pixels(w, h, 0, tc).shape[0] * 4
+    send = torch.zeros(n_floats)
+    flat = torch.from_numpy(full.reshape(-1, 4))
+    valid = torch.from_numpy(pix >= 0)
+    send.view(-1, 4)[: pix.shape[0]][valid] = flat[torch.from_numpy(pix[pix >= 0])]
+    recv = gather_packed(send, rank, world)
+    if rank == 0:
+        acc = np.zeros((h * w, 4), dtype=np.float32)
+        for src, buf in enumerate(recv):
+            (t_r, t_c), (s_r, _) = shard_layout(src, world, sample_shards)
+            p = owned_pixels(w, h, t_r, t_c)
+            vals = buf.view(-1, 4)[: p.shape[0]].numpy()[p >= 0]
+            if s_r > 0:
+                acc[p[p >= 0]] = acc[p[p >= 0]] + vals
+            else:
+                acc[p[p >= 0]] = vals
+        expect = None
+        for s_r in range(sample_shards):
+            expect, _, _, _ = sc.render(fd, w, h, spp=spp, max_depth=4, seed=9, samples=(s_r * spp // sample_shards, (s_r + 1) * spp // sample_shards),
+                                        accum=expect, want_ids=False, want_rgba=False)
+        assert bits_equal(acc.reshape(h, w, 4), expect), "gathered image differs (sample_shards=%%d)" %% sample_shards
+dist.barrier()
+dist.destroy_process_group()
+sys.stdout.write("rank%%d_ok\n" %% rank); sys.stdout.flush()
+"""
+
+
+def test_two_rank_gather_on_gloo(tmp_path):
+    """The N>1 path's host logic (tile ownership, packed layout, gather to rank 0, ordered sample-shard sum)
+    with world_size 2 on CPU; the per-rank pixels come from the oracle instead of the GPU."""
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER % {"root": ROOT})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29531")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "rank0_ok" in r.stdout and "rank1_ok" in r.stdout
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """bench.py --impl reference times the CPU restatement and prints the contract's JSON line."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--workload", "cfg2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["unit"] == "Mrays/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0

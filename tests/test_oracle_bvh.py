@@ -1,0 +1,104 @@
+"""CPU tests of rule S (the order-independent nearest-sphere rule the LBVH path implements) inside the
+oracle: the oracle's own LBVH traversal must equal its linear scan exactly, on whole frames and on
+individual adversarial rays; the literal chain rule of Tracer.comp:398-412 may differ only in ties."""
+import numpy as np
+import pytest
+
+from helpers import apply_scene, bits_equal
+
+
+@pytest.mark.parametrize("n,seed", [(1, 1), (2, 2), (3, 3), (40, 4), (700, 5)])
+def test_bvh_equals_linear_scan_frames(vk, oracle, n, seed):
+    scene = vk.scenes.random_spheres(n, seed=seed)
+    sc = apply_scene(oracle, scene).build_bvh()
+    assert sc.bvh_nodes().shape[0] == max(n + 1 - 1, 1)          # n procedural spheres + the light
+    w, h = 80, 60
+    fd = vk.default_frame_data(aspect_ratio=w / h, seed=0.1 * seed)
+    a, ia, _, ca = sc.render(fd, w, h, spp=2, max_depth=6, sphere_mode=oracle.S_BVH, seed=seed)
+    b, ib, _, cb = sc.render(fd, w, h, spp=2, max_depth=6, sphere_mode=oracle.S_LINEAR, seed=seed)
+    assert np.array_equal(ia, ib) and bits_equal(a, b)
+    assert (ca.closest_rays, ca.shadow_rays) == (cb.closest_rays, cb.shadow_rays)
+    # the literal rule differs from rule S on at most a handful of grazing primary rays, and is reported
+    c, ic, _, _ = sc.render(fd, w, h, spp=2, max_depth=6, sphere_mode=oracle.LITERAL, seed=seed)
+    assert int((ic != ia).sum()) == ca.literal_vs_s_mismatch <= 3
+    if n >= 40:
+        assert ca.node_visits > 0 and ca.leaf_tests < cb.leaf_tests     # the tree actually prunes
+
+
+def test_bvh_equals_linear_scan_random_rays(vk, oracle):
+    """Rays from inside the cloud, axis-parallel rays, rays starting on sphere surfaces."""
+    scene = vk.scenes.random_spheres(500, seed=9)
+    sc = apply_scene(oracle, scene).build_bvh()
+    rng = np.random.default_rng(11)
+    sph = scene.spheres
+    hits = 0
+    for k in range(4000):
+        if k % 4 == 0:
+            i = rng.integers(0, len(sph))
+            n = rng.normal(size=3); n /= np.linalg.norm(n)
+            o = sph[i, :3] + n * sph[i, 3]                        # on a surface (self-intersection guard t > EPSILON)
+        else:
+            o = rng.uniform(-60, 60, 3)
+        d = rng.normal(size=3)
+        if k % 2 == 1:                                            # aim at (or graze) some sphere
+            j = rng.integers(0, len(sph))
+            d = sph[j, :3] + rng.normal(size=3) * sph[j, 3] * 0.7 - o
+        if k % 5 == 0:
+            d[rng.integers(0, 3)] = 0.0
+        if k % 50 == 0:
+            d = np.eye(3)[rng.integers(0, 3)] * rng.choice([-1.0, 1.0])
+        d = (d / np.linalg.norm(d)).astype(np.float32)
+        bound = float(rng.choice([3000.0, 50.0, 5.0]))
+        a = sc.query_spheres(oracle.S_BVH, o, d, bound)
+        b = sc.query_spheres(oracle.S_LINEAR, o, d, bound)
+        assert a[0] == b[0] and (a[0] < 0 or a[1] == b[1])
+        hits += a[0] >= 0
+    assert hits > 500
+
+
+def test_rule_s_tie_break_is_lowest_index(vk, oracle):
+    """Coincident spheres: rule S returns the lowest index; the literal chain rule returns the last one."""
+    scene = vk.scenes.tracer_default()
+    scene.spheres = np.array([[0, 10, 0, 2]] * 5, dtype=np.float32)
+    scene.sphere_mat = np.array([4] * 5, dtype=np.uint32)
+    sc = apply_scene(oracle, scene).build_bvh()
+    o, d = [0, 10, -20], [0, 0, 1]
+    assert sc.query_spheres(oracle.S_BVH, o, d, 3000.0)[0] == 0
+    assert sc.query_spheres(oracle.S_LINEAR, o, d, 3000.0)[0] == 0
+    assert sc.query_spheres(oracle.LITERAL, o, d, 3000.0)[0] == 4          # +EPSILON chain: a later one overrides
+    assert sc.query_spheres(oracle.S_BVH, o, d, 17.0)[0] == -1             # bound is exclusive: t = 18 is out
+    assert sc.query_spheres(oracle.S_BVH, o, d, 18.001)[0] == 0
+
+
+def test_bvh_tree_invariants(vk, oracle):
+    scene = vk.scenes.random_spheres(300, seed=3)
+    sc = apply_scene(oracle, scene).build_bvh()
+    nodes = sc.bvh_nodes()
+    n = scene.spheres.shape[0]
+    assert nodes.shape == (n - 1, 16)
+    recs = nodes.reshape(-1, 2, 8)
+    kind = recs[..., 7].view(np.int32)
+    index = recs[..., 6].view(np.int32)
+    assert set(np.unique(kind)) == {0, 1}
+    assert sorted(index[kind == 1].tolist()) == list(range(n))              # every sphere is exactly one leaf
+    inner = sorted(index[kind == 0].tolist())
+    assert inner == list(range(1, n - 1))                                   # every inner node but the root has one parent
+
+    def box_of(rec):
+        if rec[7].view(np.int32) == 1:
+            rp = rec[4]
+            return rec[0:3] - rp, rec[0:3] + rp
+        return rec[0:3], np.array([rec[3], rec[4], rec[5]])
+
+    # every child box is contained in the union stored one level up (exact min/max)
+    for i in range(n - 1):
+        for k in range(2):
+            rec = recs[i, k]
+            if rec[7].view(np.int32) == 0:
+                lo, hi = box_of(rec)
+                c = recs[rec[6].view(np.int32)]
+                l0, h0 = box_of(c[0]); l1, h1 = box_of(c[1])
+                assert np.array_equal(lo, np.minimum(l0, l1)) and np.array_equal(hi, np.maximum(h0, h1))
+            else:
+                s = scene.spheres[rec[6].view(np.int32)]
+                assert np.array_equal(rec[0:4], s) and rec[4] == np.float32(s[3] * np.float32(1.001) + np.float32(0.001))

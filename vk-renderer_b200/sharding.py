@@ -5,14 +5,47 @@ single-GPU render; sample shards are summed on rank 0 in rank order (determinist
 
 Rank layout for world = T * S: tile_rank = rank % T, sample_rank = rank // T.
 """
+import numpy as np
 import torch
 import torch.distributed as dist
+
+TILE = 32
+TILE_PX = TILE * TILE
 
 
 def shard_layout(rank, world, sample_shards=1):
     assert world % sample_shards == 0
     tiles = world // sample_shards
     return (rank % tiles, tiles), (rank // tiles, sample_shards)
+
+
+def owned_pixels(width, height, tile_rank, tile_count):
+    """Pixel index (y * width + x, or -1 outside the image) of every packed slot of a tile shard: the
+    host-side statement of the kernels' slot_to_pixel (csrc/vkrt_render.cu).  Slots go tile by tile
+    (tiles tile_rank, tile_rank + tile_count, ...), 32 consecutive slots are an 8x4 pixel block."""
+    tiles_x, tiles_y = (width + TILE - 1) // TILE, (height + TILE - 1) // TILE
+    n_tiles = tiles_x * tiles_y
+    owned = (n_tiles - tile_rank + tile_count - 1) // tile_count if tile_rank < n_tiles else 0
+    w = np.arange(owned * TILE_PX, dtype=np.int64)
+    lt, inn = w >> 10, w & 1023
+    gt = tile_rank + lt * tile_count
+    tx, ty = gt % tiles_x, gt // tiles_x
+    blk, l = inn >> 5, inn & 31
+    px = tx * TILE + (blk & 3) * 8 + (l & 7)
+    py = ty * TILE + (blk >> 2) * 4 + (l >> 3)
+    pix = py * width + px
+    pix[(px >= width) | (py >= height)] = -1
+    return pix
+
+
+def gather_packed(send, rank, world, group=None):
+    """dist.gather of equally sized packed shard buffers to rank 0; returns the list there, else None."""
+    recv = [torch.zeros_like(send) for _ in range(world)] if rank == 0 else None
+    if world > 1:
+        dist.gather(send, recv, dst=0, group=group)
+    elif rank == 0:
+        recv[0].copy_(send)
+    return recv
 
 
 class FrameGather:
@@ -23,14 +56,12 @@ class FrameGather:
         self.stream, self.device = stream, device
         (self.tile_rank, self.tiles), (self.sample_rank, self.samples) = shard_layout(rank, world, sample_shards)
         self.n_floats = renderer.shard_floats(0)          # the largest shard; every rank sends this size
-        dev = device if device.type == "cuda" else "cpu"
-        self.send = torch.zeros(self.n_floats, dtype=torch.float32, device=dev)
-        self.recv = [torch.zeros(self.n_floats, dtype=torch.float32, device=dev) for _ in range(world)] if rank == 0 else None
+        self.send = torch.zeros(self.n_floats, dtype=torch.float32, device=device)
+        self.recv = [torch.zeros(self.n_floats, dtype=torch.float32, device=device) for _ in range(world)] if rank == 0 else None
 
     def gather(self):
         """After renderer.draw(): collects every shard into rank 0's full accumulator."""
-        ctx = torch.cuda.stream(self.stream) if self.stream is not None else _Null()
-        with ctx:
+        with torch.cuda.stream(self.stream):
             self.r.pack_shard_into(self.send.data_ptr(), self.n_floats)
             if self.world > 1:
                 dist.gather(self.send, self.recv, dst=0, group=self.group)
@@ -39,8 +70,3 @@ class FrameGather:
                 for src, buf in enumerate(bufs):
                     (tile_rank, tiles), (sample_rank, _) = shard_layout(src, self.world, self.samples)
                     self.r.unpack_shard(buf.data_ptr(), tile_rank, tiles, add=(sample_rank > 0))
-
-
-class _Null:
-    def __enter__(self): return self
-    def __exit__(self, *a): return False
