@@ -350,12 +350,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
-    ap.add_argument("--variant", default="mega", choices=["mega", "wavefront"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "mega", "wavefront"],
+                    help="auto = wavefront for the LBVH scenes (cfg3/cfg4), megakernel for the 10-primitive default scene (cfg2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--micro", action="store_true", help="also run the FP32 / L2 microbenchmarks")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    if args.variant == "auto":
+        args.variant = "mega" if args.workload == "cfg2" else "wavefront"
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
