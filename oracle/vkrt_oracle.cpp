@@ -347,16 +347,13 @@ inline SBest s_query_bvh(const orc_scene &sc, const Ray &ray, float eps, float B
         for (int k = 0; k < 2; ++k) {
             const BvhChild &c = n.c[k];
             float tn, tf;
-            if (c.kind == 1) {                                  // leaf: record holds the sphere itself
-                const orc_sphere s{c.a[0], c.a[1], c.a[2], c.a[3]};
-                V3 lo, hi; sphere_box(s, lo, hi);
-                if (!slab_test(sr, lo, hi, tn, tf) || !(tn <= best.t)) continue;
+            const V3 lo{c.a[0], c.a[1], c.a[2]}, hi{c.a[3], c.b[0], c.b[1]};
+            if (!slab_test(sr, lo, hi, tn, tf) || !(tn <= best.t)) continue;
+            if (c.kind == 1) {                                  // leaf: the record holds the sphere's own padded box
                 ++st.leaves;
-                s_consider(ray, s, c.index, tn, eps, B, best);
+                s_consider(ray, sc.spheres[c.index], c.index, tn, eps, B, best);
                 if (any && best.idx >= 0) return best;
             } else {
-                const V3 lo{c.a[0], c.a[1], c.a[2]}, hi{c.a[3], c.b[0], c.b[1]};
-                if (!slab_test(sr, lo, hi, tn, tf) || !(tn <= best.t)) continue;
                 next[nn] = c.index; tnx[nn] = tn; ++nn;
             }
         }
@@ -765,9 +762,9 @@ int orc_scene_build_bvh(orc_scene *s)
     if (n == 0) return 0;
     auto leaf_child = [&](int sphere) {
         BvhChild c{};
-        const orc_sphere &sp = s->spheres[sphere];
-        c.a[0] = sp.cx; c.a[1] = sp.cy; c.a[2] = sp.cz; c.a[3] = sp.r;
-        c.b[0] = sphere_pad_radius(sp.r); c.b[1] = 0.0f; c.index = sphere; c.kind = 1;
+        V3 lo, hi; sphere_box(s->spheres[sphere], lo, hi);
+        c.a[0] = lo.x; c.a[1] = lo.y; c.a[2] = lo.z; c.a[3] = hi.x;
+        c.b[0] = hi.y; c.b[1] = hi.z; c.index = sphere; c.kind = 1;
         return c;
     };
     if (n == 1) { BvhNode nd; nd.c[0] = leaf_child(0); nd.c[1] = leaf_child(0); s->bvh.push_back(nd); return 0; }

@@ -85,20 +85,18 @@ def test_bvh_tree_invariants(vk, oracle):
     assert inner == list(range(1, n - 1))                                   # every inner node but the root has one parent
 
     def box_of(rec):
-        if rec[7].view(np.int32) == 1:
-            rp = rec[4]
-            return rec[0:3] - rp, rec[0:3] + rp
         return rec[0:3], np.array([rec[3], rec[4], rec[5]])
 
     # every child box is contained in the union stored one level up (exact min/max)
     for i in range(n - 1):
         for k in range(2):
             rec = recs[i, k]
+            lo, hi = box_of(rec)
             if rec[7].view(np.int32) == 0:
-                lo, hi = box_of(rec)
                 c = recs[rec[6].view(np.int32)]
                 l0, h0 = box_of(c[0]); l1, h1 = box_of(c[1])
                 assert np.array_equal(lo, np.minimum(l0, l1)) and np.array_equal(hi, np.maximum(h0, h1))
-            else:
+            else:                                                            # leaf: the sphere's own padded box
                 s = scene.spheres[rec[6].view(np.int32)]
-                assert np.array_equal(rec[0:4], s) and rec[4] == np.float32(s[3] * np.float32(1.001) + np.float32(0.001))
+                rp = np.float32(s[3] * np.float32(1.001) + np.float32(0.001))
+                assert np.array_equal(lo, s[:3] - rp) and np.array_equal(hi, s[:3] + rp)

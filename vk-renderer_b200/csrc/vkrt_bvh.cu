@@ -192,15 +192,12 @@ __global__ void __launch_bounds__(256) k_karras(const uint32_t *__restrict__ cod
 }
 
 // ---- refit + pack: one thread per leaf walks up; the second arrival at a node owns it ---------
-__device__ __forceinline__ void write_child(float4 *node, int k, bool leaf, float4 sphere, int index, const float *lo, const float *hi)
+// child record (32 B): {lo.x lo.y lo.z hi.x | hi.y hi.z index kind}; kind 0 = inner node `index`,
+// kind 1 = leaf = sphere `index`, whose record holds the sphere's own padded box
+__device__ __forceinline__ void write_child(float4 *node, int k, bool leaf, int index, const float *lo, const float *hi)
 {
-    if (leaf) {
-        node[2 * k] = sphere;
-        node[2 * k + 1] = make_float4(sphere_pad_radius(sphere.w), 0.0f, __int_as_float(index), __int_as_float(1));
-    } else {
-        node[2 * k] = make_float4(lo[0], lo[1], lo[2], hi[0]);
-        node[2 * k + 1] = make_float4(hi[1], hi[2], __int_as_float(index), __int_as_float(0));
-    }
+    node[2 * k] = make_float4(lo[0], lo[1], lo[2], hi[0]);
+    node[2 * k + 1] = make_float4(hi[1], hi[2], __int_as_float(index), __int_as_float(leaf ? 1 : 0));
 }
 __device__ __forceinline__ void leaf_box(float4 s, float *lo, float *hi)
 {
@@ -224,7 +221,6 @@ __global__ void __launch_bounds__(256) k_refit(const float4 *__restrict__ sph, c
         __threadfence();
         const int2 c = children[node];
         float lo[2][3], hi[2][3];
-        float4 sp[2];
         int idx[2];
         bool is_leaf[2];
 #pragma unroll
@@ -233,16 +229,14 @@ __global__ void __launch_bounds__(256) k_refit(const float4 *__restrict__ sph, c
             is_leaf[k] = ch < 0;
             if (is_leaf[k]) {
                 idx[k] = (int)sorted_idx[~ch];
-                sp[k] = sph[idx[k]];
-                leaf_box(sp[k], lo[k], hi[k]);
+                leaf_box(sph[idx[k]], lo[k], hi[k]);
             } else {
                 idx[k] = ch;
                 const volatile float4 *pl = box_lo + ch, *ph = box_hi + ch;
                 lo[k][0] = pl->x; lo[k][1] = pl->y; lo[k][2] = pl->z;
                 hi[k][0] = ph->x; hi[k][1] = ph->y; hi[k][2] = ph->z;
-                sp[k] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            write_child(nodes + 4 * (size_t)node, k, is_leaf[k], sp[k], idx[k], lo[k], hi[k]);
+            write_child(nodes + 4 * (size_t)node, k, is_leaf[k], idx[k], lo[k], hi[k]);
         }
         box_lo[node] = make_float4(fminf(lo[0][0], lo[1][0]), fminf(lo[0][1], lo[1][1]), fminf(lo[0][2], lo[1][2]), 0.f);
         box_hi[node] = make_float4(fmaxf(hi[0][0], hi[1][0]), fmaxf(hi[0][1], hi[1][1]), fmaxf(hi[0][2], hi[1][2]), 0.f);
@@ -252,9 +246,10 @@ __global__ void __launch_bounds__(256) k_refit(const float4 *__restrict__ sph, c
 
 __global__ void k_single_leaf(const float4 *__restrict__ sph, float4 *__restrict__ nodes)
 {
-    const float4 s = sph[0];
-    write_child(nodes, 0, true, s, 0, nullptr, nullptr);
-    write_child(nodes, 1, true, s, 0, nullptr, nullptr);
+    float lo[3], hi[3];
+    leaf_box(sph[0], lo, hi);
+    write_child(nodes, 0, true, 0, lo, hi);
+    write_child(nodes, 1, true, 0, lo, hi);
 }
 
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { err = _e; goto done; } } while (0)

@@ -20,9 +20,9 @@ enum { KIND_TRI = 1, KIND_SPHERE = 2, KIND_PLANE = 3 };
 // mats    : 3 x float4 per material         48 B {albedo.rgb, roughness | emissive.rgb, metalness | type,-,-,-}
 // tris    : 3 x float4 per triangle         48 B, the reference's SSBO layout verbatim
 // bvh     : 4 x float4 per inner node       64 B = two 32 B child records:
-//             inner child: {lo.x lo.y lo.z hi.x | hi.y hi.z  idx  kind=0}
-//             leaf  child: {cx   cy   cz   r    | rp   0     sphere kind=1}   (the sphere itself:
-//             a leaf costs no second dependent fetch)
+//             {lo.x lo.y lo.z hi.x | hi.y hi.z index kind}; kind 0: inner node `index`; kind 1: leaf =
+//             sphere `index`, the box being the sphere's own padded box (so both children are tested by
+//             the same branch-free code; the sphere is fetched only when its box is hit)
 struct DevScene {
     const float4 *spheres;
     const uint32_t *sphere_mat;
@@ -165,39 +165,29 @@ VKRT_DEV void trav_step(Trav &tv, int *__restrict__ stack, const DevScene &sc, V
     ldg256(np, a0, b0);
     ldg256(np + 2, a1, b1);
     if (STATS) ++st.nodes;
-    int nxt0 = -1, nxt1 = -1;
+    // both child records have the same shape {lo.xyz hi.x | hi.yz index kind}: the box tests are uniform code
     float tn0, tn1, tf;
-    {
-        const bool leaf = __float_as_int(b0.w) == 1;
-        const V3 lo = leaf ? v3(a0.x - b0.x, a0.y - b0.x, a0.z - b0.x) : v3(a0.x, a0.y, a0.z);
-        const V3 hi = leaf ? v3(a0.x + b0.x, a0.y + b0.x, a0.z + b0.x) : v3(a0.w, b0.x, b0.y);
-        const bool hit = slab_test(tv.sr, lo, hi, tn0, tf) && tn0 <= tv.best.t;
-        if (hit) {
-            if (leaf) {
-                if (STATS) ++st.leaves;
-                s_consider(o, d, a0, __float_as_int(b0.z), tn0, tv.eps, tv.B, tv.best);
-            } else nxt0 = __float_as_int(b0.z);
-        }
+    bool h0 = slab_test(tv.sr, v3(a0.x, a0.y, a0.z), v3(a0.w, b0.x, b0.y), tn0, tf) && tn0 <= tv.best.t;
+    bool h1 = slab_test(tv.sr, v3(a1.x, a1.y, a1.z), v3(a1.w, b1.x, b1.y), tn1, tf) && tn1 <= tv.best.t;
+    const int i0 = __float_as_int(b0.z), i1 = __float_as_int(b1.z);
+    // leaf children: fetch the sphere and run the reference's intersection (rule S candidate test)
+    if (h0 && __float_as_int(b0.w) != 0) {
+        if (STATS) ++st.leaves;
+        s_consider(o, d, __ldg(sc.spheres + i0), i0, tn0, tv.eps, tv.B, tv.best);
+        h0 = false;
     }
-    {
-        const bool leaf = __float_as_int(b1.w) == 1;
-        const V3 lo = leaf ? v3(a1.x - b1.x, a1.y - b1.x, a1.z - b1.x) : v3(a1.x, a1.y, a1.z);
-        const V3 hi = leaf ? v3(a1.x + b1.x, a1.y + b1.x, a1.z + b1.x) : v3(a1.w, b1.x, b1.y);
-        const bool hit = slab_test(tv.sr, lo, hi, tn1, tf) && tn1 <= tv.best.t;
-        if (hit) {
-            if (leaf) {
-                if (STATS) ++st.leaves;
-                s_consider(o, d, a1, __float_as_int(b1.z), tn1, tv.eps, tv.B, tv.best);
-            } else nxt1 = __float_as_int(b1.z);
-        }
+    if (h1 && __float_as_int(b1.w) != 0) {
+        if (STATS) ++st.leaves;
+        s_consider(o, d, __ldg(sc.spheres + i1), i1, tn1, tv.eps, tv.B, tv.best);
+        h1 = false;
     }
     if (ANY && tv.best.idx >= 0) { tv.node = -1; return; }
-    if (nxt0 >= 0 && nxt1 >= 0) {
-        const bool swap = tn1 < tn0;
-        stack[tv.sp++] = swap ? nxt0 : nxt1;
-        tv.node = swap ? nxt1 : nxt0;
-    } else if (nxt0 >= 0) tv.node = nxt0;
-    else if (nxt1 >= 0) tv.node = nxt1;
+    // descend into the nearer inner child, push the farther one, or pop
+    const bool both = h0 && h1;
+    const bool take1 = both ? (tn1 < tn0) : h1;
+    const int nearer = take1 ? i1 : i0;
+    if (both) stack[tv.sp++] = take1 ? i0 : i1;
+    if (h0 || h1) tv.node = nearer;
     else tv.node = tv.sp ? stack[--tv.sp] : -1;
 }
 

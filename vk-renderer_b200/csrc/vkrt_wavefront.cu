@@ -83,8 +83,13 @@ VKRT_DEV void wf_flush(const Stats &st, unsigned long long *counters, bool stats
     }
 }
 
-// ---- generate: Tracer.comp:561-581 (one primary ray per pixel, reused by every sample) ----------
-__global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ RenderParams rp, const __grid_constant__ WaveParams wp)
+// ---- generate: Tracer.comp:561-581 ------------------------------------------------------------------
+// Every sample of a pixel reuses ONE primary ray (:574-581, no sub-pixel jitter), so its triangle + sphere
+// query is done once per pixel here and the result is copied into the S path records of the pixel; the
+// ray counter still advances by S (it counts the reference algorithm's trace_ray invocations).
+template <bool BVH, bool STATS>
+__global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
+                                                      const __grid_constant__ WaveParams wp)
 {
     Stats st; stats_zero(st);
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -95,8 +100,23 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ Ren
     if (valid) {
         V3 o, d;
         primary_ray(rp.fd, rp.width, rp.height, px, py, o, d);
-        fo = make_float4(o.x, o.y, o.z, 0.f); fd = make_float4(d.x, d.y, d.z, 0.f);
+        Hit hit{0.f, 0, 0};
+        float cur = path_tmax(0);
+        bool found = trace_tris<true>(sc, o, d, cur, hit);
+        if (BVH) {
+            const SBest b = bvh_query<false, STATS>(sc, o, d, 1e-3f, sphere_bound<true>(cur), st);
+            if (b.idx >= 0) { cur = b.t; hit.kind = KIND_SPHERE; hit.index = (uint32_t)b.idx; found = true; }
+        } else {
+            for (uint32_t i = 0; i < sc.n_spheres; ++i) {                         // literal loop, Tracer.comp:398-412
+                const float t = sphere_intersect(o, d, __ldg(sc.spheres + i));
+                if ((t > 1e-3f) && (t < cur + 1e-3f)) { cur = t; hit.kind = KIND_SPHERE; hit.index = i; found = true; }
+            }
+        }
+        fo = make_float4(o.x, o.y, o.z, cur);
+        fd = make_float4(d.x, d.y, d.z, __uint_as_float(found ? ((hit.kind << 28) | hit.index) : 0u));
         pix = py * rp.width + px;
+        st.closest += wp.S;
+        st.paths += wp.S;
     }
     for (uint32_t sl = 0; sl < wp.S; ++sl) {
         const uint32_t p = sl * wp.n_slots + slot;
@@ -104,11 +124,10 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ Ren
             wp.po[p] = fo; wp.pd[p] = fd;
             wp.pacc[p] = make_float4(0.f, 0.f, 0.f, __uint_as_float(pix));
             wp.pmask[p] = make_float4(1.f, 1.f, 1.f, __uint_as_float(sl << 8));
-            ++st.paths;
         }
         push(wp.q_active[0], wp.cnt + C_ACTIVE0, valid, p);
     }
-    wf_flush(st, rp.counters, false);
+    wf_flush(st, rp.counters, STATS);
 }
 
 // ---- persistent trace kernel (nearest-hit for `extend`, any-hit for `shadow`) --------------------
@@ -118,12 +137,13 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ Ren
 template <bool ANY, bool BVH, bool STATS>
 __global__ void __launch_bounds__(VKRT_TRACE_BLOCK) k_wf_trace(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
                                                                 const __grid_constant__ WaveParams wp, const uint32_t *__restrict__ queue,
-                                                                const uint32_t *__restrict__ n_items_ptr, uint32_t *head)
+                                                                const uint32_t *__restrict__ n_items_ptr, uint32_t *head, uint32_t depth)
 {
     const unsigned full = 0xffffffffu, lane = threadIdx.x & 31u;
     Stats st; stats_zero(st);
     const uint32_t n_items = *n_items_ptr;
     const float EPS = 1e-3f;
+    const float tmax = path_tmax(depth);       // every ray of one extend launch is at the same depth (:444)
 
     bool has = false, drained = false;
     uint32_t path = 0, light = 0;
@@ -159,8 +179,7 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK) k_wf_trace(const __grid_cons
                         d = xyz(s); cur = s.w;
                     } else {
                         o = xyz(fo); d = xyz(fd);
-                        const uint32_t depth = __float_as_uint(wp.pmask[path].w) & 255u;
-                        cur = path_tmax(depth);
+                        cur = tmax;
                         ++st.closest;
                         found = trace_tris<true>(sc, o, d, cur, hit);
                     }
@@ -203,43 +222,6 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK) k_wf_trace(const __grid_cons
     wf_flush(st, rp.counters, STATS);
 }
 
-// ---- classify: clamp, plane loop, end missed paths, bin hits by material type ---------------------
-__global__ void __launch_bounds__(256) k_wf_classify(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
-                                                      const __grid_constant__ WaveParams wp, const uint32_t *__restrict__ queue,
-                                                      const uint32_t *__restrict__ n_ptr)
-{
-    const uint32_t n = *n_ptr;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const uint32_t i = base + threadIdx.x;
-        bool diel = false, diff = false;
-        uint32_t path = 0;
-        if (i < n) {
-            path = queue[i];
-            const float4 a = wp.pacc[path];
-            const float4 c = make_float4(gl_clamp(a.x, 0.0f, 1.0f), gl_clamp(a.y, 0.0f, 1.0f), gl_clamp(a.z, 0.0f, 1.0f), a.w);   // :441
-            if (__float_as_uint(c.x) != __float_as_uint(a.x) || __float_as_uint(c.y) != __float_as_uint(a.y) ||
-                __float_as_uint(c.z) != __float_as_uint(a.z)) wp.pacc[path] = c;
-            const float4 fo = wp.po[path], fd = wp.pd[path];
-            const uint32_t id0 = __float_as_uint(fd.w);
-            Hit hit{fo.w, id0 >> 28, id0 & 0x0fffffffu};
-            float cur = fo.w;
-            const bool found = trace_planes<true>(sc, xyz(fo), xyz(fd), cur, hit) || id0 != 0u;     // :414-428
-            const uint32_t id = found ? ((hit.kind << 28) | hit.index) : 0u;
-            if (id != id0) { wp.po[path].w = cur; wp.pd[path].w = __uint_as_float(id); }
-            const uint32_t sd = __float_as_uint(wp.pmask[path].w);
-            if (rp.hit_ids && sd == 0u && wp.s0 == rp.s_begin) rp.hit_ids[__float_as_uint(a.w)] = id;
-            if (id == 0u) wp.rad[path] = make_float4(c.x, c.y, c.z, 0.f);           // miss: break (:445)
-            else {
-                const uint32_t mat = hit.kind == KIND_TRI ? sc.tri_mat : hit.kind == KIND_SPHERE ? __ldg(sc.sphere_mat + hit.index) : sc.plane_mat[hit.index];
-                const uint32_t type = __float_as_uint(__ldg(&sc.mats[3 * mat + 2].x));
-                diel = type != 0u; diff = type == 0u;
-            }
-        }
-        push(wp.q_diel, wp.cnt + C_DIEL, diel, path);
-        push(wp.q_diff, wp.cnt + C_DIFF, diff, path);
-    }
-}
-
 VKRT_DEV void load_path(const WaveParams &wp, uint32_t path, PathState &ps, Hit &hit, uint32_t &pix, uint32_t &sl)
 {
     const float4 fo = wp.po[path], fd = wp.pd[path], fa = wp.pacc[path], fm = wp.pmask[path];
@@ -258,27 +240,65 @@ VKRT_DEV void store_path(const WaveParams &wp, uint32_t path, const PathState &p
     wp.pmask[path] = make_float4(ps.mask.x, ps.mask.y, ps.mask.z, __uint_as_float((sl << 8) | ps.depth));
 }
 
-// ---- nee: shadow rays of the diffuse bin ----------------------------------------------------------
-__global__ void __launch_bounds__(256) k_wf_nee(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
-                                                 const __grid_constant__ WaveParams wp)
+struct OccNever {
+    VKRT_DEV bool operator()(uint32_t, V3, V3, float) const { return false; }
+};
+
+// ---- classify: one pass over the active paths after `extend` ----------------------------------------
+//   firefly clamp (:441); the plane loop of trace_ray (:414-428) on top of extend's triangle/sphere result;
+//   miss -> the path ends (:445); DIELECTRIC hit -> shaded here completely (:514-549), survivors are pushed to
+//   the next active queue; DIFFUSE hit -> the light-sample shadow rays (:464-469) are generated here, their
+//   triangle/plane occluders resolved, the rest queued for the sphere any-hit kernel, and the path goes to
+//   the diffuse bin.  (Binning by material type = which queue a path is pushed to.)
+__global__ void __launch_bounds__(256, 3) k_wf_classify(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
+                                                         const __grid_constant__ WaveParams wp, const uint32_t *__restrict__ queue,
+                                                         const uint32_t *__restrict__ n_ptr, uint32_t next)
 {
     Stats st; stats_zero(st);
-    const uint32_t n = wp.cnt[C_DIFF];
+    const uint32_t n = *n_ptr;
+    const V3 cam_pos = v3(rp.fd.camera.pos.x, rp.fd.camera.pos.y, rp.fd.camera.pos.z);
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t i = base + threadIdx.x;
+        bool diff = false, alive = false;
         uint32_t path = 0, skey = 0, dim0 = 0;
         V3 P = v3(0.f);
         if (i < n) {
-            path = wp.q_diff[i];
-            const float4 fo = wp.po[path], fd = wp.pd[path], fa = wp.pacc[path], fm = wp.pmask[path];
-            P = madd3(fo.w, xyz(fd), xyz(fo));
-            const uint32_t sd = __float_as_uint(fm.w);
-            skey = sample_key(rp.fkey, __float_as_uint(fa.w), wp.s0 + (sd >> 8));
-            dim0 = (sd & 255u) * DIMS_PER_BOUNCE;
+            path = queue[i];
+            PathState ps; Hit hit; uint32_t pix, sl;
+            load_path(wp, path, ps, hit, pix, sl);
+            const V3 acc0 = ps.acc;
+            ps.acc = clamp3(ps.acc, 0.0f, 1.0f);                                                        // :441
+            const uint32_t id0 = (hit.kind << 28) | hit.index;
+            float cur = hit.t;
+            const bool found = trace_planes<true>(sc, ps.o, ps.d, cur, hit) || id0 != 0u;             // :414-428
+            hit.t = cur;
+            const uint32_t id = found ? ((hit.kind << 28) | hit.index) : 0u;
+            if (rp.hit_ids && ps.depth == 0u && sl == 0u && wp.s0 == rp.s_begin) rp.hit_ids[pix] = id;
+            if (!found) wp.rad[path] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, 0.f);               // miss: break (:445)
+            else {
+                const uint32_t mat = hit.kind == KIND_TRI ? sc.tri_mat : hit.kind == KIND_SPHERE ? __ldg(sc.sphere_mat + hit.index) : sc.plane_mat[hit.index];
+                const uint32_t type = __float_as_uint(__ldg(&sc.mats[3 * mat + 2].x));
+                skey = sample_key(rp.fkey, pix, wp.s0 + sl);
+                if (type != 0u) {                                                                      // DIELECTRIC
+                    alive = path_shade(sc, cam_pos, rp.max_depth, skey, ps, hit, OccNever{});
+                    if (alive) store_path(wp, path, ps, pix, sl);
+                    else wp.rad[path] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, 0.f);
+                } else {                                                                               // DIFFUSE
+                    diff = true;
+                    dim0 = ps.depth * DIMS_PER_BOUNCE;
+                    P = madd3(hit.t, ps.d, ps.o);
+                    if (id != id0) { wp.po[path].w = cur; wp.pd[path].w = __uint_as_float(id); }
+                    if (__float_as_uint(acc0.x) != __float_as_uint(ps.acc.x) || __float_as_uint(acc0.y) != __float_as_uint(ps.acc.y) ||
+                        __float_as_uint(acc0.z) != __float_as_uint(ps.acc.z))
+                        wp.pacc[path] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, __uint_as_float(pix));
+                }
+            }
         }
+        push(wp.q_active[next], wp.cnt + (next ? C_ACTIVE1 : C_ACTIVE0), alive, path);
+        push(wp.q_diff, wp.cnt + C_DIFF, diff, path);
         for (uint32_t l = 0; l < sc.n_lights; ++l) {
             bool queue_it = false;
-            if (i < n) {
+            if (diff) {
                 V3 L; float t;
                 nee_sample(sc, P, l, skey, dim0, L, t);
                 ++st.shadow;
@@ -302,33 +322,23 @@ struct OccFlags {
     const uint8_t *occ;
     VKRT_DEV bool operator()(uint32_t l, V3, V3, float) const { return occ[l] != 0; }
 };
-struct OccNever {
-    VKRT_DEV bool operator()(uint32_t, V3, V3, float) const { return false; }
-};
-
-// ---- shade one material bin + Russian roulette -----------------------------------------------------
-template <bool DIFFUSE>
+// ---- shade the diffuse bin (:451-513) with the occlusion flags + Russian roulette (:545-549) ---------
 __global__ void __launch_bounds__(256, 3) k_wf_shade(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
                                                       const __grid_constant__ WaveParams wp, uint32_t next)
 {
-    const uint32_t *queue = DIFFUSE ? wp.q_diff : wp.q_diel;
-    const uint32_t n = wp.cnt[DIFFUSE ? C_DIFF : C_DIEL];
+    const uint32_t n = wp.cnt[C_DIFF];
     const V3 cam_pos = v3(rp.fd.camera.pos.x, rp.fd.camera.pos.y, rp.fd.camera.pos.z);
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t i = base + threadIdx.x;
         bool alive = false;
         uint32_t path = 0;
         if (i < n) {
-            path = queue[i];
+            path = wp.q_diff[i];
             PathState ps; Hit hit; uint32_t pix, sl;
             load_path(wp, path, ps, hit, pix, sl);
             const uint32_t skey = sample_key(rp.fkey, pix, wp.s0 + sl);
-            if (DIFFUSE) {
-                const OccFlags occ{wp.occ + (size_t)path * sc.n_lights};
-                alive = path_shade(sc, cam_pos, rp.max_depth, skey, ps, hit, occ);
-            } else {
-                alive = path_shade(sc, cam_pos, rp.max_depth, skey, ps, hit, OccNever{});
-            }
+            const OccFlags occ{wp.occ + (size_t)path * sc.n_lights};
+            alive = path_shade(sc, cam_pos, rp.max_depth, skey, ps, hit, occ);
             if (alive) store_path(wp, path, ps, pix, sl);
             else wp.rad[path] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, 0.f);
         }
@@ -414,7 +424,7 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
         if ((e = cudaMalloc((void **)&wb.frame_sum, (size_t)rp.n_work * sizeof(float4))) != cudaSuccess) return e;
     }
 
-    auto pick_trace = [&](bool any) -> void (*)(const DevScene, const RenderParams, const WaveParams, const uint32_t *, const uint32_t *, uint32_t *) {
+    auto pick_trace = [&](bool any) -> void (*)(const DevScene, const RenderParams, const WaveParams, const uint32_t *, const uint32_t *, uint32_t *, uint32_t) {
         if (any) return bvh ? (stats ? k_wf_trace<true, true, true> : k_wf_trace<true, true, false>)
                             : (stats ? k_wf_trace<true, false, true> : k_wf_trace<true, false, false>);
         return bvh ? (stats ? k_wf_trace<false, true, true> : k_wf_trace<false, true, false>)
@@ -438,19 +448,24 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
         wp.n_slots = rp.n_work;
         wp.n_lights = sc.n_lights;
         if ((e = cudaMemsetAsync(wb.counts, 0, 64 * sizeof(uint32_t), st)) != cudaSuccess) return e;
-        k_wf_generate<<<(wp.n_slots + 255u) / 256u, 256, 0, st>>>(rp, wp); ++launches;
+        {
+            void (*k_gen)(const DevScene, const RenderParams, const WaveParams) =
+                bvh ? (stats ? k_wf_generate<true, true> : k_wf_generate<true, false>)
+                    : (stats ? k_wf_generate<false, true> : k_wf_generate<false, false>);
+            k_gen<<<(wp.n_slots + 255u) / 256u, 256, 0, st>>>(sc, rp, wp); ++launches;
+        }
         for (uint32_t depth = 0; depth < rp.max_depth; ++depth) {
             const uint32_t cur = depth & 1u, nxt = cur ^ 1u;
             const uint32_t *n_active = wb.counts + (cur ? C_ACTIVE1 : C_ACTIVE0);
             k_wf_reset<<<1, 1, 0, st>>>(wb.counts, nxt); ++launches;
-            k_extend<<<grid_e, VKRT_TRACE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_active[cur], n_active, wb.counts + C_HEAD_EXTEND); ++launches;
-            k_wf_classify<<<grid_shade, 256, 0, st>>>(sc, rp, wp, wp.q_active[cur], n_active); ++launches;
-            k_wf_shade<false><<<grid_shade, 256, 0, st>>>(sc, rp, wp, nxt); ++launches;
-            if (sc.n_lights) {
-                k_wf_nee<<<grid_shade, 256, 0, st>>>(sc, rp, wp); ++launches;
-                k_shadow<<<grid_s, VKRT_TRACE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_shadow, wb.counts + C_SHADOW, wb.counts + C_HEAD_SHADOW); ++launches;
+            if (depth > 0) {       // depth 0 was traced once per pixel by `generate`
+                k_extend<<<grid_e, VKRT_TRACE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_active[cur], n_active, wb.counts + C_HEAD_EXTEND, depth); ++launches;
             }
-            k_wf_shade<true><<<grid_shade, 256, 0, st>>>(sc, rp, wp, nxt); ++launches;
+            k_wf_classify<<<grid_shade, 256, 0, st>>>(sc, rp, wp, wp.q_active[cur], n_active, nxt); ++launches;
+            if (sc.n_lights) {
+                k_shadow<<<grid_s, VKRT_TRACE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_shadow, wb.counts + C_SHADOW, wb.counts + C_HEAD_SHADOW, depth); ++launches;
+            }
+            k_wf_shade<<<grid_shade, 256, 0, st>>>(sc, rp, wp, nxt); ++launches;
         }
         k_wf_reduce<<<(wp.n_slots + 255u) / 256u, 256, 0, st>>>(rp, wp, wb.frame_sum, wv == 0, wv + 1 == n_waves); ++launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
