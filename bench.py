@@ -55,17 +55,21 @@ def frame_data_for(V, w, h, step):
 
 
 class ClockSampler:
-    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md clocks line).  The sampler is started
+    before the warm-up (nvidia-smi needs ~0.1-0.3 s to come up) and only the rows whose arrival time falls
+    inside [mark_begin, mark_end] are used; if the timed region was shorter than the sampling period the
+    rows taken under load during the warm-up are used and that is said in "window"."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.idx, self.rows, self.proc = gpu_index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -74,7 +78,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -84,17 +94,24 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= self.t1]
+        window = "timed region"
+        if not inside:
+            inside = [r for t, r in self.rows if self.t0 is None or t <= self.t1]
+            window = "warm-up + timed region (timed region shorter than the sampling period)"
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for r in inside:
             try:
-                sm.append(float(r[1])); mx = float(r[2])
+                v = float(r[1]); mx = float(r[2])
             except Exception:
                 continue
+            sm.append(v)
             for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
                 if len(r) > col and r[col].lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        busy = [v for v in sm if v > 500.0] or sm        # idle samples before the first launch read 120 MHz
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(busy), "window": window}
 
 
 def measured_peaks():
@@ -241,21 +258,23 @@ def run_ours(args):
         torch.cuda.synchronize(device)
 
     # -------- device-resident timing ("value") ------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         step(i)
     barrier()
     r.reset_counters()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     trace_ms = []
     barrier()
+    sampler.mark_begin()
     ev0.record(stream)
     for i in range(args.steps):
         step(args.warmup + i)
     ev1.record(stream)
     barrier()
+    sampler.mark_end()
     ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     cnt = r.counters()

@@ -28,6 +28,9 @@
 #ifndef VKRT_TRACE_BLOCK
 #define VKRT_TRACE_BLOCK 128
 #endif
+#ifndef VKRT_SHADE_MINBLOCKS
+#define VKRT_SHADE_MINBLOCKS 2      // __launch_bounds__(256, n) of the streaming shade/classify kernels
+#endif
 
 namespace vkrt {
 
@@ -250,7 +253,7 @@ struct OccNever {
 //   the next active queue; DIFFUSE hit -> the light-sample shadow rays (:464-469) are generated here, their
 //   triangle/plane occluders resolved, the rest queued for the sphere any-hit kernel, and the path goes to
 //   the diffuse bin.  (Binning by material type = which queue a path is pushed to.)
-__global__ void __launch_bounds__(256, 3) k_wf_classify(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
+__global__ void __launch_bounds__(256, VKRT_SHADE_MINBLOCKS) k_wf_classify(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
                                                          const __grid_constant__ WaveParams wp, const uint32_t *__restrict__ queue,
                                                          const uint32_t *__restrict__ n_ptr, uint32_t next)
 {
@@ -323,7 +326,7 @@ struct OccFlags {
     VKRT_DEV bool operator()(uint32_t l, V3, V3, float) const { return occ[l] != 0; }
 };
 // ---- shade the diffuse bin (:451-513) with the occlusion flags + Russian roulette (:545-549) ---------
-__global__ void __launch_bounds__(256, 3) k_wf_shade(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
+__global__ void __launch_bounds__(256, VKRT_SHADE_MINBLOCKS) k_wf_shade(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
                                                       const __grid_constant__ WaveParams wp, uint32_t next)
 {
     const uint32_t n = wp.cnt[C_DIFF];
