@@ -279,7 +279,8 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     cnt = r.counters()
     launches_per_step = r.last_frame_timing()[2] + (1 if world > 1 else 0) + ((world + 1) if (world > 1 and rank == 0) else 0)
-    rays = torch.tensor([cnt.closest_rays + cnt.shadow_rays, cnt.closest_rays, cnt.shadow_rays, cnt.paths], dtype=torch.float64, device=device)
+    rays = torch.tensor([cnt.closest_rays + cnt.shadow_rays, cnt.closest_rays, cnt.shadow_rays, cnt.paths,
+                         cnt.shared_primary_rays, cnt.zero_term_shadow_rays], dtype=torch.float64, device=device)
     t = torch.tensor([ms_total], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(rays, op=dist.ReduceOp.SUM)
@@ -345,6 +346,11 @@ def run_ours(args):
                 "ms_per_frame": ms_total / args.steps,
                 "rays_per_frame": total_rays / args.steps, "closest_rays": float(rays[1].item()) / args.steps,
                 "shadow_rays": float(rays[2].item()) / args.steps, "paths_per_frame": float(rays[3].item()) / args.steps,
+                "rays_note": "rays = trace_ray invocations of the reference algorithm; of these, shared_primary_rays (samples 2..S of a "
+                             "pixel reuse the pixel's single primary-ray query) and zero_term_shadow_rays (unoccluded contribution exactly 0) "
+                             "need no traversal of their own",
+                "shared_primary_rays": float(rays[4].item()) / args.steps, "zero_term_shadow_rays": float(rays[5].item()) / args.steps,
+                "traversed_rays_per_frame": (total_rays - float(rays[4].item()) - float(rays[5].item())) / args.steps,
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 96 * world, "d2h_bytes_per_step": n_px * 4,
                         "ms_per_step": 1e3 * float(e2e_t.item()) / args.steps,
                         "note": "vkrt_draw(host FrameData) + resolve + rgba8 D2H into pinned memory each step, wall clock"},

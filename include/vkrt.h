@@ -208,6 +208,9 @@ typedef struct vkrt_counters {
     uint64_t leaf_tests;    /* sphere tests made from BVH leaves (VKRT_FLAG_STATS) */
     uint64_t paths;         /* radiance() invocations */
     uint64_t frames;
+    /* of the rays above, those that were answered without a traversal of their own: */
+    uint64_t shared_primary_rays;   /* samples 2..S of a pixel reuse the pixel's one primary-ray query (Tracer.comp:574-581) */
+    uint64_t zero_term_shadow_rays; /* shadow rays whose unoccluded contribution is exactly 0 (light behind the surface) */
 } vkrt_counters;
 VKRT_API vkrt_error vkrt_get_counters(vkrt_ctx *ctx, vkrt_counters *out);
 VKRT_API vkrt_error vkrt_reset_counters(vkrt_ctx *ctx);

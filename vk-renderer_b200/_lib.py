@@ -53,7 +53,8 @@ class CreateInfo(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("node_visits", C.c_uint64),
-                ("leaf_tests", C.c_uint64), ("paths", C.c_uint64), ("frames", C.c_uint64)]
+                ("leaf_tests", C.c_uint64), ("paths", C.c_uint64), ("frames", C.c_uint64),
+                ("shared_primary_rays", C.c_uint64), ("zero_term_shadow_rays", C.c_uint64)]
 
 
 class BvhInfo(C.Structure):

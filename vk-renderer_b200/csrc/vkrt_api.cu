@@ -137,6 +137,8 @@ vkrt_error upload_scene(vkrt_ctx *c)
     std::memset(&d, 0, sizeof(d));
     d.spheres = c->d_spheres; d.sphere_mat = c->d_sphere_mat; d.mats = c->d_mats; d.tris = c->d_tris;
     d.bvh = c->use_bvh ? c->bvh.nodes : nullptr;
+    d.qbvh = c->use_bvh ? c->bvh.qnodes : nullptr;
+    for (int a = 0; a < 3; ++a) { d.qscale[a] = c->bvh.grid[3 + a]; d.qbase2[a] = c->bvh.grid[6 + a]; }
     d.n_nodes = c->use_bvh ? c->bvh.n_nodes : 0;
     d.n_spheres = (uint32_t)c->spheres.size(); d.n_tris = (uint32_t)c->tris.size(); d.tri_mat = c->tri_mat;
     d.n_planes = (uint32_t)c->planes.size(); d.n_mats = (uint32_t)c->mats.size();
@@ -242,7 +244,7 @@ VKRT_API vkrt_error vkrt_destroy(vkrt_ctx *c)
     DeviceGuard g(c->info.device_id);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_spheres); cudaFree(c->d_sphere_mat); cudaFree(c->d_mats); cudaFree(c->d_tris);
-    cudaFree(c->bvh.nodes); cudaFree(c->d_accum); cudaFree(c->d_hit_ids);
+    cudaFree(c->bvh.nodes); cudaFree(c->bvh.qnodes); cudaFree(c->d_accum); cudaFree(c->d_hit_ids);
     for (auto p : c->d_rgba) cudaFree(p);
     cudaFree(c->d_counters); cudaFree(c->d_work_head); cudaFree(c->d_packed);
     if (c->wave_ready) wave_free(c->wave);
@@ -537,6 +539,7 @@ VKRT_API vkrt_error vkrt_get_counters(vkrt_ctx *c, vkrt_counters *out)
     CU(c, cudaStreamSynchronize(c->stream));
     out->closest_rays = h[CNT_CLOSEST]; out->shadow_rays = h[CNT_SHADOW]; out->node_visits = h[CNT_NODES];
     out->leaf_tests = h[CNT_LEAVES]; out->paths = h[CNT_PATHS]; out->frames = c->frames;
+    out->shared_primary_rays = h[CNT_SHARED]; out->zero_term_shadow_rays = h[CNT_SKIPPED];
     return VKRT_SUCCESS;
 }
 VKRT_API vkrt_error vkrt_reset_counters(vkrt_ctx *c)

@@ -26,20 +26,21 @@ enum { KIND_TRI = 1, KIND_SPHERE = 2, KIND_PLANE = 3 };
 struct DevScene {
     const float4 *spheres;
     const uint32_t *sphere_mat;
-    const float4 *bvh;
+    const float4 *bvh;            // exact 64-byte nodes (introspection; traversal when VKRT_QNODES == 0)
+    const uint4 *qbvh;            // 32-byte traversal nodes with 16-bit quantised child boxes
     const float4 *tris;
     const float4 *mats;
     uint32_t n_spheres, n_tris, tri_mat, n_planes, n_lights, n_nodes, n_mats, _pad;
     float4 planes[MAX_PLANES];
     uint32_t plane_mat[MAX_PLANES];
     uint32_t lights[MAX_LIGHTS];
-    uint32_t _pad2[2];
+    float qscale[3], qbase2[3];   // decode: fma(float(2^23 + q), qscale, qbase2), rounded down (lo) / up (hi)
 };
 
 struct Material { V3 albedo; float roughness; V3 emissive; float metalness; uint32_t type; };
 
-struct Stats { uint32_t closest, shadow, nodes, leaves, paths; };
-VKRT_DEV void stats_zero(Stats &s) { s.closest = s.shadow = s.nodes = s.leaves = s.paths = 0; }
+struct Stats { uint32_t closest, shadow, nodes, leaves, paths, skipped, shared; };
+VKRT_DEV void stats_zero(Stats &s) { s.closest = s.shadow = s.nodes = s.leaves = s.paths = s.skipped = s.shared = 0; }
 
 struct Hit { float t; uint32_t kind, index; };
 
@@ -130,6 +131,22 @@ VKRT_DEV void s_consider(V3 o, V3 d, float4 sph, int i, float tn, float eps, flo
     else if (t < best.t || (t == best.t && i < best.idx)) { best.t = t; best.idx = i; }
 }
 
+#ifndef VKRT_PREFETCH_FAR
+#define VKRT_PREFETCH_FAR 0
+#endif
+#ifndef VKRT_QNODES
+#define VKRT_QNODES 0
+#endif
+VKRT_DEV void ldg256u(const uint4 *p, uint4 &a, uint4 &b)
+{
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
+// 16-bit field -> the float 2^23 + q (one PRMT), then one directed-rounding FFMA decodes the coordinate
+VKRT_DEV float q_lo16(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)); }
+VKRT_DEV float q_hi16(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)); }
+
 VKRT_DEV void ldg256(const float4 *p, float4 &a, float4 &b)
 {
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -155,38 +172,78 @@ VKRT_DEV void trav_init(Trav &tv, const DevScene &sc, V3 o, V3 d, float eps, flo
     tv.sp = 0;
     tv.node = sc.n_nodes ? 0 : -1;
 }
+// the exact rule-S leaf test: the sphere's own padded box, then the reference's intersection formula
+template <bool STATS>
+VKRT_DEV void leaf_test(Trav &tv, const DevScene &sc, V3 o, V3 d, int si, Stats &st)
+{
+    const float4 sph = __ldg(sc.spheres + si);
+    const float rp = sphere_pad_radius(sph.w);
+    float tn, tf;
+    if (slab_test(tv.sr, v3(sph.x - rp, sph.y - rp, sph.z - rp), v3(sph.x + rp, sph.y + rp, sph.z + rp), tn, tf) && tn <= tv.best.t) {
+        if (STATS) ++st.leaves;
+        s_consider(o, d, sph, si, tn, tv.eps, tv.B, tv.best);
+    }
+}
+
 template <bool ANY, bool STATS>
 VKRT_DEV void trav_step(Trav &tv, int *__restrict__ stack, const DevScene &sc, V3 o, V3 d, Stats &st)
 {
-    // one 64-byte node = two 256-bit loads (LDG.E.256, sm_100): the traversal is bound by L1TEX request
-    // throughput (scattered lines), so halving the number of load instructions per node matters
+    float tn0, tn1, tf;
+    bool h0, h1, leaf0, leaf1;
+    int i0, i1;
+#if VKRT_QNODES
+    // one 32-byte node = ONE 256-bit load (LDG.E.256): the traversal is bound by the L1TEX data pipe
+    // (scattered sectors), so halving the bytes per node matters more than the 24 decode instructions.
+    // The decoded boxes enclose the children's decoded / exact boxes as floats (the builder checks it with
+    // this same decode), so the monotone slab test keeps rule S exact.
+    uint4 w0, w1;
+    ldg256u(sc.qbvh + 2 * (size_t)tv.node, w0, w1);
+    if (STATS) ++st.nodes;
+    {
+        const V3 lo = v3(__fmaf_rd(q_lo16(w0.x), sc.qscale[0], sc.qbase2[0]), __fmaf_rd(q_hi16(w0.x), sc.qscale[1], sc.qbase2[1]),
+                         __fmaf_rd(q_lo16(w0.y), sc.qscale[2], sc.qbase2[2]));
+        const V3 hi = v3(__fmaf_ru(q_hi16(w0.y), sc.qscale[0], sc.qbase2[0]), __fmaf_ru(q_lo16(w0.z), sc.qscale[1], sc.qbase2[1]),
+                         __fmaf_ru(q_hi16(w0.z), sc.qscale[2], sc.qbase2[2]));
+        h0 = slab_test(tv.sr, lo, hi, tn0, tf) && tn0 <= tv.best.t;
+    }
+    {
+        const V3 lo = v3(__fmaf_rd(q_lo16(w1.x), sc.qscale[0], sc.qbase2[0]), __fmaf_rd(q_hi16(w1.x), sc.qscale[1], sc.qbase2[1]),
+                         __fmaf_rd(q_lo16(w1.y), sc.qscale[2], sc.qbase2[2]));
+        const V3 hi = v3(__fmaf_ru(q_hi16(w1.y), sc.qscale[0], sc.qbase2[0]), __fmaf_ru(q_lo16(w1.z), sc.qscale[1], sc.qbase2[1]),
+                         __fmaf_ru(q_hi16(w1.z), sc.qscale[2], sc.qbase2[2]));
+        h1 = slab_test(tv.sr, lo, hi, tn1, tf) && tn1 <= tv.best.t;
+    }
+    leaf0 = (w0.w >> 31) != 0u; leaf1 = (w1.w >> 31) != 0u;
+    i0 = (int)(w0.w & 0x7fffffffu); i1 = (int)(w1.w & 0x7fffffffu);
+#else
     const float4 *np = sc.bvh + 4 * (size_t)tv.node;
     float4 a0, b0, a1, b1;
     ldg256(np, a0, b0);
     ldg256(np + 2, a1, b1);
     if (STATS) ++st.nodes;
-    // both child records have the same shape {lo.xyz hi.x | hi.yz index kind}: the box tests are uniform code
-    float tn0, tn1, tf;
-    bool h0 = slab_test(tv.sr, v3(a0.x, a0.y, a0.z), v3(a0.w, b0.x, b0.y), tn0, tf) && tn0 <= tv.best.t;
-    bool h1 = slab_test(tv.sr, v3(a1.x, a1.y, a1.z), v3(a1.w, b1.x, b1.y), tn1, tf) && tn1 <= tv.best.t;
-    const int i0 = __float_as_int(b0.z), i1 = __float_as_int(b1.z);
-    // leaf children: fetch the sphere and run the reference's intersection (rule S candidate test)
-    if (h0 && __float_as_int(b0.w) != 0) {
-        if (STATS) ++st.leaves;
-        s_consider(o, d, __ldg(sc.spheres + i0), i0, tn0, tv.eps, tv.B, tv.best);
-        h0 = false;
-    }
-    if (h1 && __float_as_int(b1.w) != 0) {
-        if (STATS) ++st.leaves;
-        s_consider(o, d, __ldg(sc.spheres + i1), i1, tn1, tv.eps, tv.B, tv.best);
-        h1 = false;
-    }
+    h0 = slab_test(tv.sr, v3(a0.x, a0.y, a0.z), v3(a0.w, b0.x, b0.y), tn0, tf) && tn0 <= tv.best.t;
+    h1 = slab_test(tv.sr, v3(a1.x, a1.y, a1.z), v3(a1.w, b1.x, b1.y), tn1, tf) && tn1 <= tv.best.t;
+    leaf0 = __float_as_int(b0.w) != 0; leaf1 = __float_as_int(b1.w) != 0;
+    i0 = __float_as_int(b0.z); i1 = __float_as_int(b1.z);
+#endif
+    // leaf children: the quantised / stored box was only a pre-filter
+    if (h0 && leaf0) { leaf_test<STATS>(tv, sc, o, d, i0, st); h0 = false; }
+    if (h1 && leaf1) { leaf_test<STATS>(tv, sc, o, d, i1, st); h1 = false; }
     if (ANY && tv.best.idx >= 0) { tv.node = -1; return; }
     // descend into the nearer inner child, push the farther one, or pop
     const bool both = h0 && h1;
     const bool take1 = both ? (tn1 < tn0) : h1;
     const int nearer = take1 ? i1 : i0;
-    if (both) stack[tv.sp++] = take1 ? i0 : i1;
+    if (both) {
+        const int far = take1 ? i0 : i1;
+        stack[tv.sp++] = far;
+#if VKRT_PREFETCH_FAR
+        // the pushed (farther) child is visited later unless it gets culled: pull its node towards L1 now
+        const float4 *fp = sc.bvh + 4 * (size_t)far;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(fp));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(fp + 2));
+#endif
+    }
     if (h0 || h1) tv.node = nearer;
     else tv.node = tv.sp ? stack[--tv.sp] : -1;
 }
@@ -346,22 +403,58 @@ VKRT_DEV void nee_sample(const DevScene &sc, V3 P, uint32_t l, uint32_t skey, ui
     L = jitter(l0, VKRT_TWO_PI * u01(skey, dim0 + SLOT_LIGHT + 2 * l + 1), sqrtf(1.0f - cosa * cosa), cosa);
 }
 
-// occlusion query used by the megakernel: trace the shadow ray in place (Tracer.comp:471-473)
+// what light l adds to `e` when it is not occluded (Tracer.comp:475-502)
+VKRT_DEV V3 light_term(const DevScene &sc, const Surface &sf, const Material &mat, V3 cam_pos, uint32_t l, V3 L, float t)
+{
+    const uint32_t li = sc.lights[l];
+    const float sr = __ldg(&sc.spheres[li].w);
+    const V3 semis = xyz(__ldg(sc.mats + 3 * __ldg(sc.sphere_mat + li) + 1));
+    V3 attenuation = semis * 1.0f / pow_(t / sr + 1.0f, 2.0f);
+    attenuation = (attenuation - v3(0.001f)) / (1.0f - 0.001f);
+    attenuation = v3(gl_max(attenuation.x, 0.0f), gl_max(attenuation.y, 0.0f), gl_max(attenuation.z, 0.0f));
+    V3 F0 = v3(0.04f);
+    F0 = mix3(F0, mat.albedo, mat.metalness);
+    const V3 V = normalize3(cam_pos - sf.P);
+    const V3 H = normalize3(V + L);
+    const float NDF = distribution_ggx(sf.N, H, mat.roughness);
+    const float G = geometry_smith(sf.N, V, L, mat.roughness);
+    const V3 F = fresnel_schlick(gl_max(dot3(H, V), 0.0f), F0);
+    V3 kD = v3(1.0f) - F;
+    kD = kD * (1.0f - mat.metalness);
+    const V3 numerator = (NDF * G) * F;
+    const float denominator = 4.0f * gl_max(dot3(sf.N, V), 0.0f) * gl_max(dot3(sf.N, L), 0.0f);
+    const V3 specular = numerator / gl_max(denominator, 0.001f);
+    const float NdotL = gl_max(dot3(sf.N, L), 0.0f);
+    return (kD * mat.albedo / VKRT_PI + specular) * attenuation * NdotL;
+}
+// A term that is exactly zero in all three channels (typically N.L <= 0: the light is behind the surface)
+// cannot change `e` whether the shadow ray is occluded or not, so that ray need not be traced; a NaN term
+// is not "zero" and is traced like any other.  The ray still counts as a trace_ray invocation.
+VKRT_DEV bool term_is_zero(V3 c) { return c.x == 0.0f && c.y == 0.0f && c.z == 0.0f; }
+
+// light evaluation used by the megakernel: sample, evaluate, trace the shadow ray in place (Tracer.comp:464-503).
+// Returns what is added to `e` (+0 when occluded: e + 0 == e bit for bit).
 template <bool BVH, bool STATS>
-struct OccTrace {
-    const DevScene &sc; Stats &st;
-    VKRT_DEV bool operator()(uint32_t, V3 P, V3 L, float t) const
+struct LightTrace {
+    const DevScene &sc; Stats &st; V3 cam_pos; uint32_t skey, dim0;
+    VKRT_DEV V3 operator()(uint32_t l, const Surface &sf, const Material &mat) const
     {
+        V3 L; float t;
+        nee_sample(sc, sf.P, l, skey, dim0, L, t);
         Hit sh{t, 0, 0};
-        return trace_ray<true, BVH, true, STATS>(sc, P, L, sh, st);
+        if (!BVH)     // 10-primitive scenes: the ray is cheaper than the BRDF, keep the shader's order
+            return trace_ray<true, BVH, true, STATS>(sc, sf.P, L, sh, st) ? v3(0.0f) : light_term(sc, sf, mat, cam_pos, l, L, t);
+        const V3 term = light_term(sc, sf, mat, cam_pos, l, L, t);
+        if (term_is_zero(term)) { ++st.shadow; ++st.skipped; return v3(0.0f); }
+        return trace_ray<true, BVH, true, STATS>(sc, sf.P, L, sh, st) ? v3(0.0f) : term;
     }
 };
 
-// Shades the hit (the light loop asks `occluded(l, P, L, t)` for every emissive sphere) and rolls
-// Russian roulette.  Returns true when the path continues into the next depth iteration.
-template <class Occ>
+// Shades the hit (the light loop asks `lights(l, surface, material)` for every emissive sphere's
+// contribution) and rolls Russian roulette.  Returns true when the path continues into the next depth iteration.
+template <class Lights>
 VKRT_DEV bool path_shade(const DevScene &sc, V3 cam_pos, uint32_t max_depth, uint32_t skey, PathState &ps,
-                         const Hit &hit, const Occ &occluded)
+                         const Hit &hit, const Lights &lights)
 {
     const uint32_t dim0 = ps.depth * DIMS_PER_BOUNCE;
     const Surface sf = surface_of(sc, ps.o, ps.d, hit);
@@ -371,32 +464,7 @@ VKRT_DEV bool path_shade(const DevScene &sc, V3 cam_pos, uint32_t max_depth, uin
         const V3 dj = jitter(sf.N, VKRT_TWO_PI * u01(skey, dim0 + SLOT_PHI), sqrtf(r2), sqrtf(1.0f - r2)) *
                       (1.0f - mat.metalness);
         V3 e = v3(0.0f);
-        for (uint32_t l = 0; l < sc.n_lights; ++l) {
-            V3 L; float t;
-            nee_sample(sc, sf.P, l, skey, dim0, L, t);
-            if (!occluded(l, sf.P, L, t)) {
-                const uint32_t li = sc.lights[l];
-                const float sr = __ldg(&sc.spheres[li].w);
-                const V3 semis = xyz(__ldg(sc.mats + 3 * __ldg(sc.sphere_mat + li) + 1));
-                V3 attenuation = semis * 1.0f / pow_(t / sr + 1.0f, 2.0f);
-                attenuation = (attenuation - v3(0.001f)) / (1.0f - 0.001f);
-                attenuation = v3(gl_max(attenuation.x, 0.0f), gl_max(attenuation.y, 0.0f), gl_max(attenuation.z, 0.0f));
-                V3 F0 = v3(0.04f);
-                F0 = mix3(F0, mat.albedo, mat.metalness);
-                const V3 V = normalize3(cam_pos - sf.P);
-                const V3 H = normalize3(V + L);
-                const float NDF = distribution_ggx(sf.N, H, mat.roughness);
-                const float G = geometry_smith(sf.N, V, L, mat.roughness);
-                const V3 F = fresnel_schlick(gl_max(dot3(H, V), 0.0f), F0);
-                V3 kD = v3(1.0f) - F;
-                kD = kD * (1.0f - mat.metalness);
-                const V3 numerator = (NDF * G) * F;
-                const float denominator = 4.0f * gl_max(dot3(sf.N, V), 0.0f) * gl_max(dot3(sf.N, L), 0.0f);
-                const V3 specular = numerator / gl_max(denominator, 0.001f);
-                const float NdotL = gl_max(dot3(sf.N, L), 0.0f);
-                e = e + (kD * mat.albedo / VKRT_PI + specular) * attenuation * NdotL;
-            }
-        }
+        for (uint32_t l = 0; l < sc.n_lights; ++l) e = e + lights(l, sf, mat);
         const bool all_pos = mat.emissive.x > 0.0f && mat.emissive.y > 0.0f && mat.emissive.z > 0.0f;
         const V3 emissive = all_pos ? normalize3(mat.emissive) : v3(0.0f);
         ps.acc = ps.acc + ps.mask * (emissive + e);
@@ -431,8 +499,8 @@ VKRT_DEV bool path_bounce(const DevScene &sc, V3 cam_pos, uint32_t max_depth, ui
     const bool found = trace_ray<true, BVH, false, STATS>(sc, ps.o, ps.d, hit, st);
     if (primary_id) *primary_id = found ? ((hit.kind << 28) | hit.index) : 0u;
     if (!found) return false;
-    const OccTrace<BVH, STATS> occ{sc, st};
-    return path_shade(sc, cam_pos, max_depth, skey, ps, hit, occ);
+    const LightTrace<BVH, STATS> lights{sc, st, cam_pos, skey, ps.depth * DIMS_PER_BOUNCE};
+    return path_shade(sc, cam_pos, max_depth, skey, ps, hit, lights);
 }
 
 // ---- primary ray: Tracer.comp:561-574 == Raytracer.comp:361-376 -------------------------------

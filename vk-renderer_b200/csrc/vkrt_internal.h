@@ -26,7 +26,7 @@ struct RenderParams {
 };
 
 enum { TILE = 32, TILE_PX = TILE * TILE };
-enum { CNT_CLOSEST = 0, CNT_SHADOW = 1, CNT_NODES = 2, CNT_LEAVES = 3, CNT_PATHS = 4, CNT_N = 8 };
+enum { CNT_CLOSEST = 0, CNT_SHADOW = 1, CNT_NODES = 2, CNT_LEAVES = 3, CNT_PATHS = 4, CNT_SKIPPED = 5, CNT_SHARED = 6, CNT_N = 8 };
 
 struct LaunchCfg { int sm_count; };
 
@@ -50,6 +50,7 @@ struct WaveBuffers {
     uint32_t *counts;             // queue counters and work-fetch heads
     float4 *sample_rad;           // finished radiance per (pixel slot, sample in wave); reduced in sample order
     float4 *shadow;               // light-sample shadow rays {L.xyz, t_light}, n_lights per path
+    float4 *term;                 // their unoccluded contributions (evaluated before the ray is queued)
     uint8_t *occ;                 // their any-hit results
     uint32_t *queue_shadow;       // (path << 4 | light) items that still need the sphere any-hit query
     float4 *frame_sum;            // running per-slot sum when a frame needs more than one wave
@@ -62,7 +63,9 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
 
 // vkrt_bvh.cu
 struct BvhBuild {
-    float4 *nodes = nullptr;      // 4 float4 per inner node
+    float4 *nodes = nullptr;      // exact nodes: 4 float4 per inner node (introspection, tests)
+    uint4 *qnodes = nullptr;      // traversal nodes: 2 uint4 per inner node, 16-bit quantised child boxes
+    float grid[9] = {0};          // quantisation grid: base xyz, scale xyz, base2 xyz
     uint32_t n_nodes = 0;
     float build_ms = 0.f;
     uint32_t launches = 0;

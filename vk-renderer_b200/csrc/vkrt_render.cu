@@ -26,13 +26,16 @@ VKRT_DEV void flush_stats(const Stats &st, unsigned long long *counters, bool st
 {
     const unsigned full = 0xffffffffu;
     const uint32_t c = __reduce_add_sync(full, st.closest), s = __reduce_add_sync(full, st.shadow),
-                   p = __reduce_add_sync(full, st.paths);
+                   p = __reduce_add_sync(full, st.paths), k = __reduce_add_sync(full, st.skipped),
+                   h = __reduce_add_sync(full, st.shared);
     uint32_t n = 0, l = 0;
     if (stats) { n = __reduce_add_sync(full, st.nodes); l = __reduce_add_sync(full, st.leaves); }
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(counters + CNT_CLOSEST, (unsigned long long)c);
         atomicAdd(counters + CNT_SHADOW, (unsigned long long)s);
         atomicAdd(counters + CNT_PATHS, (unsigned long long)p);
+        if (k) atomicAdd(counters + CNT_SKIPPED, (unsigned long long)k);
+        if (h) atomicAdd(counters + CNT_SHARED, (unsigned long long)h);
         if (stats) { atomicAdd(counters + CNT_NODES, (unsigned long long)n); atomicAdd(counters + CNT_LEAVES, (unsigned long long)l); }
     }
 }

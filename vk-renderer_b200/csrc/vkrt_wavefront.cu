@@ -28,6 +28,9 @@
 #ifndef VKRT_TRACE_BLOCK
 #define VKRT_TRACE_BLOCK 128
 #endif
+#ifndef VKRT_TRACE_MINBLOCKS
+#define VKRT_TRACE_MINBLOCKS 1
+#endif
 #ifndef VKRT_SHADE_MINBLOCKS
 #define VKRT_SHADE_MINBLOCKS 2      // __launch_bounds__(256, n) of the streaming shade/classify kernels
 #endif
@@ -37,7 +40,7 @@ namespace vkrt {
 enum { C_ACTIVE0 = 0, C_ACTIVE1 = 1, C_DIEL = 2, C_DIFF = 3, C_SHADOW = 4, C_HEAD_EXTEND = 5, C_HEAD_SHADOW = 6, C_N = 8 };
 
 struct WaveParams {
-    float4 *po, *pd, *pacc, *pmask, *sh, *rad;
+    float4 *po, *pd, *pacc, *pmask, *sh, *term, *rad;
     uint32_t *q_active[2], *q_diel, *q_diff, *q_shadow;
     uint8_t *occ;
     uint32_t *cnt;
@@ -74,13 +77,16 @@ VKRT_DEV void wf_flush(const Stats &st, unsigned long long *counters, bool stats
 {
     const unsigned full = 0xffffffffu;
     const uint32_t c = __reduce_add_sync(full, st.closest), s = __reduce_add_sync(full, st.shadow),
-                   p = __reduce_add_sync(full, st.paths);
+                   p = __reduce_add_sync(full, st.paths), k = __reduce_add_sync(full, st.skipped),
+                   h = __reduce_add_sync(full, st.shared);
     uint32_t n = 0, l = 0;
     if (stats) { n = __reduce_add_sync(full, st.nodes); l = __reduce_add_sync(full, st.leaves); }
     if ((threadIdx.x & 31) == 0) {
         if (c) atomicAdd(counters + CNT_CLOSEST, (unsigned long long)c);
         if (s) atomicAdd(counters + CNT_SHADOW, (unsigned long long)s);
         if (p) atomicAdd(counters + CNT_PATHS, (unsigned long long)p);
+        if (k) atomicAdd(counters + CNT_SKIPPED, (unsigned long long)k);
+        if (h) atomicAdd(counters + CNT_SHARED, (unsigned long long)h);
         if (stats && n) atomicAdd(counters + CNT_NODES, (unsigned long long)n);
         if (stats && l) atomicAdd(counters + CNT_LEAVES, (unsigned long long)l);
     }
@@ -119,6 +125,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ Dev
         fd = make_float4(d.x, d.y, d.z, __uint_as_float(found ? ((hit.kind << 28) | hit.index) : 0u));
         pix = py * rp.width + px;
         st.closest += wp.S;
+        st.shared += wp.S - 1u;
         st.paths += wp.S;
     }
     for (uint32_t sl = 0; sl < wp.S; ++sl) {
@@ -138,7 +145,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ Dev
 //              result -> po.w (t so far), pd.w (id so far); the plane loop follows in classify
 // ANY = true : item i -> queue[i] = path * 16 + light; ray (P, sh.xyz), bound sh.w; spheres only; -> occ
 template <bool ANY, bool BVH, bool STATS>
-__global__ void __launch_bounds__(VKRT_TRACE_BLOCK) k_wf_trace(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
+__global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_trace(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
                                                                 const __grid_constant__ WaveParams wp, const uint32_t *__restrict__ queue,
                                                                 const uint32_t *__restrict__ n_items_ptr, uint32_t *head, uint32_t depth)
 {
@@ -243,8 +250,8 @@ VKRT_DEV void store_path(const WaveParams &wp, uint32_t path, const PathState &p
     wp.pmask[path] = make_float4(ps.mask.x, ps.mask.y, ps.mask.z, __uint_as_float((sl << 8) | ps.depth));
 }
 
-struct OccNever {
-    VKRT_DEV bool operator()(uint32_t, V3, V3, float) const { return false; }
+struct LightsNone {      // the dielectric branch never evaluates a light
+    VKRT_DEV V3 operator()(uint32_t, const Surface &, const Material &) const { return v3(0.0f); }
 };
 
 // ---- classify: one pass over the active paths after `extend` ----------------------------------------
@@ -264,7 +271,8 @@ __global__ void __launch_bounds__(256, VKRT_SHADE_MINBLOCKS) k_wf_classify(const
         const uint32_t i = base + threadIdx.x;
         bool diff = false, alive = false;
         uint32_t path = 0, skey = 0, dim0 = 0;
-        V3 P = v3(0.f);
+        Surface sf; sf.P = v3(0.f); sf.N = v3(0.f); sf.mat = 0;
+        Material dmat{};
         if (i < n) {
             path = queue[i];
             PathState ps; Hit hit; uint32_t pix, sl;
@@ -283,13 +291,14 @@ __global__ void __launch_bounds__(256, VKRT_SHADE_MINBLOCKS) k_wf_classify(const
                 const uint32_t type = __float_as_uint(__ldg(&sc.mats[3 * mat + 2].x));
                 skey = sample_key(rp.fkey, pix, wp.s0 + sl);
                 if (type != 0u) {                                                                      // DIELECTRIC
-                    alive = path_shade(sc, cam_pos, rp.max_depth, skey, ps, hit, OccNever{});
+                    alive = path_shade(sc, cam_pos, rp.max_depth, skey, ps, hit, LightsNone{});
                     if (alive) store_path(wp, path, ps, pix, sl);
                     else wp.rad[path] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, 0.f);
                 } else {                                                                               // DIFFUSE
                     diff = true;
                     dim0 = ps.depth * DIMS_PER_BOUNCE;
-                    P = madd3(hit.t, ps.d, ps.o);
+                    sf = surface_of(sc, ps.o, ps.d, hit);
+                    dmat = load_material(sc, sf.mat);
                     if (id != id0) { wp.po[path].w = cur; wp.pd[path].w = __uint_as_float(id); }
                     if (__float_as_uint(acc0.x) != __float_as_uint(ps.acc.x) || __float_as_uint(acc0.y) != __float_as_uint(ps.acc.y) ||
                         __float_as_uint(acc0.z) != __float_as_uint(ps.acc.z))
@@ -303,15 +312,20 @@ __global__ void __launch_bounds__(256, VKRT_SHADE_MINBLOCKS) k_wf_classify(const
             bool queue_it = false;
             if (diff) {
                 V3 L; float t;
-                nee_sample(sc, P, l, skey, dim0, L, t);
+                nee_sample(sc, sf.P, l, skey, dim0, L, t);
                 ++st.shadow;
+                // the unoccluded contribution is evaluated first: an exactly-zero term (N.L <= 0) needs no ray
+                const V3 term = light_term(sc, sf, dmat, cam_pos, l, L, t);
+                bool occluded = term_is_zero(term);
+                if (occluded) ++st.skipped;
                 // any-hit is a plain OR over the primitive classes: triangles and planes here,
                 // spheres (bound t + EPSILON, unchanged because nothing was accepted before them) in `shadow`
                 Hit h{t, 0, 0};
                 float cur = t;
-                bool occluded = trace_tris<true>(sc, P, L, cur, h);
-                if (!occluded) { cur = t; occluded = trace_planes<true>(sc, P, L, cur, h); }
+                if (!occluded) occluded = trace_tris<true>(sc, sf.P, L, cur, h);
+                if (!occluded) { cur = t; occluded = trace_planes<true>(sc, sf.P, L, cur, h); }
                 wp.sh[(size_t)path * sc.n_lights + l] = make_float4(L.x, L.y, L.z, t);
+                wp.term[(size_t)path * sc.n_lights + l] = make_float4(term.x, term.y, term.z, 0.f);
                 if (occluded) wp.occ[(size_t)path * sc.n_lights + l] = 1;
                 queue_it = !occluded;
             }
@@ -321,9 +335,9 @@ __global__ void __launch_bounds__(256, VKRT_SHADE_MINBLOCKS) k_wf_classify(const
     wf_flush(st, rp.counters, false);
 }
 
-struct OccFlags {
-    const uint8_t *occ;
-    VKRT_DEV bool operator()(uint32_t l, V3, V3, float) const { return occ[l] != 0; }
+struct LightsStored {    // the terms were evaluated by classify, the occlusion flags by classify / shadow
+    const uint8_t *occ; const float4 *term;
+    VKRT_DEV V3 operator()(uint32_t l, const Surface &, const Material &) const { return occ[l] != 0 ? v3(0.0f) : xyz(term[l]); }
 };
 // ---- shade the diffuse bin (:451-513) with the occlusion flags + Russian roulette (:545-549) ---------
 __global__ void __launch_bounds__(256, VKRT_SHADE_MINBLOCKS) k_wf_shade(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
@@ -340,8 +354,8 @@ __global__ void __launch_bounds__(256, VKRT_SHADE_MINBLOCKS) k_wf_shade(const __
             PathState ps; Hit hit; uint32_t pix, sl;
             load_path(wp, path, ps, hit, pix, sl);
             const uint32_t skey = sample_key(rp.fkey, pix, wp.s0 + sl);
-            const OccFlags occ{wp.occ + (size_t)path * sc.n_lights};
-            alive = path_shade(sc, cam_pos, rp.max_depth, skey, ps, hit, occ);
+            const LightsStored lights{wp.occ + (size_t)path * sc.n_lights, wp.term + (size_t)path * sc.n_lights};
+            alive = path_shade(sc, cam_pos, rp.max_depth, skey, ps, hit, lights);
             if (alive) store_path(wp, path, ps, pix, sl);
             else wp.rad[path] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, 0.f);
         }
@@ -398,7 +412,7 @@ void wave_free(WaveBuffers &wb)
 {
     cudaFree(wb.ray_o); cudaFree(wb.ray_d); cudaFree(wb.acc); cudaFree(wb.mask); cudaFree(wb.sample_rad);
     cudaFree(wb.queue[0]); cudaFree(wb.queue[1]); cudaFree(wb.queue_mat[0]); cudaFree(wb.queue_mat[1]); cudaFree(wb.counts);
-    cudaFree(wb.shadow); cudaFree(wb.occ); cudaFree(wb.frame_sum); cudaFree(wb.queue_shadow);
+    cudaFree(wb.shadow); cudaFree(wb.occ); cudaFree(wb.frame_sum); cudaFree(wb.queue_shadow); cudaFree(wb.term);
     wb = WaveBuffers{};
 }
 
@@ -415,9 +429,10 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
     if (S > spp) S = spp;
     // shadow-ray storage depends on the light count of the scene: (re)allocate lazily
     if (wb.shadow_lights < nl) {
-        cudaFree(wb.shadow); cudaFree(wb.occ); cudaFree(wb.queue_shadow);
-        wb.shadow = nullptr; wb.occ = nullptr; wb.queue_shadow = nullptr;
+        cudaFree(wb.shadow); cudaFree(wb.occ); cudaFree(wb.queue_shadow); cudaFree(wb.term);
+        wb.shadow = nullptr; wb.occ = nullptr; wb.queue_shadow = nullptr; wb.term = nullptr;
         if ((e = cudaMalloc((void **)&wb.shadow, wb.capacity * nl * sizeof(float4))) != cudaSuccess) return e;
+        if ((e = cudaMalloc((void **)&wb.term, wb.capacity * nl * sizeof(float4))) != cudaSuccess) return e;
         if ((e = cudaMalloc((void **)&wb.occ, wb.capacity * nl)) != cudaSuccess) return e;
         if ((e = cudaMalloc((void **)&wb.queue_shadow, wb.capacity * nl * sizeof(uint32_t))) != cudaSuccess) return e;
         wb.shadow_lights = nl;
@@ -442,7 +457,7 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
 
     for (uint32_t wv = 0; wv < n_waves; ++wv) {
         WaveParams wp{};
-        wp.po = wb.ray_o; wp.pd = wb.ray_d; wp.pacc = wb.acc; wp.pmask = wb.mask; wp.sh = wb.shadow; wp.rad = wb.sample_rad;
+        wp.po = wb.ray_o; wp.pd = wb.ray_d; wp.pacc = wb.acc; wp.pmask = wb.mask; wp.sh = wb.shadow; wp.term = wb.term; wp.rad = wb.sample_rad;
         wp.q_active[0] = wb.queue[0]; wp.q_active[1] = wb.queue[1]; wp.q_diel = wb.queue_mat[0]; wp.q_diff = wb.queue_mat[1];
         wp.q_shadow = wb.queue_shadow;
         wp.occ = wb.occ; wp.cnt = wb.counts;
