@@ -127,7 +127,8 @@ inline V3 operator*(V3 a, V3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
 inline V3 operator/(V3 a, V3 b) { return {a.x / b.x, a.y / b.y, a.z / b.z}; }
 inline V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
 inline V3 operator*(float s, V3 a) { return {a.x * s, a.y * s, a.z * s}; }
-inline V3 operator/(V3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+// vec3 / scalar: one correctly rounded reciprocal, three multiplies (how GPUs lower it; GLSL allows 2.5 ULP on '/')
+inline V3 operator/(V3 a, float s) { const float inv = 1.0f / s; return {a.x * inv, a.y * inv, a.z * inv}; }
 inline V3 operator-(V3 a) { return {-a.x, -a.y, -a.z}; }
 inline float dot3(V3 a, V3 b) { return fma_(a.z, b.z, fma_(a.y, b.y, a.x * b.x)); }
 inline V3 cross3(V3 a, V3 b)

@@ -111,7 +111,8 @@ VKRT_DEV V3 operator*(V3 a, V3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
 VKRT_DEV V3 operator/(V3 a, V3 b) { return {a.x / b.x, a.y / b.y, a.z / b.z}; }
 VKRT_DEV V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
 VKRT_DEV V3 operator*(float s, V3 a) { return {a.x * s, a.y * s, a.z * s}; }
-VKRT_DEV V3 operator/(V3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+// vec3 / scalar: one correctly rounded reciprocal, three multiplies (part of the arithmetic contract)
+VKRT_DEV V3 operator/(V3 a, float s) { const float inv = 1.0f / s; return {a.x * inv, a.y * inv, a.z * inv}; }
 VKRT_DEV V3 operator-(V3 a) { return {-a.x, -a.y, -a.z}; }
 VKRT_DEV float dot3(V3 a, V3 b) { return fma_(a.z, b.z, fma_(a.y, b.y, a.x * b.x)); }
 VKRT_DEV V3 cross3(V3 a, V3 b)

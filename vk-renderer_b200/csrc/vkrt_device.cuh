@@ -279,7 +279,18 @@ VKRT_DEV bool trace_planes(const DevScene &sc, V3 o, V3 d, float &cur, Hit &hit)
     const float EPS = TRACER ? 1e-3f : 0.01f;
     bool found = false;
     for (uint32_t i = 0; i < sc.n_planes; ++i) {
-        const float t = TRACER ? plane_intersect_tracer(o, d, sc.planes[i]) : plane_intersect_raytracer(o, d, sc.planes[i]);
+        // t = -(len + o.N) / (d.N) clamped at 0 is accepted iff EPS < t < cur (-EPS).  Two rejections need no
+        // IEEE division and are exact: (a) the quotient's sign is the XOR of the operands' signs, so unless
+        // num and dn are both non-zero with equal signs t is 0 / NaN -> rejected; (b) if |num| exceeds
+        // cur * |dn| by more than a few ulps the correctly rounded quotient is >= cur -> rejected.
+        const float4 p = sc.planes[i];
+        const V3 N = xyz(p);
+        const float dn = dot3(d, N);
+        const float num = -(p.w + dot3(o, N));
+        const bool same_sign = (num > 0.0f && dn > 0.0f) || (num < 0.0f && dn < 0.0f);
+        if (same_sign && gl_abs(num) > (cur * gl_abs(dn)) * 1.000001f) continue;
+        if (!same_sign && num == num && dn == dn) continue;
+        const float t = TRACER ? plane_intersect_tracer(o, d, p) : plane_intersect_raytracer(o, d, p);
         const bool acc = TRACER ? ((t > EPS) && (t < cur - EPS)) : (t > EPS && t < cur);
         if (acc) { cur = t; hit.kind = KIND_PLANE; hit.index = i; found = true; }
     }

@@ -25,11 +25,17 @@
 #ifndef VKRT_REFILL
 #define VKRT_REFILL 20      // refill the warp when fewer than this many lanes are still traversing
 #endif
+#ifndef VKRT_FETCH_CHUNK
+#define VKRT_FETCH_CHUNK 128   // ray indices a warp reserves per atomicAdd on the queue head
+#endif
 #ifndef VKRT_TRACE_BLOCK
 #define VKRT_TRACE_BLOCK 128
 #endif
 #ifndef VKRT_TRACE_MINBLOCKS
 #define VKRT_TRACE_MINBLOCKS 1
+#endif
+#ifndef VKRT_SHADE_BLOCK
+#define VKRT_SHADE_BLOCK 256
 #endif
 #ifndef VKRT_SHADE_MINBLOCKS
 #define VKRT_SHADE_MINBLOCKS 2      // __launch_bounds__(256, n) of the streaming shade/classify kernels
@@ -71,6 +77,35 @@ VKRT_DEV void push(uint32_t *queue, uint32_t *count, bool want, uint32_t value)
     if ((int)lane == leader) base = atomicAdd(count, (uint32_t)__popc(m));
     base = __shfl_sync(full, base, leader);
     if (want) queue[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+
+// block-aggregated queue push: the warps' counts meet in shared memory and ONE atomicAdd per block and
+// queue reserves the slots (queue counters are single addresses: with one atomic per warp they become the
+// bottleneck of the streaming kernels -- same-address atomics serialise in L2).  All threads of the block
+// must call it (two __syncthreads inside).
+template <int NQ>
+VKRT_DEV void push_block(uint32_t *const (&queue)[NQ], uint32_t *const (&count)[NQ], const bool (&want)[NQ], const uint32_t (&value)[NQ])
+{
+    __shared__ uint32_t s_cnt[NQ][32];
+    __shared__ uint32_t s_base[NQ];
+    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31u) >> 5;
+    unsigned m[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        m[q] = __ballot_sync(full, want[q]);
+        if (lane == 0) s_cnt[q][warp] = (uint32_t)__popc(m[q]);
+    }
+    __syncthreads();
+    if (threadIdx.x < NQ) {
+        uint32_t tot = 0;
+        for (unsigned w = 0; w < n_warps; ++w) { const uint32_t c = s_cnt[threadIdx.x][w]; s_cnt[threadIdx.x][w] = tot; tot += c; }
+        s_base[threadIdx.x] = tot ? atomicAdd(count[threadIdx.x], tot) : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+        if (want[q]) queue[q][s_base[q] + s_cnt[q][warp] + (uint32_t)__popc(m[q] & ((1u << lane) - 1u))] = value[q];
+    __syncthreads();      // s_cnt / s_base are reused by the next call
 }
 
 VKRT_DEV void wf_flush(const Stats &st, unsigned long long *counters, bool stats)
@@ -135,7 +170,9 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ Dev
             wp.pacc[p] = make_float4(0.f, 0.f, 0.f, __uint_as_float(pix));
             wp.pmask[p] = make_float4(1.f, 1.f, 1.f, __uint_as_float(sl << 8));
         }
-        push(wp.q_active[0], wp.cnt + C_ACTIVE0, valid, p);
+        uint32_t *const qs[1] = {wp.q_active[0]}; uint32_t *const cs[1] = {wp.cnt + C_ACTIVE0};
+        const bool ws[1] = {valid}; const uint32_t vs[1] = {p};
+        push_block<1>(qs, cs, ws, vs);
     }
     wf_flush(st, rp.counters, STATS);
 }
@@ -156,6 +193,7 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
     const float tmax = path_tmax(depth);       // every ray of one extend launch is at the same depth (:444)
 
     bool has = false, drained = false;
+    uint32_t res_base = 0, res_left = 0;       // this warp's current reservation of queue items (warp-uniform)
     uint32_t path = 0, light = 0;
     V3 o = v3(0.f), d = v3(0.f);
     Hit hit{0.f, 0, 0};
@@ -169,12 +207,21 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
         const bool need = !has && !drained;
         const unsigned m = __ballot_sync(full, need);
         if (m) {
-            const int leader = __ffs(m) - 1;
-            uint32_t base = 0;
-            if ((int)lane == leader) base = atomicAdd(head, (uint32_t)__popc(m));
-            base = __shfl_sync(full, base, leader);
+            // the warp reserves ray indices VKRT_FETCH_CHUNK at a time (one atomicAdd by one lane, broadcast
+            // with __shfl_sync) and hands them to the lanes that need work from that reservation
+            const uint32_t cnt = (uint32_t)__popc(m);
+            uint32_t new_base = 0;
+            if (res_left < cnt) {
+                const int leader = __ffs(m) - 1;
+                if ((int)lane == leader) new_base = atomicAdd(head, (uint32_t)VKRT_FETCH_CHUNK);
+                new_base = __shfl_sync(full, new_base, leader);
+            }
+            const uint32_t rank = (uint32_t)__popc(m & ((1u << lane) - 1u));
+            const uint32_t my_item = rank < res_left ? res_base + rank : new_base + (rank - res_left);
+            if (res_left < cnt) { res_base = new_base + (cnt - res_left); res_left = (uint32_t)VKRT_FETCH_CHUNK - (cnt - res_left); }
+            else { res_base += cnt; res_left -= cnt; }
             if (need) {
-                const uint32_t item = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                const uint32_t item = my_item;
                 if (item >= n_items) drained = true;
                 else {
                     has = true;
@@ -260,7 +307,7 @@ struct LightsNone {      // the dielectric branch never evaluates a light
 //   the next active queue; DIFFUSE hit -> the light-sample shadow rays (:464-469) are generated here, their
 //   triangle/plane occluders resolved, the rest queued for the sphere any-hit kernel, and the path goes to
 //   the diffuse bin.  (Binning by material type = which queue a path is pushed to.)
-__global__ void __launch_bounds__(256, VKRT_SHADE_MINBLOCKS) k_wf_classify(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
+__global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_SHADE_MINBLOCKS) k_wf_classify(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
                                                          const __grid_constant__ WaveParams wp, const uint32_t *__restrict__ queue,
                                                          const uint32_t *__restrict__ n_ptr, uint32_t next)
 {
@@ -340,7 +387,7 @@ struct LightsStored {    // the terms were evaluated by classify, the occlusion 
     VKRT_DEV V3 operator()(uint32_t l, const Surface &, const Material &) const { return occ[l] != 0 ? v3(0.0f) : xyz(term[l]); }
 };
 // ---- shade the diffuse bin (:451-513) with the occlusion flags + Russian roulette (:545-549) ---------
-__global__ void __launch_bounds__(256, VKRT_SHADE_MINBLOCKS) k_wf_shade(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
+__global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_SHADE_MINBLOCKS) k_wf_shade(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
                                                       const __grid_constant__ WaveParams wp, uint32_t next)
 {
     const uint32_t n = wp.cnt[C_DIFF];
@@ -453,7 +500,7 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_extend, VKRT_TRACE_BLOCK, 0)) != cudaSuccess) return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_shadow, VKRT_TRACE_BLOCK, 0)) != cudaSuccess) return e;
     const unsigned grid_e = (unsigned)(sm_count * (occ_e > 0 ? occ_e : 1)), grid_s = (unsigned)(sm_count * (occ_s > 0 ? occ_s : 1));
-    const unsigned grid_shade = (unsigned)sm_count * 8u;
+    const unsigned grid_shade = (unsigned)sm_count * 8u * (256u / VKRT_SHADE_BLOCK);
 
     for (uint32_t wv = 0; wv < n_waves; ++wv) {
         WaveParams wp{};
@@ -479,11 +526,11 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
             if (depth > 0) {       // depth 0 was traced once per pixel by `generate`
                 k_extend<<<grid_e, VKRT_TRACE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_active[cur], n_active, wb.counts + C_HEAD_EXTEND, depth); ++launches;
             }
-            k_wf_classify<<<grid_shade, 256, 0, st>>>(sc, rp, wp, wp.q_active[cur], n_active, nxt); ++launches;
+            k_wf_classify<<<grid_shade, VKRT_SHADE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_active[cur], n_active, nxt); ++launches;
             if (sc.n_lights) {
                 k_shadow<<<grid_s, VKRT_TRACE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_shadow, wb.counts + C_SHADOW, wb.counts + C_HEAD_SHADOW, depth); ++launches;
             }
-            k_wf_shade<<<grid_shade, 256, 0, st>>>(sc, rp, wp, nxt); ++launches;
+            k_wf_shade<<<grid_shade, VKRT_SHADE_BLOCK, 0, st>>>(sc, rp, wp, nxt); ++launches;
         }
         k_wf_reduce<<<(wp.n_slots + 255u) / 256u, 256, 0, st>>>(rp, wp, wb.frame_sum, wv == 0, wv + 1 == n_waves); ++launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
