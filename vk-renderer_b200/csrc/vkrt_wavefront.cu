@@ -309,14 +309,14 @@ struct LightsNone {      // the dielectric branch never evaluates a light
 //   the diffuse bin.  (Binning by material type = which queue a path is pushed to.)
 __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_SHADE_MINBLOCKS) k_wf_classify(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
                                                          const __grid_constant__ WaveParams wp, const uint32_t *__restrict__ queue,
-                                                         const uint32_t *__restrict__ n_ptr, uint32_t next)
+                                                         const uint32_t *__restrict__ n_ptr)
 {
     Stats st; stats_zero(st);
     const uint32_t n = *n_ptr;
     const V3 cam_pos = v3(rp.fd.camera.pos.x, rp.fd.camera.pos.y, rp.fd.camera.pos.z);
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t i = base + threadIdx.x;
-        bool diff = false, alive = false;
+        bool diff = false, diel = false;
         uint32_t path = 0, skey = 0, dim0 = 0;
         Surface sf; sf.P = v3(0.f); sf.N = v3(0.f); sf.mat = 0;
         Material dmat{};
@@ -337,23 +337,21 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_SHADE_MINBLOCKS) k_wf_c
                 const uint32_t mat = hit.kind == KIND_TRI ? sc.tri_mat : hit.kind == KIND_SPHERE ? __ldg(sc.sphere_mat + hit.index) : sc.plane_mat[hit.index];
                 const uint32_t type = __float_as_uint(__ldg(&sc.mats[3 * mat + 2].x));
                 skey = sample_key(rp.fkey, pix, wp.s0 + sl);
-                if (type != 0u) {                                                                      // DIELECTRIC
-                    alive = path_shade(sc, cam_pos, rp.max_depth, skey, ps, hit, LightsNone{});
-                    if (alive) store_path(wp, path, ps, pix, sl);
-                    else wp.rad[path] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, 0.f);
-                } else {                                                                               // DIFFUSE
+                // the record keeps the final hit and the clamped accumulator for the shade kernels
+                if (id != id0) { wp.po[path].w = cur; wp.pd[path].w = __uint_as_float(id); }
+                if (__float_as_uint(acc0.x) != __float_as_uint(ps.acc.x) || __float_as_uint(acc0.y) != __float_as_uint(ps.acc.y) ||
+                    __float_as_uint(acc0.z) != __float_as_uint(ps.acc.z))
+                    wp.pacc[path] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, __uint_as_float(pix));
+                if (type != 0u) diel = true;                                                           // DIELECTRIC bin
+                else {                                                                                 // DIFFUSE bin
                     diff = true;
                     dim0 = ps.depth * DIMS_PER_BOUNCE;
                     sf = surface_of(sc, ps.o, ps.d, hit);
                     dmat = load_material(sc, sf.mat);
-                    if (id != id0) { wp.po[path].w = cur; wp.pd[path].w = __uint_as_float(id); }
-                    if (__float_as_uint(acc0.x) != __float_as_uint(ps.acc.x) || __float_as_uint(acc0.y) != __float_as_uint(ps.acc.y) ||
-                        __float_as_uint(acc0.z) != __float_as_uint(ps.acc.z))
-                        wp.pacc[path] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, __uint_as_float(pix));
                 }
             }
         }
-        push(wp.q_active[next], wp.cnt + (next ? C_ACTIVE1 : C_ACTIVE0), alive, path);
+        push(wp.q_diel, wp.cnt + C_DIEL, diel, path);
         push(wp.q_diff, wp.cnt + C_DIFF, diff, path);
         for (uint32_t l = 0; l < sc.n_lights; ++l) {
             bool queue_it = false;
@@ -371,9 +369,11 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_SHADE_MINBLOCKS) k_wf_c
                 float cur = t;
                 if (!occluded) occluded = trace_tris<true>(sc, sf.P, L, cur, h);
                 if (!occluded) { cur = t; occluded = trace_planes<true>(sc, sf.P, L, cur, h); }
-                wp.sh[(size_t)path * sc.n_lights + l] = make_float4(L.x, L.y, L.z, t);
-                wp.term[(size_t)path * sc.n_lights + l] = make_float4(term.x, term.y, term.z, 0.f);
-                if (occluded) wp.occ[(size_t)path * sc.n_lights + l] = 1;
+                wp.occ[(size_t)path * sc.n_lights + l] = occluded ? 1 : 0;     // `shadow` overwrites the 0 of queued rays
+                if (!occluded) {
+                    wp.sh[(size_t)path * sc.n_lights + l] = make_float4(L.x, L.y, L.z, t);
+                    wp.term[(size_t)path * sc.n_lights + l] = make_float4(term.x, term.y, term.z, 0.f);
+                }
                 queue_it = !occluded;
             }
             push(wp.q_shadow, wp.cnt + C_SHADOW, queue_it, (path << 4) | l);
@@ -386,23 +386,30 @@ struct LightsStored {    // the terms were evaluated by classify, the occlusion 
     const uint8_t *occ; const float4 *term;
     VKRT_DEV V3 operator()(uint32_t l, const Surface &, const Material &) const { return occ[l] != 0 ? v3(0.0f) : xyz(term[l]); }
 };
-// ---- shade the diffuse bin (:451-513) with the occlusion flags + Russian roulette (:545-549) ---------
+// ---- shade one material bin + Russian roulette (:545-549): DIFFUSE (:451-513) uses the stored light terms and
+// occlusion flags, DIELECTRIC (:514-542) needs no light -----------------------------------------------------
+template <bool DIFFUSE>
 __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_SHADE_MINBLOCKS) k_wf_shade(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
                                                       const __grid_constant__ WaveParams wp, uint32_t next)
 {
-    const uint32_t n = wp.cnt[C_DIFF];
+    const uint32_t *queue = DIFFUSE ? wp.q_diff : wp.q_diel;
+    const uint32_t n = wp.cnt[DIFFUSE ? C_DIFF : C_DIEL];
     const V3 cam_pos = v3(rp.fd.camera.pos.x, rp.fd.camera.pos.y, rp.fd.camera.pos.z);
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t i = base + threadIdx.x;
         bool alive = false;
         uint32_t path = 0;
         if (i < n) {
-            path = wp.q_diff[i];
+            path = queue[i];
             PathState ps; Hit hit; uint32_t pix, sl;
             load_path(wp, path, ps, hit, pix, sl);
             const uint32_t skey = sample_key(rp.fkey, pix, wp.s0 + sl);
-            const LightsStored lights{wp.occ + (size_t)path * sc.n_lights, wp.term + (size_t)path * sc.n_lights};
-            alive = path_shade(sc, cam_pos, rp.max_depth, skey, ps, hit, lights);
+            if (DIFFUSE) {
+                const LightsStored lights{wp.occ + (size_t)path * sc.n_lights, wp.term + (size_t)path * sc.n_lights};
+                alive = path_shade(sc, cam_pos, rp.max_depth, skey, ps, hit, lights);
+            } else {
+                alive = path_shade(sc, cam_pos, rp.max_depth, skey, ps, hit, LightsNone{});
+            }
             if (alive) store_path(wp, path, ps, pix, sl);
             else wp.rad[path] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, 0.f);
         }
@@ -526,11 +533,12 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
             if (depth > 0) {       // depth 0 was traced once per pixel by `generate`
                 k_extend<<<grid_e, VKRT_TRACE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_active[cur], n_active, wb.counts + C_HEAD_EXTEND, depth); ++launches;
             }
-            k_wf_classify<<<grid_shade, VKRT_SHADE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_active[cur], n_active, nxt); ++launches;
+            k_wf_classify<<<grid_shade, VKRT_SHADE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_active[cur], n_active); ++launches;
+            k_wf_shade<false><<<grid_shade, VKRT_SHADE_BLOCK, 0, st>>>(sc, rp, wp, nxt); ++launches;
             if (sc.n_lights) {
                 k_shadow<<<grid_s, VKRT_TRACE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_shadow, wb.counts + C_SHADOW, wb.counts + C_HEAD_SHADOW, depth); ++launches;
             }
-            k_wf_shade<<<grid_shade, VKRT_SHADE_BLOCK, 0, st>>>(sc, rp, wp, nxt); ++launches;
+            k_wf_shade<true><<<grid_shade, VKRT_SHADE_BLOCK, 0, st>>>(sc, rp, wp, nxt); ++launches;
         }
         k_wf_reduce<<<(wp.n_slots + 255u) / 256u, 256, 0, st>>>(rp, wp, wb.frame_sum, wv == 0, wv + 1 == n_waves); ++launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
