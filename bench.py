@@ -289,12 +289,17 @@ def run_ours(args):
     total_rays = float(rays[0].item())
     value = total_rays / (ms_total * 1e-3) / 1e6
 
-    # per-launch duration of the dominant kernel, live, on its own stream (library-side CUDA events)
+    # duration of the dominant kernel(s), live: the library brackets every traversal-kernel launch (the megakernel,
+    # or each extend / shadow launch of the wavefront) with CUDA events on the stream it launches on
+    trav_ms, trav_launches = [], 0
     for i in range(min(args.steps, 5)):
         step(args.warmup + i)
+        ms, nl = r.last_frame_traversal_timing()
+        trav_ms.append(ms); trav_launches = nl
         trace_ms.append(r.last_frame_timing()[0])
     barrier()
-    kernel_ms = statistics.mean(trace_ms)
+    kernel_ms = statistics.mean(trav_ms)
+    frame_kernels_ms = statistics.mean(trace_ms)
 
     # -------- end-to-end through the public API with host buffers ("e2e") -----------------------
     barrier()
@@ -316,20 +321,33 @@ def run_ours(args):
         rs.draw(frame_data_for(V, w, h, args.warmup + i))
     sc = rs.counters()
     rs.close()
-    owned_px = n_px / world
-    # per launch: 64 B per BVH node fetched (leaf spheres are embedded in the node: no extra bytes), per nearest hit
-    # 16 B sphere + 4 B material id + 36 B material, per shadow ray 16 B light sphere + 12 B emissive, 16 B accumulator store
-    alg_bytes = (sc.node_visits * 64 + sc.closest_rays * (16 + 4 + 36) + sc.shadow_rays * (16 + 12)) / n_stat + owned_px * 16
+    traversed = (sc.closest_rays - sc.shared_primary_rays) + (sc.shadow_rays - sc.zero_term_shadow_rays)
+    mega = variant == V.VARIANT_MEGAKERNEL
+    # algorithmic bytes of the traversal kernels per frame: 64 B per BVH node visited + 16 B per
+    # sphere fetched at a leaf + per traversed ray its 32 B record read (origin, direction) and 8 B result write
+    # (wavefront) / per pixel the 16 B accumulator store (megakernel, which also shades: + 56 B per nearest hit for
+    # sphere, material id and material)
+    alg_bytes = (sc.node_visits * 64 + sc.leaf_tests * 16) / n_stat
+    if mega:
+        alg_bytes += sc.closest_rays * (16 + 4 + 36) / n_stat + (n_px / world) * 16
+    else:
+        alg_bytes += traversed * (32 + 8) / n_stat
     hbm_peak, peak_src = measured_peaks()
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_path_mega" if variant == V.VARIANT_MEGAKERNEL else "wavefront extend+shade",
+    traffic = ncu_traffic(args.workload + ("_mega" if mega else "_wavefront"))
+    roofline = {"bound": "hbm", "kernel": "k_path_mega<BVH>" if mega else "k_wf_trace<ANY,BVH> (extend + shadow launches of one frame)",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
-                "nodes_per_ray": sc.node_visits / max(sc.closest_rays + sc.shadow_rays, 1),
-                "leaf_tests_per_ray": sc.leaf_tests / max(sc.closest_rays + sc.shadow_rays, 1),
-                "note": "scene + BVH (%.1f MB) is L2-resident on B200: the bytes are served by L1/L2, so frac is vs HBM only "
-                        "for reference; the kernel is latency/divergence-bound (DESIGN.md)" % (bvh.n_nodes * 64 / 1e6)}
+                "traffic": traffic, "peak_source": peak_src,
+                "launches_per_frame": trav_launches, "kernel_ms_per_frame": kernel_ms,
+                "kernel_ms_per_launch": kernel_ms / max(trav_launches, 1),
+                "algorithmic_bytes_per_frame": alg_bytes, "algorithmic_bytes_per_launch": alg_bytes / max(trav_launches, 1),
+                "share_of_frame": kernel_ms / max(frame_kernels_ms, 1e-9),
+                "nodes_per_traversed_ray": sc.node_visits / max(traversed, 1),
+                "leaf_tests_per_traversed_ray": sc.leaf_tests / max(traversed, 1),
+                "note": "traffic = ncu dram bytes per frame for the same launches (profiles/traffic.json). The tree (%.1f MB) is "
+                        "L2/L1-resident, so achieved can exceed what DRAM delivers; the limiter is L1TEX request throughput + "
+                        "traversal divergence (DESIGN.md section 4), the HBM fraction is the contract's reference number"
+                        % (bvh.n_nodes * 64 / 1e6)}
 
     if rank == 0:
         cpu = None

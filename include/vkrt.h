@@ -219,6 +219,11 @@ VKRT_API vkrt_error vkrt_reset_counters(vkrt_ctx *ctx);
 VKRT_API vkrt_error vkrt_last_frame_timing(vkrt_ctx *ctx, float *trace_ms, float *total_ms,
                                            uint32_t *n_launches);
 
+/* Device milliseconds summed over the traversal-kernel launches of the last frame (the megakernel's one
+ * launch, or every extend / shadow launch of the wavefront), each bracketed by its own CUDA events, and
+ * how many launches that was.  This is the duration bench.py's roofline divides by. */
+VKRT_API vkrt_error vkrt_last_frame_traversal_timing(vkrt_ctx *ctx, float *traversal_ms, uint32_t *n_launches);
+
 /* ------------------------------------------------------------------------- */
 /* BVH introspection (tests, DESIGN.md byte accounting)                       */
 /* ------------------------------------------------------------------------- */

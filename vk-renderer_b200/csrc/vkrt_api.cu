@@ -565,6 +565,28 @@ VKRT_API vkrt_error vkrt_last_frame_timing(vkrt_ctx *c, float *trace_ms, float *
     return VKRT_SUCCESS;
 }
 
+VKRT_API vkrt_error vkrt_last_frame_traversal_timing(vkrt_ctx *c, float *traversal_ms, uint32_t *n_launches)
+{
+    if (!c) return VKRT_BAD_ARG;
+    if (!c->timing_valid) return fail(c, VKRT_BAD_ARG, "no frame drawn yet");
+    DeviceGuard g(c->info.device_id);
+    CU(c, cudaEventSynchronize(c->ev_end));
+    float sum = 0.f; uint32_t n = 0;
+    if (c->info.integrator == VKRT_INTEGRATOR_PATH && c->info.variant == VKRT_VARIANT_WAVEFRONT && c->wave_ready) {
+        for (uint32_t i = 0; i + 1 < c->wave.n_ev; i += 2) {
+            float ms = 0.f;
+            CU(c, cudaEventElapsedTime(&ms, c->wave.ev[i], c->wave.ev[i + 1]));
+            sum += ms; ++n;
+        }
+    } else {
+        CU(c, cudaEventElapsedTime(&sum, c->ev_trace0, c->ev_trace1));
+        n = 1;
+    }
+    if (traversal_ms) *traversal_ms = sum;
+    if (n_launches) *n_launches = n;
+    return VKRT_SUCCESS;
+}
+
 // ---- sharding -------------------------------------------------------------------------------------
 VKRT_API vkrt_error vkrt_shard_floats(vkrt_ctx *c, uint32_t tile_rank, size_t *n_floats)
 {

@@ -55,6 +55,9 @@ struct WaveBuffers {
     uint32_t *queue_shadow;       // (path << 4 | light) items that still need the sphere any-hit query
     float4 *frame_sum;            // running per-slot sum when a frame needs more than one wave
     uint32_t shadow_lights;
+    // CUDA-event pairs around every traversal-kernel launch of the last frame (roofline timing)
+    cudaEvent_t ev[128];
+    uint32_t n_ev, ev_created;
 };
 cudaError_t wave_alloc(WaveBuffers &wb, size_t capacity);
 void wave_free(WaveBuffers &wb);

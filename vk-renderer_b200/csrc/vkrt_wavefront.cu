@@ -467,6 +467,7 @@ void wave_free(WaveBuffers &wb)
     cudaFree(wb.ray_o); cudaFree(wb.ray_d); cudaFree(wb.acc); cudaFree(wb.mask); cudaFree(wb.sample_rad);
     cudaFree(wb.queue[0]); cudaFree(wb.queue[1]); cudaFree(wb.queue_mat[0]); cudaFree(wb.queue_mat[1]); cudaFree(wb.counts);
     cudaFree(wb.shadow); cudaFree(wb.occ); cudaFree(wb.frame_sum); cudaFree(wb.queue_shadow); cudaFree(wb.term);
+    for (uint32_t i = 0; i < wb.ev_created; ++i) cudaEventDestroy(wb.ev[i]);
     wb = WaveBuffers{};
 }
 
@@ -509,6 +510,11 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
     const unsigned grid_e = (unsigned)(sm_count * (occ_e > 0 ? occ_e : 1)), grid_s = (unsigned)(sm_count * (occ_s > 0 ? occ_s : 1));
     const unsigned grid_shade = (unsigned)sm_count * 8u * (256u / VKRT_SHADE_BLOCK);
 
+    if (!wb.ev_created) {
+        for (uint32_t i = 0; i < 128; ++i) if ((e = cudaEventCreate(&wb.ev[i])) != cudaSuccess) return e; else wb.ev_created = i + 1;
+    }
+    wb.n_ev = 0;
+    auto ev_mark = [&]() { if (wb.n_ev < 128) cudaEventRecord(wb.ev[wb.n_ev++], st); };
     for (uint32_t wv = 0; wv < n_waves; ++wv) {
         WaveParams wp{};
         wp.po = wb.ray_o; wp.pd = wb.ray_d; wp.pacc = wb.acc; wp.pmask = wb.mask; wp.sh = wb.shadow; wp.term = wb.term; wp.rad = wb.sample_rad;
@@ -531,12 +537,16 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
             const uint32_t *n_active = wb.counts + (cur ? C_ACTIVE1 : C_ACTIVE0);
             k_wf_reset<<<1, 1, 0, st>>>(wb.counts, nxt); ++launches;
             if (depth > 0) {       // depth 0 was traced once per pixel by `generate`
+                ev_mark();
                 k_extend<<<grid_e, VKRT_TRACE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_active[cur], n_active, wb.counts + C_HEAD_EXTEND, depth); ++launches;
+                ev_mark();
             }
             k_wf_classify<<<grid_shade, VKRT_SHADE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_active[cur], n_active); ++launches;
             k_wf_shade<false><<<grid_shade, VKRT_SHADE_BLOCK, 0, st>>>(sc, rp, wp, nxt); ++launches;
             if (sc.n_lights) {
+                ev_mark();
                 k_shadow<<<grid_s, VKRT_TRACE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_shadow, wb.counts + C_SHADOW, wb.counts + C_HEAD_SHADOW, depth); ++launches;
+                ev_mark();
             }
             k_wf_shade<true><<<grid_shade, VKRT_SHADE_BLOCK, 0, st>>>(sc, rp, wp, nxt); ++launches;
         }

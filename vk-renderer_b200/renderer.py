@@ -163,6 +163,11 @@ class Renderer:
         self._ck(self.lib.vkrt_last_frame_timing(self.ctx, C.byref(a), C.byref(b), C.byref(n)))
         return a.value, b.value, n.value
 
+    def last_frame_traversal_timing(self):
+        a, n = C.c_float(), C.c_uint32()
+        self._ck(self.lib.vkrt_last_frame_traversal_timing(self.ctx, C.byref(a), C.byref(n)))
+        return a.value, n.value
+
     def stream_ptr(self):
         s = C.c_void_p()
         self._ck(self.lib.vkrt_get_stream(self.ctx, C.byref(s)))
