@@ -43,13 +43,15 @@
 
 namespace vkrt {
 
-enum { C_ACTIVE0 = 0, C_ACTIVE1 = 1, C_DIEL = 2, C_DIFF = 3, C_SHADOW = 4, C_HEAD_EXTEND = 5, C_HEAD_SHADOW = 6, C_N = 8 };
+// one counter set per depth iteration (no reset launches): paths entering the depth, the material bins, the
+// shadow-ray queue and the two work-fetch heads; survivors are counted in the NEXT depth's set
+enum { C_ACTIVE = 0, C_DIEL = 2, C_DIFF = 3, C_SHADOW = 4, C_HEAD_EXTEND = 5, C_HEAD_SHADOW = 6, C_N = 8, C_SETS = 257 };
 
 struct WaveParams {
     float4 *po, *pd, *pacc, *pmask, *sh, *term, *rad;
     uint32_t *q_active[2], *q_diel, *q_diff, *q_shadow;
     uint8_t *occ;
-    uint32_t *cnt;
+    uint32_t *cnt, *cnt_next;    // counter set of this depth / of the next depth
     uint32_t s0, S;          // first sample of the wave, samples per pixel in the wave
     uint32_t n_slots;        // = RenderParams.n_work
     uint32_t n_lights;
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ Dev
             wp.pacc[p] = make_float4(0.f, 0.f, 0.f, __uint_as_float(pix));
             wp.pmask[p] = make_float4(1.f, 1.f, 1.f, __uint_as_float(sl << 8));
         }
-        uint32_t *const qs[1] = {wp.q_active[0]}; uint32_t *const cs[1] = {wp.cnt + C_ACTIVE0};
+        uint32_t *const qs[1] = {wp.q_active[0]}; uint32_t *const cs[1] = {wp.cnt + C_ACTIVE};
         const bool ws[1] = {valid}; const uint32_t vs[1] = {p};
         push_block<1>(qs, cs, ws, vs);
     }
@@ -386,15 +388,13 @@ struct LightsStored {    // the terms were evaluated by classify, the occlusion 
     const uint8_t *occ; const float4 *term;
     VKRT_DEV V3 operator()(uint32_t l, const Surface &, const Material &) const { return occ[l] != 0 ? v3(0.0f) : xyz(term[l]); }
 };
-// ---- shade one material bin + Russian roulette (:545-549): DIFFUSE (:451-513) uses the stored light terms and
-// occlusion flags, DIELECTRIC (:514-542) needs no light -----------------------------------------------------
+// ---- shade both material bins + Russian roulette (:545-549): the DIELECTRIC bin (:514-542) needs no light, the
+// DIFFUSE bin (:451-513) uses the stored light terms and occlusion flags; survivors go to the next depth's queue
 template <bool DIFFUSE>
-__global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_SHADE_MINBLOCKS) k_wf_shade(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
-                                                      const __grid_constant__ WaveParams wp, uint32_t next)
+VKRT_DEV void shade_bin(const DevScene &sc, const RenderParams &rp, const WaveParams &wp, uint32_t next, V3 cam_pos)
 {
     const uint32_t *queue = DIFFUSE ? wp.q_diff : wp.q_diel;
     const uint32_t n = wp.cnt[DIFFUSE ? C_DIFF : C_DIEL];
-    const V3 cam_pos = v3(rp.fd.camera.pos.x, rp.fd.camera.pos.y, rp.fd.camera.pos.z);
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t i = base + threadIdx.x;
         bool alive = false;
@@ -413,15 +413,15 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_SHADE_MINBLOCKS) k_wf_s
             if (alive) store_path(wp, path, ps, pix, sl);
             else wp.rad[path] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, 0.f);
         }
-        push(wp.q_active[next], wp.cnt + (next ? C_ACTIVE1 : C_ACTIVE0), alive, path);
+        push(wp.q_active[next], wp.cnt_next + C_ACTIVE, alive, path);
     }
 }
-
-// resets the per-iteration counters (one tiny launch instead of several memsets)
-__global__ void k_wf_reset(uint32_t *cnt, uint32_t clear_active)
+__global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_SHADE_MINBLOCKS) k_wf_shade(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
+                                                      const __grid_constant__ WaveParams wp, uint32_t next)
 {
-    cnt[C_DIEL] = 0; cnt[C_DIFF] = 0; cnt[C_SHADOW] = 0; cnt[C_HEAD_EXTEND] = 0; cnt[C_HEAD_SHADOW] = 0;
-    cnt[clear_active ? C_ACTIVE1 : C_ACTIVE0] = 0;
+    const V3 cam_pos = v3(rp.fd.camera.pos.x, rp.fd.camera.pos.y, rp.fd.camera.pos.z);
+    shade_bin<false>(sc, rp, wp, next, cam_pos);
+    shade_bin<true>(sc, rp, wp, next, cam_pos);
 }
 
 // ---- reduce: per pixel, add the wave's samples in sample order -------------------------------------
@@ -457,7 +457,7 @@ cudaError_t wave_alloc(WaveBuffers &wb, size_t capacity)
     A(wb.queue[1], capacity * sizeof(uint32_t));
     A(wb.queue_mat[0], capacity * sizeof(uint32_t));
     A(wb.queue_mat[1], capacity * sizeof(uint32_t));
-    A(wb.counts, 64 * sizeof(uint32_t));
+    A(wb.counts, (size_t)C_SETS * C_N * sizeof(uint32_t));
 #undef A
     return cudaSuccess;
 }
@@ -520,12 +520,12 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
         wp.po = wb.ray_o; wp.pd = wb.ray_d; wp.pacc = wb.acc; wp.pmask = wb.mask; wp.sh = wb.shadow; wp.term = wb.term; wp.rad = wb.sample_rad;
         wp.q_active[0] = wb.queue[0]; wp.q_active[1] = wb.queue[1]; wp.q_diel = wb.queue_mat[0]; wp.q_diff = wb.queue_mat[1];
         wp.q_shadow = wb.queue_shadow;
-        wp.occ = wb.occ; wp.cnt = wb.counts;
+        wp.occ = wb.occ; wp.cnt = wb.counts; wp.cnt_next = wb.counts + C_N;
         wp.s0 = rp.s_begin + wv * S;
         wp.S = (wp.s0 + S <= rp.s_end) ? S : (rp.s_end - wp.s0);
         wp.n_slots = rp.n_work;
         wp.n_lights = sc.n_lights;
-        if ((e = cudaMemsetAsync(wb.counts, 0, 64 * sizeof(uint32_t), st)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(wb.counts, 0, (size_t)(rp.max_depth + 1) * C_N * sizeof(uint32_t), st)) != cudaSuccess) return e;
         {
             void (*k_gen)(const DevScene, const RenderParams, const WaveParams) =
                 bvh ? (stats ? k_wf_generate<true, true> : k_wf_generate<true, false>)
@@ -534,21 +534,21 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
         }
         for (uint32_t depth = 0; depth < rp.max_depth; ++depth) {
             const uint32_t cur = depth & 1u, nxt = cur ^ 1u;
-            const uint32_t *n_active = wb.counts + (cur ? C_ACTIVE1 : C_ACTIVE0);
-            k_wf_reset<<<1, 1, 0, st>>>(wb.counts, nxt); ++launches;
+            wp.cnt = wb.counts + (size_t)depth * C_N;
+            wp.cnt_next = wp.cnt + C_N;
+            const uint32_t *n_active = wp.cnt + C_ACTIVE;
             if (depth > 0) {       // depth 0 was traced once per pixel by `generate`
                 ev_mark();
-                k_extend<<<grid_e, VKRT_TRACE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_active[cur], n_active, wb.counts + C_HEAD_EXTEND, depth); ++launches;
+                k_extend<<<grid_e, VKRT_TRACE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_active[cur], n_active, wp.cnt + C_HEAD_EXTEND, depth); ++launches;
                 ev_mark();
             }
             k_wf_classify<<<grid_shade, VKRT_SHADE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_active[cur], n_active); ++launches;
-            k_wf_shade<false><<<grid_shade, VKRT_SHADE_BLOCK, 0, st>>>(sc, rp, wp, nxt); ++launches;
             if (sc.n_lights) {
                 ev_mark();
-                k_shadow<<<grid_s, VKRT_TRACE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_shadow, wb.counts + C_SHADOW, wb.counts + C_HEAD_SHADOW, depth); ++launches;
+                k_shadow<<<grid_s, VKRT_TRACE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_shadow, wp.cnt + C_SHADOW, wp.cnt + C_HEAD_SHADOW, depth); ++launches;
                 ev_mark();
             }
-            k_wf_shade<true><<<grid_shade, VKRT_SHADE_BLOCK, 0, st>>>(sc, rp, wp, nxt); ++launches;
+            k_wf_shade<<<grid_shade, VKRT_SHADE_BLOCK, 0, st>>>(sc, rp, wp, nxt); ++launches;
         }
         k_wf_reduce<<<(wp.n_slots + 255u) / 256u, 256, 0, st>>>(rp, wp, wb.frame_sum, wv == 0, wv + 1 == n_waves); ++launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
