@@ -24,6 +24,10 @@ static_assert(sizeof(vkrt_triangle) == 48, "Triangle must be 48 B (ref: Include/
 static_assert(sizeof(vkrt_material) == 48 && sizeof(vkrt_sphere) == 16 && sizeof(vkrt_plane) == 16, "scene records");
 static_assert(sizeof(DevScene) <= 1024 && sizeof(RenderParams) <= 512, "kernel parameter budget");
 
+#ifndef VKRT_WAVE_LANES
+#define VKRT_WAVE_LANES 2      // wavefront: waves of a frame alternate between this many buffer sets / streams
+#endif
+
 static thread_local std::string g_create_error;
 
 struct vkrt_ctx {
@@ -66,7 +70,7 @@ struct vkrt_ctx {
     uint32_t *d_work_head = nullptr;
     float4 *d_packed = nullptr;
     uint64_t frames = 0;
-    WaveBuffers wave{};
+    WaveEngine wave{};
     bool wave_ready = false;
 
     cudaEvent_t ev_begin = nullptr, ev_trace0 = nullptr, ev_trace1 = nullptr, ev_end = nullptr;
@@ -247,7 +251,7 @@ VKRT_API vkrt_error vkrt_destroy(vkrt_ctx *c)
     cudaFree(c->bvh.nodes); cudaFree(c->bvh.qnodes); cudaFree(c->d_accum); cudaFree(c->d_hit_ids);
     for (auto p : c->d_rgba) cudaFree(p);
     cudaFree(c->d_counters); cudaFree(c->d_work_head); cudaFree(c->d_packed);
-    if (c->wave_ready) wave_free(c->wave);
+    if (c->wave_ready) wave_engine_free(c->wave);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_trace0) cudaEventDestroy(c->ev_trace0);
     if (c->ev_trace1) cudaEventDestroy(c->ev_trace1);
@@ -421,11 +425,14 @@ VKRT_API vkrt_error vkrt_draw(vkrt_ctx *c, const vkrt_frame_data *frame)
             CU(c, launch_whitted(c->dev, rp, c->use_bvh, stats, c->stream)); ++launches;
         } else if (c->info.variant == VKRT_VARIANT_WAVEFRONT) {
             if (!c->wave_ready) {
-                // up to 16 samples of every owned pixel per wave, at most 64 Mi path records (~7 GB of HBM)
+                // two lanes of up to 8 samples of every owned pixel each (one lane when spp == 1), at most
+                // 32 Mi path records per lane (~3.5 GB of HBM)
                 const size_t slots = (size_t)c->owned_tiles * TILE_PX;
-                size_t per_wave = c->spp < 16 ? c->spp : 16;
-                while (per_wave > 1 && slots * per_wave > ((size_t)64 << 20)) --per_wave;
-                CU(c, wave_alloc(c->wave, slots * per_wave));
+                const uint32_t lanes = c->spp >= 2 ? VKRT_WAVE_LANES : 1;
+                size_t per_wave = (c->spp + lanes - 1) / lanes;
+                if (per_wave > 16 / lanes) per_wave = 16 / lanes;
+                while (per_wave > 1 && slots * per_wave > ((size_t)64 << 20) / lanes) --per_wave;
+                CU(c, wave_engine_init(c->wave, slots * per_wave, lanes));
                 c->wave_ready = true;
             }
             uint32_t nl = 0;
@@ -573,11 +580,12 @@ VKRT_API vkrt_error vkrt_last_frame_traversal_timing(vkrt_ctx *c, float *travers
     CU(c, cudaEventSynchronize(c->ev_end));
     float sum = 0.f; uint32_t n = 0;
     if (c->info.integrator == VKRT_INTEGRATOR_PATH && c->info.variant == VKRT_VARIANT_WAVEFRONT && c->wave_ready) {
-        for (uint32_t i = 0; i + 1 < c->wave.n_ev; i += 2) {
-            float ms = 0.f;
-            CU(c, cudaEventElapsedTime(&ms, c->wave.ev[i], c->wave.ev[i + 1]));
-            sum += ms; ++n;
-        }
+        for (uint32_t l = 0; l < c->wave.n_lanes; ++l)
+            for (uint32_t i = 0; i + 1 < c->wave.lane[l].n_ev; i += 2) {
+                float ms = 0.f;
+                CU(c, cudaEventElapsedTime(&ms, c->wave.lane[l].ev[i], c->wave.lane[l].ev[i + 1]));
+                sum += ms; ++n;
+            }
     } else {
         CU(c, cudaEventElapsedTime(&sum, c->ev_trace0, c->ev_trace1));
         n = 1;

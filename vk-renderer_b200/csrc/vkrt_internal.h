@@ -53,7 +53,6 @@ struct WaveBuffers {
     float4 *term;                 // their unoccluded contributions (evaluated before the ray is queued)
     uint8_t *occ;                 // their any-hit results
     uint32_t *queue_shadow;       // (path << 4 | light) items that still need the sphere any-hit query
-    float4 *frame_sum;            // running per-slot sum when a frame needs more than one wave
     uint32_t shadow_lights;
     // CUDA-event pairs around every traversal-kernel launch of the last frame (roofline timing)
     cudaEvent_t ev[128];
@@ -61,7 +60,17 @@ struct WaveBuffers {
 };
 cudaError_t wave_alloc(WaveBuffers &wb, size_t capacity);
 void wave_free(WaveBuffers &wb);
-cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, WaveBuffers &wb, bool bvh, bool stats,
+// up to two lanes (buffer set + stream) whose waves overlap on the GPU
+struct WaveEngine {
+    WaveBuffers lane[2];
+    cudaStream_t stream[2];
+    cudaEvent_t ev_fork, ev_reduce[2];
+    float4 *frame_sum;            // running per-slot sum across the waves of a frame
+    uint32_t n_lanes;
+};
+cudaError_t wave_engine_init(WaveEngine &eng, size_t lane_capacity, uint32_t n_lanes);
+void wave_engine_free(WaveEngine &eng);
+cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, WaveEngine &eng, bool bvh, bool stats,
                                   int sm_count, cudaStream_t st, uint32_t *n_launches);
 
 // vkrt_bvh.cu

@@ -466,23 +466,15 @@ void wave_free(WaveBuffers &wb)
 {
     cudaFree(wb.ray_o); cudaFree(wb.ray_d); cudaFree(wb.acc); cudaFree(wb.mask); cudaFree(wb.sample_rad);
     cudaFree(wb.queue[0]); cudaFree(wb.queue[1]); cudaFree(wb.queue_mat[0]); cudaFree(wb.queue_mat[1]); cudaFree(wb.counts);
-    cudaFree(wb.shadow); cudaFree(wb.occ); cudaFree(wb.frame_sum); cudaFree(wb.queue_shadow); cudaFree(wb.term);
+    cudaFree(wb.shadow); cudaFree(wb.occ); cudaFree(wb.queue_shadow); cudaFree(wb.term);
     for (uint32_t i = 0; i < wb.ev_created; ++i) cudaEventDestroy(wb.ev[i]);
     wb = WaveBuffers{};
 }
 
-cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, WaveBuffers &wb, bool bvh, bool stats,
-                                  int sm_count, cudaStream_t st, uint32_t *n_launches)
+// lazily sizes the per-scene buffers of one lane
+static cudaError_t lane_prepare(WaveBuffers &wb, uint32_t nl)
 {
     cudaError_t e;
-    uint32_t launches = 0;
-    const uint32_t spp = rp.s_end - rp.s_begin;
-    const uint32_t nl = sc.n_lights ? sc.n_lights : 1;
-    // samples per wave: as many as fit the path capacity
-    uint32_t S = (uint32_t)(wb.capacity / rp.n_work);
-    if (S == 0 || wb.capacity >= ((size_t)1 << 28)) return cudaErrorMemoryAllocation;   // shadow items pack path << 4
-    if (S > spp) S = spp;
-    // shadow-ray storage depends on the light count of the scene: (re)allocate lazily
     if (wb.shadow_lights < nl) {
         cudaFree(wb.shadow); cudaFree(wb.occ); cudaFree(wb.queue_shadow); cudaFree(wb.term);
         wb.shadow = nullptr; wb.occ = nullptr; wb.queue_shadow = nullptr; wb.term = nullptr;
@@ -492,9 +484,62 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
         if ((e = cudaMalloc((void **)&wb.queue_shadow, wb.capacity * nl * sizeof(uint32_t))) != cudaSuccess) return e;
         wb.shadow_lights = nl;
     }
+    if (!wb.ev_created) {
+        for (uint32_t i = 0; i < 128; ++i) if ((e = cudaEventCreate(&wb.ev[i])) != cudaSuccess) return e; else wb.ev_created = i + 1;
+    }
+    wb.n_ev = 0;
+    return cudaSuccess;
+}
+
+cudaError_t wave_engine_init(WaveEngine &eng, size_t lane_capacity, uint32_t n_lanes)
+{
+    cudaError_t e;
+    eng = WaveEngine{};
+    eng.n_lanes = n_lanes;
+    for (uint32_t l = 0; l < n_lanes; ++l) {
+        if ((e = wave_alloc(eng.lane[l], lane_capacity)) != cudaSuccess) { wave_engine_free(eng); return e; }
+        if (n_lanes > 1) {
+            if ((e = cudaStreamCreateWithFlags(&eng.stream[l], cudaStreamNonBlocking)) != cudaSuccess) { wave_engine_free(eng); return e; }
+            if ((e = cudaEventCreateWithFlags(&eng.ev_reduce[l], cudaEventDisableTiming)) != cudaSuccess) { wave_engine_free(eng); return e; }
+        }
+    }
+    if (n_lanes > 1 && (e = cudaEventCreateWithFlags(&eng.ev_fork, cudaEventDisableTiming)) != cudaSuccess) { wave_engine_free(eng); return e; }
+    return cudaSuccess;
+}
+
+void wave_engine_free(WaveEngine &eng)
+{
+    for (uint32_t l = 0; l < 2; ++l) {
+        wave_free(eng.lane[l]);
+        if (eng.stream[l]) { cudaStreamSynchronize(eng.stream[l]); cudaStreamDestroy(eng.stream[l]); }
+        if (eng.ev_reduce[l]) cudaEventDestroy(eng.ev_reduce[l]);
+    }
+    if (eng.ev_fork) cudaEventDestroy(eng.ev_fork);
+    cudaFree(eng.frame_sum);
+    eng = WaveEngine{};
+}
+
+// A frame is cut into waves of S samples per pixel.  With two lanes the waves alternate between two buffer
+// sets on two streams, so the launch gaps and the drain tails of one wave's ~34 small kernels are filled by the
+// other wave's kernels (this matters most when a GPU owns only 1/8 of the tiles); the per-pixel sums are still
+// formed in sample order because the `reduce` launches are chained with events, wave after wave.
+cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, WaveEngine &eng, bool bvh, bool stats,
+                                  int sm_count, cudaStream_t st, uint32_t *n_launches)
+{
+    cudaError_t e;
+    uint32_t launches = 0;
+    const uint32_t spp = rp.s_end - rp.s_begin;
+    const uint32_t nl = sc.n_lights ? sc.n_lights : 1;
+    const uint32_t n_lanes = eng.n_lanes;
+    // samples per wave: as many as fit a lane, and at least `n_lanes` waves per frame when there are enough samples
+    uint32_t S = (uint32_t)(eng.lane[0].capacity / rp.n_work);
+    if (S == 0 || eng.lane[0].capacity >= ((size_t)1 << 28)) return cudaErrorMemoryAllocation;   // shadow items pack path << 4
+    if (S > spp) S = spp;
+    if (n_lanes > 1 && spp >= n_lanes && S > (spp + n_lanes - 1) / n_lanes) S = (spp + n_lanes - 1) / n_lanes;
     const uint32_t n_waves = (spp + S - 1) / S;
-    if (n_waves > 1 && !wb.frame_sum) {
-        if ((e = cudaMalloc((void **)&wb.frame_sum, (size_t)rp.n_work * sizeof(float4))) != cudaSuccess) return e;
+    for (uint32_t l = 0; l < n_lanes; ++l) if ((e = lane_prepare(eng.lane[l], nl)) != cudaSuccess) return e;
+    if (n_waves > 1 && !eng.frame_sum) {
+        if ((e = cudaMalloc((void **)&eng.frame_sum, (size_t)rp.n_work * sizeof(float4))) != cudaSuccess) return e;
     }
 
     auto pick_trace = [&](bool any) -> void (*)(const DevScene, const RenderParams, const WaveParams, const uint32_t *, const uint32_t *, uint32_t *, uint32_t) {
@@ -510,12 +555,16 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
     const unsigned grid_e = (unsigned)(sm_count * (occ_e > 0 ? occ_e : 1)), grid_s = (unsigned)(sm_count * (occ_s > 0 ? occ_s : 1));
     const unsigned grid_shade = (unsigned)sm_count * 8u * (256u / VKRT_SHADE_BLOCK);
 
-    if (!wb.ev_created) {
-        for (uint32_t i = 0; i < 128; ++i) if ((e = cudaEventCreate(&wb.ev[i])) != cudaSuccess) return e; else wb.ev_created = i + 1;
+    const bool fork = n_lanes > 1 && n_waves > 1;
+    if (fork) {
+        if ((e = cudaEventRecord(eng.ev_fork, st)) != cudaSuccess) return e;
+        for (uint32_t l = 0; l < n_lanes; ++l) if ((e = cudaStreamWaitEvent(eng.stream[l], eng.ev_fork, 0)) != cudaSuccess) return e;
     }
-    wb.n_ev = 0;
-    auto ev_mark = [&]() { if (wb.n_ev < 128) cudaEventRecord(wb.ev[wb.n_ev++], st); };
     for (uint32_t wv = 0; wv < n_waves; ++wv) {
+        const uint32_t lane = fork ? wv % n_lanes : 0u;
+        WaveBuffers &wb = eng.lane[lane];
+        cudaStream_t ls = fork ? eng.stream[lane] : st;
+        auto ev_mark = [&]() { if (wb.n_ev < 128) cudaEventRecord(wb.ev[wb.n_ev++], ls); };
         WaveParams wp{};
         wp.po = wb.ray_o; wp.pd = wb.ray_d; wp.pacc = wb.acc; wp.pmask = wb.mask; wp.sh = wb.shadow; wp.term = wb.term; wp.rad = wb.sample_rad;
         wp.q_active[0] = wb.queue[0]; wp.q_active[1] = wb.queue[1]; wp.q_diel = wb.queue_mat[0]; wp.q_diff = wb.queue_mat[1];
@@ -525,12 +574,12 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
         wp.S = (wp.s0 + S <= rp.s_end) ? S : (rp.s_end - wp.s0);
         wp.n_slots = rp.n_work;
         wp.n_lights = sc.n_lights;
-        if ((e = cudaMemsetAsync(wb.counts, 0, (size_t)(rp.max_depth + 1) * C_N * sizeof(uint32_t), st)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(wb.counts, 0, (size_t)(rp.max_depth + 1) * C_N * sizeof(uint32_t), ls)) != cudaSuccess) return e;
         {
             void (*k_gen)(const DevScene, const RenderParams, const WaveParams) =
                 bvh ? (stats ? k_wf_generate<true, true> : k_wf_generate<true, false>)
                     : (stats ? k_wf_generate<false, true> : k_wf_generate<false, false>);
-            k_gen<<<(wp.n_slots + 255u) / 256u, 256, 0, st>>>(sc, rp, wp); ++launches;
+            k_gen<<<(wp.n_slots + 255u) / 256u, 256, 0, ls>>>(sc, rp, wp); ++launches;
         }
         for (uint32_t depth = 0; depth < rp.max_depth; ++depth) {
             const uint32_t cur = depth & 1u, nxt = cur ^ 1u;
@@ -539,20 +588,24 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
             const uint32_t *n_active = wp.cnt + C_ACTIVE;
             if (depth > 0) {       // depth 0 was traced once per pixel by `generate`
                 ev_mark();
-                k_extend<<<grid_e, VKRT_TRACE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_active[cur], n_active, wp.cnt + C_HEAD_EXTEND, depth); ++launches;
+                k_extend<<<grid_e, VKRT_TRACE_BLOCK, 0, ls>>>(sc, rp, wp, wp.q_active[cur], n_active, wp.cnt + C_HEAD_EXTEND, depth); ++launches;
                 ev_mark();
             }
-            k_wf_classify<<<grid_shade, VKRT_SHADE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_active[cur], n_active); ++launches;
+            k_wf_classify<<<grid_shade, VKRT_SHADE_BLOCK, 0, ls>>>(sc, rp, wp, wp.q_active[cur], n_active); ++launches;
             if (sc.n_lights) {
                 ev_mark();
-                k_shadow<<<grid_s, VKRT_TRACE_BLOCK, 0, st>>>(sc, rp, wp, wp.q_shadow, wp.cnt + C_SHADOW, wp.cnt + C_HEAD_SHADOW, depth); ++launches;
+                k_shadow<<<grid_s, VKRT_TRACE_BLOCK, 0, ls>>>(sc, rp, wp, wp.q_shadow, wp.cnt + C_SHADOW, wp.cnt + C_HEAD_SHADOW, depth); ++launches;
                 ev_mark();
             }
-            k_wf_shade<<<grid_shade, VKRT_SHADE_BLOCK, 0, st>>>(sc, rp, wp, nxt); ++launches;
+            k_wf_shade<<<grid_shade, VKRT_SHADE_BLOCK, 0, ls>>>(sc, rp, wp, nxt); ++launches;
         }
-        k_wf_reduce<<<(wp.n_slots + 255u) / 256u, 256, 0, st>>>(rp, wp, wb.frame_sum, wv == 0, wv + 1 == n_waves); ++launches;
+        // the running per-pixel sum continues in wave order: wait for the previous wave's reduce
+        if (fork && wv > 0 && (e = cudaStreamWaitEvent(ls, eng.ev_reduce[(wv - 1) % n_lanes], 0)) != cudaSuccess) return e;
+        k_wf_reduce<<<(wp.n_slots + 255u) / 256u, 256, 0, ls>>>(rp, wp, eng.frame_sum, wv == 0, wv + 1 == n_waves); ++launches;
+        if (fork && (e = cudaEventRecord(eng.ev_reduce[lane], ls)) != cudaSuccess) return e;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
+    if (fork && (e = cudaStreamWaitEvent(st, eng.ev_reduce[(n_waves - 1) % n_lanes], 0)) != cudaSuccess) return e;
     if (n_launches) *n_launches = launches;
     return cudaSuccess;
 }
