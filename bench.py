@@ -223,6 +223,8 @@ def run_ours(args):
     scene, use_bvh = make_scene(V, args.workload)
     variant = V.VARIANT_WAVEFRONT if args.variant == "wavefront" else V.VARIANT_MEGAKERNEL
     tile_shard, sample_shard = shard_layout(rank, world, 1)
+    if args.shard_of > 1 and world == 1:          # diagnostic: one GPU renders tile shard 0 of N (no exchange)
+        tile_shard = (0, args.shard_of)
     stream = torch.cuda.Stream(device=device)
 
     def make_renderer(flags):
@@ -397,6 +399,7 @@ def main():
                     help="auto = wavefront for the LBVH scenes (cfg3/cfg4), megakernel for the 10-primitive default scene (cfg2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--micro", action="store_true", help="also run the FP32 / L2 microbenchmarks")
+    ap.add_argument("--shard-of", type=int, default=1, help="diagnostic (1 GPU): render only tile shard 0 of N, to size the fixed per-frame costs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -60,11 +60,11 @@ struct WaveBuffers {
 };
 cudaError_t wave_alloc(WaveBuffers &wb, size_t capacity);
 void wave_free(WaveBuffers &wb);
-// up to two lanes (buffer set + stream) whose waves overlap on the GPU
+// up to four lanes (buffer set + stream) whose waves overlap on the GPU
 struct WaveEngine {
-    WaveBuffers lane[2];
-    cudaStream_t stream[2];
-    cudaEvent_t ev_fork, ev_reduce[2];
+    WaveBuffers lane[4];
+    cudaStream_t stream[4];
+    cudaEvent_t ev_fork, ev_reduce[4];
     float4 *frame_sum;            // running per-slot sum across the waves of a frame
     uint32_t n_lanes;
 };

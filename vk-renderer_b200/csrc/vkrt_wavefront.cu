@@ -509,7 +509,7 @@ cudaError_t wave_engine_init(WaveEngine &eng, size_t lane_capacity, uint32_t n_l
 
 void wave_engine_free(WaveEngine &eng)
 {
-    for (uint32_t l = 0; l < 2; ++l) {
+    for (uint32_t l = 0; l < 4; ++l) {
         wave_free(eng.lane[l]);
         if (eng.stream[l]) { cudaStreamSynchronize(eng.stream[l]); cudaStreamDestroy(eng.stream[l]); }
         if (eng.ev_reduce[l]) cudaEventDestroy(eng.ev_reduce[l]);
