@@ -271,9 +271,11 @@ def run_ours(args):
     trace_ms = []
     barrier()
     sampler.mark_begin()
+    r.flush()
     ev0.record(stream)
     for i in range(args.steps):
         step(args.warmup + i)
+    r.flush()                      # frames in flight end on the library's lane streams: order them before ev1
     ev1.record(stream)
     barrier()
     sampler.mark_end()

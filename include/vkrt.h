@@ -145,6 +145,11 @@ VKRT_API vkrt_error vkrt_destroy(vkrt_ctx *ctx);
 VKRT_API vkrt_error vkrt_draw(vkrt_ctx *ctx, const vkrt_frame_data *frame);
 /* ref: GraphicsDevice::WaitIdle (Include/GraphicsDevice.h:96) */
 VKRT_API vkrt_error vkrt_wait_idle(vkrt_ctx *ctx);
+/* Like the reference (FRAMES_IN_FLIGHT = 2, Draw only waits for the fence of the slot it reuses,
+ * Source/GraphicsDevice.cpp:1217), consecutive vkrt_draw calls overlap on the device.  Every library call that
+ * consumes a frame waits for it by itself; vkrt_flush makes the context's stream wait for the frames in flight
+ * (device-side, no host sync) for callers that enqueue their own work or events on that stream. */
+VKRT_API vkrt_error vkrt_flush(vkrt_ctx *ctx);
 
 /* Runtime knobs that are compile-time constants in the shader (Tracer.comp:179-180). */
 VKRT_API vkrt_error vkrt_set_sampling(vkrt_ctx *ctx, uint32_t spp, uint32_t max_depth);

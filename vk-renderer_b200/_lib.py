@@ -75,6 +75,7 @@ SIGNATURES = {
     "vkrt_destroy": ([_vp], C.c_int8),
     "vkrt_draw": ([_vp, _P(FrameData)], C.c_int8),
     "vkrt_wait_idle": ([_vp], C.c_int8),
+    "vkrt_flush": ([_vp], C.c_int8),
     "vkrt_set_sampling": ([_vp, _u32, _u32], C.c_int8),
     "vkrt_set_seed": ([_vp, C.c_uint64], C.c_int8),
     "vkrt_set_frame_index": ([_vp, _u32], C.c_int8),

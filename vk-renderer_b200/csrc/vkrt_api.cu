@@ -73,7 +73,8 @@ struct vkrt_ctx {
     WaveEngine wave{};
     bool wave_ready = false;
 
-    cudaEvent_t ev_begin = nullptr, ev_trace0 = nullptr, ev_trace1 = nullptr, ev_end = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_trace0 = nullptr, ev_trace1 = nullptr, ev_end = nullptr, ev_consumed = nullptr;
+    bool pending_join = false;     // the last frame ended on a lane stream that `stream` has not waited for yet
     bool timing_valid = false;
     uint32_t last_launches = 0;
 };
@@ -111,6 +112,7 @@ vkrt_material make_mat(float r, float g, float b, float e, float rough, float me
 vkrt_error upload_scene(vkrt_ctx *c)
 {
     if (!c->scene_dirty) return VKRT_SUCCESS;
+    cudaDeviceSynchronize();          // frames in flight may still read the buffers replaced below
     for (uint32_t m : c->sphere_mat) if (m >= c->mats.size()) return fail(c, VKRT_BAD_ARG, "sphere material id out of range");
     for (uint32_t m : c->plane_mat) if (m >= c->mats.size()) return fail(c, VKRT_BAD_ARG, "plane material id out of range");
     if (!c->tris.empty() && c->tri_mat >= c->mats.size()) return fail(c, VKRT_BAD_ARG, "triangle material id out of range");
@@ -154,6 +156,15 @@ vkrt_error upload_scene(vkrt_ctx *c)
     for (size_t i = 0; i < lights.size(); ++i) d.lights[i] = lights[i];
     c->scene_dirty = false;
     return VKRT_SUCCESS;
+}
+
+// Frames of the wavefront variant end on a lane stream (two frames in flight).  Everything that consumes a frame
+// through the context's stream first makes that stream wait for the frame's completion event.
+cudaError_t join(vkrt_ctx *c)
+{
+    if (!c->pending_join) return cudaSuccess;
+    c->pending_join = false;
+    return cudaStreamWaitEvent(c->stream, c->ev_end, 0);
 }
 
 void fill_params(vkrt_ctx *c, RenderParams &rp)
@@ -236,6 +247,7 @@ VKRT_API vkrt_error vkrt_create(const vkrt_create_info *info, vkrt_ctx **out_ctx
     CC(cudaMemsetAsync(c->d_work_head, 0, 64, c->stream));
     CC(cudaEventCreate(&c->ev_begin)); CC(cudaEventCreate(&c->ev_trace0));
     CC(cudaEventCreate(&c->ev_trace1)); CC(cudaEventCreate(&c->ev_end));
+    CC(cudaEventCreateWithFlags(&c->ev_consumed, cudaEventDisableTiming));
     CC(cudaStreamSynchronize(c->stream));
 #undef CC
     *out_ctx = c;
@@ -256,6 +268,7 @@ VKRT_API vkrt_error vkrt_destroy(vkrt_ctx *c)
     if (c->ev_trace0) cudaEventDestroy(c->ev_trace0);
     if (c->ev_trace1) cudaEventDestroy(c->ev_trace1);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
+    if (c->ev_consumed) cudaEventDestroy(c->ev_consumed);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return VKRT_SUCCESS;
@@ -274,6 +287,7 @@ VKRT_API vkrt_error vkrt_reset_accum(vkrt_ctx *c)
 {
     if (!c) return VKRT_BAD_ARG;
     DeviceGuard g(c->info.device_id);
+    CU(c, join(c));
     CU(c, launch_clear_accum(c->d_accum, (size_t)c->info.width * c->info.height, c->stream));
     c->accum_valid = false;
     return VKRT_SUCCESS;
@@ -417,13 +431,22 @@ VKRT_API vkrt_error vkrt_draw(vkrt_ctx *c, const vkrt_frame_data *frame)
     const bool stats = (c->info.flags & VKRT_FLAG_STATS) != 0;
     uint32_t launches = 0;
 
-    CU(c, cudaEventRecord(c->ev_begin, c->stream));
-    CU(c, cudaMemsetAsync(c->d_work_head, 0, 64, c->stream));
-    CU(c, cudaEventRecord(c->ev_trace0, c->stream));
+    // everything enqueued on the stream so far may still read the previous frame's accumulator / AOVs / image, and
+    // so may that frame's own resolve on its lane stream: the stream joins the previous frame first (that does not
+    // hold back the new frame's lanes, which only wait for ev_consumed where they overwrite those buffers)
+    CU(c, join(c));
+    CU(c, cudaEventRecord(c->ev_consumed, c->stream));
+    cudaStream_t tail = c->stream;
+    const bool wavefront = c->info.integrator == VKRT_INTEGRATOR_PATH && c->info.variant == VKRT_VARIANT_WAVEFRONT;
+    if (!wavefront) {
+        CU(c, join(c));
+        CU(c, cudaEventRecord(c->ev_begin, c->stream));
+        CU(c, cudaMemsetAsync(c->d_work_head, 0, 64, c->stream));
+    }
     if (rp.n_work > 0 && rp.s_end > rp.s_begin) {
         if (c->info.integrator == VKRT_INTEGRATOR_WHITTED) {
             CU(c, launch_whitted(c->dev, rp, c->use_bvh, stats, c->stream)); ++launches;
-        } else if (c->info.variant == VKRT_VARIANT_WAVEFRONT) {
+        } else if (wavefront) {
             if (!c->wave_ready) {
                 // two lanes of up to 8 samples of every owned pixel each (one lane when spp == 1), at most
                 // 32 Mi path records per lane (~3.5 GB of HBM)
@@ -436,18 +459,23 @@ VKRT_API vkrt_error vkrt_draw(vkrt_ctx *c, const vkrt_frame_data *frame)
                 c->wave_ready = true;
             }
             uint32_t nl = 0;
-            CU(c, launch_path_wavefront(c->dev, rp, c->wave, c->use_bvh, stats, c->sm_count, c->stream, &nl));
+            CU(c, launch_path_wavefront(c->dev, rp, c->wave, c->use_bvh, stats, c->sm_count, c->stream, c->ev_consumed,
+                                        c->ev_begin, &tail, &nl));
             launches += nl;
         } else {
             CU(c, launch_path_mega(c->dev, rp, c->use_bvh, stats, c->sm_count, c->stream)); ++launches;
         }
+    } else if (wavefront) {
+        CU(c, join(c));
+        CU(c, cudaEventRecord(c->ev_begin, c->stream));
     }
-    CU(c, cudaEventRecord(c->ev_trace1, c->stream));
+    CU(c, cudaEventRecord(c->ev_trace1, tail));
     c->cur_target = (c->cur_target + 1) % (uint32_t)c->d_rgba.size();   // currentFrame = (currentFrame + 1) % FRAMES_IN_FLIGHT (:1341)
     if (!(c->info.flags & VKRT_FLAG_NO_RESOLVE)) {
-        CU(c, launch_resolve(rp, c->info.integrator, c->d_rgba[c->cur_target], c->stream)); ++launches;
+        CU(c, launch_resolve(rp, c->info.integrator, c->d_rgba[c->cur_target], tail)); ++launches;
     }
-    CU(c, cudaEventRecord(c->ev_end, c->stream));
+    CU(c, cudaEventRecord(c->ev_end, tail));
+    c->pending_join = (tail != c->stream);
     c->timing_valid = true;
     c->last_launches = launches;
     c->accum_valid = true;
@@ -460,6 +488,7 @@ VKRT_API vkrt_error vkrt_resolve(vkrt_ctx *c)
 {
     if (!c) return VKRT_BAD_ARG;
     DeviceGuard g(c->info.device_id);
+    CU(c, join(c));
     RenderParams rp;
     fill_params(c, rp);
     CU(c, launch_resolve(rp, c->info.integrator, c->d_rgba[c->cur_target], c->stream));
@@ -470,7 +499,17 @@ VKRT_API vkrt_error vkrt_wait_idle(vkrt_ctx *c)
 {
     if (!c) return VKRT_BAD_ARG;
     DeviceGuard g(c->info.device_id);
+    CU(c, join(c));
     CU(c, cudaStreamSynchronize(c->stream));
+    return VKRT_SUCCESS;
+}
+
+/* Makes the context's stream wait (on the device, no host sync) for every frame in flight. */
+VKRT_API vkrt_error vkrt_flush(vkrt_ctx *c)
+{
+    if (!c) return VKRT_BAD_ARG;
+    DeviceGuard g(c->info.device_id);
+    CU(c, join(c));
     return VKRT_SUCCESS;
 }
 
@@ -478,6 +517,7 @@ VKRT_API vkrt_error vkrt_wait_idle(vkrt_ctx *c)
 VKRT_API vkrt_error vkrt_get_rgba8(vkrt_ctx *c, void **dev_ptr, size_t *pitch)
 {
     if (!c || !dev_ptr) return VKRT_BAD_ARG;
+    { DeviceGuard g(c->info.device_id); CU(c, join(c)); }
     *dev_ptr = c->d_rgba[c->cur_target];
     if (pitch) *pitch = (size_t)c->info.width * 4;
     return VKRT_SUCCESS;
@@ -485,6 +525,7 @@ VKRT_API vkrt_error vkrt_get_rgba8(vkrt_ctx *c, void **dev_ptr, size_t *pitch)
 VKRT_API vkrt_error vkrt_get_accum(vkrt_ctx *c, float **dev_ptr)
 {
     if (!c || !dev_ptr) return VKRT_BAD_ARG;
+    { DeviceGuard g(c->info.device_id); CU(c, join(c)); }
     *dev_ptr = (float *)c->d_accum;
     return VKRT_SUCCESS;
 }
@@ -492,6 +533,7 @@ VKRT_API vkrt_error vkrt_get_hit_ids(vkrt_ctx *c, uint32_t **dev_ptr)
 {
     if (!c || !dev_ptr) return VKRT_BAD_ARG;
     if (!c->d_hit_ids) return fail(c, VKRT_BAD_ARG, "context created without VKRT_FLAG_HIT_IDS");
+    { DeviceGuard g(c->info.device_id); CU(c, join(c)); }
     *dev_ptr = c->d_hit_ids;
     return VKRT_SUCCESS;
 }
@@ -507,6 +549,7 @@ static vkrt_error read_back(vkrt_ctx *c, void *host, const void *dev, size_t hav
     if (!host || !dev) return fail(c, VKRT_BAD_ARG, "null buffer");
     if (bytes < have) return fail(c, VKRT_BAD_ARG, "host buffer too small");
     DeviceGuard g(c->info.device_id);
+    CU(c, join(c));
     CU(c, cudaMemcpyAsync(host, dev, have, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     return VKRT_SUCCESS;
@@ -522,6 +565,7 @@ VKRT_API vkrt_error vkrt_read_rgba8_async(vkrt_ctx *c, void *host, size_t bytes)
     const size_t have = (size_t)c->info.width * c->info.height * 4;
     if (bytes < have) return fail(c, VKRT_BAD_ARG, "host buffer too small");
     DeviceGuard g(c->info.device_id);
+    CU(c, join(c));
     CU(c, cudaMemcpyAsync(host, c->d_rgba[c->cur_target], have, cudaMemcpyDeviceToHost, c->stream));
     return VKRT_SUCCESS;
 }
@@ -542,6 +586,7 @@ VKRT_API vkrt_error vkrt_get_counters(vkrt_ctx *c, vkrt_counters *out)
     if (!c || !out) return VKRT_BAD_ARG;
     DeviceGuard g(c->info.device_id);
     unsigned long long h[CNT_N];
+    CU(c, join(c));
     CU(c, cudaMemcpyAsync(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     out->closest_rays = h[CNT_CLOSEST]; out->shadow_rays = h[CNT_SHADOW]; out->node_visits = h[CNT_NODES];
@@ -553,6 +598,7 @@ VKRT_API vkrt_error vkrt_reset_counters(vkrt_ctx *c)
 {
     if (!c) return VKRT_BAD_ARG;
     DeviceGuard g(c->info.device_id);
+    CU(c, join(c));
     CU(c, cudaMemsetAsync(c->d_counters, 0, CNT_N * sizeof(unsigned long long), c->stream));
     c->frames = 0;
     return VKRT_SUCCESS;
@@ -564,7 +610,7 @@ VKRT_API vkrt_error vkrt_last_frame_timing(vkrt_ctx *c, float *trace_ms, float *
     DeviceGuard g(c->info.device_id);
     CU(c, cudaEventSynchronize(c->ev_end));
     float a = 0.f, b = 0.f;
-    CU(c, cudaEventElapsedTime(&a, c->ev_trace0, c->ev_trace1));
+    CU(c, cudaEventElapsedTime(&a, c->ev_begin, c->ev_trace1));
     CU(c, cudaEventElapsedTime(&b, c->ev_begin, c->ev_end));
     if (trace_ms) *trace_ms = a;
     if (total_ms) *total_ms = b;
@@ -615,6 +661,7 @@ VKRT_API vkrt_error vkrt_pack_shard(vkrt_ctx *c, float **dev_ptr, size_t *n_floa
         CU(c, cudaMalloc(&c->d_packed, max_slots * sizeof(float4)));
         CU(c, cudaMemsetAsync(c->d_packed, 0, max_slots * sizeof(float4), c->stream));
     }
+    CU(c, join(c));
     RenderParams rp;
     fill_params(c, rp);
     if (rp.n_work) CU(c, launch_pack(rp, c->d_packed, c->stream));
@@ -626,6 +673,7 @@ VKRT_API vkrt_error vkrt_pack_shard_into(vkrt_ctx *c, float *dev_dst, size_t n_f
 {
     if (!c || !dev_dst) return VKRT_BAD_ARG;
     DeviceGuard g(c->info.device_id);
+    CU(c, join(c));
     RenderParams rp;
     fill_params(c, rp);
     if (n_floats < (size_t)rp.n_work * 4) return fail(c, VKRT_BAD_ARG, "shard buffer too small");
@@ -636,6 +684,7 @@ VKRT_API vkrt_error vkrt_unpack_shard(vkrt_ctx *c, const float *dev_packed, uint
 {
     if (!c || !dev_packed || tile_count == 0 || tile_rank >= tile_count) return VKRT_BAD_ARG;
     DeviceGuard g(c->info.device_id);
+    CU(c, join(c));
     CU(c, launch_unpack(c->d_accum, (const float4 *)dev_packed, c->info.width, c->info.height, tile_rank, tile_count, add, c->stream));
     c->accum_valid = true;
     return VKRT_SUCCESS;

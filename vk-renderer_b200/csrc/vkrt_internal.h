@@ -67,11 +67,18 @@ struct WaveEngine {
     cudaEvent_t ev_fork, ev_reduce[4];
     float4 *frame_sum;            // running per-slot sum across the waves of a frame
     uint32_t n_lanes;
+    uint32_t wave_seq;            // waves launched so far: lanes alternate across frame boundaries too
+    uint32_t prev_reduce_lane; bool have_prev_reduce;
 };
 cudaError_t wave_engine_init(WaveEngine &eng, size_t lane_capacity, uint32_t n_lanes);
 void wave_engine_free(WaveEngine &eng);
+// ev_consumed: recorded by the caller on `st` once everything that still reads the accumulator / AOVs of the
+// previous frame has been enqueued; only the kernels that overwrite those wait for it, so the bulk of a frame
+// overlaps the tail (and the read-back / gather) of the frame before -- two frames in flight, like the
+// reference's FRAMES_IN_FLIGHT (Source/Main.cpp:110).  *tail = the stream the frame's last kernel went to.
 cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, WaveEngine &eng, bool bvh, bool stats,
-                                  int sm_count, cudaStream_t st, uint32_t *n_launches);
+                                  int sm_count, cudaStream_t st, cudaEvent_t ev_consumed, cudaEvent_t ev_begin,
+                                  cudaStream_t *tail, uint32_t *n_launches);
 
 // vkrt_bvh.cu
 struct BvhBuild {

@@ -524,7 +524,8 @@ void wave_engine_free(WaveEngine &eng)
 // other wave's kernels (this matters most when a GPU owns only 1/8 of the tiles); the per-pixel sums are still
 // formed in sample order because the `reduce` launches are chained with events, wave after wave.
 cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, WaveEngine &eng, bool bvh, bool stats,
-                                  int sm_count, cudaStream_t st, uint32_t *n_launches)
+                                  int sm_count, cudaStream_t st, cudaEvent_t ev_consumed, cudaEvent_t ev_begin,
+                                  cudaStream_t *tail, uint32_t *n_launches)
 {
     cudaError_t e;
     uint32_t launches = 0;
@@ -555,15 +556,18 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
     const unsigned grid_e = (unsigned)(sm_count * (occ_e > 0 ? occ_e : 1)), grid_s = (unsigned)(sm_count * (occ_s > 0 ? occ_s : 1));
     const unsigned grid_shade = (unsigned)sm_count * 8u * (256u / VKRT_SHADE_BLOCK);
 
-    const bool fork = n_lanes > 1 && n_waves > 1;
-    if (fork) {
-        if ((e = cudaEventRecord(eng.ev_fork, st)) != cudaSuccess) return e;
-        for (uint32_t l = 0; l < n_lanes; ++l) if ((e = cudaStreamWaitEvent(eng.stream[l], eng.ev_fork, 0)) != cudaSuccess) return e;
-    }
+    // with lanes the waves never wait for `st` as a whole (that would serialise consecutive frames): see ev_consumed
+    const bool fork = n_lanes > 1;
+    cudaStream_t ls = st;
     for (uint32_t wv = 0; wv < n_waves; ++wv) {
-        const uint32_t lane = fork ? wv % n_lanes : 0u;
+        const uint32_t lane = fork ? (eng.wave_seq++ % n_lanes) : 0u;
         WaveBuffers &wb = eng.lane[lane];
-        cudaStream_t ls = fork ? eng.stream[lane] : st;
+        ls = fork ? eng.stream[lane] : st;
+        if (wv == 0) {
+            // the primary-hit AOV is written early in the frame: it must not overtake a pending read of the last one
+            if (fork && rp.hit_ids && (e = cudaStreamWaitEvent(ls, ev_consumed, 0)) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(ev_begin, ls)) != cudaSuccess) return e;
+        }
         auto ev_mark = [&]() { if (wb.n_ev < 128) cudaEventRecord(wb.ev[wb.n_ev++], ls); };
         WaveParams wp{};
         wp.po = wb.ray_o; wp.pd = wb.ray_d; wp.pacc = wb.acc; wp.pmask = wb.mask; wp.sh = wb.shadow; wp.term = wb.term; wp.rad = wb.sample_rad;
@@ -599,13 +603,19 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
             }
             k_wf_shade<<<grid_shade, VKRT_SHADE_BLOCK, 0, ls>>>(sc, rp, wp, nxt); ++launches;
         }
-        // the running per-pixel sum continues in wave order: wait for the previous wave's reduce
-        if (fork && wv > 0 && (e = cudaStreamWaitEvent(ls, eng.ev_reduce[(wv - 1) % n_lanes], 0)) != cudaSuccess) return e;
+        // the running per-pixel sum continues in wave order: wait for the previous wave's reduce (also across
+        // frames: frame_sum is one buffer); the last reduce overwrites the accumulator, which the previous frame's
+        // resolve / pack / read-back may still be reading
+        if (fork && eng.have_prev_reduce && (e = cudaStreamWaitEvent(ls, eng.ev_reduce[eng.prev_reduce_lane], 0)) != cudaSuccess) return e;
+        if (fork && wv + 1 == n_waves && (e = cudaStreamWaitEvent(ls, ev_consumed, 0)) != cudaSuccess) return e;
         k_wf_reduce<<<(wp.n_slots + 255u) / 256u, 256, 0, ls>>>(rp, wp, eng.frame_sum, wv == 0, wv + 1 == n_waves); ++launches;
-        if (fork && (e = cudaEventRecord(eng.ev_reduce[lane], ls)) != cudaSuccess) return e;
+        if (fork) {
+            if ((e = cudaEventRecord(eng.ev_reduce[lane], ls)) != cudaSuccess) return e;
+            eng.prev_reduce_lane = lane; eng.have_prev_reduce = true;
+        }
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
-    if (fork && (e = cudaStreamWaitEvent(st, eng.ev_reduce[(n_waves - 1) % n_lanes], 0)) != cudaSuccess) return e;
+    if (tail) *tail = ls;
     if (n_launches) *n_launches = launches;
     return cudaSuccess;
 }

@@ -125,6 +125,9 @@ class Renderer:
             frame_data = L.FrameData.from_buffer_copy(bytes(frame_data))
         self._ck(self.lib.vkrt_draw(self.ctx, C.byref(frame_data)))
 
+    def flush(self):
+        self._ck(self.lib.vkrt_flush(self.ctx))
+
     def wait_idle(self):
         self._ck(self.lib.vkrt_wait_idle(self.ctx))
 
