@@ -229,6 +229,10 @@ VKRT_API vkrt_error vkrt_last_frame_timing(vkrt_ctx *ctx, float *trace_ms, float
  * how many launches that was.  This is the duration bench.py's roofline divides by. */
 VKRT_API vkrt_error vkrt_last_frame_traversal_timing(vkrt_ctx *ctx, float *traversal_ms, uint32_t *n_launches);
 
+/* Diagnostics: per-launch start/end times of the most recent wavefront frame, as text lines
+ * "lane kernel start_ms end_ms" (relative to the frame's first launch). */
+VKRT_API vkrt_error vkrt_debug_dump_timeline(vkrt_ctx *ctx, const char *path);
+
 /* ------------------------------------------------------------------------- */
 /* BVH introspection (tests, DESIGN.md byte accounting)                       */
 /* ------------------------------------------------------------------------- */

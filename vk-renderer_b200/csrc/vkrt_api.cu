@@ -628,6 +628,8 @@ VKRT_API vkrt_error vkrt_last_frame_traversal_timing(vkrt_ctx *c, float *travers
     if (c->info.integrator == VKRT_INTEGRATOR_PATH && c->info.variant == VKRT_VARIANT_WAVEFRONT && c->wave_ready) {
         for (uint32_t l = 0; l < c->wave.n_lanes; ++l)
             for (uint32_t i = 0; i + 1 < c->wave.lane[l].n_ev; i += 2) {
+                const uint8_t tag = c->wave.lane[l].ev_tag[i / 2];
+                if (tag != 1 && tag != 3) continue;           // extend / shadow launches only
                 float ms = 0.f;
                 CU(c, cudaEventElapsedTime(&ms, c->wave.lane[l].ev[i], c->wave.lane[l].ev[i + 1]));
                 sum += ms; ++n;
@@ -638,6 +640,31 @@ VKRT_API vkrt_error vkrt_last_frame_traversal_timing(vkrt_ctx *c, float *travers
     }
     if (traversal_ms) *traversal_ms = sum;
     if (n_launches) *n_launches = n;
+    return VKRT_SUCCESS;
+}
+
+/* Diagnostics: writes "lane kernel start_ms end_ms" for every launch of the most recent wavefront frame
+ * (times relative to the frame's first launch) -- a poor man's timeline, there is no nsys in the image. */
+VKRT_API vkrt_error vkrt_debug_dump_timeline(vkrt_ctx *c, const char *path)
+{
+    if (!c || !path) return VKRT_BAD_ARG;
+    if (!c->timing_valid || !c->wave_ready) return fail(c, VKRT_BAD_ARG, "no wavefront frame drawn yet");
+    DeviceGuard g(c->info.device_id);
+    CU(c, cudaEventSynchronize(c->ev_end));
+    FILE *f = std::fopen(path, "w");
+    if (!f) return fail(c, VKRT_BAD_ARG, "cannot open timeline file");
+    static const char *names[6] = {"generate", "extend", "classify", "shadow", "shade", "reduce"};
+    for (uint32_t l = 0; l < c->wave.n_lanes; ++l)
+        for (uint32_t i = 0; i + 1 < c->wave.lane[l].n_ev; i += 2) {
+            float a = 0.f, b = 0.f;
+            if (cudaEventElapsedTime(&a, c->ev_begin, c->wave.lane[l].ev[i]) != cudaSuccess ||
+                cudaEventElapsedTime(&b, c->ev_begin, c->wave.lane[l].ev[i + 1]) != cudaSuccess) { cudaGetLastError(); continue; }
+            std::fprintf(f, "%u %s %.4f %.4f\n", l, names[c->wave.lane[l].ev_tag[i / 2] % 6], a, b);
+        }
+    float tot = 0.f;
+    cudaEventElapsedTime(&tot, c->ev_begin, c->ev_end);
+    std::fprintf(f, "frame total %.4f\n", tot);
+    std::fclose(f);
     return VKRT_SUCCESS;
 }
 

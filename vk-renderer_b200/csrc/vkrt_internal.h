@@ -56,6 +56,7 @@ struct WaveBuffers {
     uint32_t shadow_lights;
     // CUDA-event pairs around every traversal-kernel launch of the last frame (roofline timing)
     cudaEvent_t ev[128];
+    uint8_t ev_tag[64];           // kernel of pair k = (ev[2k], ev[2k+1]): 0 generate 1 extend 2 classify 3 shadow 4 shade 5 reduce
     uint32_t n_ev, ev_created;
 };
 cudaError_t wave_alloc(WaveBuffers &wb, size_t capacity);

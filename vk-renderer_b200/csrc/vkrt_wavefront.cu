@@ -568,7 +568,9 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
             if (fork && rp.hit_ids && (e = cudaStreamWaitEvent(ls, ev_consumed, 0)) != cudaSuccess) return e;
             if ((e = cudaEventRecord(ev_begin, ls)) != cudaSuccess) return e;
         }
-        auto ev_mark = [&]() { if (wb.n_ev < 128) cudaEventRecord(wb.ev[wb.n_ev++], ls); };
+        // every launch of the wave is bracketed by timing events (roofline timing, vkrt_debug_dump_timeline)
+        auto ev_open = [&](uint8_t tag) { if (wb.n_ev + 1 < 128) { wb.ev_tag[wb.n_ev / 2] = tag; cudaEventRecord(wb.ev[wb.n_ev++], ls); } };
+        auto ev_close = [&]() { if (wb.n_ev < 128 && (wb.n_ev & 1u)) cudaEventRecord(wb.ev[wb.n_ev++], ls); };
         WaveParams wp{};
         wp.po = wb.ray_o; wp.pd = wb.ray_d; wp.pacc = wb.acc; wp.pmask = wb.mask; wp.sh = wb.shadow; wp.term = wb.term; wp.rad = wb.sample_rad;
         wp.q_active[0] = wb.queue[0]; wp.q_active[1] = wb.queue[1]; wp.q_diel = wb.queue_mat[0]; wp.q_diff = wb.queue_mat[1];
@@ -583,7 +585,9 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
             void (*k_gen)(const DevScene, const RenderParams, const WaveParams) =
                 bvh ? (stats ? k_wf_generate<true, true> : k_wf_generate<true, false>)
                     : (stats ? k_wf_generate<false, true> : k_wf_generate<false, false>);
+            ev_open(0);
             k_gen<<<(wp.n_slots + 255u) / 256u, 256, 0, ls>>>(sc, rp, wp); ++launches;
+            ev_close();
         }
         for (uint32_t depth = 0; depth < rp.max_depth; ++depth) {
             const uint32_t cur = depth & 1u, nxt = cur ^ 1u;
@@ -591,24 +595,30 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
             wp.cnt_next = wp.cnt + C_N;
             const uint32_t *n_active = wp.cnt + C_ACTIVE;
             if (depth > 0) {       // depth 0 was traced once per pixel by `generate`
-                ev_mark();
+                ev_open(1);
                 k_extend<<<grid_e, VKRT_TRACE_BLOCK, 0, ls>>>(sc, rp, wp, wp.q_active[cur], n_active, wp.cnt + C_HEAD_EXTEND, depth); ++launches;
-                ev_mark();
+                ev_close();
             }
+            ev_open(2);
             k_wf_classify<<<grid_shade, VKRT_SHADE_BLOCK, 0, ls>>>(sc, rp, wp, wp.q_active[cur], n_active); ++launches;
+            ev_close();
             if (sc.n_lights) {
-                ev_mark();
+                ev_open(3);
                 k_shadow<<<grid_s, VKRT_TRACE_BLOCK, 0, ls>>>(sc, rp, wp, wp.q_shadow, wp.cnt + C_SHADOW, wp.cnt + C_HEAD_SHADOW, depth); ++launches;
-                ev_mark();
+                ev_close();
             }
+            ev_open(4);
             k_wf_shade<<<grid_shade, VKRT_SHADE_BLOCK, 0, ls>>>(sc, rp, wp, nxt); ++launches;
+            ev_close();
         }
         // the running per-pixel sum continues in wave order: wait for the previous wave's reduce (also across
         // frames: frame_sum is one buffer); the last reduce overwrites the accumulator, which the previous frame's
         // resolve / pack / read-back may still be reading
         if (fork && eng.have_prev_reduce && (e = cudaStreamWaitEvent(ls, eng.ev_reduce[eng.prev_reduce_lane], 0)) != cudaSuccess) return e;
         if (fork && wv + 1 == n_waves && (e = cudaStreamWaitEvent(ls, ev_consumed, 0)) != cudaSuccess) return e;
+        ev_open(5);
         k_wf_reduce<<<(wp.n_slots + 255u) / 256u, 256, 0, ls>>>(rp, wp, eng.frame_sum, wv == 0, wv + 1 == n_waves); ++launches;
+        ev_close();
         if (fork) {
             if ((e = cudaEventRecord(eng.ev_reduce[lane], ls)) != cudaSuccess) return e;
             eng.prev_reduce_lane = lane; eng.have_prev_reduce = true;

@@ -171,6 +171,9 @@ class Renderer:
         self._ck(self.lib.vkrt_last_frame_traversal_timing(self.ctx, C.byref(a), C.byref(n)))
         return a.value, n.value
 
+    def dump_timeline(self, path):
+        self._ck(self.lib.vkrt_debug_dump_timeline(self.ctx, path.encode()))
+
     def stream_ptr(self):
         s = C.c_void_p()
         self._ck(self.lib.vkrt_get_stream(self.ctx, C.byref(s)))
