@@ -143,8 +143,7 @@ vkrt_error upload_scene(vkrt_ctx *c)
     std::memset(&d, 0, sizeof(d));
     d.spheres = c->d_spheres; d.sphere_mat = c->d_sphere_mat; d.mats = c->d_mats; d.tris = c->d_tris;
     d.bvh = c->use_bvh ? c->bvh.nodes : nullptr;
-    d.qbvh = c->use_bvh ? c->bvh.qnodes : nullptr;
-    for (int a = 0; a < 3; ++a) { d.qscale[a] = c->bvh.grid[3 + a]; d.qbase2[a] = c->bvh.grid[6 + a]; }
+    d.bvh4 = c->use_bvh ? c->bvh.nodes4 : nullptr;
     d.n_nodes = c->use_bvh ? c->bvh.n_nodes : 0;
     d.n_spheres = (uint32_t)c->spheres.size(); d.n_tris = (uint32_t)c->tris.size(); d.tri_mat = c->tri_mat;
     d.n_planes = (uint32_t)c->planes.size(); d.n_mats = (uint32_t)c->mats.size();
@@ -260,7 +259,7 @@ VKRT_API vkrt_error vkrt_destroy(vkrt_ctx *c)
     DeviceGuard g(c->info.device_id);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_spheres); cudaFree(c->d_sphere_mat); cudaFree(c->d_mats); cudaFree(c->d_tris);
-    cudaFree(c->bvh.nodes); cudaFree(c->bvh.qnodes); cudaFree(c->d_accum); cudaFree(c->d_hit_ids);
+    cudaFree(c->bvh.nodes); cudaFree(c->bvh.nodes4); cudaFree(c->d_accum); cudaFree(c->d_hit_ids);
     for (auto p : c->d_rgba) cudaFree(p);
     cudaFree(c->d_counters); cudaFree(c->d_work_head); cudaFree(c->d_packed);
     if (c->wave_ready) wave_engine_free(c->wave);
@@ -635,7 +634,7 @@ VKRT_API vkrt_error vkrt_last_frame_traversal_timing(vkrt_ctx *c, float *travers
                 sum += ms; ++n;
             }
     } else {
-        CU(c, cudaEventElapsedTime(&sum, c->ev_trace0, c->ev_trace1));
+        CU(c, cudaEventElapsedTime(&sum, c->ev_begin, c->ev_trace1));
         n = 1;
     }
     if (traversal_ms) *traversal_ms = sum;

@@ -17,24 +17,17 @@ __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i
 
 __global__ void k_bounds_init(int *b)
 {
-    if (threadIdx.x < 3) b[threadIdx.x] = 0x7fffffff;          // min of the centres
-    else if (threadIdx.x < 7) b[threadIdx.x] = (int)0x80000000; // max of the centres, [6] = max radius
+    if (threadIdx.x < 3) b[threadIdx.x] = 0x7fffffff;          // min
+    else if (threadIdx.x < 6) b[threadIdx.x] = (int)0x80000000; // max
 }
 
 __global__ void __launch_bounds__(256) k_bounds(const float4 *__restrict__ sph, uint32_t n, int *b)
 {
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    float rmax = -INFINITY;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 s = sph[i];
         lo[0] = fminf(lo[0], s.x); lo[1] = fminf(lo[1], s.y); lo[2] = fminf(lo[2], s.z);
         hi[0] = fmaxf(hi[0], s.x); hi[1] = fmaxf(hi[1], s.y); hi[2] = fmaxf(hi[2], s.z);
-        rmax = fmaxf(rmax, s.w);
-    }
-    {
-        int r = f2ord(rmax);
-        r = __reduce_max_sync(0xffffffffu, r);
-        if ((threadIdx.x & 31) == 0) atomicMax(b + 6, r);
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -198,55 +191,6 @@ __global__ void __launch_bounds__(256) k_karras(const uint32_t *__restrict__ cod
     if (i == 0) parent_inner[0] = -1;
 }
 
-// ---- 16-bit quantisation grid of the traversal nodes (DESIGN.md "Quantised nodes") -------------------
-// grid[0..2] = base, [3..5] = scale, [6..8] = base2 = base - 2^23 * scale.  A coordinate q in [0, 65535]
-// decodes as fma(float(2^23 + q), scale, base2), rounded DOWN for box minima and UP for box maxima;
-// quantize_lo/hi pick the tightest q whose decoded value still encloses x, checked with the decode itself.
-__global__ void k_grid(const int *__restrict__ b, float *__restrict__ grid)
-{
-    const int a = threadIdx.x;
-    if (a >= 3) return;
-    const float rp = sphere_pad_radius(fmaxf(ord2f(b[6]), 0.0f));
-    const float lo = ord2f(b[a]) - rp, hi = ord2f(b[3 + a]) + rp;
-    float sc = (hi - lo) / 65024.0f;
-    if (!(sc > 1e-12f)) sc = 1e-6f;
-    const float base = lo - 128.0f * sc;
-    grid[a] = base; grid[3 + a] = sc; grid[6 + a] = __fmaf_rn(-8388608.0f, sc, base);
-}
-__device__ __forceinline__ float dq_lo(uint32_t q, float sc, float base2) { return __fmaf_rd(__uint_as_float(0x4B000000u | q), sc, base2); }
-__device__ __forceinline__ float dq_hi(uint32_t q, float sc, float base2) { return __fmaf_ru(__uint_as_float(0x4B000000u | q), sc, base2); }
-__device__ __forceinline__ uint32_t quantize_lo(float x, float base, float sc, float base2)
-{
-    int q = (int)floorf((x - base) / sc);
-    q = min(max(q, 0), 65535);
-    while (q > 0 && dq_lo((uint32_t)q, sc, base2) > x) --q;
-    while (q < 65535 && dq_lo((uint32_t)q + 1u, sc, base2) <= x) ++q;
-    return (uint32_t)q;
-}
-__device__ __forceinline__ uint32_t quantize_hi(float x, float base, float sc, float base2)
-{
-    int q = (int)ceilf((x - base) / sc);
-    q = min(max(q, 0), 65535);
-    while (q < 65535 && dq_hi((uint32_t)q, sc, base2) < x) ++q;
-    while (q > 0 && dq_hi((uint32_t)q - 1u, sc, base2) >= x) --q;
-    return (uint32_t)q;
-}
-// quantised child record (16 B): {lo.x | lo.y << 16, lo.z | hi.x << 16, hi.y | hi.z << 16, index | leaf << 31};
-// lo/hi come back as the DECODED box so that the parent can enclose exactly what the traversal will test
-__device__ __forceinline__ void write_qchild(uint4 *qnode, int k, bool leaf, int index, const float *grid, float *lo, float *hi)
-{
-    uint32_t ql[3], qh[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        ql[a] = quantize_lo(lo[a], grid[a], grid[3 + a], grid[6 + a]);
-        qh[a] = quantize_hi(hi[a], grid[a], grid[3 + a], grid[6 + a]);
-        lo[a] = dq_lo(ql[a], grid[3 + a], grid[6 + a]);
-        hi[a] = dq_hi(qh[a], grid[3 + a], grid[6 + a]);
-    }
-    qnode[k] = make_uint4(ql[0] | (ql[1] << 16), ql[2] | (qh[0] << 16), qh[1] | (qh[2] << 16),
-                          (uint32_t)index | (leaf ? 0x80000000u : 0u));
-}
-
 // ---- refit + pack: one thread per leaf walks up; the second arrival at a node owns it ---------
 // child record (32 B): {lo.x lo.y lo.z hi.x | hi.y hi.z index kind}; kind 0 = inner node `index`,
 // kind 1 = leaf = sphere `index`, whose record holds the sphere's own padded box
@@ -266,22 +210,17 @@ __global__ void __launch_bounds__(256) k_refit(const float4 *__restrict__ sph, c
                                                 const int2 *__restrict__ children, const int *__restrict__ parent_inner,
                                                 const int *__restrict__ parent_leaf, int *__restrict__ arrivals,
                                                 float4 *__restrict__ box_lo, float4 *__restrict__ box_hi,
-                                                float4 *__restrict__ nodes, float4 *__restrict__ qbox_lo,
-                                                float4 *__restrict__ qbox_hi, uint4 *__restrict__ qnodes,
-                                                const float *__restrict__ grid_dev)
+                                                float4 *__restrict__ nodes)
 {
     const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
     if (leaf >= n) return;
-    float grid[9];
-#pragma unroll
-    for (int a = 0; a < 9; ++a) grid[a] = grid_dev[a];
     int node = parent_leaf[leaf];
     while (node >= 0) {
         __threadfence();
         if (atomicAdd(arrivals + node, 1) == 0) return;      // the sibling subtree is not done yet
         __threadfence();
         const int2 c = children[node];
-        float lo[2][3], hi[2][3], qlo[2][3], qhi[2][3];
+        float lo[2][3], hi[2][3];
         int idx[2];
         bool is_leaf[2];
 #pragma unroll
@@ -291,45 +230,55 @@ __global__ void __launch_bounds__(256) k_refit(const float4 *__restrict__ sph, c
             if (is_leaf[k]) {
                 idx[k] = (int)sorted_idx[~ch];
                 leaf_box(sph[idx[k]], lo[k], hi[k]);
-#pragma unroll
-                for (int a = 0; a < 3; ++a) { qlo[k][a] = lo[k][a]; qhi[k][a] = hi[k][a]; }
             } else {
                 idx[k] = ch;
                 const volatile float4 *pl = box_lo + ch, *ph = box_hi + ch;
                 lo[k][0] = pl->x; lo[k][1] = pl->y; lo[k][2] = pl->z;
                 hi[k][0] = ph->x; hi[k][1] = ph->y; hi[k][2] = ph->z;
-                const volatile float4 *ql = qbox_lo + ch, *qh = qbox_hi + ch;
-                qlo[k][0] = ql->x; qlo[k][1] = ql->y; qlo[k][2] = ql->z;
-                qhi[k][0] = qh->x; qhi[k][1] = qh->y; qhi[k][2] = qh->z;
             }
             write_child(nodes + 4 * (size_t)node, k, is_leaf[k], idx[k], lo[k], hi[k]);
-            write_qchild(qnodes + 2 * (size_t)node, k, is_leaf[k], idx[k], grid, qlo[k], qhi[k]);
         }
-        qbox_lo[node] = make_float4(fminf(qlo[0][0], qlo[1][0]), fminf(qlo[0][1], qlo[1][1]), fminf(qlo[0][2], qlo[1][2]), 0.f);
-        qbox_hi[node] = make_float4(fmaxf(qhi[0][0], qhi[1][0]), fmaxf(qhi[0][1], qhi[1][1]), fmaxf(qhi[0][2], qhi[1][2]), 0.f);
         box_lo[node] = make_float4(fminf(lo[0][0], lo[1][0]), fminf(lo[0][1], lo[1][1]), fminf(lo[0][2], lo[1][2]), 0.f);
         box_hi[node] = make_float4(fmaxf(hi[0][0], hi[1][0]), fmaxf(hi[0][1], hi[1][1]), fmaxf(hi[0][2], hi[1][2]), 0.f);
         node = parent_inner[node];
     }
 }
 
-__global__ void k_single_leaf(const float4 *__restrict__ sph, float4 *__restrict__ nodes, uint4 *__restrict__ qnodes,
-                              float *__restrict__ grid)
+__global__ void k_single_leaf(const float4 *__restrict__ sph, float4 *__restrict__ nodes)
 {
     float lo[3], hi[3];
-    const float4 s = sph[0];
-    leaf_box(s, lo, hi);
+    leaf_box(sph[0], lo, hi);
     write_child(nodes, 0, true, 0, lo, hi);
     write_child(nodes, 1, true, 0, lo, hi);
-    for (int a = 0; a < 3; ++a) {
-        float sc = (hi[a] - lo[a]) / 65024.0f;
-        if (!(sc > 1e-12f)) sc = 1e-6f;
-        const float base = lo[a] - 128.0f * sc;
-        grid[a] = base; grid[3 + a] = sc; grid[6 + a] = __fmaf_rn(-8388608.0f, sc, base);
+}
+
+// ---- collapse to 4-wide traversal nodes: node4[i] holds the (up to four) grandchildren of binary node i ------
+// Every binary node gets one (indices stay binary node ids, no compaction pass); the traversal only ever reaches
+// the ones on even levels below the root.  A leaf child keeps its own slot, empty slots hold an unreachable box.
+// Halving the number of dependent node fetches per ray is what matters: the kernels are bound by the latency of
+// that chain (a lone 300-step ray was the ~230 us floor of every trace launch).
+__global__ void __launch_bounds__(256) k_collapse4(const float4 *__restrict__ nodes, uint32_t n_inner, float4 *__restrict__ nodes4)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_inner) return;
+    float4 slot[8];
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float4 a = nodes[4 * (size_t)i + 2 * k], b = nodes[4 * (size_t)i + 2 * k + 1];
+        if (__float_as_int(b.w) == 1) { slot[2 * n] = a; slot[2 * n + 1] = b; ++n; }
+        else {
+            const float4 *c = nodes + 4 * (size_t)__float_as_int(b.z);
+            slot[2 * n] = c[0]; slot[2 * n + 1] = c[1]; ++n;
+            slot[2 * n] = c[2]; slot[2 * n + 1] = c[3]; ++n;
+        }
     }
-    float l2[3] = {lo[0], lo[1], lo[2]}, h2[3] = {hi[0], hi[1], hi[2]};
-    write_qchild(qnodes, 0, true, 0, grid, l2, h2);
-    write_qchild(qnodes, 1, true, 0, grid, lo, hi);
+    for (; n < 4; ++n) {
+        slot[2 * n] = make_float4(1e30f, 1e30f, 1e30f, 1e30f);
+        slot[2 * n + 1] = make_float4(1e30f, 1e30f, __int_as_float(0), __int_as_float(2));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) nodes4[8 * (size_t)i + k] = slot[k];
 }
 
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { err = _e; goto done; } } while (0)
@@ -338,11 +287,9 @@ cudaError_t build_lbvh(const float4 *d_spheres, uint32_t n, BvhBuild &out, cudaS
 {
     cudaError_t err = cudaSuccess;
     if (out.nodes) { cudaFree(out.nodes); out.nodes = nullptr; }
-    if (out.qnodes) { cudaFree(out.qnodes); out.qnodes = nullptr; }
+    if (out.nodes4) { cudaFree(out.nodes4); out.nodes4 = nullptr; }
     out.n_nodes = 0; out.build_ms = 0.f; out.launches = 0;
     if (n == 0) return cudaSuccess;
-    float *grid = nullptr;
-    float4 *qbox_lo = nullptr, *qbox_hi = nullptr;
 
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     int *bounds = nullptr, *parent_inner = nullptr, *parent_leaf = nullptr, *arrivals = nullptr;
@@ -355,16 +302,13 @@ cudaError_t build_lbvh(const float4 *d_spheres, uint32_t n, BvhBuild &out, cudaS
 
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaMalloc(&out.nodes, (size_t)n_inner * 64));
-    CK(cudaMalloc(&out.qnodes, (size_t)n_inner * 32));
-    CK(cudaMalloc(&grid, 9 * sizeof(float)));
+    CK(cudaMalloc(&out.nodes4, (size_t)n_inner * 128));
     CK(cudaEventRecord(e0, st));
     if (n == 1) {
-        k_single_leaf<<<1, 1, 0, st>>>(d_spheres, out.nodes, out.qnodes, grid); ++launches;
+        k_single_leaf<<<1, 1, 0, st>>>(d_spheres, out.nodes); ++launches;
         CK(cudaGetLastError());
     } else {
-        CK(cudaMalloc(&bounds, 8 * sizeof(int)));
-        CK(cudaMalloc(&qbox_lo, (size_t)(n - 1) * sizeof(float4)));
-        CK(cudaMalloc(&qbox_hi, (size_t)(n - 1) * sizeof(float4)));
+        CK(cudaMalloc(&bounds, 6 * sizeof(int)));
         for (int k = 0; k < 2; ++k) { CK(cudaMalloc(&keys[k], n * sizeof(uint32_t))); CK(cudaMalloc(&vals[k], n * sizeof(uint32_t))); }
         CK(cudaMalloc(&hist, (size_t)RS_DIGITS * n_blocks * sizeof(uint32_t)));
         CK(cudaMalloc(&children, (size_t)(n - 1) * sizeof(int2)));
@@ -380,7 +324,6 @@ cudaError_t build_lbvh(const float4 *d_spheres, uint32_t n, BvhBuild &out, cudaS
             unsigned g = (n + 255u) / 256u; if (g > 592u) g = 592u;   // 4 x 148 SMs
             k_bounds<<<g, 256, 0, st>>>(d_spheres, n, bounds); ++launches;
         }
-        k_grid<<<1, 32, 0, st>>>(bounds, grid); ++launches;
         k_morton<<<(n + 255u) / 256u, 256, 0, st>>>(d_spheres, n, bounds, keys[0], vals[0]); ++launches;
         int cur = 0;
         for (int pass = 0; pass < 4; ++pass) {
@@ -392,11 +335,12 @@ cudaError_t build_lbvh(const float4 *d_spheres, uint32_t n, BvhBuild &out, cudaS
         }
         k_karras<<<(n - 1 + 255u) / 256u, 256, 0, st>>>(keys[cur], (int)n, children, parent_inner, parent_leaf); ++launches;
         k_refit<<<(n + 255u) / 256u, 256, 0, st>>>(d_spheres, vals[cur], (int)n, children, parent_inner, parent_leaf, arrivals,
-                                                   box_lo, box_hi, out.nodes, qbox_lo, qbox_hi, out.qnodes, grid); ++launches;
+                                                   box_lo, box_hi, out.nodes); ++launches;
         CK(cudaGetLastError());
     }
+    k_collapse4<<<(n_inner + 255u) / 256u, 256, 0, st>>>(out.nodes, n_inner, out.nodes4); ++launches;
+    CK(cudaGetLastError());
     CK(cudaEventRecord(e1, st));
-    CK(cudaMemcpyAsync(out.grid, grid, 9 * sizeof(float), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&out.build_ms, e0, e1));
     out.n_nodes = n_inner;
@@ -406,8 +350,7 @@ done:
     if (e1) cudaEventDestroy(e1);
     cudaFree(bounds); cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); cudaFree(hist);
     cudaFree(children); cudaFree(parent_inner); cudaFree(parent_leaf); cudaFree(arrivals); cudaFree(box_lo); cudaFree(box_hi);
-    cudaFree(qbox_lo); cudaFree(qbox_hi); cudaFree(grid);
-    if (err != cudaSuccess) { cudaFree(out.nodes); cudaFree(out.qnodes); out.nodes = nullptr; out.qnodes = nullptr; }
+    if (err != cudaSuccess) { cudaFree(out.nodes); cudaFree(out.nodes4); out.nodes = nullptr; out.nodes4 = nullptr; }
     return err;
 }
 

@@ -12,7 +12,7 @@
 
 namespace vkrt {
 
-enum { MAX_PLANES = 16, BVH_STACK = 64 };
+enum { MAX_PLANES = 16, BVH_STACK = 128 };
 enum { KIND_TRI = 1, KIND_SPHERE = 2, KIND_PLANE = 3 };
 
 // ---- HBM layout (DESIGN.md "Data layout") ----------------------------------------------------
@@ -26,15 +26,15 @@ enum { KIND_TRI = 1, KIND_SPHERE = 2, KIND_PLANE = 3 };
 struct DevScene {
     const float4 *spheres;
     const uint32_t *sphere_mat;
-    const float4 *bvh;            // exact 64-byte nodes (introspection; traversal when VKRT_QNODES == 0)
-    const uint4 *qbvh;            // 32-byte traversal nodes with 16-bit quantised child boxes
+    const float4 *bvh;            // binary 64-byte nodes (two child records)
+    const float4 *bvh4;           // 4-wide 128-byte traversal nodes (four child records), indexed by binary node id
     const float4 *tris;
     const float4 *mats;
     uint32_t n_spheres, n_tris, tri_mat, n_planes, n_lights, n_nodes, n_mats, _pad;
     float4 planes[MAX_PLANES];
     uint32_t plane_mat[MAX_PLANES];
     uint32_t lights[MAX_LIGHTS];
-    float qscale[3], qbase2[3];   // decode: fma(float(2^23 + q), qscale, qbase2), rounded down (lo) / up (hi)
+    uint32_t _pad2[2];
 };
 
 struct Material { V3 albedo; float roughness; V3 emissive; float metalness; uint32_t type; };
@@ -131,22 +131,9 @@ VKRT_DEV void s_consider(V3 o, V3 d, float4 sph, int i, float tn, float eps, flo
     else if (t < best.t || (t == best.t && i < best.idx)) { best.t = t; best.idx = i; }
 }
 
-#ifndef VKRT_PREFETCH_FAR
-#define VKRT_PREFETCH_FAR 0
+#ifndef VKRT_BVH4
+#define VKRT_BVH4 0
 #endif
-#ifndef VKRT_QNODES
-#define VKRT_QNODES 0
-#endif
-VKRT_DEV void ldg256u(const uint4 *p, uint4 &a, uint4 &b)
-{
-    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
-                 : "l"(p));
-}
-// 16-bit field -> the float 2^23 + q (one PRMT), then one directed-rounding FFMA decodes the coordinate
-VKRT_DEV float q_lo16(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)); }
-VKRT_DEV float q_hi16(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)); }
-
 VKRT_DEV void ldg256(const float4 *p, float4 &a, float4 &b)
 {
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -185,67 +172,69 @@ VKRT_DEV void leaf_test(Trav &tv, const DevScene &sc, V3 o, V3 d, int si, Stats 
     }
 }
 
+VKRT_DEV void cswap(float &ta, int &ia, float &tb, int &ib)
+{
+    const bool s = tb < ta;
+    const float t = s ? tb : ta; tb = s ? ta : tb; ta = t;
+    const int i = s ? ib : ia; ib = s ? ia : ib; ia = i;
+}
+
 template <bool ANY, bool STATS>
 VKRT_DEV void trav_step(Trav &tv, int *__restrict__ stack, const DevScene &sc, V3 o, V3 d, Stats &st)
 {
-    float tn0, tn1, tf;
-    bool h0, h1, leaf0, leaf1;
-    int i0, i1;
-#if VKRT_QNODES
-    // one 32-byte node = ONE 256-bit load (LDG.E.256): the traversal is bound by the L1TEX data pipe
-    // (scattered sectors), so halving the bytes per node matters more than the 24 decode instructions.
-    // The decoded boxes enclose the children's decoded / exact boxes as floats (the builder checks it with
-    // this same decode), so the monotone slab test keeps rule S exact.
-    uint4 w0, w1;
-    ldg256u(sc.qbvh + 2 * (size_t)tv.node, w0, w1);
+#if VKRT_BVH4
+    // one 128-byte node = four child records {lo.xyz hi.x | hi.yz index kind} = four 256-bit loads in flight at once
+    const float4 *np = sc.bvh4 + 8 * (size_t)tv.node;
+    float4 a[4], b[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ldg256(np + 2 * k, a[k], b[k]);
     if (STATS) ++st.nodes;
-    {
-        const V3 lo = v3(__fmaf_rd(q_lo16(w0.x), sc.qscale[0], sc.qbase2[0]), __fmaf_rd(q_hi16(w0.x), sc.qscale[1], sc.qbase2[1]),
-                         __fmaf_rd(q_lo16(w0.y), sc.qscale[2], sc.qbase2[2]));
-        const V3 hi = v3(__fmaf_ru(q_hi16(w0.y), sc.qscale[0], sc.qbase2[0]), __fmaf_ru(q_lo16(w0.z), sc.qscale[1], sc.qbase2[1]),
-                         __fmaf_ru(q_hi16(w0.z), sc.qscale[2], sc.qbase2[2]));
-        h0 = slab_test(tv.sr, lo, hi, tn0, tf) && tn0 <= tv.best.t;
+    const float INF = __int_as_float(0x7f800000);
+    float tn[4]; int idx[4]; bool hit[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float tf;
+        hit[k] = slab_test(tv.sr, v3(a[k].x, a[k].y, a[k].z), v3(a[k].w, b[k].x, b[k].y), tn[k], tf) && tn[k] <= tv.best.t &&
+                 __float_as_int(b[k].w) != 2;
+        idx[k] = __float_as_int(b[k].z);
     }
-    {
-        const V3 lo = v3(__fmaf_rd(q_lo16(w1.x), sc.qscale[0], sc.qbase2[0]), __fmaf_rd(q_hi16(w1.x), sc.qscale[1], sc.qbase2[1]),
-                         __fmaf_rd(q_lo16(w1.y), sc.qscale[2], sc.qbase2[2]));
-        const V3 hi = v3(__fmaf_ru(q_hi16(w1.y), sc.qscale[0], sc.qbase2[0]), __fmaf_ru(q_lo16(w1.z), sc.qscale[1], sc.qbase2[1]),
-                         __fmaf_ru(q_hi16(w1.z), sc.qscale[2], sc.qbase2[2]));
-        h1 = slab_test(tv.sr, lo, hi, tn1, tf) && tn1 <= tv.best.t;
-    }
-    leaf0 = (w0.w >> 31) != 0u; leaf1 = (w1.w >> 31) != 0u;
-    i0 = (int)(w0.w & 0x7fffffffu); i1 = (int)(w1.w & 0x7fffffffu);
+    // leaf children: the stored box is the sphere's own padded box; fetch the sphere and run the rule-S leaf test
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (hit[k] && __float_as_int(b[k].w) == 1) { leaf_test<STATS>(tv, sc, o, d, idx[k], st); hit[k] = false; }
+    if (ANY && tv.best.idx >= 0) { tv.node = -1; return; }
+    // inner children still within reach, nearest first: descend into the nearest, push the others far -> near
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { hit[k] = hit[k] && tn[k] <= tv.best.t; tn[k] = hit[k] ? tn[k] : INF; c += hit[k] ? 1 : 0; }
+    cswap(tn[0], idx[0], tn[1], idx[1]); cswap(tn[2], idx[2], tn[3], idx[3]);
+    cswap(tn[0], idx[0], tn[2], idx[2]); cswap(tn[1], idx[1], tn[3], idx[3]);
+    cswap(tn[1], idx[1], tn[2], idx[2]);
+    if (c > 3) stack[tv.sp++] = idx[3];
+    if (c > 2) stack[tv.sp++] = idx[2];
+    if (c > 1) stack[tv.sp++] = idx[1];
+    if (c > 0) tv.node = idx[0];
+    else tv.node = tv.sp ? stack[--tv.sp] : -1;
 #else
     const float4 *np = sc.bvh + 4 * (size_t)tv.node;
     float4 a0, b0, a1, b1;
     ldg256(np, a0, b0);
     ldg256(np + 2, a1, b1);
     if (STATS) ++st.nodes;
-    h0 = slab_test(tv.sr, v3(a0.x, a0.y, a0.z), v3(a0.w, b0.x, b0.y), tn0, tf) && tn0 <= tv.best.t;
-    h1 = slab_test(tv.sr, v3(a1.x, a1.y, a1.z), v3(a1.w, b1.x, b1.y), tn1, tf) && tn1 <= tv.best.t;
-    leaf0 = __float_as_int(b0.w) != 0; leaf1 = __float_as_int(b1.w) != 0;
-    i0 = __float_as_int(b0.z); i1 = __float_as_int(b1.z);
-#endif
-    // leaf children: the quantised / stored box was only a pre-filter
-    if (h0 && leaf0) { leaf_test<STATS>(tv, sc, o, d, i0, st); h0 = false; }
-    if (h1 && leaf1) { leaf_test<STATS>(tv, sc, o, d, i1, st); h1 = false; }
+    float tn0, tn1, tf;
+    bool h0 = slab_test(tv.sr, v3(a0.x, a0.y, a0.z), v3(a0.w, b0.x, b0.y), tn0, tf) && tn0 <= tv.best.t;
+    bool h1 = slab_test(tv.sr, v3(a1.x, a1.y, a1.z), v3(a1.w, b1.x, b1.y), tn1, tf) && tn1 <= tv.best.t;
+    const int i0 = __float_as_int(b0.z), i1 = __float_as_int(b1.z);
+    if (h0 && __float_as_int(b0.w) != 0) { leaf_test<STATS>(tv, sc, o, d, i0, st); h0 = false; }
+    if (h1 && __float_as_int(b1.w) != 0) { leaf_test<STATS>(tv, sc, o, d, i1, st); h1 = false; }
     if (ANY && tv.best.idx >= 0) { tv.node = -1; return; }
-    // descend into the nearer inner child, push the farther one, or pop
     const bool both = h0 && h1;
     const bool take1 = both ? (tn1 < tn0) : h1;
     const int nearer = take1 ? i1 : i0;
-    if (both) {
-        const int far = take1 ? i0 : i1;
-        stack[tv.sp++] = far;
-#if VKRT_PREFETCH_FAR
-        // the pushed (farther) child is visited later unless it gets culled: pull its node towards L1 now
-        const float4 *fp = sc.bvh + 4 * (size_t)far;
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(fp));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(fp + 2));
-#endif
-    }
+    if (both) stack[tv.sp++] = take1 ? i0 : i1;
     if (h0 || h1) tv.node = nearer;
     else tv.node = tv.sp ? stack[--tv.sp] : -1;
+#endif
 }
 
 template <bool ANY, bool STATS>

@@ -83,9 +83,8 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
 
 // vkrt_bvh.cu
 struct BvhBuild {
-    float4 *nodes = nullptr;      // exact nodes: 4 float4 per inner node (introspection, tests)
-    uint4 *qnodes = nullptr;      // traversal nodes: 2 uint4 per inner node, 16-bit quantised child boxes
-    float grid[9] = {0};          // quantisation grid: base xyz, scale xyz, base2 xyz
+    float4 *nodes = nullptr;      // binary nodes: 4 float4 (two child records) per inner node
+    float4 *nodes4 = nullptr;     // 4-wide traversal nodes: 8 float4 (four child records) per binary node id
     uint32_t n_nodes = 0;
     float build_ms = 0.f;
     uint32_t launches = 0;
