@@ -184,3 +184,32 @@ def test_bench_reference_arm_runs_on_cpu():
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["unit"] == "Mrays/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+# ---- the C++ host side (csrc/host): GraphicsDevice drop-in + headless frame loop ----------------------
+def _headless():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_vkrt_build", os.path.join(ROOT, "vk-renderer_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    b.build()
+    return b.build_host()
+
+
+def test_cpp_camera_matches_reference_vector():
+    """csrc/host/Camera.cpp (no glm) reproduces the reference's own Camera.cpp for Main.cpp's default view."""
+    import json
+    exe = _headless()
+    out = subprocess.run([exe, "--print-camera"], capture_output=True, text=True, timeout=60).stdout.split()
+    got = np.array([float.fromhex(v) for v in out], dtype=np.float32).reshape(4, 3)
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "camera_poses.json")))["default_view"]["camera"]
+    assert np.array_equal(got.view(np.uint32), np.array(gold, dtype=np.float32).view(np.uint32))
+
+
+@pytest.mark.skipif(has_gpu(), reason="exercises the no-GPU failure path")
+def test_cpp_host_reports_errors_like_the_reference():
+    exe = _headless()
+    r = subprocess.run([exe, "--frames", "2"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1
+    assert "[app] - err :: no CUDA device" in r.stdout
+    assert "[app] - err :: Graphics device creation failed :: 1" in r.stdout        # Main.cpp:121, Error::NO_SUITABLE_GPU

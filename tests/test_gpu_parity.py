@@ -386,3 +386,45 @@ def test_full_size_properties_config4(vk):
         assert bits_equal(part[own], outs[0][0][own])
         r.close()
     assert tuple(total.tolist()) == outs[0][1]
+
+
+def test_cpp_headless_loop_matches_python_mirror(vk, tmp_path):
+    """The C++ GraphicsDevice drop-in driven by the headless Main.cpp loop produces the same image, byte for
+    byte, as the Python mirror driven with the same camera script and the same libc rand() seeds."""
+    import ctypes
+    import os
+    import subprocess
+    import importlib.util
+    V = vk
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("_vkrt_build", os.path.join(root, "vk-renderer_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
+    exe = b.build_host()
+    out = tmp_path / "frame.ppm"
+    frames, res = 5, 256
+    r = subprocess.run([exe, "--frames", str(frames), "--res", str(res), "--seed", "42", "--out", str(out)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "%d frames in" % frames in r.stdout
+    data = open(out, "rb").read()
+    header = b"P6\n%d %d\n255\n" % (res, res)
+    assert data.startswith(header)
+    cpp = np.frombuffer(data[len(header):], dtype=np.uint8).reshape(res, res, 3)[::-1]       # back to bottom-up rows
+
+    dev = V.GraphicsDevice()
+    assert dev.Construct(V.GraphicsDevice.CreateInfo(None, 3, 2, res, False)) == V.GraphicsDevice.Error.SUCCESS
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(42)
+    cam = V.default_camera()
+    fd = V.default_frame_data(camera=cam)
+    dev.Draw(fd)
+    for f in range(1, frames):
+        if f % 3 == 0: cam.move_forward(0.5)
+        elif f % 3 == 1: cam.move_right(0.25)
+        else: cam.move_up(0.125)
+        fd.camera = cam.data
+        dev.Draw(fd)
+    dev.WaitIdle()
+    py = dev.renderer.read_rgba8()[..., :3]
+    dev.Destruct()
+    assert np.array_equal(cpp, py)

@@ -61,7 +61,29 @@ def build(force=False, verbose=False, defines=(), out=None):
     return out
 
 
+HOST_SOURCES = ["Camera.cpp", "GraphicsDevice_cuda.cpp", "headless_main.cpp"]
+HOST_OUT = os.path.join(HERE, "vkrt_headless")
+
+
+def build_host(force=False):
+    """g++ build of the C++ host side (csrc/host): the GraphicsDevice drop-in + the headless frame loop, linked
+    against libvkrt_cuda.so (rpath $ORIGIN).  -ffp-contract=off: Camera.cpp must round like the reference's build."""
+    srcs = [os.path.join(CSRC, "host", f) for f in HOST_SOURCES]
+    deps = srcs + [os.path.join(CSRC, "host", "GraphicsDevice.h"), os.path.join(HERE, "..", "include", "vkrt.h"), OUT]
+    if not force and os.path.exists(HOST_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_OUT) for d in deps):
+        return HOST_OUT
+    cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-Wextra",
+           "-I" + os.path.join(HERE, "..", "include"), "-I" + os.path.join(CSRC, "host")] + srcs + \
+          ["-L" + HERE, "-lvkrt_cuda", "-Wl,-rpath,$ORIGIN", "-o", HOST_OUT]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("host build failed:\n" + r.stdout)
+    return HOST_OUT
+
+
 if __name__ == "__main__":
     defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
     outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))
+    if not defs and not outs:
+        print(build_host(force="--force" in sys.argv))

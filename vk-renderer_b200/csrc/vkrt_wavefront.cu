@@ -28,6 +28,9 @@
 #ifndef VKRT_FETCH_CHUNK
 #define VKRT_FETCH_CHUNK 128   // ray indices a warp reserves per atomicAdd on the queue head
 #endif
+#ifndef VKRT_TRAV_UNROLL
+#define VKRT_TRAV_UNROLL 2
+#endif
 #ifndef VKRT_TRACE_BLOCK
 #define VKRT_TRACE_BLOCK 128
 #endif
@@ -256,7 +259,9 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                 const unsigned tm = __ballot_sync(full, trav);
                 if (tm == 0) break;
                 if (__popc(tm) < VKRT_REFILL && __any_sync(full, !drained && !trav)) break;
-                if (trav) trav_step<ANY, STATS>(tv, stack, sc, o, d, st);
+#pragma unroll
+                for (int u = 0; u < VKRT_TRAV_UNROLL; ++u)     // the warp votes above cost ~10 instructions: amortise them
+                    if (has && tv.node >= 0) trav_step<ANY, STATS>(tv, stack, sc, o, d, st);
             }
         }
 
