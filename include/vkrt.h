@@ -204,6 +204,11 @@ VKRT_API vkrt_error vkrt_read_rgba8_async(vkrt_ctx *ctx, void *pinned_host, size
 /* (Re)runs only the resolve (mean, Reinhard, gamma, dither, unorm8; Tracer.comp:585-592). */
 VKRT_API vkrt_error vkrt_resolve(vkrt_ctx *ctx);
 
+/* The present filter of the reference (ref: Assets/Fullscreen.frag:14-31 with the sampler of
+ * Source/GraphicsDevice.cpp:770-794): temporal-variance-gated 4-tap blur of image slot 0 against image slot 1,
+ * resampled to an out_w x out_h framebuffer (row 0 = top, like the swapchain image).  Synchronous host copy. */
+VKRT_API vkrt_error vkrt_present(vkrt_ctx *ctx, void *host_rgba8, uint32_t out_w, uint32_t out_h);
+
 /* Ray counters, cumulative since creation / vkrt_reset_counters.  A "ray" is one trace_ray
  * invocation of the reference algorithm (Tracer.comp:374, Raytracer.comp:224). */
 typedef struct vkrt_counters {

@@ -66,6 +66,7 @@ def _load(fast):
     lib.orc_scene_read_bvh.argtypes = [vp, vp, C.c_size_t]
     lib.orc_render.argtypes = [vp, C.POINTER(Params), vp, vp, vp, vp, C.POINTER(Counters)]
     lib.orc_resolve.argtypes = [C.POINTER(Params), vp, vp, vp]
+    lib.orc_present.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, C.c_uint32]
     for fn in ("orc_sin", "orc_cos", "orc_exp2", "orc_log2"):
         getattr(lib, fn).argtypes = [C.c_float]
         getattr(lib, fn).restype = C.c_float
@@ -192,6 +193,16 @@ def resolve(frame_data, accum, integrator=PATH, seed=0, frame_index=0, fast=Fals
     out = np.zeros((h, w, 4), dtype=np.uint8)
     accum = np.ascontiguousarray(accum, dtype=np.float32)
     assert lib(fast).orc_resolve(C.byref(p), _ptr(fd), _ptr(accum), _ptr(out)) == 0
+    return out
+
+
+def present(binding0, binding1, out_w, out_h, fast=False):
+    """Fullscreen.frag on two rgba8 images (h, w, 4) -> (out_h, out_w, 4) framebuffer, row 0 = top."""
+    b0 = np.ascontiguousarray(binding0, dtype=np.uint8)
+    b1 = np.ascontiguousarray(binding1, dtype=np.uint8)
+    th, tw = b0.shape[:2]
+    out = np.zeros((out_h, out_w, 4), dtype=np.uint8)
+    assert lib(fast).orc_present(_ptr(b0), _ptr(b1), tw, th, _ptr(out), out_w, out_h) == 0
     return out
 
 

@@ -957,6 +957,48 @@ int orc_render(const orc_scene *sc, const orc_params *pp, const orc_frame_data *
     return 0;
 }
 
+// ---- Fullscreen.frag:14-31 -- the present filter ----------------------------------
+// Sampler: Source/GraphicsDevice.cpp:770-794 (bilinear, clamp-to-border, opaque black), normalised coordinates.
+// Bilinear weights are implementation-defined in Vulkan; this restatement uses exact binary32 weights
+// (texel centre at +0.5, mix() for both lerps) -- one legal execution.
+static V3 sample_bilinear(const uint8_t *img, uint32_t w, uint32_t h, float u, float v)
+{
+    const float s = u * (float)w - 0.5f, t = v * (float)h - 0.5f;
+    const float fs0 = floorf(s), ft0 = floorf(t);
+    const float fx = s - fs0, fy = t - ft0;
+    const int i0 = (int)fs0, j0 = (int)ft0;
+    auto texel = [&](int i, int j) -> V3 {
+        if (i < 0 || j < 0 || i >= (int)w || j >= (int)h) return v3(0.0f);       // VK_BORDER_COLOR_INT_OPAQUE_BLACK
+        const uint8_t *p = img + 4 * ((size_t)j * w + (size_t)i);
+        return V3{(float)p[0] / 255.0f, (float)p[1] / 255.0f, (float)p[2] / 255.0f};
+    };
+    const V3 a = mix3(texel(i0, j0), texel(i0 + 1, j0), fx), b = mix3(texel(i0, j0 + 1), texel(i0 + 1, j0 + 1), fx);
+    return mix3(a, b, fy);
+}
+
+int orc_present(const uint8_t *binding0, const uint8_t *binding1, uint32_t tw, uint32_t th, uint8_t *out, uint32_t W, uint32_t H)
+{
+    const float inv_size = 1.0f / 2048.0f;                                         // Fullscreen.frag:12
+    for (uint32_t y = 0; y < H; ++y)
+        for (uint32_t x = 0; x < W; ++x) {
+            // Fullscreen.vert:8-10: uv_coords spans [0,1] over the framebuffer, sampled at the pixel centre
+            const float us = ((float)x + 0.5f) / (float)W, ut = ((float)y + 0.5f) / (float)H;
+            const float u = us, v = 1.0f - ut;                                     // :16
+            const V3 c0 = sample_bilinear(binding0, tw, th, u, v);
+            const V3 c1 = sample_bilinear(binding1, tw, th, u, v);
+            const V3 N = sample_bilinear(binding0, tw, th, u + 0.0f * inv_size, v + 1.0f * inv_size);
+            const V3 S = sample_bilinear(binding0, tw, th, u + 0.0f * inv_size, v + -1.0f * inv_size);
+            const V3 E = sample_bilinear(binding0, tw, th, u + 1.0f * inv_size, v + 0.0f * inv_size);
+            const V3 Wc = sample_bilinear(binding0, tw, th, u + -1.0f * inv_size, v + 0.0f * inv_size);
+            const V3 dlt = c0 - c1;
+            const float vT = dot3(dlt, dlt);                                       // :26 temporal variance
+            const V3 fin = vT > 0.0005f ? (((N + S) + E) + Wc) / 4.0f : c0;         // :28
+            uint8_t *o = out + 4 * ((size_t)y * W + x);
+            o[0] = unorm8(fin.x); o[1] = unorm8(fin.y); o[2] = unorm8(fin.z); o[3] = 255;
+        }
+    return 0;
+}
+
 float orc_sin(float x) { float s, c; sincos_(x, s, c); return s; }
 float orc_cos(float x) { float s, c; sincos_(x, s, c); return c; }
 float orc_exp2(float x) { return exp2_(x); }

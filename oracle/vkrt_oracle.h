@@ -80,6 +80,10 @@ int  orc_render(const orc_scene *, const orc_params *, const orc_frame_data *,
 /* Resolve only (Tracer.comp:585-592 / Raytracer.comp:398). */
 int  orc_resolve(const orc_params *, const orc_frame_data *, const float *accum, uint8_t *rgba8);
 
+/* Fullscreen.frag: temporal-variance-gated 4-tap blur of binding 0 vs binding 1 (both tw x th rgba8, row 0 =
+ * bottom) into a W x H rgba8 framebuffer (row 0 = top). */
+int  orc_present(const uint8_t *binding0, const uint8_t *binding1, uint32_t tw, uint32_t th, uint8_t *out, uint32_t W, uint32_t H);
+
 /* unit-level entry points for known-answer tests */
 float    orc_sin(float), orc_cos(float), orc_exp2(float), orc_log2(float), orc_pow(float, float);
 uint32_t orc_pcg_hash(uint32_t);

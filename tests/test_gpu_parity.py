@@ -428,3 +428,30 @@ def test_cpp_headless_loop_matches_python_mirror(vk, tmp_path):
     py = dev.renderer.read_rgba8()[..., :3]
     dev.Destruct()
     assert np.array_equal(cpp, py)
+
+
+def test_present_filter_matches_oracle(vk, oracle):
+    """Fullscreen.frag (variance-gated NSEW blur, bilinear clamp-to-border sampler) on two
+    consecutive traced frames, resampled to the 1024x768 window of Main.cpp:92 -- byte-exact against the oracle,
+    including the reference's quirk that binding 0/1 are fixed image slots."""
+    V = vk
+    res = 256
+    r = V.Renderer(res, res, spp=4, max_depth=4, frames_in_flight=2)
+    r.use_default_scene(V.SCENE_TRACER)
+    r.set_seed(9)
+    cam = V.default_camera()
+    slots = {}
+    for f in range(3):
+        cam.move_right(2.0)
+        r.draw(V.default_frame_data(camera=cam, seed=0.1 * f))
+        slots[(f + 1) % 2] = r.read_rgba8()          # draw f writes image slot (f + 1) % 2 (cur_target advances first)
+        if f >= 1:
+            got = r.present(1024, 768)
+            want = oracle.present(slots[0], slots[1], 1024, 768)
+            assert np.array_equal(got, want), "frame %d: %d bytes differ" % (f, int((got != want).sum()))
+            assert got[..., 3].min() == 255
+    # the gate really switches: with a moving camera both branches of :28 occur
+    a, b = slots[0].astype(np.float32) / 255, slots[1].astype(np.float32) / 255
+    var = ((a - b)[..., :3] ** 2).sum(-1)
+    assert (var > 0.0005).any() and (var <= 0.0005).any()
+    r.close()

@@ -97,6 +97,7 @@ SIGNATURES = {
     "vkrt_read_hit_ids": ([_vp, _vp, _sz], C.c_int8),
     "vkrt_read_rgba8_async": ([_vp, _vp, _sz], C.c_int8),
     "vkrt_resolve": ([_vp], C.c_int8),
+    "vkrt_present": ([_vp, _vp, _u32, _u32], C.c_int8),
     "vkrt_get_counters": ([_vp, _P(Counters)], C.c_int8),
     "vkrt_reset_counters": ([_vp], C.c_int8),
     "vkrt_last_frame_timing": ([_vp, _P(C.c_float), _P(C.c_float), _P(_u32)], C.c_int8),

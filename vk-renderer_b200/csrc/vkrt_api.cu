@@ -69,6 +69,7 @@ struct vkrt_ctx {
     unsigned long long *d_counters = nullptr;
     uint32_t *d_work_head = nullptr;
     float4 *d_packed = nullptr;
+    uchar4 *d_present = nullptr; size_t present_bytes = 0;
     uint64_t frames = 0;
     WaveEngine wave{};
     bool wave_ready = false;
@@ -261,7 +262,7 @@ VKRT_API vkrt_error vkrt_destroy(vkrt_ctx *c)
     cudaFree(c->d_spheres); cudaFree(c->d_sphere_mat); cudaFree(c->d_mats); cudaFree(c->d_tris);
     cudaFree(c->bvh.nodes); cudaFree(c->bvh.nodes4); cudaFree(c->d_accum); cudaFree(c->d_hit_ids);
     for (auto p : c->d_rgba) cudaFree(p);
-    cudaFree(c->d_counters); cudaFree(c->d_work_head); cudaFree(c->d_packed);
+    cudaFree(c->d_counters); cudaFree(c->d_work_head); cudaFree(c->d_packed); cudaFree(c->d_present);
     if (c->wave_ready) wave_engine_free(c->wave);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_trace0) cudaEventDestroy(c->ev_trace0);
@@ -664,6 +665,27 @@ VKRT_API vkrt_error vkrt_debug_dump_timeline(vkrt_ctx *c, const char *path)
     cudaEventElapsedTime(&tot, c->ev_begin, c->ev_end);
     std::fprintf(f, "frame total %.4f\n", tot);
     std::fclose(f);
+    return VKRT_SUCCESS;
+}
+
+/* Assets/Fullscreen.frag on the traced images: binding 0 = image slot 0, binding 1 = image slot 1 -- fixed, as the
+ * reference writes its graphics descriptor set once (Source/GraphicsDevice.cpp:964-983) while the compute pass
+ * alternates its target, so "current" and "previous" swap roles every other frame. */
+VKRT_API vkrt_error vkrt_present(vkrt_ctx *c, void *host_rgba8, uint32_t out_w, uint32_t out_h)
+{
+    if (!c || !host_rgba8 || out_w == 0 || out_h == 0) return VKRT_BAD_ARG;
+    if (c->d_rgba.size() < 2) return fail(c, VKRT_BAD_ARG, "the present filter needs frames_in_flight >= 2");
+    DeviceGuard g(c->info.device_id);
+    CU(c, join(c));
+    const size_t bytes = (size_t)out_w * out_h * 4;
+    if (c->present_bytes < bytes) {
+        cudaFree(c->d_present); c->d_present = nullptr; c->present_bytes = 0;
+        CU(c, cudaMalloc(&c->d_present, bytes));
+        c->present_bytes = bytes;
+    }
+    CU(c, launch_present(c->d_rgba[0], c->d_rgba[1], c->info.width, c->info.height, c->d_present, out_w, out_h, c->stream));
+    CU(c, cudaMemcpyAsync(host_rgba8, c->d_present, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
     return VKRT_SUCCESS;
 }
 

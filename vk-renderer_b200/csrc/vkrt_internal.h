@@ -39,6 +39,8 @@ cudaError_t launch_pack(const RenderParams &rp, float4 *packed, cudaStream_t st)
 cudaError_t launch_unpack(float4 *accum, const float4 *packed, uint32_t width, uint32_t height, uint32_t tile_rank,
                           uint32_t tile_count, int add, cudaStream_t st);
 cudaError_t launch_clear_accum(float4 *accum, size_t n, cudaStream_t st);
+cudaError_t launch_present(const uchar4 *b0, const uchar4 *b1, uint32_t tw, uint32_t th, uchar4 *out, uint32_t W, uint32_t H,
+                           cudaStream_t st);
 
 // vkrt_wavefront.cu
 struct WaveBuffers {

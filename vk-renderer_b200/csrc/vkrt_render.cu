@@ -238,6 +238,53 @@ cudaError_t launch_unpack(float4 *accum, const float4 *packed, uint32_t width, u
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Present filter: Assets/Fullscreen.frag:14-31 on the two traced images (bilinear, clamp-to-border black
+// sampler of Source/GraphicsDevice.cpp:770-794), one thread per framebuffer pixel.
+// ------------------------------------------------------------------------------------------------
+VKRT_DEV V3 sample_bilinear(const uchar4 *__restrict__ img, uint32_t w, uint32_t h, float u, float v)
+{
+    const float s = u * (float)w - 0.5f, t = v * (float)h - 0.5f;
+    const float fs0 = floorf(s), ft0 = floorf(t);
+    const float fx = s - fs0, fy = t - ft0;
+    const int i0 = (int)fs0, j0 = (int)ft0;
+    V3 c[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = i0 + (k & 1), j = j0 + (k >> 1);
+        if (i < 0 || j < 0 || i >= (int)w || j >= (int)h) c[k] = v3(0.0f);
+        else { const uchar4 p = __ldg(img + (size_t)j * w + (size_t)i); c[k] = v3((float)p.x / 255.0f, (float)p.y / 255.0f, (float)p.z / 255.0f); }
+    }
+    return mix3(mix3(c[0], c[1], fx), mix3(c[2], c[3], fx), fy);
+}
+
+__global__ void __launch_bounds__(256) k_present(const uchar4 *__restrict__ b0, const uchar4 *__restrict__ b1, uint32_t tw, uint32_t th,
+                                                  uchar4 *__restrict__ out, uint32_t W, uint32_t H)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= W * H) return;
+    const uint32_t x = i % W, y = i / W;
+    const float inv_size = 1.0f / 2048.0f;
+    const float u = ((float)x + 0.5f) / (float)W, v = 1.0f - ((float)y + 0.5f) / (float)H;
+    const V3 c0 = sample_bilinear(b0, tw, th, u, v);
+    const V3 c1 = sample_bilinear(b1, tw, th, u, v);
+    const V3 N = sample_bilinear(b0, tw, th, u + 0.0f * inv_size, v + 1.0f * inv_size);
+    const V3 S = sample_bilinear(b0, tw, th, u + 0.0f * inv_size, v + -1.0f * inv_size);
+    const V3 E = sample_bilinear(b0, tw, th, u + 1.0f * inv_size, v + 0.0f * inv_size);
+    const V3 Wc = sample_bilinear(b0, tw, th, u + -1.0f * inv_size, v + 0.0f * inv_size);
+    const V3 dlt = c0 - c1;
+    const float vT = dot3(dlt, dlt);
+    const V3 fin = vT > 0.0005f ? (((N + S) + E) + Wc) / 4.0f : c0;
+    out[i] = make_uchar4(unorm8(fin.x), unorm8(fin.y), unorm8(fin.z), 255);
+}
+
+cudaError_t launch_present(const uchar4 *b0, const uchar4 *b1, uint32_t tw, uint32_t th, uchar4 *out, uint32_t W, uint32_t H,
+                           cudaStream_t stream)
+{
+    k_present<<<(W * H + 255u) / 256u, 256, 0, stream>>>(b0, b1, tw, th, out, W, H);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_clear_accum(float4 *accum, size_t n, cudaStream_t stream)
 {
     return cudaMemsetAsync(accum, 0, n * sizeof(float4), stream);

@@ -143,6 +143,12 @@ class Renderer:
     def read_rgba8_async(self, pinned_ptr, nbytes):
         self._ck(self.lib.vkrt_read_rgba8_async(self.ctx, pinned_ptr, nbytes))
 
+    def present(self, out_w, out_h):
+        """Fullscreen.frag on the two traced image slots -> (out_h, out_w, 4) uint8 framebuffer, row 0 = top."""
+        out = np.zeros((out_h, out_w, 4), dtype=np.uint8)
+        self._ck(self.lib.vkrt_present(self.ctx, _ptr(out), out_w, out_h))
+        return out
+
     def read_accum(self):
         out = np.zeros((self.height, self.width, 4), dtype=np.float32)
         self._ck(self.lib.vkrt_read_accum(self.ctx, _ptr(out), out.nbytes))
