@@ -455,3 +455,72 @@ def test_present_filter_matches_oracle(vk, oracle):
     var = ((a - b)[..., :3] ** 2).sum(-1)
     assert (var > 0.0005).any() and (var <= 0.0005).any()
     r.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_edge_cases(vk, oracle, variant):
+    """Ragged / degenerate inputs: 1x1 and odd-sized images, spp = 1 (single lane), depth 1, a scene with no
+    light, no spheres at all, an empty scene, triangles together with the LBVH, many lights."""
+    V = vk
+    fd = V.default_frame_data(aspect_ratio=1.5, seed=0.4)
+
+    def check(scene, w, h, spp, depth, bvh, name):
+        r = V.Renderer(w, h, spp=spp, max_depth=depth, variant=variant, flags=V.FLAG_HIT_IDS)
+        r.set_scene(scene)
+        if bvh:
+            r.build_bvh()
+        r.set_seed(4)
+        r.draw(fd)
+        acc, ids, rgba, c = r.read_accum(), r.read_hit_ids(), r.read_rgba8(), r.counters()
+        r.close()
+        sc = apply_scene(oracle, scene)
+        if bvh:
+            sc.build_bvh()
+        oacc, oids, orgba, oc = sc.render(fd, w, h, spp=spp, max_depth=depth, sphere_mode=oracle.S_BVH if bvh else oracle.LITERAL, seed=4)
+        assert np.array_equal(ids, oids), name
+        assert bits_equal(acc, oacc), name + ": " + mismatch_report(acc, oacc)
+        assert np.array_equal(rgba, orgba), name
+        assert (c.closest_rays, c.shadow_rays, c.paths) == (oc.closest_rays, oc.shadow_rays, oc.paths), name
+
+    base = V.scenes.random_spheres(50)
+    check(base, 1, 1, 1, 1, True, "1x1")
+    check(base, 37, 23, 1, 8, True, "odd size, spp 1")
+    check(base, 33, 65, 3, 1, True, "depth 1, spp 3")
+    check(base, 70, 40, 5, 3, False, "literal loop on a synthetic scene")
+
+    dark = V.scenes.random_spheres(50)
+    dark.materials[7, 4:7] = 0.0                                   # the light no longer emits: no shadow rays at all
+    check(dark, 40, 30, 2, 4, True, "no light")
+
+    planes_only = V.scenes.tracer_default()
+    planes_only.spheres = np.zeros((0, 4), np.float32); planes_only.sphere_mat = np.zeros(0, np.uint32)
+    check(planes_only, 40, 30, 2, 4, True, "no spheres, BVH over nothing")
+    check(planes_only, 40, 30, 2, 4, False, "no spheres")
+
+    empty = V.scenes.tracer_default()
+    empty.spheres = np.zeros((0, 4), np.float32); empty.sphere_mat = np.zeros(0, np.uint32)
+    empty.planes = np.zeros((0, 4), np.float32); empty.plane_mat = np.zeros(0, np.uint32)
+    empty.triangles = np.zeros((0, 12), np.float32)
+    check(empty, 16, 16, 2, 4, False, "empty scene")
+
+    tris = V.scenes.random_spheres(80)
+    rng = np.random.default_rng(3)
+    t = np.zeros((6, 12), np.float32)
+    for k in range(6):
+        c = rng.uniform([-40, 10, -40], [40, 100, 40])
+        for v in range(3):
+            t[k, 4 * v:4 * v + 3] = c + rng.uniform(-25, 25, 3)
+    tris.triangles = t
+    tris.tri_mat = 5
+    check(tris, 64, 48, 2, 5, True, "triangles + LBVH")
+
+    lights = V.scenes.random_spheres(60)
+    lights.materials[8:20, 4:7] = 40.0                             # 12 more emissive spheres: 13 lights
+    check(lights, 48, 36, 2, 3, True, "13 lights")
+    too_many = V.scenes.random_spheres(60)
+    too_many.materials[8:30, 4:7] = 40.0
+    r = V.Renderer(16, 16, variant=variant)
+    r.set_scene(too_many)
+    with pytest.raises(V.VkrtError):
+        r.draw(fd)
+    r.close()
