@@ -12,9 +12,11 @@ BASELINE.json configs[3], the configuration the north_star's target is quoted on
 
 Mrays/s counts trace_ray invocations of the reference algorithm (Tracer.comp:374): nearest-hit +
 shadow queries, counted on the device by the kernels themselves.
-N > 1 (torchrun, one rank per GPU): the frame is sharded by interleaved 32x32 screen tiles (fixed
-total work => "scaling": "strong"); every step ends with the NCCL gather of the owned accumulator
-tiles to rank 0 and the resolve there.
+N > 1 (torchrun, one rank per GPU), two shardings of the path:
+  --scaling weak   (default) sample ranges: every GPU renders 16 spp of the whole frame, so N GPUs deliver a
+                   16*N-spp frame per step (per-GPU work fixed); rank 0 sums the N accumulators in rank order
+  --scaling strong interleaved 32x32 screen tiles of the one 16-spp frame (total work fixed)
+Either way every step ends with the NCCL gather of the shards to rank 0 and the resolve there.
 """
 import argparse
 import ctypes as C
@@ -192,7 +194,7 @@ def run_reference(args):
     r = cpu_render(args.workload, per_step, steps=args.steps, warmup=args.warmup)
     line = {"impl": "reference", "metric": "Mrays/s (all bounces)", "value": r["value"], "unit": "Mrays/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_sample_step"],
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "width": w, "height": h, "spp": spp, "max_depth": depth},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -220,9 +222,12 @@ def run_ours(args):
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
 
     desc, w, h, spp, depth = WORKLOADS[args.workload]
+    weak = world > 1 and args.scaling == "weak"
+    if weak:
+        spp *= world                  # every rank renders its own range of `spp / world` = the workload's samples
     scene, use_bvh = make_scene(V, args.workload)
     variant = V.VARIANT_WAVEFRONT if args.variant == "wavefront" else V.VARIANT_MEGAKERNEL
-    tile_shard, sample_shard = shard_layout(rank, world, 1)
+    tile_shard, sample_shard = shard_layout(rank, world, world if weak else 1)
     if args.shard_of > 1 and world == 1:          # diagnostic: one GPU renders tile shard 0 of N (no exchange)
         tile_shard = (0, args.shard_of)
     stream = torch.cuda.Stream(device=device)
@@ -238,7 +243,7 @@ def run_ours(args):
 
     r = make_renderer(V.FLAG_NO_RESOLVE if world > 1 else 0)
     bvh = r.bvh_info()
-    gather = FrameGather(r, rank, world, 1, stream, device) if world > 1 else None
+    gather = FrameGather(r, rank, world, world if weak else 1, stream, device) if world > 1 else None
     n_px = w * h
     pinned = torch.empty(2, n_px * 4, dtype=torch.uint8).pin_memory() if rank == 0 else None
 
@@ -358,11 +363,13 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_render(args.workload, 15.0)
         line = {"metric": "Mrays/s (all bounces)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak" if (weak or world == 1) else "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc, "width": w, "height": h, "spp": spp, "max_depth": depth,
                            "variant": args.variant, "scene_sha": scene.digest(), "bvh_nodes": bvh.n_nodes,
-                           "bvh_build_ms": bvh.build_ms, "parallelism": "tile-shard x%d" % world,
+                           "bvh_build_ms": bvh.build_ms, "parallelism": ("sample-shard x%d (%d spp per GPU, %d-spp frame)" % (world, spp // world, spp)) if weak
+                           else "tile-shard x%d" % world,
                            "l2_policy": "every step renders a new frame (new RNG keys); accumulator (%.0f MB) + rgba8 are rewritten each step; "
                                         "scene is L2-resident by design, no flush" % (n_px * 16 / 1e6)},
                 "ms_per_frame": ms_total / args.steps,
@@ -400,6 +407,8 @@ def main():
     ap.add_argument("--variant", default="auto", choices=["auto", "mega", "wavefront"],
                     help="auto = wavefront for the LBVH scenes (cfg3/cfg4), megakernel for the 10-primitive default scene (cfg2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = sample-range shards (16 spp per GPU), strong = tile shards of the one 16-spp frame")
     ap.add_argument("--micro", action="store_true", help="also run the FP32 / L2 microbenchmarks")
     ap.add_argument("--shard-of", type=int, default=1, help="diagnostic (1 GPU): render only tile shard 0 of N, to size the fixed per-frame costs")
     args = ap.parse_args()
