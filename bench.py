@@ -303,9 +303,9 @@ def run_ours(args):
     trav_ms, trav_launches = [], 0
     for i in range(min(args.steps, 5)):
         step(args.warmup + i)
-        ms, nl = r.last_frame_traversal_timing()
+        ms, nl, all_ms = r.last_frame_traversal_timing()
         trav_ms.append(ms); trav_launches = nl
-        trace_ms.append(r.last_frame_timing()[0])
+        trace_ms.append(all_ms)
     barrier()
     kernel_ms = statistics.mean(trav_ms)
     frame_kernels_ms = statistics.mean(trace_ms)
@@ -350,7 +350,9 @@ def run_ours(args):
                 "launches_per_frame": trav_launches, "kernel_ms_per_frame": kernel_ms,
                 "kernel_ms_per_launch": kernel_ms / max(trav_launches, 1),
                 "algorithmic_bytes_per_frame": alg_bytes, "algorithmic_bytes_per_launch": alg_bytes / max(trav_launches, 1),
-                "share_of_frame": kernel_ms / max(frame_kernels_ms, 1e-9),
+                "share_of_step": kernel_ms / max(frame_kernels_ms, 1e-9),
+                "share_note": "traversal launches / all kernel launches of a frame, both summed from per-launch CUDA events "
+                              "(the wavefront's two lanes overlap, so the sums exceed ms_per_step)",
                 "nodes_per_traversed_ray": sc.node_visits / max(traversed, 1),
                 "leaf_tests_per_traversed_ray": sc.leaf_tests / max(traversed, 1),
                 "note": "traffic = ncu dram bytes per frame for the same launches (profiles/traffic.json). The tree (%.1f MB) is "

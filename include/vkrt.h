@@ -230,9 +230,11 @@ VKRT_API vkrt_error vkrt_last_frame_timing(vkrt_ctx *ctx, float *trace_ms, float
                                            uint32_t *n_launches);
 
 /* Device milliseconds summed over the traversal-kernel launches of the last frame (the megakernel's one
- * launch, or every extend / shadow launch of the wavefront), each bracketed by its own CUDA events, and
- * how many launches that was.  This is the duration bench.py's roofline divides by. */
-VKRT_API vkrt_error vkrt_last_frame_traversal_timing(vkrt_ctx *ctx, float *traversal_ms, uint32_t *n_launches);
+ * launch, or every extend / shadow launch of the wavefront), each bracketed by its own CUDA events, how many
+ * launches that was, and the same sum over ALL kernel launches of the frame (the wavefront's two lanes overlap,
+ * so these sums can exceed the frame time).  This is the duration bench.py's roofline divides by. */
+VKRT_API vkrt_error vkrt_last_frame_traversal_timing(vkrt_ctx *ctx, float *traversal_ms, uint32_t *n_launches,
+                                                     float *all_kernels_ms);
 
 /* Diagnostics: per-launch start/end times of the most recent wavefront frame, as text lines
  * "lane kernel start_ms end_ms" (relative to the frame's first launch). */

@@ -101,7 +101,7 @@ SIGNATURES = {
     "vkrt_get_counters": ([_vp, _P(Counters)], C.c_int8),
     "vkrt_reset_counters": ([_vp], C.c_int8),
     "vkrt_last_frame_timing": ([_vp, _P(C.c_float), _P(C.c_float), _P(_u32)], C.c_int8),
-    "vkrt_last_frame_traversal_timing": ([_vp, _P(C.c_float), _P(_u32)], C.c_int8),
+    "vkrt_last_frame_traversal_timing": ([_vp, _P(C.c_float), _P(_u32), _P(C.c_float)], C.c_int8),
     "vkrt_debug_dump_timeline": ([_vp, C.c_char_p], C.c_int8),
     "vkrt_get_bvh_info": ([_vp, _P(BvhInfo)], C.c_int8),
     "vkrt_read_bvh_nodes": ([_vp, _vp, _sz], C.c_int8),

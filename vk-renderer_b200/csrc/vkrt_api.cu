@@ -618,28 +618,30 @@ VKRT_API vkrt_error vkrt_last_frame_timing(vkrt_ctx *c, float *trace_ms, float *
     return VKRT_SUCCESS;
 }
 
-VKRT_API vkrt_error vkrt_last_frame_traversal_timing(vkrt_ctx *c, float *traversal_ms, uint32_t *n_launches)
+VKRT_API vkrt_error vkrt_last_frame_traversal_timing(vkrt_ctx *c, float *traversal_ms, uint32_t *n_launches, float *all_kernels_ms)
 {
     if (!c) return VKRT_BAD_ARG;
     if (!c->timing_valid) return fail(c, VKRT_BAD_ARG, "no frame drawn yet");
     DeviceGuard g(c->info.device_id);
     CU(c, cudaEventSynchronize(c->ev_end));
-    float sum = 0.f; uint32_t n = 0;
+    float sum = 0.f, all = 0.f; uint32_t n = 0;
     if (c->info.integrator == VKRT_INTEGRATOR_PATH && c->info.variant == VKRT_VARIANT_WAVEFRONT && c->wave_ready) {
         for (uint32_t l = 0; l < c->wave.n_lanes; ++l)
             for (uint32_t i = 0; i + 1 < c->wave.lane[l].n_ev; i += 2) {
                 const uint8_t tag = c->wave.lane[l].ev_tag[i / 2];
-                if (tag != 1 && tag != 3) continue;           // extend / shadow launches only
                 float ms = 0.f;
                 CU(c, cudaEventElapsedTime(&ms, c->wave.lane[l].ev[i], c->wave.lane[l].ev[i + 1]));
-                sum += ms; ++n;
+                all += ms;
+                if (tag == 1 || tag == 3) { sum += ms; ++n; }      // extend / shadow launches
             }
     } else {
         CU(c, cudaEventElapsedTime(&sum, c->ev_begin, c->ev_trace1));
+        CU(c, cudaEventElapsedTime(&all, c->ev_begin, c->ev_end));
         n = 1;
     }
     if (traversal_ms) *traversal_ms = sum;
     if (n_launches) *n_launches = n;
+    if (all_kernels_ms) *all_kernels_ms = all;
     return VKRT_SUCCESS;
 }
 

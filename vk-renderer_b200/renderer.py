@@ -173,9 +173,9 @@ class Renderer:
         return a.value, b.value, n.value
 
     def last_frame_traversal_timing(self):
-        a, n = C.c_float(), C.c_uint32()
-        self._ck(self.lib.vkrt_last_frame_traversal_timing(self.ctx, C.byref(a), C.byref(n)))
-        return a.value, n.value
+        a, n, t = C.c_float(), C.c_uint32(), C.c_float()
+        self._ck(self.lib.vkrt_last_frame_traversal_timing(self.ctx, C.byref(a), C.byref(n), C.byref(t)))
+        return a.value, n.value, t.value
 
     def dump_timeline(self, path):
         self._ck(self.lib.vkrt_debug_dump_timeline(self.ctx, path.encode()))
