@@ -31,6 +31,9 @@
 #ifndef VKRT_TRAV_UNROLL
 #define VKRT_TRAV_UNROLL 2
 #endif
+#ifndef VKRT_LEAF_BATCH
+#define VKRT_LEAF_BATCH 8    // run a leaf phase once this many lanes wait at a leaf (0: leaf tests inside the node step)
+#endif
 #ifndef VKRT_TRACE_BLOCK
 #define VKRT_TRACE_BLOCK 128
 #endif
@@ -204,8 +207,23 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
     Hit hit{0.f, 0, 0};
     bool found = false;
     float cur = 0.f;
-    Trav tv; tv.node = -1; tv.sp = 0;
+#if VKRT_LEAF_BATCH
+    const int FIN = TRAV_DONE;
+    Trav tv; tv.node = FIN; tv.sp = 0;
+#if VKRT_SMEM_STACK
+    __shared__ int s_stack[VKRT_SMEM_STACK][VKRT_TRACE_BLOCK];
+#endif
+    TravStack<VKRT_TRACE_BLOCK> stack;
+#if VKRT_SMEM_STACK
+    stack.sm = &s_stack[0][threadIdx.x];
+#else
+    stack.sm = nullptr;
+#endif
+#else
+    const int FIN = -1;
+    Trav tv; tv.node = FIN; tv.sp = 0;
     int stack[BVH_STACK];
+#endif
 
     for (;;) {
         // ---- refill the lanes that have no ray -------------------------------------------------
@@ -245,8 +263,8 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                         ++st.closest;
                         found = trace_tris<true>(sc, o, d, cur, hit);
                     }
-                    if (BVH) trav_init(tv, sc, o, d, EPS, sphere_bound<true>(cur));
-                    else tv.node = -1;
+                    if (BVH) { trav_init(tv, sc, o, d, EPS, sphere_bound<true>(cur)); if (tv.node < 0) tv.node = FIN; }
+                    else tv.node = FIN;
                 }
             }
         }
@@ -254,6 +272,24 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
 
         // ---- traverse; leave as soon as the warp has thinned out and there are rays left to fetch --
         if (BVH) {
+#if VKRT_LEAF_BATCH
+            for (;;) {
+                const bool trav = has && tv.node != FIN;
+                const unsigned tm = __ballot_sync(full, trav);
+                if (tm == 0) break;
+                if (__popc(tm) < VKRT_REFILL && __any_sync(full, !drained && !trav)) break;
+                // lanes whose next item is a scheduled leaf wait until VKRT_LEAF_BATCH of them can run the leaf test
+                // together (or nobody has an inner node left); everybody else keeps visiting inner nodes
+                const unsigned im = __ballot_sync(full, trav && tv.node >= 0);
+                if (im == 0 || __popc(tm & ~im) >= VKRT_LEAF_BATCH) {
+                    if (trav && tv.node < 0) trav_leaf_step<ANY, STATS>(tv, stack, sc, o, d, st);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < VKRT_TRAV_UNROLL; ++u)     // the warp votes above cost ~10 instructions: amortise them
+                        if (has && tv.node >= 0) trav_inner_step<STATS>(tv, stack, sc, st);
+                }
+            }
+#else
             for (;;) {
                 const bool trav = has && tv.node >= 0;
                 const unsigned tm = __ballot_sync(full, trav);
@@ -263,10 +299,11 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                 for (int u = 0; u < VKRT_TRAV_UNROLL; ++u)     // the warp votes above cost ~10 instructions: amortise them
                     if (has && tv.node >= 0) trav_step<ANY, STATS>(tv, stack, sc, o, d, st);
             }
+#endif
         }
 
         // ---- finish the lanes whose traversal is over ---------------------------------------------
-        if (has && tv.node < 0) {
+        if (has && tv.node == FIN) {
             if (BVH) {
                 if (tv.best.idx >= 0) { cur = tv.best.t; hit.kind = KIND_SPHERE; hit.index = (uint32_t)tv.best.idx; found = true; }
             } else {
