@@ -39,12 +39,16 @@ WORKLOADS = {
              3840, 2160, 64, 8),
     "cfg2": ("reference default scene (Tracer.comp:186-211), 1920x1080, 16 spp, depth 8, literal primitive loop",
              1920, 1080, 16, 8),
+    # BASELINE.json configs[4]: the multi-GPU case (N > 1: interleaved tiles x 2 sample halves, --scaling strong implied);
+    # one step is ~256 cfg4 frames of work, so run it with a small --steps
+    "cfg5": ("synthetic 100k procedural spheres, 7680x4320, 256 spp, depth 8, device LBVH, tile x sample shards",
+             7680, 4320, 256, 8),
 }
 SEED = 2026
 
 
 def make_scene(V, workload):
-    if workload == "cfg4":
+    if workload in ("cfg4", "cfg5"):
         return V.scenes.grid_spheres(), True
     if workload == "cfg3":
         return V.scenes.random_spheres(1024), True
@@ -145,7 +149,7 @@ def cpu_render(workload, target_seconds, steps=1, warmup=0):
     from vk_renderer_b200.device import default_frame_data
     O.build()
     desc, w, h, spp, depth = WORKLOADS[workload]
-    scene = {"cfg4": scenes.grid_spheres, "cfg3": lambda: scenes.random_spheres(1024), "cfg2": scenes.tracer_default}[workload]()
+    scene = {"cfg4": scenes.grid_spheres, "cfg5": scenes.grid_spheres, "cfg3": lambda: scenes.random_spheres(1024), "cfg2": scenes.tracer_default}[workload]()
     use_bvh = workload != "cfg2"
     sc = O.Scene(fast=True)
     sc.set_materials(scene.materials); sc.set_spheres(scene.spheres, scene.sphere_mat)
@@ -222,12 +226,15 @@ def run_ours(args):
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
 
     desc, w, h, spp, depth = WORKLOADS[args.workload]
-    weak = world > 1 and args.scaling == "weak"
+    weak = world > 1 and args.scaling == "weak" and args.workload != "cfg5"
     if weak:
         spp *= world                  # every rank renders its own range of `spp / world` = the workload's samples
+    # sample shards of the frame: weak = one per rank; cfg5 = tiles x 2 sample halves; else tiles only
+    n_sample_shards = world if weak else (args.sample_shards or (2 if (args.workload == "cfg5" and world % 2 == 0) else 1))
+    assert world % n_sample_shards == 0 and spp % n_sample_shards == 0
     scene, use_bvh = make_scene(V, args.workload)
     variant = V.VARIANT_WAVEFRONT if args.variant == "wavefront" else V.VARIANT_MEGAKERNEL
-    tile_shard, sample_shard = shard_layout(rank, world, world if weak else 1)
+    tile_shard, sample_shard = shard_layout(rank, world, n_sample_shards)
     if args.shard_of > 1 and world == 1:          # diagnostic: one GPU renders tile shard 0 of N (no exchange)
         tile_shard = (0, args.shard_of)
     stream = torch.cuda.Stream(device=device)
@@ -243,7 +250,7 @@ def run_ours(args):
 
     r = make_renderer(V.FLAG_NO_RESOLVE if world > 1 else 0)
     bvh = r.bvh_info()
-    gather = FrameGather(r, rank, world, world if weak else 1, stream, device) if world > 1 else None
+    gather = FrameGather(r, rank, world, n_sample_shards, stream, device) if world > 1 else None
     n_px = w * h
     pinned = torch.empty(2, n_px * 4, dtype=torch.uint8).pin_memory() if rank == 0 else None
 
@@ -371,7 +378,8 @@ def run_ours(args):
                 "config": {"workload": desc, "width": w, "height": h, "spp": spp, "max_depth": depth,
                            "variant": args.variant, "scene_sha": scene.digest(), "bvh_nodes": bvh.n_nodes,
                            "bvh_build_ms": bvh.build_ms, "parallelism": ("sample-shard x%d (%d spp per GPU, %d-spp frame)" % (world, spp // world, spp)) if weak
-                           else "tile-shard x%d" % world,
+                           else ("tile-shard x%d" % world if n_sample_shards == 1 else
+                                 "tile-shard x%d x sample-shard x%d (%d spp each)" % (world // n_sample_shards, n_sample_shards, spp // n_sample_shards)),
                            "l2_policy": "every step renders a new frame (new RNG keys); accumulator (%.0f MB) + rgba8 are rewritten each step; "
                                         "scene is L2-resident by design, no flush" % (n_px * 16 / 1e6)},
                 "ms_per_frame": ms_total / args.steps,
@@ -411,6 +419,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = sample-range shards (16 spp per GPU), strong = tile shards of the one 16-spp frame")
+    ap.add_argument("--sample-shards", type=int, default=0,
+                    help="N > 1, --scaling strong: split the ranks into tiles x this many sample ranges (default: 2 for cfg5, else 1)")
     ap.add_argument("--micro", action="store_true", help="also run the FP32 / L2 microbenchmarks")
     ap.add_argument("--shard-of", type=int, default=1, help="diagnostic (1 GPU): render only tile shard 0 of N, to size the fixed per-frame costs")
     args = ap.parse_args()

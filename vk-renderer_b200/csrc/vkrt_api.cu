@@ -145,6 +145,8 @@ vkrt_error upload_scene(vkrt_ctx *c)
     d.spheres = c->d_spheres; d.sphere_mat = c->d_sphere_mat; d.mats = c->d_mats; d.tris = c->d_tris;
     d.bvh = c->use_bvh ? c->bvh.nodes : nullptr;
     d.bvh4 = c->use_bvh ? c->bvh.nodes4 : nullptr;
+    d.qbvh = c->use_bvh ? c->bvh.qnodes : nullptr;
+    for (int k = 0; k < 3; ++k) { d.qs[k] = c->bvh.qgrid[k]; d.qb2[k] = c->bvh.qgrid[3 + k]; }
     d.n_nodes = c->use_bvh ? c->bvh.n_nodes : 0;
     d.n_spheres = (uint32_t)c->spheres.size(); d.n_tris = (uint32_t)c->tris.size(); d.tri_mat = c->tri_mat;
     d.n_planes = (uint32_t)c->planes.size(); d.n_mats = (uint32_t)c->mats.size();
@@ -260,7 +262,7 @@ VKRT_API vkrt_error vkrt_destroy(vkrt_ctx *c)
     DeviceGuard g(c->info.device_id);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_spheres); cudaFree(c->d_sphere_mat); cudaFree(c->d_mats); cudaFree(c->d_tris);
-    cudaFree(c->bvh.nodes); cudaFree(c->bvh.nodes4); cudaFree(c->d_accum); cudaFree(c->d_hit_ids);
+    cudaFree(c->bvh.nodes); cudaFree(c->bvh.nodes4); cudaFree(c->bvh.qnodes); cudaFree(c->d_accum); cudaFree(c->d_hit_ids);
     for (auto p : c->d_rgba) cudaFree(p);
     cudaFree(c->d_counters); cudaFree(c->d_work_head); cudaFree(c->d_packed); cudaFree(c->d_present);
     if (c->wave_ready) wave_engine_free(c->wave);

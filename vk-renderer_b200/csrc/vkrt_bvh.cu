@@ -281,6 +281,59 @@ __global__ void __launch_bounds__(256) k_collapse4(const float4 *__restrict__ no
     for (int k = 0; k < 8; ++k) nodes4[8 * (size_t)i + k] = slot[k];
 }
 
+// ---- 32-byte traversal nodes on a 16-bit grid (vkrt_device.cuh "32-byte nodes") -------------------------
+// grid[0..2] = s, grid[3..5] = b2; the coordinate a code q stands for is X(q) = (2^23 + q) * s + b2 in REAL
+// arithmetic.  Codes are chosen with X(q_lo) <= lo and X(q_hi) >= hi, evaluated in double precision and then
+// moved one more step outward (the double evaluation may round), by a monotone function of the coordinate, so
+// that the coded boxes of the tree nest exactly like the exact boxes they were made from.
+__global__ void k_qgrid(const float4 *__restrict__ nodes, float *__restrict__ grid)
+{
+    const int a = threadIdx.x;
+    if (a >= 3) return;
+    // scene box = union of the root's two child boxes: {lo.x lo.y lo.z hi.x | hi.y hi.z ...}
+    const float4 a0 = nodes[0], b0 = nodes[1], a1 = nodes[2], b1 = nodes[3];
+    const float lo0[3] = {a0.x, a0.y, a0.z}, hi0[3] = {a0.w, b0.x, b0.y}, lo1[3] = {a1.x, a1.y, a1.z}, hi1[3] = {a1.w, b1.x, b1.y};
+    const float lo = fminf(lo0[a], lo1[a]), hi = fmaxf(hi0[a], hi1[a]);
+    float s = (hi - lo) / 65024.0f;
+    if (!(s > 1e-12f)) s = 1e-6f;
+    const float base = lo - 128.0f * s;
+    grid[a] = s;
+    grid[3 + a] = __fmaf_rn(-8388608.0f, s, base);
+}
+__device__ __forceinline__ double q_coord(int q, float s, float b2) { return (double)(8388608 + q) * (double)s + (double)b2; }
+__device__ __forceinline__ uint32_t quantize_lo(float x, float s, float b2)
+{
+    int q = (int)floor(((double)x - q_coord(0, s, b2)) / (double)s);
+    q = min(max(q, 0), 65535);
+    while (q > 0 && q_coord(q, s, b2) > (double)x) --q;
+    while (q < 65535 && q_coord(q + 1, s, b2) <= (double)x) ++q;
+    return (uint32_t)max(q - 1, 0);
+}
+__device__ __forceinline__ uint32_t quantize_hi(float x, float s, float b2)
+{
+    int q = (int)ceil(((double)x - q_coord(0, s, b2)) / (double)s);
+    q = min(max(q, 0), 65535);
+    while (q < 65535 && q_coord(q, s, b2) < (double)x) ++q;
+    while (q > 0 && q_coord(q - 1, s, b2) >= (double)x) --q;
+    return (uint32_t)min(q + 1, 65535);
+}
+__global__ void __launch_bounds__(256) k_quantize(const float4 *__restrict__ nodes, uint32_t n_inner, const float *__restrict__ grid,
+                                                   uint4 *__restrict__ qnodes)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_inner) return;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float4 a = nodes[4 * (size_t)i + 2 * k], b = nodes[4 * (size_t)i + 2 * k + 1];
+        const float lo[3] = {a.x, a.y, a.z}, hi[3] = {a.w, b.x, b.y};
+        uint32_t w[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) w[c] = quantize_lo(lo[c], grid[c], grid[3 + c]) | (quantize_hi(hi[c], grid[c], grid[3 + c]) << 16);
+        const int ref = __float_as_int(b.z) ^ -__float_as_int(b.w);      // inner node index, or ~sphere for a leaf
+        qnodes[2 * (size_t)i + k] = make_uint4(w[0], w[1], w[2], (uint32_t)ref);
+    }
+}
+
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { err = _e; goto done; } } while (0)
 
 cudaError_t build_lbvh(const float4 *d_spheres, uint32_t n, BvhBuild &out, cudaStream_t st)
@@ -288,6 +341,8 @@ cudaError_t build_lbvh(const float4 *d_spheres, uint32_t n, BvhBuild &out, cudaS
     cudaError_t err = cudaSuccess;
     if (out.nodes) { cudaFree(out.nodes); out.nodes = nullptr; }
     if (out.nodes4) { cudaFree(out.nodes4); out.nodes4 = nullptr; }
+    if (out.qnodes) { cudaFree(out.qnodes); out.qnodes = nullptr; }
+    float *grid = nullptr;
     out.n_nodes = 0; out.build_ms = 0.f; out.launches = 0;
     if (n == 0) return cudaSuccess;
 
@@ -303,6 +358,8 @@ cudaError_t build_lbvh(const float4 *d_spheres, uint32_t n, BvhBuild &out, cudaS
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaMalloc(&out.nodes, (size_t)n_inner * 64));
     CK(cudaMalloc(&out.nodes4, (size_t)n_inner * 128));
+    CK(cudaMalloc(&out.qnodes, (size_t)n_inner * 32));
+    CK(cudaMalloc(&grid, 6 * sizeof(float)));
     CK(cudaEventRecord(e0, st));
     if (n == 1) {
         k_single_leaf<<<1, 1, 0, st>>>(d_spheres, out.nodes); ++launches;
@@ -340,7 +397,11 @@ cudaError_t build_lbvh(const float4 *d_spheres, uint32_t n, BvhBuild &out, cudaS
     }
     k_collapse4<<<(n_inner + 255u) / 256u, 256, 0, st>>>(out.nodes, n_inner, out.nodes4); ++launches;
     CK(cudaGetLastError());
+    k_qgrid<<<1, 32, 0, st>>>(out.nodes, grid); ++launches;
+    k_quantize<<<(n_inner + 255u) / 256u, 256, 0, st>>>(out.nodes, n_inner, grid, out.qnodes); ++launches;
+    CK(cudaGetLastError());
     CK(cudaEventRecord(e1, st));
+    CK(cudaMemcpyAsync(out.qgrid, grid, 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&out.build_ms, e0, e1));
     out.n_nodes = n_inner;
@@ -350,7 +411,8 @@ done:
     if (e1) cudaEventDestroy(e1);
     cudaFree(bounds); cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); cudaFree(hist);
     cudaFree(children); cudaFree(parent_inner); cudaFree(parent_leaf); cudaFree(arrivals); cudaFree(box_lo); cudaFree(box_hi);
-    if (err != cudaSuccess) { cudaFree(out.nodes); cudaFree(out.nodes4); out.nodes = nullptr; out.nodes4 = nullptr; }
+    cudaFree(grid);
+    if (err != cudaSuccess) { cudaFree(out.nodes); cudaFree(out.nodes4); cudaFree(out.qnodes); out.nodes = nullptr; out.nodes4 = nullptr; out.qnodes = nullptr; }
     return err;
 }
 

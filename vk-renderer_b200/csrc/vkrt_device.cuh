@@ -28,13 +28,14 @@ struct DevScene {
     const uint32_t *sphere_mat;
     const float4 *bvh;            // binary 64-byte nodes (two child records)
     const float4 *bvh4;           // 4-wide 128-byte traversal nodes (four child records), indexed by binary node id
+    const uint4 *qbvh;            // 32-byte traversal nodes (two child records with 16-bit box coordinates)
     const float4 *tris;
     const float4 *mats;
     uint32_t n_spheres, n_tris, tri_mat, n_planes, n_lights, n_nodes, n_mats, _pad;
     float4 planes[MAX_PLANES];
     uint32_t plane_mat[MAX_PLANES];
     uint32_t lights[MAX_LIGHTS];
-    uint32_t _pad2[2];
+    float qs[3], qb2[3];          // the 16-bit grid of qbvh: coordinate of code q = (2^23 + q) * qs + qb2
 };
 
 struct Material { V3 albedo; float roughness; V3 emissive; float metalness; uint32_t type; };
@@ -269,6 +270,73 @@ struct TravStack {
         return lm[sp - VKRT_SMEM_STACK];
     }
 };
+// ---- 32-byte nodes (VKRT_QNODES) ----------------------------------------------------------------------
+// The trace kernels are bound by L1TEX wavefronts of scattered node fetches (one per lane and 32-byte
+// sector), so the inner step reads ONE sector per node: two child records {x: lo | hi << 16, y, z, ref} whose
+// 16-bit codes q stand for the real coordinate X(q) = (2^23 + q) * qs + qb2.  The builder picks codes with
+// X(q_lo) <= lo and X(q_hi) >= hi of the exact box (vkrt_bvh.cu::k_quantize), monotonically, so coded boxes
+// nest like the exact ones.  The slab test works on the codes directly: one PRMT turns a code into the float
+// 2^23 + q, one directed-rounding FMA with per-ray constants gives a LOWER bound of the entry parameter
+// (fma.rd, C_dn) and an UPPER bound of the exit parameter (fma.ru, C_up) of the real-arithmetic slab test of
+// the coded box -- hence of the float slab test of every exact box inside it (a float <= a real x is <= RN(x)).
+// An ancestor is therefore never rejected when the exact rule-S test of a sphere below it passes, and rule S's
+// answer is unchanged (DESIGN.md "Rule S"); a coded box only ever lets a few more rays through.
+#ifndef VKRT_QNODES
+#define VKRT_QNODES 1
+#endif
+struct QRay { V3 a, cdn, cup; uint32_t selx, sely, selz; };
+VKRT_DEV QRay qray_setup(const DevScene &sc, const SlabRay &sr)
+{
+    QRay q;
+    const float inv[3] = {sr.inv.x, sr.inv.y, sr.inv.z}, oinv[3] = {sr.oinv.x, sr.oinv.y, sr.oinv.z};
+    float a[3], cdn[3], cup[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        a[k] = __fmul_rn(sc.qs[k], inv[k]);
+        // |(2^23 + q) * (a - qs * inv)| < 0.51 |a| for q < 2^16
+        const float m = __fmul_ru(0.51f, gl_abs(a[k]));
+        cdn[k] = __fsub_rd(__fmaf_rd(sc.qb2[k], inv[k], -oinv[k]), m);
+        cup[k] = __fadd_ru(__fmaf_ru(sc.qb2[k], inv[k], -oinv[k]), m);
+    }
+    q.a = v3(a[0], a[1], a[2]); q.cdn = v3(cdn[0], cdn[1], cdn[2]); q.cup = v3(cup[0], cup[1], cup[2]);
+    // PRMT selector of the NEAR plane's code: the low half (lo) for a positive direction, the high half (hi) else
+    q.selx = inv[0] < 0.0f ? 0x7632u : 0x7610u;
+    q.sely = inv[1] < 0.0f ? 0x7632u : 0x7610u;
+    q.selz = inv[2] < 0.0f ? 0x7632u : 0x7610u;
+    return q;
+}
+VKRT_DEV void ldg256u(const uint4 *p, uint4 &a, uint4 &b)
+{
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
+VKRT_DEV bool qslab_test(const QRay &q, uint4 w, float &tn)
+{
+    const float nx = __uint_as_float(__byte_perm(w.x, 0x4B000000u, q.selx)), fx = __uint_as_float(__byte_perm(w.x, 0x4B000000u, q.selx ^ 0x22u));
+    const float ny = __uint_as_float(__byte_perm(w.y, 0x4B000000u, q.sely)), fy = __uint_as_float(__byte_perm(w.y, 0x4B000000u, q.sely ^ 0x22u));
+    const float nz = __uint_as_float(__byte_perm(w.z, 0x4B000000u, q.selz)), fz = __uint_as_float(__byte_perm(w.z, 0x4B000000u, q.selz ^ 0x22u));
+    tn = fmaxf(fmaxf(__fmaf_rd(nx, q.a.x, q.cdn.x), __fmaf_rd(ny, q.a.y, q.cdn.y)), __fmaf_rd(nz, q.a.z, q.cdn.z));
+    const float tf = fminf(fminf(__fmaf_ru(fx, q.a.x, q.cup.x), __fmaf_ru(fy, q.a.y, q.cup.y)), __fmaf_ru(fz, q.a.z, q.cup.z));
+    return tn <= tf && tf >= 0.0f;
+}
+template <bool STATS, class Stack>
+VKRT_DEV void trav_inner_step_q(Trav &tv, const QRay &q, Stack &stack, const DevScene &sc, Stats &st)
+{
+    uint4 w0, w1;
+    ldg256u(sc.qbvh + 2 * (size_t)tv.node, w0, w1);
+    if (STATS) ++st.nodes;
+    float tn0, tn1;
+    const bool h0 = qslab_test(q, w0, tn0) && tn0 <= tv.best.t;
+    const bool h1 = qslab_test(q, w1, tn1) && tn1 <= tv.best.t;
+    const int c0 = (int)w0.w, c1 = (int)w1.w;          // inner node index, or ~sphere for a leaf
+    const bool both = h0 && h1;
+    const bool take1 = both ? (tn1 < tn0) : h1;
+    if (both) stack.push(tv.sp, take1 ? c0 : c1);
+    if (h0 || h1) tv.node = take1 ? c1 : c0;
+    else tv.node = tv.sp ? stack.pop(tv.sp) : (int)TRAV_DONE;
+}
+
 template <bool STATS, class Stack>
 VKRT_DEV void trav_inner_step(Trav &tv, Stack &stack, const DevScene &sc, Stats &st)
 {

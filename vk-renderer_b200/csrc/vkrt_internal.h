@@ -45,8 +45,7 @@ cudaError_t launch_present(const uchar4 *b0, const uchar4 *b1, uint32_t tw, uint
 // vkrt_wavefront.cu
 struct WaveBuffers {
     size_t capacity;              // path records per wave
-    float4 *ray_o, *ray_d;        // origin.xyz + t_hit ; dir.xyz + hit id bits
-    float4 *acc, *mask;           // acc.xyz + pixel bits ; mask.xyz + (sample_in_wave << 8 | depth) bits
+    float4 *rec;                  // 64-byte path records: {origin.xyz t_hit | dir.xyz hit id | acc.xyz pixel | mask.xyz sample<<8|depth}
     uint32_t *queue[2];           // active path indices (ping-pong over depth iterations)
     uint32_t *queue_mat[2];       // material bins of the shade stage: [0] dielectric, [1] diffuse
     uint32_t *counts;             // queue counters and work-fetch heads
@@ -87,6 +86,8 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
 struct BvhBuild {
     float4 *nodes = nullptr;      // binary nodes: 4 float4 (two child records) per inner node
     float4 *nodes4 = nullptr;     // 4-wide traversal nodes: 8 float4 (four child records) per binary node id
+    uint4 *qnodes = nullptr;      // 32-byte traversal nodes: two 16-byte child records on the 16-bit grid below
+    float qgrid[6] = {0, 0, 0, 0, 0, 0};   // per axis: scale s[3], offset b2[3]; coordinate of code q = (2^23 + q) * s + b2
     uint32_t n_nodes = 0;
     float build_ms = 0.f;
     uint32_t launches = 0;

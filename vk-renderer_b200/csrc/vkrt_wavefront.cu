@@ -1,7 +1,10 @@
 // Wavefront variant of the path integrator (Assets/Tracer.comp::radiance, :433-553).
 //
-// One "wave" holds S samples of every owned pixel as path records in HBM (SoA float4s, sample-major:
-// path = sample_in_wave * n_slots + pixel_slot, so every kernel reads and writes them coalesced).
+// One "wave" holds S samples of every owned pixel as path records in HBM: one 64-byte record per path =
+// two 32-byte sectors {origin.xyz t_hit | dir.xyz hit id} {acc.xyz pixel | mask.xyz sample<<8|depth}, each moved by
+// ONE 256-bit load / store.  Records are sample-major (path = sample_in_wave * n_slots + pixel_slot); as the
+// depth iterations thin the paths out, a surviving path still costs exactly its own two sectors of DRAM traffic
+// (with one float4 array per field every access dragged in half a sector of a dead neighbour).
 // Per depth iteration the queues are processed by small kernels:
 //
 //   extend   persistent warps pull rays from the active queue (one atomicAdd per warp for all lanes
@@ -38,13 +41,13 @@
 #define VKRT_TRACE_BLOCK 128
 #endif
 #ifndef VKRT_TRACE_MINBLOCKS
-#define VKRT_TRACE_MINBLOCKS 1
+#define VKRT_TRACE_MINBLOCKS 9     // 56 registers: the occupancy the exact-node kernel had, with the 32-byte nodes
 #endif
 #ifndef VKRT_SHADE_BLOCK
 #define VKRT_SHADE_BLOCK 256
 #endif
 #ifndef VKRT_SHADE_MINBLOCKS
-#define VKRT_SHADE_MINBLOCKS 2      // __launch_bounds__(256, n) of the streaming shade/classify kernels
+#define VKRT_SHADE_MINBLOCKS 4      // __launch_bounds__(256, n) of the streaming shade/classify kernels
 #endif
 
 namespace vkrt {
@@ -54,7 +57,7 @@ namespace vkrt {
 enum { C_ACTIVE = 0, C_DIEL = 2, C_DIFF = 3, C_SHADOW = 4, C_HEAD_EXTEND = 5, C_HEAD_SHADOW = 6, C_N = 8, C_SETS = 257 };
 
 struct WaveParams {
-    float4 *po, *pd, *pacc, *pmask, *sh, *term, *rad;
+    float4 *rec, *sh, *term, *rad;   // rec: 4 float4 per path (see the top of the file)
     uint32_t *q_active[2], *q_diel, *q_diff, *q_shadow;
     uint8_t *occ;
     uint32_t *cnt, *cnt_next;    // counter set of this depth / of the next depth
@@ -62,6 +65,20 @@ struct WaveParams {
     uint32_t n_slots;        // = RenderParams.n_work
     uint32_t n_lights;
 };
+
+VKRT_DEV void ld256(const float4 *p, float4 &a, float4 &b)
+{
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p) : "memory");
+}
+VKRT_DEV void st256(float4 *p, float4 a, float4 b)
+{
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
+VKRT_DEV float4 *rec_ray(const WaveParams &wp, uint32_t path) { return wp.rec + 4 * (size_t)path; }
+VKRT_DEV float4 *rec_state(const WaveParams &wp, uint32_t path) { return wp.rec + 4 * (size_t)path + 2; }
 
 VKRT_DEV bool slot_to_pixel_w(const RenderParams &rp, uint32_t w, uint32_t &px, uint32_t &py)
 {
@@ -174,9 +191,8 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ Dev
     for (uint32_t sl = 0; sl < wp.S; ++sl) {
         const uint32_t p = sl * wp.n_slots + slot;
         if (valid) {
-            wp.po[p] = fo; wp.pd[p] = fd;
-            wp.pacc[p] = make_float4(0.f, 0.f, 0.f, __uint_as_float(pix));
-            wp.pmask[p] = make_float4(1.f, 1.f, 1.f, __uint_as_float(sl << 8));
+            st256(rec_ray(wp, p), fo, fd);
+            st256(rec_state(wp, p), make_float4(0.f, 0.f, 0.f, __uint_as_float(pix)), make_float4(1.f, 1.f, 1.f, __uint_as_float(sl << 8)));
         }
         uint32_t *const qs[1] = {wp.q_active[0]}; uint32_t *const cs[1] = {wp.cnt + C_ACTIVE};
         const bool ws[1] = {valid}; const uint32_t vs[1] = {p};
@@ -214,6 +230,9 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
     __shared__ int s_stack[VKRT_SMEM_STACK][VKRT_TRACE_BLOCK];
 #endif
     TravStack<VKRT_TRACE_BLOCK> stack;
+#if VKRT_QNODES
+    QRay qr;
+#endif
 #if VKRT_SMEM_STACK
     stack.sm = &s_stack[0][threadIdx.x];
 #else
@@ -251,7 +270,8 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                     const uint32_t q = queue[item];
                     path = ANY ? (q >> 4) : q;
                     light = ANY ? (q & 15u) : 0u;
-                    const float4 fo = wp.po[path], fd = wp.pd[path];
+                    float4 fo, fd;
+                    ld256(rec_ray(wp, path), fo, fd);
                     found = false; hit.kind = 0; hit.index = 0;
                     if (ANY) {
                         const float4 s = wp.sh[(size_t)path * wp.n_lights + light];
@@ -263,7 +283,12 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                         ++st.closest;
                         found = trace_tris<true>(sc, o, d, cur, hit);
                     }
-                    if (BVH) { trav_init(tv, sc, o, d, EPS, sphere_bound<true>(cur)); if (tv.node < 0) tv.node = FIN; }
+                    if (BVH) {
+                        trav_init(tv, sc, o, d, EPS, sphere_bound<true>(cur)); if (tv.node < 0) tv.node = FIN;
+#if VKRT_LEAF_BATCH && VKRT_QNODES
+                        qr = qray_setup(sc, tv.sr);
+#endif
+                    }
                     else tv.node = FIN;
                 }
             }
@@ -286,7 +311,11 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                 } else {
 #pragma unroll
                     for (int u = 0; u < VKRT_TRAV_UNROLL; ++u)     // the warp votes above cost ~10 instructions: amortise them
+#if VKRT_QNODES
+                        if (has && tv.node >= 0) trav_inner_step_q<STATS>(tv, qr, stack, sc, st);
+#else
                         if (has && tv.node >= 0) trav_inner_step<STATS>(tv, stack, sc, st);
+#endif
                 }
             }
 #else
@@ -314,8 +343,8 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
             }
             if (ANY) wp.occ[(size_t)path * wp.n_lights + light] = found ? 1 : 0;
             else {
-                wp.po[path].w = cur;
-                wp.pd[path].w = __uint_as_float(found ? ((hit.kind << 28) | hit.index) : 0u);
+                rec_ray(wp, path)[0].w = cur;
+                rec_ray(wp, path)[1].w = __uint_as_float(found ? ((hit.kind << 28) | hit.index) : 0u);
             }
             has = false;
         }
@@ -325,7 +354,9 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
 
 VKRT_DEV void load_path(const WaveParams &wp, uint32_t path, PathState &ps, Hit &hit, uint32_t &pix, uint32_t &sl)
 {
-    const float4 fo = wp.po[path], fd = wp.pd[path], fa = wp.pacc[path], fm = wp.pmask[path];
+    float4 fo, fd, fa, fm;
+    ld256(rec_ray(wp, path), fo, fd);
+    ld256(rec_state(wp, path), fa, fm);
     ps.o = xyz(fo); ps.d = xyz(fd); ps.acc = xyz(fa); ps.mask = xyz(fm);
     const uint32_t sd = __float_as_uint(fm.w);
     ps.depth = sd & 255u; sl = sd >> 8;
@@ -335,10 +366,9 @@ VKRT_DEV void load_path(const WaveParams &wp, uint32_t path, PathState &ps, Hit 
 }
 VKRT_DEV void store_path(const WaveParams &wp, uint32_t path, const PathState &ps, uint32_t pix, uint32_t sl)
 {
-    wp.po[path] = make_float4(ps.o.x, ps.o.y, ps.o.z, 0.f);
-    wp.pd[path] = make_float4(ps.d.x, ps.d.y, ps.d.z, 0.f);
-    wp.pacc[path] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, __uint_as_float(pix));
-    wp.pmask[path] = make_float4(ps.mask.x, ps.mask.y, ps.mask.z, __uint_as_float((sl << 8) | ps.depth));
+    st256(rec_ray(wp, path), make_float4(ps.o.x, ps.o.y, ps.o.z, 0.f), make_float4(ps.d.x, ps.d.y, ps.d.z, 0.f));
+    st256(rec_state(wp, path), make_float4(ps.acc.x, ps.acc.y, ps.acc.z, __uint_as_float(pix)),
+          make_float4(ps.mask.x, ps.mask.y, ps.mask.z, __uint_as_float((sl << 8) | ps.depth)));
 }
 
 struct LightsNone {      // the dielectric branch never evaluates a light
@@ -382,10 +412,10 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_SHADE_MINBLOCKS) k_wf_c
                 const uint32_t type = __float_as_uint(__ldg(&sc.mats[3 * mat + 2].x));
                 skey = sample_key(rp.fkey, pix, wp.s0 + sl);
                 // the record keeps the final hit and the clamped accumulator for the shade kernels
-                if (id != id0) { wp.po[path].w = cur; wp.pd[path].w = __uint_as_float(id); }
+                if (id != id0) { rec_ray(wp, path)[0].w = cur; rec_ray(wp, path)[1].w = __uint_as_float(id); }
                 if (__float_as_uint(acc0.x) != __float_as_uint(ps.acc.x) || __float_as_uint(acc0.y) != __float_as_uint(ps.acc.y) ||
                     __float_as_uint(acc0.z) != __float_as_uint(ps.acc.z))
-                    wp.pacc[path] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, __uint_as_float(pix));
+                    rec_state(wp, path)[0] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, __uint_as_float(pix));
                 if (type != 0u) diel = true;                                                           // DIELECTRIC bin
                 else {                                                                                 // DIFFUSE bin
                     diff = true;
@@ -490,10 +520,7 @@ cudaError_t wave_alloc(WaveBuffers &wb, size_t capacity)
     wb.capacity = capacity;
     cudaError_t e;
 #define A(ptr, bytes) do { e = cudaMalloc((void **)&(ptr), (bytes)); if (e != cudaSuccess) { wave_free(wb); return e; } } while (0)
-    A(wb.ray_o, capacity * sizeof(float4));
-    A(wb.ray_d, capacity * sizeof(float4));
-    A(wb.acc, capacity * sizeof(float4));
-    A(wb.mask, capacity * sizeof(float4));
+    A(wb.rec, capacity * 4 * sizeof(float4));
     A(wb.sample_rad, capacity * sizeof(float4));
     A(wb.queue[0], capacity * sizeof(uint32_t));
     A(wb.queue[1], capacity * sizeof(uint32_t));
@@ -506,7 +533,7 @@ cudaError_t wave_alloc(WaveBuffers &wb, size_t capacity)
 
 void wave_free(WaveBuffers &wb)
 {
-    cudaFree(wb.ray_o); cudaFree(wb.ray_d); cudaFree(wb.acc); cudaFree(wb.mask); cudaFree(wb.sample_rad);
+    cudaFree(wb.rec); cudaFree(wb.sample_rad);
     cudaFree(wb.queue[0]); cudaFree(wb.queue[1]); cudaFree(wb.queue_mat[0]); cudaFree(wb.queue_mat[1]); cudaFree(wb.counts);
     cudaFree(wb.shadow); cudaFree(wb.occ); cudaFree(wb.queue_shadow); cudaFree(wb.term);
     for (uint32_t i = 0; i < wb.ev_created; ++i) cudaEventDestroy(wb.ev[i]);
@@ -614,7 +641,7 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
         auto ev_open = [&](uint8_t tag) { if (wb.n_ev + 1 < 128) { wb.ev_tag[wb.n_ev / 2] = tag; cudaEventRecord(wb.ev[wb.n_ev++], ls); } };
         auto ev_close = [&]() { if (wb.n_ev < 128 && (wb.n_ev & 1u)) cudaEventRecord(wb.ev[wb.n_ev++], ls); };
         WaveParams wp{};
-        wp.po = wb.ray_o; wp.pd = wb.ray_d; wp.pacc = wb.acc; wp.pmask = wb.mask; wp.sh = wb.shadow; wp.term = wb.term; wp.rad = wb.sample_rad;
+        wp.rec = wb.rec; wp.sh = wb.shadow; wp.term = wb.term; wp.rad = wb.sample_rad;
         wp.q_active[0] = wb.queue[0]; wp.q_active[1] = wb.queue[1]; wp.q_diel = wb.queue_mat[0]; wp.q_diff = wb.queue_mat[1];
         wp.q_shadow = wb.queue_shadow;
         wp.occ = wb.occ; wp.cnt = wb.counts; wp.cnt_next = wb.counts + C_N;
