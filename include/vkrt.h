@@ -253,6 +253,10 @@ typedef struct vkrt_bvh_info {
 VKRT_API vkrt_error vkrt_get_bvh_info(vkrt_ctx *ctx, vkrt_bvh_info *out);
 /* Copies the packed nodes (n_nodes * 16 floats) to the host. */
 VKRT_API vkrt_error vkrt_read_bvh_nodes(vkrt_ctx *ctx, float *host, size_t bytes);
+/* Copies the 32-byte traversal nodes (n_nodes * 8 uint32: two child records {x: lo | hi << 16, y, z, ref}, ref =
+ * inner node index or ~sphere) and their 16-bit grid (scale[3], offset[3]: the coordinate of code q is
+ * (2^23 + q) * scale + offset) to the host.  Introspection for the containment tests. */
+VKRT_API vkrt_error vkrt_read_bvh_qnodes(vkrt_ctx *ctx, uint32_t *host, size_t bytes, float grid[6]);
 
 /* ------------------------------------------------------------------------- */
 /* Sharding (one context per GPU; the exchange itself is done by the caller,  */

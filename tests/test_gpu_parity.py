@@ -94,6 +94,52 @@ def test_bvh_tree_matches_oracle_tree(vk, oracle, n):
     r.close()
 
 
+@pytest.mark.parametrize("n", [1, 2, 17, 1024, 20000])
+def test_bvh_quantised_nodes_enclose_exact_nodes(vk, n):
+    """The 32-byte traversal nodes (16-bit codes) must enclose the exact child boxes in REAL arithmetic -- checked
+    here with exact integer/rational arithmetic on the float bits -- and nest like them (parent codes enclose the
+    children's codes).  That is what keeps the LBVH traversal identical to rule S's linear scan."""
+    from fractions import Fraction
+    V = vk
+    scene = V.scenes.random_spheres(n) if n <= 1024 else V.scenes.grid_spheres(nx=30, ny=25, nz=27)
+    if n <= 1024:
+        scene.spheres, scene.sphere_mat = scene.spheres[1:], scene.sphere_mat[1:]
+    r = V.Renderer(64, 64)
+    r.set_scene(scene)
+    r.build_bvh()
+    exact = r.bvh_nodes().reshape(-1, 2, 8)                 # [node][child] {lo.xyz hi.x | hi.yz index kind}
+    qn, grid = r.bvh_qnodes()
+    qn = qn.reshape(-1, 2, 4)
+    r.close()
+    lo = exact[:, :, 0:3].astype(np.float64)
+    hi = np.stack([exact[:, :, 3], exact[:, :, 4], exact[:, :, 5]], axis=-1).astype(np.float64)
+    idx = np.ascontiguousarray(exact[:, :, 6]).view(np.int32)
+    kind = np.ascontiguousarray(exact[:, :, 7]).view(np.int32)
+    qlo = (qn[:, :, 0:3] & 0xffff).astype(np.int64)
+    qhi = (qn[:, :, 0:3] >> 16).astype(np.int64)
+    ref = np.ascontiguousarray(qn[:, :, 3]).view(np.int32)
+    assert np.array_equal(ref, np.where(kind != 0, ~idx, idx))
+    assert np.all(qlo <= qhi)
+    # float64 holds (2^23 + q) * s exactly (24 + 24 bits); adding the offset may round, so compare with a margin of
+    # half a grid step first (vectorised) and exactly (Fraction) on a sample
+    s, b2 = grid[0:3].astype(np.float64), grid[3:6].astype(np.float64)
+    xlo, xhi = (8388608 + qlo) * s + b2, (8388608 + qhi) * s + b2
+    assert np.all(xlo <= lo - 0.5 * s) and np.all(xhi >= hi + 0.5 * s)
+    assert np.all(lo - xlo < 3.0 * s) and np.all(xhi - hi < 3.0 * s)          # ... and they are tight
+    rng = np.random.default_rng(5)
+    for node in rng.integers(0, qn.shape[0], size=min(200, qn.shape[0])):
+        for k in range(2):
+            for a in range(3):
+                X = lambda q: Fraction(8388608 + int(q)) * Fraction(float(grid[a])) + Fraction(float(grid[3 + a]))
+                assert X(qlo[node, k, a]) <= Fraction(float(exact[node, k, a]))
+                assert X(qhi[node, k, a]) >= Fraction(float(hi[node, k, a]))
+    # nesting: an inner child's coded box encloses the coded boxes of that child's own two children
+    inner = kind == 0
+    ci = idx[inner]
+    plo, phi = qlo[inner], qhi[inner]
+    assert np.all(plo[:, None, :] <= qlo[ci]) and np.all(phi[:, None, :] >= qhi[ci])
+
+
 def test_bvh_duplicate_centres(vk, oracle):
     """Many identical Morton codes (coincident centres) exercise the index tie-break of the hierarchy."""
     V = vk

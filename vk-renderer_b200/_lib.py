@@ -105,6 +105,7 @@ SIGNATURES = {
     "vkrt_debug_dump_timeline": ([_vp, C.c_char_p], C.c_int8),
     "vkrt_get_bvh_info": ([_vp, _P(BvhInfo)], C.c_int8),
     "vkrt_read_bvh_nodes": ([_vp, _vp, _sz], C.c_int8),
+    "vkrt_read_bvh_qnodes": ([_vp, _vp, _sz, _P(C.c_float)], C.c_int8),
     "vkrt_pack_shard": ([_vp, _P(_vp), _P(_sz)], C.c_int8),
     "vkrt_pack_shard_into": ([_vp, _vp, _sz], C.c_int8),
     "vkrt_shard_floats": ([_vp, _u32, _P(_sz)], C.c_int8),

@@ -415,6 +415,18 @@ VKRT_API vkrt_error vkrt_read_bvh_nodes(vkrt_ctx *c, float *host, size_t bytes)
     return VKRT_SUCCESS;
 }
 
+VKRT_API vkrt_error vkrt_read_bvh_qnodes(vkrt_ctx *c, uint32_t *host, size_t bytes, float grid[6])
+{
+    if (!c || !host || !grid) return VKRT_BAD_ARG;
+    if (!c->use_bvh) return fail(c, VKRT_BAD_ARG, "no BVH built");
+    if (bytes < (size_t)c->bvh.n_nodes * 32) return fail(c, VKRT_BAD_ARG, "buffer too small");
+    DeviceGuard g(c->info.device_id);
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaMemcpy(host, c->bvh.qnodes, (size_t)c->bvh.n_nodes * 32, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 6; ++k) grid[k] = c->bvh.qgrid[k];
+    return VKRT_SUCCESS;
+}
+
 // ---- per-frame ----------------------------------------------------------------------------------
 VKRT_API vkrt_error vkrt_draw(vkrt_ctx *c, const vkrt_frame_data *frame)
 {

@@ -32,7 +32,7 @@
 #define VKRT_FETCH_CHUNK 128   // ray indices a warp reserves per atomicAdd on the queue head
 #endif
 #ifndef VKRT_TRAV_UNROLL
-#define VKRT_TRAV_UNROLL 2
+#define VKRT_TRAV_UNROLL 3
 #endif
 #ifndef VKRT_LEAF_BATCH
 #define VKRT_LEAF_BATCH 8    // run a leaf phase once this many lanes wait at a leaf (0: leaf tests inside the node step)
@@ -42,6 +42,9 @@
 #endif
 #ifndef VKRT_TRACE_MINBLOCKS
 #define VKRT_TRACE_MINBLOCKS 9     // 56 registers: the occupancy the exact-node kernel had, with the 32-byte nodes
+#endif
+#ifndef VKRT_TRACE_RESIDENT
+#define VKRT_TRACE_RESIDENT 0       // cap of resident trace blocks per SM (0: as many as fit)
 #endif
 #ifndef VKRT_SHADE_BLOCK
 #define VKRT_SHADE_BLOCK 256
@@ -622,6 +625,11 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
     int occ_e = 0, occ_s = 0;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_extend, VKRT_TRACE_BLOCK, 0)) != cudaSuccess) return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_shadow, VKRT_TRACE_BLOCK, 0)) != cudaSuccess) return e;
+#if VKRT_TRACE_RESIDENT
+    // leave room on every SM for the other lane's streaming kernels (complementary: they wait on DRAM, this is ALU work)
+    if (occ_e > VKRT_TRACE_RESIDENT) occ_e = VKRT_TRACE_RESIDENT;
+    if (occ_s > VKRT_TRACE_RESIDENT) occ_s = VKRT_TRACE_RESIDENT;
+#endif
     const unsigned grid_e = (unsigned)(sm_count * (occ_e > 0 ? occ_e : 1)), grid_s = (unsigned)(sm_count * (occ_s > 0 ? occ_s : 1));
     const unsigned grid_shade = (unsigned)sm_count * 8u * (256u / VKRT_SHADE_BLOCK);
 

@@ -107,6 +107,15 @@ class Renderer:
             self._ck(self.lib.vkrt_read_bvh_nodes(self.ctx, _ptr(out), out.nbytes))
         return out
 
+    def bvh_qnodes(self):
+        """-> ((n, 8) uint32 traversal nodes, grid[6] float32): two child records {x: lo | hi << 16, y, z, ref}."""
+        n = self.bvh_info().n_nodes
+        out = np.zeros((n, 8), dtype=np.uint32)
+        grid = (C.c_float * 6)()
+        if n:
+            self._ck(self.lib.vkrt_read_bvh_qnodes(self.ctx, _ptr(out), out.nbytes, grid))
+        return out, np.array(list(grid), dtype=np.float32)
+
     # ---- frame --------------------------------------------------------------------------------
     def set_sampling(self, spp, max_depth):
         self._ck(self.lib.vkrt_set_sampling(self.ctx, spp, max_depth))
