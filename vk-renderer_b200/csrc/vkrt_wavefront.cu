@@ -46,6 +46,9 @@
 #ifndef VKRT_TRACE_RESIDENT
 #define VKRT_TRACE_RESIDENT 0       // cap of resident trace blocks per SM (0: as many as fit)
 #endif
+#ifndef VKRT_BLOCK_PUSH
+#define VKRT_BLOCK_PUSH 1          // classify / shade: one queue-counter atomicAdd per block instead of per warp
+#endif
 #ifndef VKRT_SHADE_BLOCK
 #define VKRT_SHADE_BLOCK 256
 #endif
@@ -428,8 +431,16 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_SHADE_MINBLOCKS) k_wf_c
                 }
             }
         }
+#if VKRT_BLOCK_PUSH
+        {
+            uint32_t *const qs[2] = {wp.q_diel, wp.q_diff}; uint32_t *const cs[2] = {wp.cnt + C_DIEL, wp.cnt + C_DIFF};
+            const bool ws[2] = {diel, diff}; const uint32_t vs[2] = {path, path};
+            push_block<2>(qs, cs, ws, vs);
+        }
+#else
         push(wp.q_diel, wp.cnt + C_DIEL, diel, path);
         push(wp.q_diff, wp.cnt + C_DIFF, diff, path);
+#endif
         for (uint32_t l = 0; l < sc.n_lights; ++l) {
             bool queue_it = false;
             if (diff) {
@@ -453,7 +464,15 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_SHADE_MINBLOCKS) k_wf_c
                 }
                 queue_it = !occluded;
             }
+#if VKRT_BLOCK_PUSH
+            {
+                uint32_t *const qs[1] = {wp.q_shadow}; uint32_t *const cs[1] = {wp.cnt + C_SHADOW};
+                const bool ws[1] = {queue_it}; const uint32_t vs[1] = {(path << 4) | l};
+                push_block<1>(qs, cs, ws, vs);
+            }
+#else
             push(wp.q_shadow, wp.cnt + C_SHADOW, queue_it, (path << 4) | l);
+#endif
         }
     }
     wf_flush(st, rp.counters, false);
@@ -488,7 +507,15 @@ VKRT_DEV void shade_bin(const DevScene &sc, const RenderParams &rp, const WavePa
             if (alive) store_path(wp, path, ps, pix, sl);
             else wp.rad[path] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, 0.f);
         }
+#if VKRT_BLOCK_PUSH
+        {
+            uint32_t *const qs[1] = {wp.q_active[next]}; uint32_t *const cs[1] = {wp.cnt_next + C_ACTIVE};
+            const bool ws[1] = {alive}; const uint32_t vs[1] = {path};
+            push_block<1>(qs, cs, ws, vs);
+        }
+#else
         push(wp.q_active[next], wp.cnt_next + C_ACTIVE, alive, path);
+#endif
     }
 }
 __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_SHADE_MINBLOCKS) k_wf_shade(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
