@@ -339,11 +339,12 @@ def run_ours(args):
     rs.close()
     traversed = (sc.closest_rays - sc.shared_primary_rays) + (sc.shadow_rays - sc.zero_term_shadow_rays)
     mega = variant == V.VARIANT_MEGAKERNEL
-    # algorithmic bytes of the traversal kernels per frame: 64 B per BVH node visited + 16 B per
-    # sphere fetched at a leaf + per traversed ray its 32 B record read (origin, direction) and 8 B result write
-    # (wavefront) / per pixel the 16 B accumulator store (megakernel, which also shades: + 56 B per nearest hit for
-    # sphere, material id and material)
-    alg_bytes = (sc.node_visits * 64 + sc.leaf_tests * 16) / n_stat
+    # algorithmic bytes of the traversal kernels per frame: one BVH node per visit (the wavefront
+    # walks the 32-byte quantised nodes, the megakernel the exact 64-byte ones) + 16 B per sphere fetched at a leaf +
+    # per traversed ray its 32 B record read (origin, direction) and 8 B result write (wavefront) / per pixel the 16 B
+    # accumulator store (megakernel, which also shades: + 56 B per nearest hit for sphere, material id and material)
+    node_bytes = 64 if mega else 32
+    alg_bytes = (sc.node_visits * node_bytes + sc.leaf_tests * 16) / n_stat
     if mega:
         alg_bytes += sc.closest_rays * (16 + 4 + 36) / n_stat + (n_px / world) * 16
     else:
@@ -362,10 +363,11 @@ def run_ours(args):
                               "(the wavefront's two lanes overlap, so the sums exceed ms_per_step)",
                 "nodes_per_traversed_ray": sc.node_visits / max(traversed, 1),
                 "leaf_tests_per_traversed_ray": sc.leaf_tests / max(traversed, 1),
-                "note": "traffic = ncu dram bytes per frame for the same launches (profiles/traffic.json). The tree (%.1f MB) is "
-                        "L2/L1-resident, so achieved can exceed what DRAM delivers; the limiter is L1TEX request throughput + "
-                        "traversal divergence (DESIGN.md section 4), the HBM fraction is the contract's reference number"
-                        % (bvh.n_nodes * 64 / 1e6)}
+                "node_bytes": node_bytes,
+                "note": "traffic = ncu dram bytes per launch for the same launches (profiles/traffic.json). The tree (%.1f MB) is "
+                        "L2/L1-resident, so achieved can exceed what DRAM delivers; the limiter is the SM's ALU pipe + lane "
+                        "utilisation of the traversal loop (DESIGN.md section 4), the HBM fraction is the contract's reference number"
+                        % (bvh.n_nodes * node_bytes / 1e6)}
 
     if rank == 0:
         cpu = None

@@ -356,11 +356,11 @@ VKRT_DEV void trav_inner_step(Trav &tv, Stack &stack, const DevScene &sc, Stats 
     if (h0 || h1) tv.node = take1 ? c1 : c0;
     else tv.node = tv.sp ? stack.pop(tv.sp) : (int)TRAV_DONE;
 }
-template <bool ANY, bool STATS, class Stack>
-VKRT_DEV void trav_leaf_step(Trav &tv, Stack &stack, const DevScene &sc, V3 o, V3 d, Stats &st)
+template <bool STATS, class Stack>
+VKRT_DEV void trav_leaf_step(Trav &tv, Stack &stack, const DevScene &sc, V3 o, V3 d, bool any, Stats &st)
 {
     leaf_test<STATS>(tv, sc, o, d, ~tv.node, st);
-    if (ANY && tv.best.idx >= 0) { tv.node = TRAV_DONE; return; }
+    if (any && tv.best.idx >= 0) { tv.node = TRAV_DONE; return; }
     tv.node = tv.sp ? stack.pop(tv.sp) : (int)TRAV_DONE;
 }
 
@@ -579,9 +579,11 @@ struct LightTrace {
 
 // Shades the hit (the light loop asks `lights(l, surface, material)` for every emissive sphere's
 // contribution) and rolls Russian roulette.  Returns true when the path continues into the next depth iteration.
+// `emissive_used` receives the emissive term that was added next to the light sum (DIFFUSE branch only; the
+// fused wavefront needs it to form the accumulator for the other outcome of a pending shadow ray).
 template <class Lights>
 VKRT_DEV bool path_shade(const DevScene &sc, V3 cam_pos, uint32_t max_depth, uint32_t skey, PathState &ps,
-                         const Hit &hit, const Lights &lights)
+                         const Hit &hit, const Lights &lights, V3 *emissive_used = nullptr)
 {
     const uint32_t dim0 = ps.depth * DIMS_PER_BOUNCE;
     const Surface sf = surface_of(sc, ps.o, ps.d, hit);
@@ -594,6 +596,7 @@ VKRT_DEV bool path_shade(const DevScene &sc, V3 cam_pos, uint32_t max_depth, uin
         for (uint32_t l = 0; l < sc.n_lights; ++l) e = e + lights(l, sf, mat);
         const bool all_pos = mat.emissive.x > 0.0f && mat.emissive.y > 0.0f && mat.emissive.z > 0.0f;
         const V3 emissive = all_pos ? normalize3(mat.emissive) : v3(0.0f);
+        if (emissive_used) *emissive_used = emissive;
         ps.acc = ps.acc + ps.mask * (emissive + e);
         ps.mask = ps.mask * mat.albedo;
         const V3 nd = normalize3(reflect3(ps.d, sf.N) + dj);

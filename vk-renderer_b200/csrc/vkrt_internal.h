@@ -52,6 +52,7 @@ struct WaveBuffers {
     float4 *sample_rad;           // finished radiance per (pixel slot, sample in wave); reduced in sample order
     float4 *shadow;               // light-sample shadow rays {L.xyz, t_light}, n_lights per path
     float4 *term;                 // their unoccluded contributions (evaluated before the ray is queued)
+    float4 *shrec;                // fused pipeline (one light): 64-byte shadow records {P.xyz t | L.xyz ended | acc_if_visible.xyz pixel | -}
     uint8_t *occ;                 // their any-hit results
     uint32_t *queue_shadow;       // (path << 4 | light) items that still need the sphere any-hit query
     uint32_t shadow_lights;

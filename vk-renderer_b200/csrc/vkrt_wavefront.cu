@@ -46,6 +46,12 @@
 #ifndef VKRT_TRACE_RESIDENT
 #define VKRT_TRACE_RESIDENT 0       // cap of resident trace blocks per SM (0: as many as fit)
 #endif
+#ifndef VKRT_LOGIC_MINBLOCKS
+#define VKRT_LOGIC_MINBLOCKS 4      // __launch_bounds__(256, n) of the fused classify + shade kernel
+#endif
+#ifndef VKRT_FUSED
+#define VKRT_FUSED 1               // scenes with <= 1 light: logic + mixed trace (2 launches per depth) instead of 4
+#endif
 #ifndef VKRT_BLOCK_PUSH
 #define VKRT_BLOCK_PUSH 1          // classify / shade: one queue-counter atomicAdd per block instead of per warp
 #endif
@@ -60,10 +66,11 @@ namespace vkrt {
 
 // one counter set per depth iteration (no reset launches): paths entering the depth, the material bins, the
 // shadow-ray queue and the two work-fetch heads; survivors are counted in the NEXT depth's set
-enum { C_ACTIVE = 0, C_DIEL = 2, C_DIFF = 3, C_SHADOW = 4, C_HEAD_EXTEND = 5, C_HEAD_SHADOW = 6, C_N = 8, C_SETS = 257 };
+enum { C_ACTIVE = 0, C_DIEL = 2, C_DIFF = 3, C_SHADOW = 4, C_HEAD_EXTEND = 5, C_HEAD_SHADOW = 6, C_ZERO = 7, C_N = 8, C_SETS = 257 };
 
 struct WaveParams {
     float4 *rec, *sh, *term, *rad;   // rec: 4 float4 per path (see the top of the file)
+    float4 *shrec;                   // fused pipeline: 4 float4 per path {P.xyz t | L.xyz dead | acc_if_visible.xyz pixel | -}
     uint32_t *q_active[2], *q_diel, *q_diff, *q_shadow;
     uint8_t *occ;
     uint32_t *cnt, *cnt_next;    // counter set of this depth / of the next depth
@@ -208,17 +215,27 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ Dev
 }
 
 // ---- persistent trace kernel (nearest-hit for `extend`, any-hit for `shadow`) --------------------
-// ANY = false: item i -> path queue[i]; ray (po, pd), bound 3000/(depth+1)^2; triangles, then spheres;
-//              result -> po.w (t so far), pd.w (id so far); the plane loop follows in classify
-// ANY = true : item i -> queue[i] = path * 16 + light; ray (P, sh.xyz), bound sh.w; spheres only; -> occ
-template <bool ANY, bool BVH, bool STATS>
+// nearest-hit item: path queue[i]; ray = the record's (origin, dir), bound 3000/(depth+1)^2; triangles, then spheres;
+//                   result -> the record's t_hit / hit id; the plane loop follows in classify / logic
+// any-hit item, MODE 1 (four-kernel pipeline): queue[i] = path * 16 + light; ray (P, sh.xyz), bound sh.w; spheres only; -> occ
+// any-hit item, MODE 2 (fused pipeline): queue_sh[i] = path; ray and bound from shrec; an UNOCCLUDED ray stores the
+//                   accumulator `logic` prepared for that outcome into the path record (or the path's final radiance)
+// MODE 0: nearest-hit items only.  MODE 2: ONE launch traces the nearest-hit rays of depth d and the shadow rays of
+// depth d-1 -- item i < n_ext is a nearest-hit item, the rest are shadow items (the longer rays go first); lanes of
+// one warp may hold either kind, the traversal is the same code.
+enum { TRACE_EXTEND = 0, TRACE_SHADOW = 1, TRACE_MIXED = 2 };
+template <int MODE, bool BVH, bool STATS>
 __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_trace(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
                                                                 const __grid_constant__ WaveParams wp, const uint32_t *__restrict__ queue,
-                                                                const uint32_t *__restrict__ n_items_ptr, uint32_t *head, uint32_t depth)
+                                                                const uint32_t *__restrict__ n_items_ptr, const uint32_t *__restrict__ queue_sh,
+                                                                const uint32_t *__restrict__ n_sh_ptr, uint32_t *head, uint32_t depth)
 {
     const unsigned full = 0xffffffffu, lane = threadIdx.x & 31u;
     Stats st; stats_zero(st);
-    const uint32_t n_items = *n_items_ptr;
+    const uint32_t n_ext = MODE == TRACE_SHADOW ? 0u : *n_items_ptr;
+    const uint32_t n_items = MODE == TRACE_SHADOW ? *n_items_ptr : (MODE == TRACE_MIXED ? n_ext + *n_sh_ptr : n_ext);
+    bool any = MODE == TRACE_SHADOW;
+    static_assert(MODE != TRACE_MIXED || VKRT_LEAF_BATCH != 0, "the mixed trace kernel needs the phase-split traversal");
     const float EPS = 1e-3f;
     const float tmax = path_tmax(depth);       // every ray of one extend launch is at the same depth (:444)
 
@@ -273,16 +290,20 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                 if (item >= n_items) drained = true;
                 else {
                     has = true;
-                    const uint32_t q = queue[item];
-                    path = ANY ? (q >> 4) : q;
-                    light = ANY ? (q & 15u) : 0u;
+                    if (MODE == TRACE_MIXED) any = item >= n_ext;
+                    const uint32_t q = (MODE == TRACE_MIXED && any) ? queue_sh[item - n_ext] : queue[item];
+                    path = MODE == TRACE_SHADOW ? (q >> 4) : q;
+                    light = MODE == TRACE_SHADOW ? (q & 15u) : 0u;
                     float4 fo, fd;
-                    ld256(rec_ray(wp, path), fo, fd);
+                    ld256(MODE == TRACE_MIXED && any ? wp.shrec + 4 * (size_t)path : rec_ray(wp, path), fo, fd);
                     found = false; hit.kind = 0; hit.index = 0;
-                    if (ANY) {
+                    if (MODE == TRACE_SHADOW) {
                         const float4 s = wp.sh[(size_t)path * wp.n_lights + light];
                         o = madd3(fo.w, xyz(fd), xyz(fo));           // the hit point P (== surface_of's P)
                         d = xyz(s); cur = s.w;
+                    } else if (MODE == TRACE_MIXED && any) {
+                        o = xyz(fo); d = xyz(fd); cur = fo.w;        // shrec: {P.xyz t | L.xyz dead}
+                        light = __float_as_uint(fd.w);               // "the path ended at this bounce"
                     } else {
                         o = xyz(fo); d = xyz(fd);
                         cur = tmax;
@@ -313,7 +334,7 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                 // together (or nobody has an inner node left); everybody else keeps visiting inner nodes
                 const unsigned im = __ballot_sync(full, trav && tv.node >= 0);
                 if (im == 0 || __popc(tm & ~im) >= VKRT_LEAF_BATCH) {
-                    if (trav && tv.node < 0) trav_leaf_step<ANY, STATS>(tv, stack, sc, o, d, st);
+                    if (trav && tv.node < 0) trav_leaf_step<STATS>(tv, stack, sc, o, d, any, st);
                 } else {
 #pragma unroll
                     for (int u = 0; u < VKRT_TRAV_UNROLL; ++u)     // the warp votes above cost ~10 instructions: amortise them
@@ -332,7 +353,7 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                 if (__popc(tm) < VKRT_REFILL && __any_sync(full, !drained && !trav)) break;
 #pragma unroll
                 for (int u = 0; u < VKRT_TRAV_UNROLL; ++u)     // the warp votes above cost ~10 instructions: amortise them
-                    if (has && tv.node >= 0) trav_step<ANY, STATS>(tv, stack, sc, o, d, st);
+                    if (has && tv.node >= 0) trav_step<MODE == TRACE_SHADOW, STATS>(tv, stack, sc, o, d, st);
             }
 #endif
         }
@@ -347,8 +368,14 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                     if ((t > EPS) && (t < cur + EPS)) { cur = t; hit.kind = KIND_SPHERE; hit.index = i; found = true; }
                 }
             }
-            if (ANY) wp.occ[(size_t)path * wp.n_lights + light] = found ? 1 : 0;
-            else {
+            if (MODE == TRACE_SHADOW) wp.occ[(size_t)path * wp.n_lights + light] = found ? 1 : 0;
+            else if (MODE == TRACE_MIXED && any) {
+                if (!found) {        // unoccluded: the light's term counts (Tracer.comp:473-503)
+                    const float4 a1 = wp.shrec[4 * (size_t)path + 2];
+                    if (light) wp.rad[path] = make_float4(a1.x, a1.y, a1.z, 0.f);
+                    else rec_state(wp, path)[0] = a1;
+                }
+            } else {
                 rec_ray(wp, path)[0].w = cur;
                 rec_ray(wp, path)[1].w = __uint_as_float(found ? ((hit.kind << 28) | hit.index) : 0u);
             }
@@ -526,6 +553,80 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_SHADE_MINBLOCKS) k_wf_s
     shade_bin<true>(sc, rp, wp, next, cam_pos);
 }
 
+// ---- fused pipeline (scenes with at most one emissive sphere): `logic` = classify + shade in one pass ------------
+// With one light the light sum of a DIFFUSE hit is  e = 0 + (occluded ? 0 : term)  (Tracer.comp:457-503), so both
+// possible accumulators are known before the shadow ray is traced:
+//     acc_occluded = acc + mask * (emissive + (0 + 0))          acc_visible = acc + mask * (emissive + (0 + term))
+// `logic` shades the path completely with acc_occluded (next ray, mask, Russian roulette, the record or the final
+// radiance) and leaves {P, t, L, "path ended", acc_visible} for the shadow ray; the trace launch of the NEXT depth
+// (TRACE_MIXED) answers it next to that depth's nearest-hit rays and, if the ray is unoccluded, stores acc_visible.
+// The firefly clamp of the next iteration (:441) reads the accumulator after that launch, so every value is formed
+// by the same operations in the same order as in radiance(); per depth the wave costs two launches instead of four
+// and one pass over the path records instead of two.
+struct LightsDeferred {
+    const DevScene &sc; V3 cam_pos; uint32_t skey, dim0; Stats &st;
+    bool *need_ray; V3 *L, *term; float *t;
+    VKRT_DEV V3 operator()(uint32_t l, const Surface &sf, const Material &mat) const
+    {
+        V3 Ld; float td;
+        nee_sample(sc, sf.P, l, skey, dim0, Ld, td);
+        ++st.shadow;
+        const V3 tm = light_term(sc, sf, mat, cam_pos, l, Ld, td);
+        bool occluded = term_is_zero(tm);
+        if (occluded) ++st.skipped;
+        Hit h{td, 0, 0};
+        float cur = td;
+        if (!occluded) occluded = trace_tris<true>(sc, sf.P, Ld, cur, h);
+        if (!occluded) { cur = td; occluded = trace_planes<true>(sc, sf.P, Ld, cur, h); }
+        *need_ray = !occluded; *L = Ld; *term = tm; *t = td;
+        return v3(0.0f);          // shade as if occluded; the visible outcome is formed by the caller
+    }
+};
+__global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wf_logic(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
+                                                      const __grid_constant__ WaveParams wp, const uint32_t *__restrict__ queue,
+                                                      const uint32_t *__restrict__ n_ptr, uint32_t next)
+{
+    Stats st; stats_zero(st);
+    const uint32_t n = *n_ptr;
+    const V3 cam_pos = v3(rp.fd.camera.pos.x, rp.fd.camera.pos.y, rp.fd.camera.pos.z);
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        bool alive = false, need_ray = false;
+        uint32_t path = 0;
+        if (i < n) {
+            path = queue[i];
+            PathState ps; Hit hit; uint32_t pix, sl;
+            load_path(wp, path, ps, hit, pix, sl);
+            ps.acc = clamp3(ps.acc, 0.0f, 1.0f);                                                        // :441
+            const uint32_t id0 = (hit.kind << 28) | hit.index;
+            float cur = hit.t;
+            const bool found = trace_planes<true>(sc, ps.o, ps.d, cur, hit) || id0 != 0u;             // :414-428
+            hit.t = cur;
+            if (rp.hit_ids && ps.depth == 0u && sl == 0u && wp.s0 == rp.s_begin) rp.hit_ids[pix] = found ? ((hit.kind << 28) | hit.index) : 0u;
+            if (found) {
+                const uint32_t skey = sample_key(rp.fkey, pix, wp.s0 + sl);
+                const V3 acc_b = ps.acc, mask_b = ps.mask, P = madd3(hit.t, ps.d, ps.o);    // P == surface_of's P
+                V3 L = v3(0.0f), term = v3(0.0f), emis = v3(0.0f);
+                float t = 0.0f;
+                const LightsDeferred lights{sc, cam_pos, skey, ps.depth * DIMS_PER_BOUNCE, st, &need_ray, &L, &term, &t};
+                alive = path_shade(sc, cam_pos, rp.max_depth, skey, ps, hit, lights, &emis);
+                if (need_ray) {
+                    const V3 acc_v = acc_b + mask_b * (emis + (v3(0.0f) + term));
+                    float4 *sr = wp.shrec + 4 * (size_t)path;
+                    st256(sr, make_float4(P.x, P.y, P.z, t), make_float4(L.x, L.y, L.z, __uint_as_float(alive ? 0u : 1u)));
+                    sr[2] = make_float4(acc_v.x, acc_v.y, acc_v.z, __uint_as_float(pix));
+                }
+                if (alive) store_path(wp, path, ps, pix, sl);
+            } 
+            if (!alive) wp.rad[path] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, 0.f);               // miss (:445) or the path ended
+        }
+        uint32_t *const qs[2] = {wp.q_active[next], wp.q_shadow}; uint32_t *const cs[2] = {wp.cnt_next + C_ACTIVE, wp.cnt + C_SHADOW};
+        const bool ws[2] = {alive, need_ray}; const uint32_t vs[2] = {path, path};
+        push_block<2>(qs, cs, ws, vs);
+    }
+    wf_flush(st, rp.counters, false);
+}
+
 // ---- reduce: per pixel, add the wave's samples in sample order -------------------------------------
 __global__ void __launch_bounds__(256) k_wf_reduce(const __grid_constant__ RenderParams rp, const __grid_constant__ WaveParams wp,
                                                     float4 *__restrict__ frame_sum, uint32_t first_wave, uint32_t last_wave)
@@ -565,7 +666,7 @@ void wave_free(WaveBuffers &wb)
 {
     cudaFree(wb.rec); cudaFree(wb.sample_rad);
     cudaFree(wb.queue[0]); cudaFree(wb.queue[1]); cudaFree(wb.queue_mat[0]); cudaFree(wb.queue_mat[1]); cudaFree(wb.counts);
-    cudaFree(wb.shadow); cudaFree(wb.occ); cudaFree(wb.queue_shadow); cudaFree(wb.term);
+    cudaFree(wb.shadow); cudaFree(wb.occ); cudaFree(wb.queue_shadow); cudaFree(wb.term); cudaFree(wb.shrec);
     for (uint32_t i = 0; i < wb.ev_created; ++i) cudaEventDestroy(wb.ev[i]);
     wb = WaveBuffers{};
 }
@@ -638,17 +739,26 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
     if (n_lanes > 1 && spp >= n_lanes && S > (spp + n_lanes - 1) / n_lanes) S = (spp + n_lanes - 1) / n_lanes;
     const uint32_t n_waves = (spp + S - 1) / S;
     for (uint32_t l = 0; l < n_lanes; ++l) if ((e = lane_prepare(eng.lane[l], nl)) != cudaSuccess) return e;
+    if (VKRT_FUSED != 0 && VKRT_LEAF_BATCH != 0 && sc.n_lights == 1)
+        for (uint32_t l = 0; l < n_lanes; ++l)
+            if (!eng.lane[l].shrec && (e = cudaMalloc((void **)&eng.lane[l].shrec, eng.lane[l].capacity * 4 * sizeof(float4))) != cudaSuccess) return e;
     if (n_waves > 1 && !eng.frame_sum) {
         if ((e = cudaMalloc((void **)&eng.frame_sum, (size_t)rp.n_work * sizeof(float4))) != cudaSuccess) return e;
     }
 
-    auto pick_trace = [&](bool any) -> void (*)(const DevScene, const RenderParams, const WaveParams, const uint32_t *, const uint32_t *, uint32_t *, uint32_t) {
-        if (any) return bvh ? (stats ? k_wf_trace<true, true, true> : k_wf_trace<true, true, false>)
-                            : (stats ? k_wf_trace<true, false, true> : k_wf_trace<true, false, false>);
-        return bvh ? (stats ? k_wf_trace<false, true, true> : k_wf_trace<false, true, false>)
-                   : (stats ? k_wf_trace<false, false, true> : k_wf_trace<false, false, false>);
+    typedef void (*trace_fn)(const DevScene, const RenderParams, const WaveParams, const uint32_t *, const uint32_t *, const uint32_t *,
+                             const uint32_t *, uint32_t *, uint32_t);
+    auto pick_trace = [&](int mode) -> trace_fn {
+        if (mode == TRACE_SHADOW) return bvh ? (stats ? k_wf_trace<TRACE_SHADOW, true, true> : k_wf_trace<TRACE_SHADOW, true, false>)
+                                             : (stats ? k_wf_trace<TRACE_SHADOW, false, true> : k_wf_trace<TRACE_SHADOW, false, false>);
+        if (mode == TRACE_MIXED) return bvh ? (stats ? k_wf_trace<TRACE_MIXED, true, true> : k_wf_trace<TRACE_MIXED, true, false>)
+                                            : (stats ? k_wf_trace<TRACE_MIXED, false, true> : k_wf_trace<TRACE_MIXED, false, false>);
+        return bvh ? (stats ? k_wf_trace<TRACE_EXTEND, true, true> : k_wf_trace<TRACE_EXTEND, true, false>)
+                   : (stats ? k_wf_trace<TRACE_EXTEND, false, true> : k_wf_trace<TRACE_EXTEND, false, false>);
     };
-    auto k_extend = pick_trace(false), k_shadow = pick_trace(true);
+    // scenes with at most one light take the fused pipeline (logic + mixed trace), the others the four-kernel one
+    const bool fused = VKRT_FUSED != 0 && VKRT_LEAF_BATCH != 0 && sc.n_lights <= 1;
+    trace_fn k_extend = pick_trace((fused && sc.n_lights) ? TRACE_MIXED : TRACE_EXTEND), k_shadow = pick_trace(fused ? TRACE_MIXED : TRACE_SHADOW);
     int occ_e = 0, occ_s = 0;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_extend, VKRT_TRACE_BLOCK, 0)) != cudaSuccess) return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_shadow, VKRT_TRACE_BLOCK, 0)) != cudaSuccess) return e;
@@ -676,7 +786,7 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
         auto ev_open = [&](uint8_t tag) { if (wb.n_ev + 1 < 128) { wb.ev_tag[wb.n_ev / 2] = tag; cudaEventRecord(wb.ev[wb.n_ev++], ls); } };
         auto ev_close = [&]() { if (wb.n_ev < 128 && (wb.n_ev & 1u)) cudaEventRecord(wb.ev[wb.n_ev++], ls); };
         WaveParams wp{};
-        wp.rec = wb.rec; wp.sh = wb.shadow; wp.term = wb.term; wp.rad = wb.sample_rad;
+        wp.rec = wb.rec; wp.shrec = wb.shrec; wp.sh = wb.shadow; wp.term = wb.term; wp.rad = wb.sample_rad;
         wp.q_active[0] = wb.queue[0]; wp.q_active[1] = wb.queue[1]; wp.q_diel = wb.queue_mat[0]; wp.q_diff = wb.queue_mat[1];
         wp.q_shadow = wb.queue_shadow;
         wp.occ = wb.occ; wp.cnt = wb.counts; wp.cnt_next = wb.counts + C_N;
@@ -698,9 +808,28 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
             wp.cnt = wb.counts + (size_t)depth * C_N;
             wp.cnt_next = wp.cnt + C_N;
             const uint32_t *n_active = wp.cnt + C_ACTIVE;
+            if (fused) {
+                // this depth's nearest-hit rays and the previous depth's shadow rays in one launch, then `logic`
+                if (depth > 0) {
+                    ev_open(1);
+                    k_extend<<<grid_e, VKRT_TRACE_BLOCK, 0, ls>>>(sc, rp, wp, wp.q_active[cur], n_active, wp.q_shadow, wp.cnt - C_N + C_SHADOW,
+                                                                   wp.cnt + C_HEAD_EXTEND, depth); ++launches;
+                    ev_close();
+                }
+                ev_open(2);
+                k_wf_logic<<<grid_shade, VKRT_SHADE_BLOCK, 0, ls>>>(sc, rp, wp, wp.q_active[cur], n_active, nxt); ++launches;
+                ev_close();
+                if (depth + 1 == rp.max_depth && sc.n_lights) {      // the last depth's shadow rays (no nearest-hit items left)
+                    ev_open(3);
+                    k_shadow<<<grid_s, VKRT_TRACE_BLOCK, 0, ls>>>(sc, rp, wp, wp.q_active[nxt], wp.cnt_next + C_ZERO, wp.q_shadow, wp.cnt + C_SHADOW,
+                                                                   wp.cnt_next + C_HEAD_EXTEND, depth + 1); ++launches;
+                    ev_close();
+                }
+                continue;
+            }
             if (depth > 0) {       // depth 0 was traced once per pixel by `generate`
                 ev_open(1);
-                k_extend<<<grid_e, VKRT_TRACE_BLOCK, 0, ls>>>(sc, rp, wp, wp.q_active[cur], n_active, wp.cnt + C_HEAD_EXTEND, depth); ++launches;
+                k_extend<<<grid_e, VKRT_TRACE_BLOCK, 0, ls>>>(sc, rp, wp, wp.q_active[cur], n_active, nullptr, nullptr, wp.cnt + C_HEAD_EXTEND, depth); ++launches;
                 ev_close();
             }
             ev_open(2);
@@ -708,7 +837,7 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
             ev_close();
             if (sc.n_lights) {
                 ev_open(3);
-                k_shadow<<<grid_s, VKRT_TRACE_BLOCK, 0, ls>>>(sc, rp, wp, wp.q_shadow, wp.cnt + C_SHADOW, wp.cnt + C_HEAD_SHADOW, depth); ++launches;
+                k_shadow<<<grid_s, VKRT_TRACE_BLOCK, 0, ls>>>(sc, rp, wp, wp.q_shadow, wp.cnt + C_SHADOW, nullptr, nullptr, wp.cnt + C_HEAD_SHADOW, depth); ++launches;
                 ev_close();
             }
             ev_open(4);
