@@ -5,5 +5,5 @@ M=gpu__time_duration.sum,smsp__thread_inst_executed_per_inst_executed.ratio,sm__
 B="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
 ncu --metrics $M --clock-control none -c 210 --csv --log-file gpurun_out/${P}_launches.csv $B > gpurun_out/${P}_b1.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_wf_trace -c 2 -f -o gpurun_out/${P}_full_trace $B > gpurun_out/${P}_b2.log 2>&1
-ncu --set full --clock-control none --import-source on -k "regex:k_wf_(classify|shade)" -c 2 -f -o gpurun_out/${P}_full_shade $B > gpurun_out/${P}_b3.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:k_wf_(classify|shade|logic)" -c 2 -f -o gpurun_out/${P}_full_shade $B > gpurun_out/${P}_b3.log 2>&1
 ls -la gpurun_out | grep ${P}_

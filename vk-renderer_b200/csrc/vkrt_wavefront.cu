@@ -52,6 +52,9 @@
 #ifndef VKRT_FUSED
 #define VKRT_FUSED 1               // scenes with <= 1 light: logic + mixed trace (2 launches per depth) instead of 4
 #endif
+#ifndef VKRT_FUSED_GENERATE
+#define VKRT_FUSED_GENERATE 1      // fused pipeline: depth 0 is shaded inside generate (one primary hit per pixel)
+#endif
 #ifndef VKRT_BLOCK_PUSH
 #define VKRT_BLOCK_PUSH 1          // classify / shade: one queue-counter atomicAdd per block instead of per warp
 #endif
@@ -582,6 +585,28 @@ struct LightsDeferred {
         return v3(0.0f);          // shade as if occluded; the visible outcome is formed by the caller
     }
 };
+// one path after its nearest hit is final (`found`, `hit` include the plane loop; ps.acc is already clamped, :441)
+VKRT_DEV void logic_path(const DevScene &sc, const RenderParams &rp, const WaveParams &wp, V3 cam_pos, uint32_t path, PathState &ps,
+                         const Hit &hit, bool found, uint32_t pix, uint32_t sl, Stats &st, bool &alive, bool &need_ray)
+{
+    alive = false; need_ray = false;
+    if (found) {
+        const uint32_t skey = sample_key(rp.fkey, pix, wp.s0 + sl);
+        const V3 acc_b = ps.acc, mask_b = ps.mask, P = madd3(hit.t, ps.d, ps.o);    // P == surface_of's P
+        V3 L = v3(0.0f), term = v3(0.0f), emis = v3(0.0f);
+        float t = 0.0f;
+        const LightsDeferred lights{sc, cam_pos, skey, ps.depth * DIMS_PER_BOUNCE, st, &need_ray, &L, &term, &t};
+        alive = path_shade(sc, cam_pos, rp.max_depth, skey, ps, hit, lights, &emis);
+        if (need_ray) {
+            const V3 acc_v = acc_b + mask_b * (emis + (v3(0.0f) + term));
+            float4 *sr = wp.shrec + 4 * (size_t)path;
+            st256(sr, make_float4(P.x, P.y, P.z, t), make_float4(L.x, L.y, L.z, __uint_as_float(alive ? 0u : 1u)));
+            sr[2] = make_float4(acc_v.x, acc_v.y, acc_v.z, __uint_as_float(pix));
+        }
+        if (alive) store_path(wp, path, ps, pix, sl);
+    }
+    if (!alive) wp.rad[path] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, 0.f);               // miss (:445) or the path ended
+}
 __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wf_logic(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
                                                       const __grid_constant__ WaveParams wp, const uint32_t *__restrict__ queue,
                                                       const uint32_t *__restrict__ n_ptr, uint32_t next)
@@ -603,28 +628,65 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wf_l
             const bool found = trace_planes<true>(sc, ps.o, ps.d, cur, hit) || id0 != 0u;             // :414-428
             hit.t = cur;
             if (rp.hit_ids && ps.depth == 0u && sl == 0u && wp.s0 == rp.s_begin) rp.hit_ids[pix] = found ? ((hit.kind << 28) | hit.index) : 0u;
-            if (found) {
-                const uint32_t skey = sample_key(rp.fkey, pix, wp.s0 + sl);
-                const V3 acc_b = ps.acc, mask_b = ps.mask, P = madd3(hit.t, ps.d, ps.o);    // P == surface_of's P
-                V3 L = v3(0.0f), term = v3(0.0f), emis = v3(0.0f);
-                float t = 0.0f;
-                const LightsDeferred lights{sc, cam_pos, skey, ps.depth * DIMS_PER_BOUNCE, st, &need_ray, &L, &term, &t};
-                alive = path_shade(sc, cam_pos, rp.max_depth, skey, ps, hit, lights, &emis);
-                if (need_ray) {
-                    const V3 acc_v = acc_b + mask_b * (emis + (v3(0.0f) + term));
-                    float4 *sr = wp.shrec + 4 * (size_t)path;
-                    st256(sr, make_float4(P.x, P.y, P.z, t), make_float4(L.x, L.y, L.z, __uint_as_float(alive ? 0u : 1u)));
-                    sr[2] = make_float4(acc_v.x, acc_v.y, acc_v.z, __uint_as_float(pix));
-                }
-                if (alive) store_path(wp, path, ps, pix, sl);
-            } 
-            if (!alive) wp.rad[path] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, 0.f);               // miss (:445) or the path ended
+            logic_path(sc, rp, wp, cam_pos, path, ps, hit, found, pix, sl, st, alive, need_ray);
         }
         uint32_t *const qs[2] = {wp.q_active[next], wp.q_shadow}; uint32_t *const cs[2] = {wp.cnt_next + C_ACTIVE, wp.cnt + C_SHADOW};
         const bool ws[2] = {alive, need_ray}; const uint32_t vs[2] = {path, path};
         push_block<2>(qs, cs, ws, vs);
     }
     wf_flush(st, rp.counters, false);
+}
+
+// generate + logic of depth 0 in one pass (fused pipeline): every sample of a pixel starts from the same primary hit
+// (Tracer.comp:574-581), so the query, the plane loop, the surface and the material are found once per pixel and
+// the S samples are shaded from registers; no depth-0 path record is written and read back.
+template <bool BVH, bool STATS>
+__global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wf_generate_logic(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
+                                                                                      const __grid_constant__ WaveParams wp)
+{
+    Stats st; stats_zero(st);
+    const V3 cam_pos = v3(rp.fd.camera.pos.x, rp.fd.camera.pos.y, rp.fd.camera.pos.z);
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t px = 0, py = 0;
+    const bool valid = slot < wp.n_slots && slot_to_pixel_w(rp, slot, px, py);
+    V3 o = v3(0.f), d = v3(0.f);
+    Hit hit{0.f, 0, 0};
+    bool found = false;
+    uint32_t pix = 0;
+    if (valid) {
+        primary_ray(rp.fd, rp.width, rp.height, px, py, o, d);
+        float cur = path_tmax(0);
+        found = trace_tris<true>(sc, o, d, cur, hit);
+        if (BVH) {
+            const SBest b = bvh_query<false, STATS>(sc, o, d, 1e-3f, sphere_bound<true>(cur), st);
+            if (b.idx >= 0) { cur = b.t; hit.kind = KIND_SPHERE; hit.index = (uint32_t)b.idx; found = true; }
+        } else {
+            for (uint32_t i = 0; i < sc.n_spheres; ++i) {                         // literal loop, Tracer.comp:398-412
+                const float t = sphere_intersect(o, d, __ldg(sc.spheres + i));
+                if ((t > 1e-3f) && (t < cur + 1e-3f)) { cur = t; hit.kind = KIND_SPHERE; hit.index = i; found = true; }
+            }
+        }
+        found = trace_planes<true>(sc, o, d, cur, hit) || found;                 // :414-428
+        hit.t = cur;
+        pix = py * rp.width + px;
+        if (rp.hit_ids && wp.s0 == rp.s_begin) rp.hit_ids[pix] = found ? ((hit.kind << 28) | hit.index) : 0u;
+        st.closest += wp.S;
+        st.shared += wp.S - 1u;
+        st.paths += wp.S;
+    }
+    for (uint32_t sl = 0; sl < wp.S; ++sl) {
+        const uint32_t path = sl * wp.n_slots + slot;
+        bool alive = false, need_ray = false;
+        if (valid) {
+            PathState ps;
+            path_begin(ps, o, d);                   // acc = 0: the firefly clamp of :441 leaves it unchanged
+            logic_path(sc, rp, wp, cam_pos, path, ps, hit, found, pix, sl, st, alive, need_ray);
+        }
+        uint32_t *const qs[2] = {wp.q_active[1], wp.q_shadow}; uint32_t *const cs[2] = {wp.cnt_next + C_ACTIVE, wp.cnt + C_SHADOW};
+        const bool ws[2] = {alive, need_ray}; const uint32_t vs[2] = {path, path};
+        push_block<2>(qs, cs, ws, vs);
+    }
+    wf_flush(st, rp.counters, STATS);
 }
 
 // ---- reduce: per pixel, add the wave's samples in sample order -------------------------------------
@@ -795,7 +857,15 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
         wp.n_slots = rp.n_work;
         wp.n_lights = sc.n_lights;
         if ((e = cudaMemsetAsync(wb.counts, 0, (size_t)(rp.max_depth + 1) * C_N * sizeof(uint32_t), ls)) != cudaSuccess) return e;
-        {
+        if (fused && VKRT_FUSED_GENERATE) {
+            void (*k_gen)(const DevScene, const RenderParams, const WaveParams) =
+                bvh ? (stats ? k_wf_generate_logic<true, true> : k_wf_generate_logic<true, false>)
+                    : (stats ? k_wf_generate_logic<false, true> : k_wf_generate_logic<false, false>);
+            wp.cnt = wb.counts; wp.cnt_next = wb.counts + C_N;
+            ev_open(0);
+            k_gen<<<(wp.n_slots + VKRT_SHADE_BLOCK - 1u) / VKRT_SHADE_BLOCK, VKRT_SHADE_BLOCK, 0, ls>>>(sc, rp, wp); ++launches;
+            ev_close();
+        } else {
             void (*k_gen)(const DevScene, const RenderParams, const WaveParams) =
                 bvh ? (stats ? k_wf_generate<true, true> : k_wf_generate<true, false>)
                     : (stats ? k_wf_generate<false, true> : k_wf_generate<false, false>);
@@ -816,9 +886,11 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
                                                                    wp.cnt + C_HEAD_EXTEND, depth); ++launches;
                     ev_close();
                 }
-                ev_open(2);
-                k_wf_logic<<<grid_shade, VKRT_SHADE_BLOCK, 0, ls>>>(sc, rp, wp, wp.q_active[cur], n_active, nxt); ++launches;
-                ev_close();
+                if (depth > 0 || !VKRT_FUSED_GENERATE) {     // depth 0 was shaded by generate_logic
+                    ev_open(2);
+                    k_wf_logic<<<grid_shade, VKRT_SHADE_BLOCK, 0, ls>>>(sc, rp, wp, wp.q_active[cur], n_active, nxt); ++launches;
+                    ev_close();
+                }
                 if (depth + 1 == rp.max_depth && sc.n_lights) {      // the last depth's shadow rays (no nearest-hit items left)
                     ev_open(3);
                     k_shadow<<<grid_s, VKRT_TRACE_BLOCK, 0, ls>>>(sc, rp, wp, wp.q_active[nxt], wp.cnt_next + C_ZERO, wp.q_shadow, wp.cnt + C_SHADOW,
