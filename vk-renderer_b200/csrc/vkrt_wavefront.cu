@@ -55,6 +55,9 @@
 #ifndef VKRT_FUSED_GENERATE
 #define VKRT_FUSED_GENERATE 1      // fused pipeline: depth 0 is shaded inside generate (one primary hit per pixel)
 #endif
+#ifndef VKRT_SPEC_LEAF
+#define VKRT_SPEC_LEAF 0           // trace: park the first scheduled leaf and keep walking inner nodes
+#endif
 #ifndef VKRT_BLOCK_PUSH
 #define VKRT_BLOCK_PUSH 1          // classify / shade: one queue-counter atomicAdd per block instead of per warp
 #endif
@@ -269,6 +272,7 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
     Trav tv; tv.node = FIN; tv.sp = 0;
     int stack[BVH_STACK];
 #endif
+    int pend = FIN;                            // VKRT_SPEC_LEAF: the parked leaf (~sphere); FIN = none
 
     for (;;) {
         // ---- refill the lanes that have no ray -------------------------------------------------
@@ -327,7 +331,39 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
 
         // ---- traverse; leave as soon as the warp has thinned out and there are rays left to fetch --
         if (BVH) {
-#if VKRT_LEAF_BATCH
+#if VKRT_LEAF_BATCH && VKRT_SPEC_LEAF
+            // a lane that reaches a scheduled leaf parks it in `pend` and keeps walking inner nodes (the leaf test is
+            // only postponed: any order of box and leaf tests gives rule S's answer, a later test merely culls later);
+            // it waits only when a second leaf arrives while the first is still parked.  Leaf tests run when
+            // VKRT_LEAF_BATCH lanes have one parked, or nobody has an inner node left.
+            for (;;) {
+                const bool trav = has && (tv.node != FIN || pend != FIN);
+                const unsigned tm = __ballot_sync(full, trav);
+                if (tm == 0) break;
+                if (__popc(tm) < VKRT_REFILL && __any_sync(full, !drained && !trav)) break;
+                const unsigned im = __ballot_sync(full, trav && tv.node >= 0);
+                const unsigned pm = __ballot_sync(full, trav && pend != FIN);
+                if (im == 0 || __popc(pm) >= VKRT_LEAF_BATCH) {
+                    if (trav && pend != FIN) {
+                        leaf_test<STATS>(tv, sc, o, d, ~pend, st);
+                        pend = FIN;
+                        if (any && tv.best.idx >= 0) tv.node = FIN;                  // any-hit: answered
+                    }
+                    if (trav && tv.node < 0 && tv.node != FIN) { pend = tv.node; tv.node = tv.sp ? stack.pop(tv.sp) : FIN; }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < VKRT_TRAV_UNROLL; ++u)
+                        if (has && tv.node >= 0) {
+#if VKRT_QNODES
+                            trav_inner_step_q<STATS>(tv, qr, stack, sc, st);
+#else
+                            trav_inner_step<STATS>(tv, stack, sc, st);
+#endif
+                            if (tv.node < 0 && tv.node != FIN && pend == FIN) { pend = tv.node; tv.node = tv.sp ? stack.pop(tv.sp) : FIN; }
+                        }
+                }
+            }
+#elif VKRT_LEAF_BATCH
             for (;;) {
                 const bool trav = has && tv.node != FIN;
                 const unsigned tm = __ballot_sync(full, trav);
@@ -362,7 +398,7 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
         }
 
         // ---- finish the lanes whose traversal is over ---------------------------------------------
-        if (has && tv.node == FIN) {
+        if (has && tv.node == FIN && pend == FIN) {
             if (BVH) {
                 if (tv.best.idx >= 0) { cur = tv.best.t; hit.kind = KIND_SPHERE; hit.index = (uint32_t)tv.best.idx; found = true; }
             } else {
