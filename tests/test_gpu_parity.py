@@ -563,6 +563,10 @@ def test_edge_cases(vk, oracle, variant):
     lights = V.scenes.random_spheres(60)
     lights.materials[8:20, 4:7] = 40.0                             # 12 more emissive spheres: 13 lights
     check(lights, 48, 36, 2, 3, True, "13 lights")
+    two = V.scenes.random_spheres(60)
+    two.materials[8, 4:7] = 40.0                                   # 2 lights: the first scene past the fused (<= 1 light) pipeline
+    check(two, 48, 36, 3, 4, True, "2 lights")
+    check(two, 48, 36, 3, 4, False, "2 lights, literal loop")
     too_many = V.scenes.random_spheres(60)
     too_many.materials[8:30, 4:7] = 40.0
     r = V.Renderer(16, 16, variant=variant)

@@ -41,7 +41,7 @@
 #define VKRT_TRACE_BLOCK 128
 #endif
 #ifndef VKRT_TRACE_MINBLOCKS
-#define VKRT_TRACE_MINBLOCKS 9     // 56 registers: the occupancy the exact-node kernel had, with the 32-byte nodes
+#define VKRT_TRACE_MINBLOCKS 12    // 40 registers, 48 warps/SM: latency hiding beats the few spills (9/10/11/12/14/16 measured)
 #endif
 #ifndef VKRT_TRACE_RESIDENT
 #define VKRT_TRACE_RESIDENT 0       // cap of resident trace blocks per SM (0: as many as fit)
@@ -57,6 +57,9 @@
 #endif
 #ifndef VKRT_SPEC_LEAF
 #define VKRT_SPEC_LEAF 0           // trace: park the first scheduled leaf and keep walking inner nodes
+#endif
+#ifndef VKRT_COLD_SMEM
+#define VKRT_COLD_SMEM (VKRT_LEAF_BATCH && VKRT_QNODES && !VKRT_SPEC_LEAF)   // trace: leaf-test-only ray state in shared memory
 #endif
 #ifndef VKRT_BLOCK_PUSH
 #define VKRT_BLOCK_PUSH 1          // classify / shade: one queue-counter atomicAdd per block instead of per warp
@@ -272,6 +275,9 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
     Trav tv; tv.node = FIN; tv.sp = 0;
     int stack[BVH_STACK];
 #endif
+#if VKRT_COLD_SMEM
+    __shared__ float s_cold[12][VKRT_TRACE_BLOCK];
+#endif
     int pend = FIN;                            // VKRT_SPEC_LEAF: the parked leaf (~sphere); FIN = none
 
     for (;;) {
@@ -321,6 +327,15 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                         trav_init(tv, sc, o, d, EPS, sphere_bound<true>(cur)); if (tv.node < 0) tv.node = FIN;
 #if VKRT_LEAF_BATCH && VKRT_QNODES
                         qr = qray_setup(sc, tv.sr);
+#endif
+#if VKRT_COLD_SMEM
+                        {
+                            float *cs = &s_cold[0][threadIdx.x];
+                            cs[0] = o.x; cs[VKRT_TRACE_BLOCK] = o.y; cs[2 * VKRT_TRACE_BLOCK] = o.z;
+                            cs[3 * VKRT_TRACE_BLOCK] = d.x; cs[4 * VKRT_TRACE_BLOCK] = d.y; cs[5 * VKRT_TRACE_BLOCK] = d.z;
+                            cs[6 * VKRT_TRACE_BLOCK] = tv.sr.inv.x; cs[7 * VKRT_TRACE_BLOCK] = tv.sr.inv.y; cs[8 * VKRT_TRACE_BLOCK] = tv.sr.inv.z;
+                            cs[9 * VKRT_TRACE_BLOCK] = tv.sr.oinv.x; cs[10 * VKRT_TRACE_BLOCK] = tv.sr.oinv.y; cs[11 * VKRT_TRACE_BLOCK] = tv.sr.oinv.z;
+                        }
 #endif
                     }
                     else tv.node = FIN;
@@ -373,7 +388,20 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                 // together (or nobody has an inner node left); everybody else keeps visiting inner nodes
                 const unsigned im = __ballot_sync(full, trav && tv.node >= 0);
                 if (im == 0 || __popc(tm & ~im) >= VKRT_LEAF_BATCH) {
-                    if (trav && tv.node < 0) trav_leaf_step<STATS>(tv, stack, sc, o, d, any, st);
+                    if (trav && tv.node < 0) {
+#if VKRT_COLD_SMEM
+                        // the ray's origin, direction and exact slab constants are only needed here: they live in shared
+                        // memory ([field][thread], conflict-free) so the node loop's registers hold nothing cold
+                        const float *cs = &s_cold[0][threadIdx.x];
+                        const V3 co = v3(cs[0], cs[VKRT_TRACE_BLOCK], cs[2 * VKRT_TRACE_BLOCK]);
+                        const V3 cd = v3(cs[3 * VKRT_TRACE_BLOCK], cs[4 * VKRT_TRACE_BLOCK], cs[5 * VKRT_TRACE_BLOCK]);
+                        tv.sr.inv = v3(cs[6 * VKRT_TRACE_BLOCK], cs[7 * VKRT_TRACE_BLOCK], cs[8 * VKRT_TRACE_BLOCK]);
+                        tv.sr.oinv = v3(cs[9 * VKRT_TRACE_BLOCK], cs[10 * VKRT_TRACE_BLOCK], cs[11 * VKRT_TRACE_BLOCK]);
+                        trav_leaf_step<STATS>(tv, stack, sc, co, cd, any, st);
+#else
+                        trav_leaf_step<STATS>(tv, stack, sc, o, d, any, st);
+#endif
+                    }
                 } else {
 #pragma unroll
                     for (int u = 0; u < VKRT_TRAV_UNROLL; ++u)     // the warp votes above cost ~10 instructions: amortise them
