@@ -399,6 +399,17 @@ def run_ours(args):
                 "clocks": clocks, "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if not use_bvh:
+            # the compute-bound small scenes: algorithmic FLOP/s against the FP32 FFMA peak measured on this GPU
+            # (~200 flops per brute-force trace_ray of the default Tracer scene, ~250 per DIFFUSE shading
+            # event with its light sample = one per shadow ray here, ~60 per other shading event; FMA = 2 flops)
+            fp32_peak = V.measure_fp32_peak(local)
+            shading = float(rays[2].item())
+            flops = total_rays * 200.0 + shading * 250.0 + max(float(rays[1].item()) - shading, 0.0) * 60.0
+            line["fp32"] = {"achieved": flops / (ms_total * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                            "frac": flops / (ms_total * 1e-3) / 1e12 / fp32_peak, "peak_source": "measured FFMA chain (vkrt_measure_fp32_peak)",
+                            "note": "algorithmic flops of the reference algorithm, not executed instructions; pipe utilisation "
+                                    "from ncu is in profiles/ (metrics_k_path_mega_cfg2)"}
         if args.micro:
             line["fp32_peak_tflops_measured"] = V.measure_fp32_peak(local)
             line["l2_read_gbs_measured"] = V.measure_l2_bandwidth(local)
