@@ -47,8 +47,11 @@ VKRT_DEV void flush_stats(const Stats &st, unsigned long long *counters, bool st
 // fetches a new pixel slot: the lanes that need work are found with __ballot_sync, one lane does a
 // single atomicAdd for all of them and the base is broadcast with __shfl_sync.
 // ------------------------------------------------------------------------------------------------
+#ifndef VKRT_MEGA_MINBLOCKS
+#define VKRT_MEGA_MINBLOCKS 8      // 64 registers: 1/6/8/10/12 measured on the default scene (10.27 / 9.67 / 9.47 / 9.94 / 10.29 ms)
+#endif
 template <bool BVH, bool STATS>
-__global__ void __launch_bounds__(128) k_path_mega(const __grid_constant__ DevScene sc,
+__global__ void __launch_bounds__(128, VKRT_MEGA_MINBLOCKS) k_path_mega(const __grid_constant__ DevScene sc,
                                                     const __grid_constant__ RenderParams rp)
 {
     const unsigned full = 0xffffffffu;
