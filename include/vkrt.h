@@ -209,6 +209,52 @@ VKRT_API vkrt_error vkrt_resolve(vkrt_ctx *ctx);
  * resampled to an out_w x out_h framebuffer (row 0 = top, like the swapchain image).  Synchronous host copy. */
 VKRT_API vkrt_error vkrt_present(vkrt_ctx *ctx, void *host_rgba8, uint32_t out_w, uint32_t out_h);
 
+/* ------------------------------------------------------------------------- */
+/* Vulkan <-> CUDA interop: the traced images the engine presents             */
+/* (ref: traced_images[FRAMES_IN_FLIGHT], Source/GraphicsDevice.cpp:664-699;  */
+/*  the barriers around the dispatch, :1234-1252 and :1268-1284)              */
+/* ------------------------------------------------------------------------- */
+/* The engine allocates traced_images[slot] with VkExternalMemoryImageCreateInfo +
+ * VkExportMemoryAllocateInfo (VK_EXTERNAL_MEMORY_HANDLE_TYPE_OPAQUE_FD_BIT), exports the memory with
+ * vkGetMemoryFdKHR and hands the fd over here; from then on the resolve of every frame whose target is `slot`
+ * (slot = frame number % frames_in_flight, like state.currentFrame, :1341) is written straight into that memory,
+ * so Fullscreen.vert/.frag sample it unchanged and no copy crosses PCIe.  On success the library owns the fd
+ * (cudaImportExternalMemory semantics); on failure the caller still does. */
+enum { VKRT_TILING_LINEAR  = 0,   /* a VkBuffer, or a VK_IMAGE_TILING_LINEAR image: rows of row_pitch bytes          */
+       VKRT_TILING_OPTIMAL = 1 }; /* the reference's VK_IMAGE_TILING_OPTIMAL R8G8B8A8_UNORM image (:672-673):
+                                     mapped as a CUDA mipmapped array (1 level), written through a surface object */
+typedef struct vkrt_external_image {
+    uint32_t struct_size;      /* = sizeof(vkrt_external_image) */
+    int32_t  fd;               /* from vkGetMemoryFdKHR */
+    uint64_t allocation_size;  /* VkMemoryAllocateInfo.allocationSize (:692) */
+    uint64_t offset;           /* memoryOffset of vkBindImageMemory / vkBindBufferMemory (:697: 0) */
+    uint32_t tiling;           /* VKRT_TILING_* */
+    uint32_t row_pitch;        /* LINEAR: bytes per row (VkSubresourceLayout.rowPitch); 0 = width * 4 */
+    uint32_t dedicated;        /* the allocation used VkMemoryDedicatedAllocateInfo */
+    uint32_t _pad;
+} vkrt_external_image;
+VKRT_API vkrt_error vkrt_import_vk_image(vkrt_ctx *ctx, uint32_t slot, const vkrt_external_image *image);
+/* Same write path for linear device memory the caller maps by itself (a CUDA allocation, or an external buffer it
+ * imported on its own): the resolve of frames whose target is `slot` goes to dev_ptr, rows row_pitch bytes apart
+ * (0 = width * 4).  The memory stays the caller's.  dev_ptr = NULL returns the slot to the library's own image. */
+VKRT_API vkrt_error vkrt_bind_rgba8_target(vkrt_ctx *ctx, uint32_t slot, void *dev_ptr, size_t row_pitch);
+/* Diagnostics: backs `slot` by a library-owned CUDA array written through a surface object, i.e. the write path of
+ * a VKRT_TILING_OPTIMAL import without a Vulkan allocation behind it (what the GPU tests drive). */
+VKRT_API vkrt_error vkrt_debug_bind_array_target(vkrt_ctx *ctx, uint32_t slot);
+/* The two vkCmdPipelineBarriers become one semaphore pair per slot, exported by the engine with vkGetSemaphoreFdKHR
+ * (OPAQUE_FD; binary or timeline):
+ *   VKRT_SEMAPHORE_ACQUIRE  signalled by the engine in the last submit that samples image `slot` before the
+ *                           library's next write to it; the n-th resolve into the slot (n >= 2) waits for it
+ *                           (timeline: for value n - 1) before it writes -- replaces the barrier at :1234-1252;
+ *   VKRT_SEMAPHORE_RELEASE  signalled by the library on its stream after the n-th resolve into the slot (timeline:
+ *                           to value n); the engine's submit that samples the image waits for it -- :1268-1284.
+ * Without semaphores the caller orders the two APIs itself (vkrt_wait_idle / a fence). */
+enum { VKRT_SEMAPHORE_ACQUIRE = 0, VKRT_SEMAPHORE_RELEASE = 1 };
+VKRT_API vkrt_error vkrt_import_vk_semaphore(vkrt_ctx *ctx, uint32_t slot, uint32_t which, int32_t fd, uint32_t timeline);
+/* Waits for the frames in flight, then destroys every imported object and binding; all slots return to the
+ * library's own images. */
+VKRT_API vkrt_error vkrt_release_external(vkrt_ctx *ctx);
+
 /* Ray counters, cumulative since creation / vkrt_reset_counters.  A "ray" is one trace_ray
  * invocation of the reference algorithm (Tracer.comp:374, Raytracer.comp:224). */
 typedef struct vkrt_counters {

@@ -490,7 +490,7 @@ def test_present_filter_matches_oracle(vk, oracle):
     for f in range(3):
         cam.move_right(2.0)
         r.draw(V.default_frame_data(camera=cam, seed=0.1 * f))
-        slots[(f + 1) % 2] = r.read_rgba8()          # draw f writes image slot (f + 1) % 2 (cur_target advances first)
+        slots[f % 2] = r.read_rgba8()                # draw f writes image slot f % 2 like state.currentFrame (:1341)
         if f >= 1:
             got = r.present(1024, 768)
             want = oracle.present(slots[0], slots[1], 1024, 768)

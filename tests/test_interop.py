@@ -1,0 +1,243 @@
+"""The Vulkan <-> CUDA interop boundary of the traced images (include/vkrt.h "interop"; ref:
+Source/GraphicsDevice.cpp:664-699 traced_images, :1234-1284 the barriers around the dispatch).
+
+There is no Vulkan loader in the image, so no test can hold a real vkGetMemoryFdKHR handle.  What is tested:
+the two write paths an import ends in -- pitched linear memory and a CUDA array behind a surface object --
+byte for byte against the oracle's resolve, the slot rotation (currentFrame, :1341), every argument check, a
+foreign fd being refused without harming the context, and (when the driver accepts it) a genuine
+cudaImportExternalMemory round trip of a POSIX-fd allocation exported by CUDA's own VMM API.
+CPU part: the structs and the argument checks that need no device."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+W, H, SPP, DEPTH = 150, 90, 2, 4        # not multiples of 16 / 32: the pitched rows and the edge tiles are exercised
+
+
+def _oracle_frames(oracle, V, n):
+    sc = oracle.Scene().use_default(oracle.SCENE_TRACER)
+    out = []
+    for i in range(n):
+        fd = V.default_frame_data(aspect_ratio=W / H, seed=0.125 * (i + 1))
+        _, _, rgba, _ = sc.render(fd, W, H, spp=SPP, max_depth=DEPTH, integrator=oracle.PATH, seed=3, frame_index=i)
+        out.append((fd, rgba))
+    return out
+
+
+def _renderer(V, variant=0):
+    r = V.Renderer(W, H, spp=SPP, max_depth=DEPTH, variant=variant)
+    r.use_default_scene(V.SCENE_TRACER)
+    r.set_seed(3)
+    return r
+
+
+# ---- CPU -------------------------------------------------------------------------------------------
+def test_external_image_struct_layout(vk):
+    L = vk._lib
+    assert C.sizeof(L.ExternalImage) == 40
+    assert (L.ExternalImage.fd.offset, L.ExternalImage.allocation_size.offset, L.ExternalImage.offset.offset,
+            L.ExternalImage.tiling.offset, L.ExternalImage.row_pitch.offset, L.ExternalImage.dedicated.offset) == (4, 8, 16, 24, 28, 32)
+    assert (L.TILING_LINEAR, L.TILING_OPTIMAL, L.SEMAPHORE_ACQUIRE, L.SEMAPHORE_RELEASE) == (0, 1, 0, 1)
+
+
+def test_interop_entry_points_reject_null_context(vk):
+    lib = vk._lib.load()
+    im = vk._lib.ExternalImage(struct_size=C.sizeof(vk._lib.ExternalImage), fd=0, allocation_size=1 << 20)
+    assert lib.vkrt_import_vk_image(None, 0, C.byref(im)) == vk._lib.BAD_ARG
+    assert lib.vkrt_bind_rgba8_target(None, 0, None, 0) == vk._lib.BAD_ARG
+    assert lib.vkrt_debug_bind_array_target(None, 0) == vk._lib.BAD_ARG
+    assert lib.vkrt_import_vk_semaphore(None, 0, 0, 0, 0) == vk._lib.BAD_ARG
+    assert lib.vkrt_release_external(None) == vk._lib.BAD_ARG
+
+
+# ---- GPU -------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", [0, 1])
+def test_bound_linear_targets_receive_the_resolve(vk, oracle, variant):
+    """vkrt_bind_rgba8_target: pitched rows, slot rotation like state.currentFrame, padding untouched."""
+    import torch
+    V = vk
+    frames = _oracle_frames(oracle, V, 3)
+    pitch = W * 4 + 72
+    bufs = [torch.full((H, pitch), 0xAB, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    r = _renderer(V, variant)
+    for s in range(2):
+        r.bind_rgba8_target(s, bufs[s].data_ptr(), pitch)
+    torch.cuda.synchronize()
+    for i, (fd, orgba) in enumerate(frames):
+        slot = i % 2                                        # frame k -> traced_images[k % FRAMES_IN_FLIGHT] (:1341)
+        r.set_frame_index(i)
+        r.draw(fd)
+        got = r.read_rgba8()                                # cudaMemcpy2D out of the bound target
+        assert np.array_equal(got, orgba)
+        ptr, p = r.rgba8_ptr()
+        assert (ptr, p) == (bufs[slot].data_ptr(), pitch)
+        r.wait_idle()
+        host = bufs[slot].cpu().numpy()
+        assert np.array_equal(host[:, :W * 4].reshape(H, W, 4), orgba)
+        assert (host[:, W * 4:] == 0xAB).all()              # the row padding belongs to the caller
+        if i == 0:
+            assert (bufs[1].cpu().numpy() == 0xAB).all()    # the other slot has not been written yet
+    # back to the library's own image
+    r.bind_rgba8_target(0, None)
+    r.bind_rgba8_target(1, None)
+    before = [b.clone() for b in bufs]
+    r.set_frame_index(0)
+    r.draw(frames[0][0])
+    assert np.array_equal(r.read_rgba8(), frames[0][1])
+    r.wait_idle()
+    assert all(torch.equal(a, b) for a, b in zip(before, bufs))
+    r.close()
+
+
+@pytest.mark.gpu
+def test_array_surface_targets_receive_the_resolve(vk, oracle):
+    """The write path of an imported VK_IMAGE_TILING_OPTIMAL image: CUDA array + surf2Dwrite."""
+    V = vk
+    frames = _oracle_frames(oracle, V, 2)
+    r = _renderer(V, 1)
+    r.debug_bind_array_target(0)
+    r.debug_bind_array_target(1)
+    for i, (fd, orgba) in enumerate(frames):
+        r.set_frame_index(i)
+        r.draw(fd)
+        assert np.array_equal(r.read_rgba8(), orgba)
+    with pytest.raises(V.VkrtError) as e:
+        r.rgba8_ptr()
+    assert e.value.code == V._lib.BAD_ARG and "no linear pointer" in str(e.value)
+    with pytest.raises(V.VkrtError) as e:
+        r.present(64, 48)
+    assert e.value.code == V._lib.BAD_ARG
+    r.release_external()                                    # everything returns to the library's own images
+    r.set_frame_index(0)
+    r.draw(frames[0][0])
+    assert np.array_equal(r.read_rgba8(), frames[0][1])
+    assert r.present(64, 48).shape == (48, 64, 4)
+    r.close()
+
+
+@pytest.mark.gpu
+def test_import_argument_checks_and_foreign_fd(vk, oracle):
+    V, L = vk, vk._lib
+    r = _renderer(V)
+    lib = r.lib
+    need = W * 4 * H
+
+    def imp(slot=0, **kw):
+        d = dict(struct_size=C.sizeof(L.ExternalImage), fd=0, allocation_size=1 << 20, offset=0, tiling=L.TILING_LINEAR, row_pitch=0)
+        d.update(kw)
+        return lib.vkrt_import_vk_image(r.ctx, slot, C.byref(L.ExternalImage(**d)))
+
+    assert imp(struct_size=8) == L.BAD_ARG
+    assert imp(slot=2) == L.BAD_ARG                          # frames_in_flight = 2
+    assert imp(fd=-1) == L.BAD_ARG
+    assert imp(tiling=7) == L.BAD_ARG
+    assert imp(row_pitch=W * 4 - 4) == L.BAD_ARG
+    assert imp(allocation_size=need - 1) == L.BAD_ARG
+    assert imp(allocation_size=need + 64, offset=128) == L.BAD_ARG
+    assert lib.vkrt_import_vk_semaphore(r.ctx, 0, 2, 0, 0) == L.BAD_ARG
+    assert lib.vkrt_import_vk_semaphore(r.ctx, 0, 0, -1, 0) == L.BAD_ARG
+    assert lib.vkrt_bind_rgba8_target(r.ctx, 0, C.c_void_p(0x1000), 0) == L.BAD_ARG       # not device memory
+    host = np.zeros(need, dtype=np.uint8)
+    assert lib.vkrt_bind_rgba8_target(r.ctx, 0, host.ctypes.data_as(C.c_void_p), 0) == L.BAD_ARG
+    # a descriptor that is not an exported GPU allocation / semaphore: refused by the driver, and the caller keeps
+    # it (ownership only moves on success); every attempt gets its own dup so a surprise success cannot double-close
+    base = os.open("/dev/null", os.O_RDWR)
+
+    def attempt(call):
+        fd = os.dup(base)
+        rc = call(fd)
+        assert rc == L.CUDA_ERROR, "a /dev/null descriptor was accepted (rc %d)" % rc
+        assert b"[app] - err ::" in lib.vkrt_last_error_string(r.ctx)
+        os.fstat(fd)                                         # still open and still ours
+        os.close(fd)
+
+    try:
+        attempt(lambda fd: imp(fd=fd, tiling=L.TILING_LINEAR))
+        attempt(lambda fd: imp(fd=fd, tiling=L.TILING_OPTIMAL))
+        attempt(lambda fd: lib.vkrt_import_vk_semaphore(r.ctx, 0, L.SEMAPHORE_ACQUIRE, fd, 0))
+        attempt(lambda fd: lib.vkrt_import_vk_semaphore(r.ctx, 1, L.SEMAPHORE_RELEASE, fd, 1))
+    finally:
+        os.close(base)
+    # the context is unharmed
+    (fd0, orgba), = _oracle_frames(oracle, V, 1)
+    r.draw(fd0)
+    assert np.array_equal(r.read_rgba8(), orgba)
+    r.close()
+
+
+@pytest.mark.gpu
+def test_import_of_a_cuda_exported_posix_fd(vk, oracle):
+    """A genuine cudaImportExternalMemory round trip: a POSIX-fd allocation made and exported with CUDA's VMM API
+    stands in for the Vulkan allocation.  Whether the runtime takes such an fd as an OPAQUE_FD external memory is
+    driver-dependent: refused => skipped (the write path itself is covered by the tests above)."""
+    import torch
+    try:
+        from cuda.bindings import driver as cu
+    except Exception as exc:                                 # pragma: no cover
+        pytest.skip("cuda-python driver bindings unavailable: %r" % (exc,))
+    V, L = vk, vk._lib
+    torch.cuda.init()
+    torch.zeros(1, device="cuda")                            # primary context current
+
+    def ok(res):
+        err = res[0]
+        if err != cu.CUresult.CUDA_SUCCESS:
+            raise RuntimeError(str(err))
+        return res[1] if len(res) == 2 else res[1:]
+
+    prop = cu.CUmemAllocationProp()
+    prop.type = cu.CUmemAllocationType.CU_MEM_ALLOCATION_TYPE_PINNED
+    prop.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
+    prop.location.id = 0
+    prop.requestedHandleTypes = cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR
+    pitch = W * 4 + 40
+    handle = va = None
+    fds = []
+    try:
+        gran = ok(cu.cuMemGetAllocationGranularity(prop, cu.CUmemAllocationGranularity_flags.CU_MEM_ALLOC_GRANULARITY_MINIMUM))
+        size = ((pitch * H + 4096 + gran - 1) // gran) * gran
+        handle = ok(cu.cuMemCreate(size, prop, 0))
+        fds = [int(ok(cu.cuMemExportToShareableHandle(handle, cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0)))
+               for _ in range(2)]
+        va = ok(cu.cuMemAddressReserve(size, 0, 0, 0))
+        ok(cu.cuMemMap(va, size, 0, handle, 0) + (None,))
+        acc = cu.CUmemAccessDesc()
+        acc.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
+        acc.location.id = 0
+        acc.flags = cu.CUmemAccess_flags.CU_MEM_ACCESS_FLAGS_PROT_READWRITE
+        ok(cu.cuMemSetAccess(va, size, [acc], 1) + (None,))
+        ok(cu.cuMemsetD8(va, 0xCD, size) + (None,))
+    except Exception as exc:
+        for f in fds:
+            os.close(f)
+        pytest.skip("CUDA VMM export unavailable here: %r" % (exc,))
+
+    r = _renderer(V)
+    im = L.ExternalImage(struct_size=C.sizeof(L.ExternalImage), fd=fds[0], allocation_size=size, offset=4096,
+                         tiling=L.TILING_LINEAR, row_pitch=pitch)
+    rc = r.lib.vkrt_import_vk_image(r.ctx, 0, C.byref(im))
+    if rc != L.SUCCESS:
+        msg = r.lib.vkrt_last_error_string(r.ctx).decode()
+        r.close()
+        for f in fds:
+            os.close(f)
+        pytest.skip("the driver does not take a VMM-exported fd as OPAQUE_FD external memory: " + msg)
+    os.close(fds[1])
+    (fd0, orgba), = _oracle_frames(oracle, V, 1)
+    r.draw(fd0)                                              # the first frame resolves into slot 0
+    assert np.array_equal(r.read_rgba8(), orgba)
+    r.wait_idle()
+    host = np.zeros(size, dtype=np.uint8)
+    ok(cu.cuMemcpyDtoH(host, va, size) + (None,))            # the same bytes through the exporter's own mapping
+    assert (host[:4096] == 0xCD).all()
+    rows = host[4096:4096 + pitch * H].reshape(H, pitch)
+    assert np.array_equal(rows[:, :W * 4].reshape(H, W, 4), orgba)
+    assert (rows[:, W * 4:] == 0xCD).all()
+    r.release_external()
+    r.close()
+    cu.cuMemUnmap(va, size)
+    cu.cuMemAddressFree(va, size)
+    cu.cuMemRelease(handle)

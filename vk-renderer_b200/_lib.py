@@ -19,6 +19,8 @@ VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT = 0, 1
 SCENE_TRACER, SCENE_RAYTRACER = 0, 1
 FLAG_PROGRESSIVE, FLAG_HIT_IDS, FLAG_STATS, FLAG_NO_RESOLVE = 1, 2, 4, 8
 MAT_DIFFUSE, MAT_DIELECTRIC = 0, 1
+TILING_LINEAR, TILING_OPTIMAL = 0, 1
+SEMAPHORE_ACQUIRE, SEMAPHORE_RELEASE = 0, 1
 
 
 class Vec3a(C.Structure):
@@ -62,6 +64,12 @@ class BvhInfo(C.Structure):
                 ("build_ms", C.c_float), ("build_launches", C.c_uint32)]
 
 
+class ExternalImage(C.Structure):  # include/vkrt.h: one exported traced image (ref: Source/GraphicsDevice.cpp:664-699)
+    _fields_ = [("struct_size", C.c_uint32), ("fd", C.c_int32), ("allocation_size", C.c_uint64), ("offset", C.c_uint64),
+                ("tiling", C.c_uint32), ("row_pitch", C.c_uint32), ("dedicated", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+assert C.sizeof(ExternalImage) == 40
 assert C.sizeof(CameraData) == 64 and C.sizeof(FrameData) == 96 and C.sizeof(Triangle) == 48
 assert C.sizeof(Material) == 48
 assert FrameData.seed.offset == 4 and FrameData.light_pos.offset == 16 and FrameData.camera.offset == 32
@@ -98,6 +106,11 @@ SIGNATURES = {
     "vkrt_read_rgba8_async": ([_vp, _vp, _sz], C.c_int8),
     "vkrt_resolve": ([_vp], C.c_int8),
     "vkrt_present": ([_vp, _vp, _u32, _u32], C.c_int8),
+    "vkrt_import_vk_image": ([_vp, _u32, _P(ExternalImage)], C.c_int8),
+    "vkrt_bind_rgba8_target": ([_vp, _u32, _vp, _sz], C.c_int8),
+    "vkrt_debug_bind_array_target": ([_vp, _u32], C.c_int8),
+    "vkrt_import_vk_semaphore": ([_vp, _u32, _u32, C.c_int32, _u32], C.c_int8),
+    "vkrt_release_external": ([_vp], C.c_int8),
     "vkrt_get_counters": ([_vp, _P(Counters)], C.c_int8),
     "vkrt_reset_counters": ([_vp], C.c_int8),
     "vkrt_last_frame_timing": ([_vp, _P(C.c_float), _P(C.c_float), _P(_u32)], C.c_int8),

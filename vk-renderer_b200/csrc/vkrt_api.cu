@@ -30,6 +30,21 @@ static_assert(sizeof(DevScene) <= 1024 && sizeof(RenderParams) <= 512, "kernel p
 
 static thread_local std::string g_create_error;
 
+// One traced-image slot whose pixels live outside the library's own dense image (include/vkrt.h "interop"): linear
+// memory the caller bound or an imported Vulkan allocation mapped as a buffer (kind 1), or a CUDA array behind a
+// surface object = an imported VK_IMAGE_TILING_OPTIMAL image / the diagnostics array (kind 2).
+struct ExtSlot {
+    int kind = 0;
+    cudaExternalMemory_t mem = nullptr;       // the imported allocation (owns the fd after a successful import)
+    cudaMipmappedArray_t mip = nullptr;       // OPTIMAL import: the image as a 1-level mipmapped array
+    cudaArray_t arr = nullptr;                // level 0 of `mip`, or the library-owned diagnostics array (own_arr)
+    bool own_arr = false;
+    cudaSurfaceObject_t surf = 0;
+    uchar4 *ptr = nullptr; size_t pitch = 0;  // kind 1
+    cudaExternalSemaphore_t sem[2] = {nullptr, nullptr};
+    uint64_t resolves = 0;                    // resolves into this slot since its semaphores were imported
+};
+
 struct vkrt_ctx {
     vkrt_create_info info{};
     int sm_count = 0;
@@ -65,6 +80,7 @@ struct vkrt_ctx {
     float4 *d_accum = nullptr;
     uint32_t *d_hit_ids = nullptr;
     std::vector<uchar4 *> d_rgba;
+    std::vector<ExtSlot> ext;      // one per rgba8 target
     uint32_t cur_target = 0;
     unsigned long long *d_counters = nullptr;
     uint32_t *d_work_head = nullptr;
@@ -185,6 +201,51 @@ void fill_params(vkrt_ctx *c, RenderParams &rp)
     rp.accum = c->d_accum; rp.hit_ids = c->d_hit_ids; rp.counters = c->d_counters; rp.work_head = c->d_work_head;
 }
 
+// detaches slot `e` from whatever backs it (the caller has made the device idle)
+void ext_release_target(ExtSlot &e)
+{
+    if (e.surf) cudaDestroySurfaceObject(e.surf);
+    if (e.own_arr && e.arr) cudaFreeArray(e.arr);
+    if (e.mip) cudaFreeMipmappedArray(e.mip);
+    if (e.mem && e.ptr) cudaFree(e.ptr);          // a mapped buffer of an imported allocation is freed with cudaFree
+    if (e.mem) cudaDestroyExternalMemory(e.mem);
+    e.kind = 0; e.surf = 0; e.arr = nullptr; e.own_arr = false; e.mip = nullptr; e.ptr = nullptr; e.pitch = 0; e.mem = nullptr;
+}
+void ext_release_semaphores(ExtSlot &e)
+{
+    for (auto &sm : e.sem) { if (sm) cudaDestroyExternalSemaphore(sm); sm = nullptr; }
+    e.resolves = 0;
+}
+vkrt_error make_idle(vkrt_ctx *c)
+{
+    CU(c, join(c));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return VKRT_SUCCESS;
+}
+
+// The resolve of the frame into the current target (Tracer.comp:585-592), bracketed by the slot's semaphores: what
+// the reference's two vkCmdPipelineBarriers around the dispatch do (Source/GraphicsDevice.cpp:1234-1252, :1268-1284).
+vkrt_error resolve_current(vkrt_ctx *c, const RenderParams &rp, cudaStream_t st)
+{
+    ExtSlot &e = c->ext[c->cur_target];
+    ResolveTarget tg{c->d_rgba[c->cur_target], (size_t)c->info.width * 4u, 0};
+    if (e.kind == 1) { tg.ptr = e.ptr; tg.pitch = e.pitch; }
+    else if (e.kind == 2) { tg.ptr = nullptr; tg.surf = e.surf; }
+    ++e.resolves;
+    if (e.sem[VKRT_SEMAPHORE_ACQUIRE] && e.resolves >= 2) {
+        cudaExternalSemaphoreWaitParams wp{};
+        wp.params.fence.value = e.resolves - 1;          // timeline semaphores; a binary semaphore ignores the value
+        CU(c, cudaWaitExternalSemaphoresAsync(&e.sem[VKRT_SEMAPHORE_ACQUIRE], &wp, 1, st));
+    }
+    CU(c, launch_resolve(rp, c->info.integrator, tg, st));
+    if (e.sem[VKRT_SEMAPHORE_RELEASE]) {
+        cudaExternalSemaphoreSignalParams sp{};
+        sp.params.fence.value = e.resolves;
+        CU(c, cudaSignalExternalSemaphoresAsync(&e.sem[VKRT_SEMAPHORE_RELEASE], &sp, 1, st));
+    }
+    return VKRT_SUCCESS;
+}
+
 } // namespace
 
 extern "C" {
@@ -242,6 +303,8 @@ VKRT_API vkrt_error vkrt_create(const vkrt_create_info *info, vkrt_ctx **out_ctx
         CC(cudaMemsetAsync(c->d_hit_ids, 0, n_px * sizeof(uint32_t), c->stream));
     }
     c->d_rgba.assign(c->info.frames_in_flight, nullptr);
+    c->ext.assign(c->info.frames_in_flight, ExtSlot{});
+    c->cur_target = c->info.frames_in_flight - 1;       // the first frame goes to image slot 0 like state.currentFrame
     for (auto &p : c->d_rgba) { CC(cudaMalloc(&p, n_px * sizeof(uchar4))); CC(cudaMemsetAsync(p, 0, n_px * sizeof(uchar4), c->stream)); }
     CC(cudaMalloc(&c->d_counters, CNT_N * sizeof(unsigned long long)));
     CC(cudaMemsetAsync(c->d_counters, 0, CNT_N * sizeof(unsigned long long), c->stream));
@@ -264,6 +327,7 @@ VKRT_API vkrt_error vkrt_destroy(vkrt_ctx *c)
     cudaFree(c->d_spheres); cudaFree(c->d_sphere_mat); cudaFree(c->d_mats); cudaFree(c->d_tris);
     cudaFree(c->bvh.nodes); cudaFree(c->bvh.nodes4); cudaFree(c->bvh.qnodes); cudaFree(c->d_accum); cudaFree(c->d_hit_ids);
     for (auto p : c->d_rgba) cudaFree(p);
+    for (auto &e : c->ext) { ext_release_target(e); ext_release_semaphores(e); }
     cudaFree(c->d_counters); cudaFree(c->d_work_head); cudaFree(c->d_packed); cudaFree(c->d_present);
     if (c->wave_ready) wave_engine_free(c->wave);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
@@ -484,9 +548,12 @@ VKRT_API vkrt_error vkrt_draw(vkrt_ctx *c, const vkrt_frame_data *frame)
         CU(c, cudaEventRecord(c->ev_begin, c->stream));
     }
     CU(c, cudaEventRecord(c->ev_trace1, tail));
-    c->cur_target = (c->cur_target + 1) % (uint32_t)c->d_rgba.size();   // currentFrame = (currentFrame + 1) % FRAMES_IN_FLIGHT (:1341)
+    // frame k targets traced_images[k % FRAMES_IN_FLIGHT] (state.currentFrame, :1234 / :1341); cur_target stays on the
+    // most recent frame's slot afterwards, which is what the read-backs return
+    c->cur_target = (c->cur_target + 1) % (uint32_t)c->d_rgba.size();
     if (!(c->info.flags & VKRT_FLAG_NO_RESOLVE)) {
-        CU(c, launch_resolve(rp, c->info.integrator, c->d_rgba[c->cur_target], tail)); ++launches;
+        r = resolve_current(c, rp, tail); ++launches;
+        if (r != VKRT_SUCCESS) return r;
     }
     CU(c, cudaEventRecord(c->ev_end, tail));
     c->pending_join = (tail != c->stream);
@@ -505,8 +572,7 @@ VKRT_API vkrt_error vkrt_resolve(vkrt_ctx *c)
     CU(c, join(c));
     RenderParams rp;
     fill_params(c, rp);
-    CU(c, launch_resolve(rp, c->info.integrator, c->d_rgba[c->cur_target], c->stream));
-    return VKRT_SUCCESS;
+    return resolve_current(c, rp, c->stream);
 }
 
 VKRT_API vkrt_error vkrt_wait_idle(vkrt_ctx *c)
@@ -532,8 +598,10 @@ VKRT_API vkrt_error vkrt_get_rgba8(vkrt_ctx *c, void **dev_ptr, size_t *pitch)
 {
     if (!c || !dev_ptr) return VKRT_BAD_ARG;
     { DeviceGuard g(c->info.device_id); CU(c, join(c)); }
-    *dev_ptr = c->d_rgba[c->cur_target];
-    if (pitch) *pitch = (size_t)c->info.width * 4;
+    const ExtSlot &e = c->ext[c->cur_target];
+    if (e.kind == 2) return fail(c, VKRT_BAD_ARG, "the current target is a CUDA array (imported OPTIMAL image): it has no linear pointer");
+    *dev_ptr = e.kind == 1 ? e.ptr : c->d_rgba[c->cur_target];
+    if (pitch) *pitch = e.kind == 1 ? e.pitch : (size_t)c->info.width * 4;
     return VKRT_SUCCESS;
 }
 VKRT_API vkrt_error vkrt_get_accum(vkrt_ctx *c, float **dev_ptr)
@@ -568,19 +636,27 @@ static vkrt_error read_back(vkrt_ctx *c, void *host, const void *dev, size_t hav
     CU(c, cudaStreamSynchronize(c->stream));
     return VKRT_SUCCESS;
 }
-VKRT_API vkrt_error vkrt_read_rgba8(vkrt_ctx *c, void *host, size_t bytes)
-{
-    if (!c) return VKRT_BAD_ARG;
-    return read_back(c, host, c->d_rgba[c->cur_target], (size_t)c->info.width * c->info.height * 4, bytes);
-}
 VKRT_API vkrt_error vkrt_read_rgba8_async(vkrt_ctx *c, void *host, size_t bytes)
 {
     if (!c || !host) return VKRT_BAD_ARG;
-    const size_t have = (size_t)c->info.width * c->info.height * 4;
+    const size_t row = (size_t)c->info.width * 4, have = row * c->info.height;
     if (bytes < have) return fail(c, VKRT_BAD_ARG, "host buffer too small");
     DeviceGuard g(c->info.device_id);
     CU(c, join(c));
-    CU(c, cudaMemcpyAsync(host, c->d_rgba[c->cur_target], have, cudaMemcpyDeviceToHost, c->stream));
+    const ExtSlot &e = c->ext[c->cur_target];
+    if (e.kind == 2) CU(c, cudaMemcpy2DFromArrayAsync(host, row, e.arr, 0, 0, row, c->info.height, cudaMemcpyDeviceToHost, c->stream));
+    else if (e.kind == 1) CU(c, cudaMemcpy2DAsync(host, row, e.ptr, e.pitch, row, c->info.height, cudaMemcpyDeviceToHost, c->stream));
+    else CU(c, cudaMemcpyAsync(host, c->d_rgba[c->cur_target], have, cudaMemcpyDeviceToHost, c->stream));
+    return VKRT_SUCCESS;
+}
+VKRT_API vkrt_error vkrt_read_rgba8(vkrt_ctx *c, void *host, size_t bytes)
+{
+    if (!c) return VKRT_BAD_ARG;
+    if (!host) return fail(c, VKRT_BAD_ARG, "null buffer");
+    const vkrt_error r = vkrt_read_rgba8_async(c, host, bytes);
+    if (r != VKRT_SUCCESS) return r;
+    DeviceGuard g(c->info.device_id);
+    CU(c, cudaStreamSynchronize(c->stream));
     return VKRT_SUCCESS;
 }
 VKRT_API vkrt_error vkrt_read_accum(vkrt_ctx *c, float *host, size_t bytes)
@@ -691,6 +767,8 @@ VKRT_API vkrt_error vkrt_present(vkrt_ctx *c, void *host_rgba8, uint32_t out_w, 
 {
     if (!c || !host_rgba8 || out_w == 0 || out_h == 0) return VKRT_BAD_ARG;
     if (c->d_rgba.size() < 2) return fail(c, VKRT_BAD_ARG, "the present filter needs frames_in_flight >= 2");
+    if (c->ext[0].kind != 0 || c->ext[1].kind != 0)
+        return fail(c, VKRT_BAD_ARG, "image slots 0/1 are external targets: the engine's own Fullscreen pass presents them");
     DeviceGuard g(c->info.device_id);
     CU(c, join(c));
     const size_t bytes = (size_t)out_w * out_h * 4;
@@ -702,6 +780,142 @@ VKRT_API vkrt_error vkrt_present(vkrt_ctx *c, void *host_rgba8, uint32_t out_w, 
     CU(c, launch_present(c->d_rgba[0], c->d_rgba[1], c->info.width, c->info.height, c->d_present, out_w, out_h, c->stream));
     CU(c, cudaMemcpyAsync(host_rgba8, c->d_present, bytes, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    return VKRT_SUCCESS;
+}
+
+// ---- Vulkan <-> CUDA interop (include/vkrt.h) -------------------------------------------------------
+VKRT_API vkrt_error vkrt_bind_rgba8_target(vkrt_ctx *c, uint32_t slot, void *dev_ptr, size_t row_pitch)
+{
+    if (!c) return VKRT_BAD_ARG;
+    if (slot >= c->ext.size()) return fail(c, VKRT_BAD_ARG, "slot >= frames_in_flight");
+    const size_t row = (size_t)c->info.width * 4;
+    if (row_pitch == 0) row_pitch = row;
+    if (dev_ptr && (row_pitch < row || (row_pitch & 3u) || ((uintptr_t)dev_ptr & 3u)))
+        return fail(c, VKRT_BAD_ARG, "row_pitch < width * 4, or pointer / pitch not 4-byte aligned");
+    DeviceGuard g(c->info.device_id);
+    if (dev_ptr) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, dev_ptr) != cudaSuccess || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)) {
+            cudaGetLastError();
+            return fail(c, VKRT_BAD_ARG, "dev_ptr is not device memory");
+        }
+    }
+    vkrt_error r = make_idle(c);
+    if (r != VKRT_SUCCESS) return r;
+    ExtSlot &e = c->ext[slot];
+    ext_release_target(e);
+    if (dev_ptr) { e.kind = 1; e.ptr = (uchar4 *)dev_ptr; e.pitch = row_pitch; }
+    return VKRT_SUCCESS;
+}
+
+VKRT_API vkrt_error vkrt_debug_bind_array_target(vkrt_ctx *c, uint32_t slot)
+{
+    if (!c) return VKRT_BAD_ARG;
+    if (slot >= c->ext.size()) return fail(c, VKRT_BAD_ARG, "slot >= frames_in_flight");
+    DeviceGuard g(c->info.device_id);
+    vkrt_error r = make_idle(c);
+    if (r != VKRT_SUCCESS) return r;
+    ExtSlot &e = c->ext[slot];
+    ext_release_target(e);
+    const cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+    CU(c, cudaMallocArray(&e.arr, &fmt, c->info.width, c->info.height, cudaArraySurfaceLoadStore));
+    e.own_arr = true;
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray; rd.res.array.array = e.arr;
+    const cudaError_t ce = cudaCreateSurfaceObject(&e.surf, &rd);
+    if (ce != cudaSuccess) { ext_release_target(e); return cuda_fail(c, ce, "cudaCreateSurfaceObject"); }
+    e.kind = 2;
+    return VKRT_SUCCESS;
+}
+
+VKRT_API vkrt_error vkrt_import_vk_image(vkrt_ctx *c, uint32_t slot, const vkrt_external_image *im)
+{
+    if (!c || !im) return VKRT_BAD_ARG;
+    if (im->struct_size != sizeof(vkrt_external_image)) return fail(c, VKRT_BAD_ARG, "vkrt_external_image.struct_size mismatch");
+    if (slot >= c->ext.size()) return fail(c, VKRT_BAD_ARG, "slot >= frames_in_flight");
+    if (im->fd < 0) return fail(c, VKRT_BAD_ARG, "bad file descriptor");
+    if (im->tiling > VKRT_TILING_OPTIMAL) return fail(c, VKRT_BAD_ARG, "unknown tiling");
+    const size_t row = (size_t)c->info.width * 4;
+    const size_t pitch = im->row_pitch ? im->row_pitch : row;
+    if (im->tiling == VKRT_TILING_LINEAR && (pitch < row || (pitch & 3u) || (im->offset & 3u)))
+        return fail(c, VKRT_BAD_ARG, "row_pitch < width * 4, or offset / pitch not 4-byte aligned");
+    const uint64_t need = im->tiling == VKRT_TILING_LINEAR ? (uint64_t)pitch * c->info.height : (uint64_t)row * c->info.height;
+    if (im->allocation_size == 0 || im->offset > im->allocation_size || im->allocation_size - im->offset < need)
+        return fail(c, VKRT_BAD_ARG, "the image does not fit in the allocation (allocation_size / offset)");
+    DeviceGuard g(c->info.device_id);
+    vkrt_error r = make_idle(c);
+    if (r != VKRT_SUCCESS) return r;
+
+    ExtSlot n;                                      // built aside: a failed import leaves the slot as it was
+    cudaExternalMemoryHandleDesc hd{};
+    hd.type = cudaExternalMemoryHandleTypeOpaqueFd;
+    hd.handle.fd = im->fd;
+    hd.size = im->allocation_size;
+    hd.flags = im->dedicated ? cudaExternalMemoryDedicated : 0;
+    cudaError_t ce = cudaImportExternalMemory(&n.mem, &hd);
+    if (ce != cudaSuccess) { cudaGetLastError(); return cuda_fail(c, ce, "cudaImportExternalMemory"); }
+    if (im->tiling == VKRT_TILING_LINEAR) {
+        cudaExternalMemoryBufferDesc bd{};
+        bd.offset = im->offset; bd.size = need;
+        void *p = nullptr;
+        ce = cudaExternalMemoryGetMappedBuffer(&p, n.mem, &bd);
+        if (ce == cudaSuccess) { n.kind = 1; n.ptr = (uchar4 *)p; n.pitch = pitch; }
+    } else {
+        cudaExternalMemoryMipmappedArrayDesc md{};
+        md.offset = im->offset;
+        md.formatDesc = cudaCreateChannelDesc<uchar4>();           // VK_FORMAT_R8G8B8A8_UNORM (:672)
+        md.extent = make_cudaExtent(c->info.width, c->info.height, 0);
+        md.flags = cudaArraySurfaceLoadStore;                       // VK_IMAGE_USAGE_STORAGE_BIT (:674)
+        md.numLevels = 1;                                           // mipLevels = 1 (:685)
+        ce = cudaExternalMemoryGetMappedMipmappedArray(&n.mip, n.mem, &md);
+        if (ce == cudaSuccess) ce = cudaGetMipmappedArrayLevel(&n.arr, n.mip, 0);
+        if (ce == cudaSuccess) {
+            cudaResourceDesc rd{};
+            rd.resType = cudaResourceTypeArray; rd.res.array.array = n.arr;
+            ce = cudaCreateSurfaceObject(&n.surf, &rd);
+        }
+        if (ce == cudaSuccess) n.kind = 2;
+    }
+    if (ce != cudaSuccess) {
+        cudaGetLastError();
+        ext_release_target(n);                      // also closes the fd: the import itself had succeeded
+        return cuda_fail(c, ce, "mapping the imported allocation");
+    }
+    ExtSlot &e = c->ext[slot];
+    ext_release_target(e);
+    e.kind = n.kind; e.mem = n.mem; e.mip = n.mip; e.arr = n.arr; e.own_arr = false; e.surf = n.surf; e.ptr = n.ptr; e.pitch = n.pitch;
+    return VKRT_SUCCESS;
+}
+
+VKRT_API vkrt_error vkrt_import_vk_semaphore(vkrt_ctx *c, uint32_t slot, uint32_t which, int32_t fd, uint32_t timeline)
+{
+    if (!c) return VKRT_BAD_ARG;
+    if (slot >= c->ext.size()) return fail(c, VKRT_BAD_ARG, "slot >= frames_in_flight");
+    if (which > VKRT_SEMAPHORE_RELEASE) return fail(c, VKRT_BAD_ARG, "unknown semaphore role");
+    if (fd < 0) return fail(c, VKRT_BAD_ARG, "bad file descriptor");
+    DeviceGuard g(c->info.device_id);
+    vkrt_error r = make_idle(c);
+    if (r != VKRT_SUCCESS) return r;
+    cudaExternalSemaphoreHandleDesc sd{};
+    sd.type = timeline ? cudaExternalSemaphoreHandleTypeTimelineSemaphoreFd : cudaExternalSemaphoreHandleTypeOpaqueFd;
+    sd.handle.fd = fd;
+    cudaExternalSemaphore_t sem = nullptr;
+    const cudaError_t ce = cudaImportExternalSemaphore(&sem, &sd);
+    if (ce != cudaSuccess) { cudaGetLastError(); return cuda_fail(c, ce, "cudaImportExternalSemaphore"); }
+    ExtSlot &e = c->ext[slot];
+    if (e.sem[which]) cudaDestroyExternalSemaphore(e.sem[which]);
+    e.sem[which] = sem;
+    e.resolves = 0;
+    return VKRT_SUCCESS;
+}
+
+VKRT_API vkrt_error vkrt_release_external(vkrt_ctx *c)
+{
+    if (!c) return VKRT_BAD_ARG;
+    DeviceGuard g(c->info.device_id);
+    vkrt_error r = make_idle(c);
+    if (r != VKRT_SUCCESS) return r;
+    for (auto &e : c->ext) { ext_release_target(e); ext_release_semaphores(e); }
     return VKRT_SUCCESS;
 }
 

@@ -34,7 +34,9 @@ struct LaunchCfg { int sm_count; };
 cudaError_t launch_path_mega(const DevScene &sc, const RenderParams &rp, bool bvh, bool stats, int sm_count,
                              cudaStream_t st);
 cudaError_t launch_whitted(const DevScene &sc, const RenderParams &rp, bool bvh, bool stats, cudaStream_t st);
-cudaError_t launch_resolve(const RenderParams &rp, uint32_t integrator, uchar4 *rgba8, cudaStream_t st);
+// where the resolve writes: dense / pitched linear memory (ptr, pitch in bytes) or a surface object (surf != 0)
+struct ResolveTarget { uchar4 *ptr; size_t pitch; cudaSurfaceObject_t surf; };
+cudaError_t launch_resolve(const RenderParams &rp, uint32_t integrator, const ResolveTarget &tg, cudaStream_t st);
 cudaError_t launch_pack(const RenderParams &rp, float4 *packed, cudaStream_t st);
 cudaError_t launch_unpack(float4 *accum, const float4 *packed, uint32_t width, uint32_t height, uint32_t tile_rank,
                           uint32_t tile_count, int add, cudaStream_t st);

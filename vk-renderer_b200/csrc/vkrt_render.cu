@@ -170,8 +170,12 @@ cudaError_t launch_whitted(const DevScene &sc, const RenderParams &rp, bool bvh,
 // Resolve: Tracer.comp:585-592 (mean, Reinhard, gamma 1/2.2, +rand()/64 dither, unorm8 store) or
 // Raytracer.comp:398 (plain unorm8 store).
 // ------------------------------------------------------------------------------------------------
+// TARGET 0: the library's dense image; 1: linear memory with a row pitch (a bound / imported buffer or
+// VK_IMAGE_TILING_LINEAR image); 2: a CUDA array behind a surface object (an imported VK_IMAGE_TILING_OPTIMAL image,
+// ref: Source/GraphicsDevice.cpp:672-673).  Texel (x, y) = imageStore(ivec2(gid.xy)) of Tracer.comp:592.
+template <int TARGET>
 __global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ RenderParams rp, uint32_t integrator,
-                                                  uchar4 *__restrict__ rgba8)
+                                                  const ResolveTarget tg)
 {
     const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= rp.width * rp.height) return;
@@ -186,13 +190,21 @@ __global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ RenderP
         const float dither = u01(sample_key(rp.fkey, pix, VKRT_DITHER_SAMPLE), 0) / 64.0f;
         o = make_uchar4(unorm8(c.x + dither), unorm8(c.y + dither), unorm8(c.z + dither), 255);
     }
-    rgba8[pix] = o;
+    if (TARGET == 0) tg.ptr[pix] = o;
+    else {
+        const uint32_t y = pix / rp.width, x = pix - y * rp.width;
+        if (TARGET == 1) *reinterpret_cast<uchar4 *>(reinterpret_cast<char *>(tg.ptr) + (size_t)y * tg.pitch + (size_t)x * 4u) = o;
+        else surf2Dwrite(o, tg.surf, (int)(x * 4u), (int)y);
+    }
 }
 
-cudaError_t launch_resolve(const RenderParams &rp, uint32_t integrator, uchar4 *rgba8, cudaStream_t stream)
+cudaError_t launch_resolve(const RenderParams &rp, uint32_t integrator, const ResolveTarget &tg, cudaStream_t stream)
 {
     const unsigned n = rp.width * rp.height;
-    k_resolve<<<(n + 255u) / 256u, 256, 0, stream>>>(rp, integrator, rgba8);
+    const unsigned grid = (n + 255u) / 256u;
+    if (tg.surf) k_resolve<2><<<grid, 256, 0, stream>>>(rp, integrator, tg);
+    else if (tg.pitch != (size_t)rp.width * 4u) k_resolve<1><<<grid, 256, 0, stream>>>(rp, integrator, tg);
+    else k_resolve<0><<<grid, 256, 0, stream>>>(rp, integrator, tg);
     return cudaGetLastError();
 }
 

@@ -204,6 +204,25 @@ class Renderer:
         self._ck(self.lib.vkrt_get_rgba8(self.ctx, C.byref(p), C.byref(pitch)))
         return p.value, pitch.value
 
+    # ---- Vulkan <-> CUDA interop (the traced images the engine presents) ----------------------------
+    def import_vk_image(self, slot, fd, allocation_size, offset=0, tiling=L.TILING_OPTIMAL, row_pitch=0, dedicated=False):
+        """traced_images[slot] exported by the engine with vkGetMemoryFdKHR (ref: Source/GraphicsDevice.cpp:664-699)."""
+        im = L.ExternalImage(struct_size=C.sizeof(L.ExternalImage), fd=fd, allocation_size=allocation_size, offset=offset,
+                             tiling=tiling, row_pitch=row_pitch, dedicated=1 if dedicated else 0)
+        self._ck(self.lib.vkrt_import_vk_image(self.ctx, slot, C.byref(im)))
+
+    def bind_rgba8_target(self, slot, dev_ptr, row_pitch=0):
+        self._ck(self.lib.vkrt_bind_rgba8_target(self.ctx, slot, C.c_void_p(dev_ptr), row_pitch))
+
+    def debug_bind_array_target(self, slot):
+        self._ck(self.lib.vkrt_debug_bind_array_target(self.ctx, slot))
+
+    def import_vk_semaphore(self, slot, which, fd, timeline=False):
+        self._ck(self.lib.vkrt_import_vk_semaphore(self.ctx, slot, which, fd, 1 if timeline else 0))
+
+    def release_external(self):
+        self._ck(self.lib.vkrt_release_external(self.ctx))
+
     # ---- sharding -----------------------------------------------------------------------------
     def pack_shard(self):
         p, n = C.c_void_p(), C.c_size_t()
