@@ -284,7 +284,33 @@ struct TravStack {
 #ifndef VKRT_QNODES
 #define VKRT_QNODES 1
 #endif
-struct QRay { V3 a, cdn, cup; uint32_t selx, sely, selz; };
+#ifndef VKRT_PRMT_ASM
+#define VKRT_PRMT_ASM 1      // 1: PRMT by inline PTX (no `& 0x7777` that __byte_perm's definition makes the compiler emit)
+#endif
+#ifndef VKRT_QSEL6
+#define VKRT_QSEL6 0         // 1: the FAR plane's selectors live in registers too (no `^ 0x22` per node and axis)
+#endif
+#ifndef VKRT_SELECT2
+#define VKRT_SELECT2 1       // 1: near/far child chosen by one predicate and two selects
+#endif
+struct QRay {
+    V3 a, cdn, cup; uint32_t selx, sely, selz;
+#if VKRT_QSEL6
+    uint32_t fselx, fsely, fselz;
+#endif
+};
+// float 2^23 + q of one 16-bit code of the packed pair `w`: sel = 0x7610 takes the low code, 0x7632 the high one.
+// Every selector nibble is <= 7, so the raw PRMT equals __byte_perm (which is defined on `sel & 0x7777`).
+VKRT_DEV float qcode(uint32_t w, uint32_t sel)
+{
+#if VKRT_PRMT_ASM
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0x4B000000u), "r"(sel));
+    return __uint_as_float(r);
+#else
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, sel));
+#endif
+}
 VKRT_DEV QRay qray_setup(const DevScene &sc, const SlabRay &sr)
 {
     QRay q;
@@ -303,6 +329,9 @@ VKRT_DEV QRay qray_setup(const DevScene &sc, const SlabRay &sr)
     q.selx = inv[0] < 0.0f ? 0x7632u : 0x7610u;
     q.sely = inv[1] < 0.0f ? 0x7632u : 0x7610u;
     q.selz = inv[2] < 0.0f ? 0x7632u : 0x7610u;
+#if VKRT_QSEL6
+    q.fselx = q.selx ^ 0x22u; q.fsely = q.sely ^ 0x22u; q.fselz = q.selz ^ 0x22u;
+#endif
     return q;
 }
 VKRT_DEV void ldg256u(const uint4 *p, uint4 &a, uint4 &b)
@@ -313,9 +342,14 @@ VKRT_DEV void ldg256u(const uint4 *p, uint4 &a, uint4 &b)
 }
 VKRT_DEV bool qslab_test(const QRay &q, uint4 w, float &tn)
 {
-    const float nx = __uint_as_float(__byte_perm(w.x, 0x4B000000u, q.selx)), fx = __uint_as_float(__byte_perm(w.x, 0x4B000000u, q.selx ^ 0x22u));
-    const float ny = __uint_as_float(__byte_perm(w.y, 0x4B000000u, q.sely)), fy = __uint_as_float(__byte_perm(w.y, 0x4B000000u, q.sely ^ 0x22u));
-    const float nz = __uint_as_float(__byte_perm(w.z, 0x4B000000u, q.selz)), fz = __uint_as_float(__byte_perm(w.z, 0x4B000000u, q.selz ^ 0x22u));
+#if VKRT_QSEL6
+    const uint32_t fsx = q.fselx, fsy = q.fsely, fsz = q.fselz;
+#else
+    const uint32_t fsx = q.selx ^ 0x22u, fsy = q.sely ^ 0x22u, fsz = q.selz ^ 0x22u;
+#endif
+    const float nx = qcode(w.x, q.selx), fx = qcode(w.x, fsx);
+    const float ny = qcode(w.y, q.sely), fy = qcode(w.y, fsy);
+    const float nz = qcode(w.z, q.selz), fz = qcode(w.z, fsz);
     tn = fmaxf(fmaxf(__fmaf_rd(nx, q.a.x, q.cdn.x), __fmaf_rd(ny, q.a.y, q.cdn.y)), __fmaf_rd(nz, q.a.z, q.cdn.z));
     const float tf = fminf(fminf(__fmaf_ru(fx, q.a.x, q.cup.x), __fmaf_ru(fy, q.a.y, q.cup.y)), __fmaf_ru(fz, q.a.z, q.cup.z));
     return tn <= tf && tf >= 0.0f;
@@ -330,11 +364,20 @@ VKRT_DEV void trav_inner_step_q(Trav &tv, const QRay &q, Stack &stack, const Dev
     const bool h0 = qslab_test(q, w0, tn0) && tn0 <= tv.best.t;
     const bool h1 = qslab_test(q, w1, tn1) && tn1 <= tv.best.t;
     const int c0 = (int)w0.w, c1 = (int)w1.w;          // inner node index, or ~sphere for a leaf
+#if VKRT_SELECT2
+    // the same choice as below (both: the nearer child first, ties -> child 0) from one predicate and two selects
+    const bool take1 = h1 && (!h0 || tn1 < tn0);
+    const int nearer = take1 ? c1 : c0, other = take1 ? c0 : c1;
+    if (h0 && h1) stack.push(tv.sp, other);
+    if (h0 || h1) tv.node = nearer;
+    else tv.node = tv.sp ? stack.pop(tv.sp) : (int)TRAV_DONE;
+#else
     const bool both = h0 && h1;
     const bool take1 = both ? (tn1 < tn0) : h1;
     if (both) stack.push(tv.sp, take1 ? c0 : c1);
     if (h0 || h1) tv.node = take1 ? c1 : c0;
     else tv.node = tv.sp ? stack.pop(tv.sp) : (int)TRAV_DONE;
+#endif
 }
 
 template <bool STATS, class Stack>
