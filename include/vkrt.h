@@ -218,8 +218,8 @@ VKRT_API vkrt_error vkrt_present(vkrt_ctx *ctx, void *host_rgba8, uint32_t out_w
  * VkExportMemoryAllocateInfo (VK_EXTERNAL_MEMORY_HANDLE_TYPE_OPAQUE_FD_BIT), exports the memory with
  * vkGetMemoryFdKHR and hands the fd over here; from then on the resolve of every frame whose target is `slot`
  * (slot = frame number % frames_in_flight, like state.currentFrame, :1341) is written straight into that memory,
- * so Fullscreen.vert/.frag sample it unchanged and no copy crosses PCIe.  On success the library owns the fd
- * (cudaImportExternalMemory semantics); on failure the caller still does. */
+ * so Fullscreen.vert/.frag sample it unchanged and no copy crosses PCIe.  The descriptor stays the caller's in every
+ * case (the library imports a duplicate of it): close it after the call. */
 enum { VKRT_TILING_LINEAR  = 0,   /* a VkBuffer, or a VK_IMAGE_TILING_LINEAR image: rows of row_pitch bytes          */
        VKRT_TILING_OPTIMAL = 1 }; /* the reference's VK_IMAGE_TILING_OPTIMAL R8G8B8A8_UNORM image (:672-673):
                                      mapped as a CUDA mipmapped array (1 level), written through a surface object */
@@ -248,7 +248,8 @@ VKRT_API vkrt_error vkrt_debug_bind_array_target(vkrt_ctx *ctx, uint32_t slot);
  *                           (timeline: for value n - 1) before it writes -- replaces the barrier at :1234-1252;
  *   VKRT_SEMAPHORE_RELEASE  signalled by the library on its stream after the n-th resolve into the slot (timeline:
  *                           to value n); the engine's submit that samples the image waits for it -- :1268-1284.
- * Without semaphores the caller orders the two APIs itself (vkrt_wait_idle / a fence). */
+ * Without semaphores the caller orders the two APIs itself (vkrt_wait_idle / a fence).  Like the image's, the
+ * descriptor stays the caller's. */
 enum { VKRT_SEMAPHORE_ACQUIRE = 0, VKRT_SEMAPHORE_RELEASE = 1 };
 VKRT_API vkrt_error vkrt_import_vk_semaphore(vkrt_ctx *ctx, uint32_t slot, uint32_t which, int32_t fd, uint32_t timeline);
 /* Waits for the frames in flight, then destroys every imported object and binding; all slots return to the

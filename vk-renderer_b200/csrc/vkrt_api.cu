@@ -4,6 +4,8 @@
 // the library owns every GPU object; the caller owns FrameData, copied inside Draw at :1258).
 #include <cstdio>
 #include <cstring>
+#include <fcntl.h>
+#include <unistd.h>
 #include <new>
 #include <string>
 #include <vector>
@@ -216,6 +218,11 @@ void ext_release_semaphores(ExtSlot &e)
     for (auto &sm : e.sem) { if (sm) cudaDestroyExternalSemaphore(sm); sm = nullptr; }
     e.resolves = 0;
 }
+// The library never consumes the caller's descriptor: it imports a duplicate.  A successful import hands the
+// duplicate to the CUDA driver; after a failed one it is closed here unless the driver already did.
+int dup_fd(int fd) { return fcntl(fd, F_DUPFD_CLOEXEC, 0); }
+void close_if_open(int fd) { if (fd >= 0 && fcntl(fd, F_GETFD) != -1) close(fd); }
+
 vkrt_error make_idle(vkrt_ctx *c)
 {
     CU(c, join(c));
@@ -847,13 +854,15 @@ VKRT_API vkrt_error vkrt_import_vk_image(vkrt_ctx *c, uint32_t slot, const vkrt_
     if (r != VKRT_SUCCESS) return r;
 
     ExtSlot n;                                      // built aside: a failed import leaves the slot as it was
+    const int own = dup_fd(im->fd);
+    if (own < 0) return fail(c, VKRT_BAD_ARG, "bad file descriptor");
     cudaExternalMemoryHandleDesc hd{};
     hd.type = cudaExternalMemoryHandleTypeOpaqueFd;
-    hd.handle.fd = im->fd;
+    hd.handle.fd = own;
     hd.size = im->allocation_size;
     hd.flags = im->dedicated ? cudaExternalMemoryDedicated : 0;
     cudaError_t ce = cudaImportExternalMemory(&n.mem, &hd);
-    if (ce != cudaSuccess) { cudaGetLastError(); return cuda_fail(c, ce, "cudaImportExternalMemory"); }
+    if (ce != cudaSuccess) { cudaGetLastError(); close_if_open(own); return cuda_fail(c, ce, "cudaImportExternalMemory"); }
     if (im->tiling == VKRT_TILING_LINEAR) {
         cudaExternalMemoryBufferDesc bd{};
         bd.offset = im->offset; bd.size = need;
@@ -878,7 +887,7 @@ VKRT_API vkrt_error vkrt_import_vk_image(vkrt_ctx *c, uint32_t slot, const vkrt_
     }
     if (ce != cudaSuccess) {
         cudaGetLastError();
-        ext_release_target(n);                      // also closes the fd: the import itself had succeeded
+        ext_release_target(n);                      // also closes the duplicate: the import itself had succeeded
         return cuda_fail(c, ce, "mapping the imported allocation");
     }
     ExtSlot &e = c->ext[slot];
@@ -896,12 +905,14 @@ VKRT_API vkrt_error vkrt_import_vk_semaphore(vkrt_ctx *c, uint32_t slot, uint32_
     DeviceGuard g(c->info.device_id);
     vkrt_error r = make_idle(c);
     if (r != VKRT_SUCCESS) return r;
+    const int own = dup_fd(fd);
+    if (own < 0) return fail(c, VKRT_BAD_ARG, "bad file descriptor");
     cudaExternalSemaphoreHandleDesc sd{};
     sd.type = timeline ? cudaExternalSemaphoreHandleTypeTimelineSemaphoreFd : cudaExternalSemaphoreHandleTypeOpaqueFd;
-    sd.handle.fd = fd;
+    sd.handle.fd = own;
     cudaExternalSemaphore_t sem = nullptr;
     const cudaError_t ce = cudaImportExternalSemaphore(&sem, &sd);
-    if (ce != cudaSuccess) { cudaGetLastError(); return cuda_fail(c, ce, "cudaImportExternalSemaphore"); }
+    if (ce != cudaSuccess) { cudaGetLastError(); close_if_open(own); return cuda_fail(c, ce, "cudaImportExternalSemaphore"); }
     ExtSlot &e = c->ext[slot];
     if (e.sem[which]) cudaDestroyExternalSemaphore(e.sem[which]);
     e.sem[which] = sem;

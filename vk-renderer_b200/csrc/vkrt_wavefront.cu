@@ -325,6 +325,9 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                     }
                     if (BVH) {
                         trav_init(tv, sc, o, d, EPS, sphere_bound<true>(cur)); if (tv.node < 0) tv.node = FIN;
+#if VKRT_LEAF_BATCH && VKRT_SENTINEL && !VKRT_SMEM_STACK
+                        stack.lm[0] = TRAV_DONE; tv.sp = 1;          // sentinel: popping it ends the traversal
+#endif
 #if VKRT_LEAF_BATCH && VKRT_QNODES
                         qr = qray_setup(sc, tv.sr);
 #endif
