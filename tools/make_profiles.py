@@ -42,7 +42,8 @@ for f in ("cfg4", "cfg4_mega", "cfg3", "cfg2", "ref"):
 # ---- ncu launch list of the bench command, per-launch metrics ----------------------------------------
 shutil.copy(G("launches_wf.csv"), P("launches_wavefront_cfg4.csv"))
 shutil.copy(G("trace_metrics.csv"), P("metrics_k_wf_trace_cfg4.csv"))
-shutil.copy(G("frame_metrics.csv"), P("metrics_frame_cfg4.csv"))
+if os.path.exists(G("frame_metrics.csv")) and os.path.getsize(G("frame_metrics.csv")) > 1000:
+    shutil.copy(G("frame_metrics.csv"), P("metrics_frame_cfg4.csv"))
 if os.path.exists(G("mega_cfg2_metrics.csv")):
     shutil.copy(G("mega_cfg2_metrics.csv"), P("metrics_k_path_mega_cfg2.csv"))
 

@@ -29,7 +29,7 @@
 #define VKRT_REFILL 20      // refill the warp when fewer than this many lanes are still traversing
 #endif
 #ifndef VKRT_FETCH_CHUNK
-#define VKRT_FETCH_CHUNK 128   // ray indices a warp reserves per atomicAdd on the queue head
+#define VKRT_FETCH_CHUNK 64   // ray indices a warp reserves per atomicAdd on the queue head
 #endif
 #ifndef VKRT_TRAV_UNROLL
 #define VKRT_TRAV_UNROLL 3
@@ -61,6 +61,12 @@
 #ifndef VKRT_COLD_SMEM
 #define VKRT_COLD_SMEM (VKRT_LEAF_BATCH && VKRT_QNODES && !VKRT_SPEC_LEAF)   // trace: leaf-test-only ray state in shared memory
 #endif
+#ifndef VKRT_RAY_LDCG
+#define VKRT_RAY_LDCG 1            // trace: ray / shadow records and queue items are read past L1 (ld.global.cg): they are used once,
+#endif                             //        L1 is kept for BVH nodes and the traversal stacks
+#ifndef VKRT_COLD_FLOATS
+#define VKRT_COLD_FLOATS 12        // trace: 12 = origin, direction and the exact slab constants wait in shared memory for the leaf
+#endif                             //        tests; 6 = origin and direction only, the slab constants are recomputed there (bit-identical)
 #ifndef VKRT_BLOCK_PUSH
 #define VKRT_BLOCK_PUSH 1          // classify / shade: one queue-counter atomicAdd per block instead of per warp
 #endif
@@ -91,6 +97,13 @@ struct WaveParams {
 VKRT_DEV void ld256(const float4 *p, float4 &a, float4 &b)
 {
     asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p) : "memory");
+}
+// the same load past L1 (cached in L2 only)
+VKRT_DEV void ld256cg(const float4 *p, float4 &a, float4 &b)
+{
+    asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                  : "l"(p) : "memory");
 }
@@ -276,7 +289,7 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
     int stack[BVH_STACK];
 #endif
 #if VKRT_COLD_SMEM
-    __shared__ float s_cold[12][VKRT_TRACE_BLOCK];
+    __shared__ float s_cold[VKRT_COLD_FLOATS][VKRT_TRACE_BLOCK];
 #endif
     int pend = FIN;                            // VKRT_SPEC_LEAF: the parked leaf (~sphere); FIN = none
 
@@ -304,11 +317,19 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                 else {
                     has = true;
                     if (MODE == TRACE_MIXED) any = item >= n_ext;
+#if VKRT_RAY_LDCG
+                    const uint32_t q = __ldcg((MODE == TRACE_MIXED && any) ? queue_sh + (item - n_ext) : queue + item);
+#else
                     const uint32_t q = (MODE == TRACE_MIXED && any) ? queue_sh[item - n_ext] : queue[item];
+#endif
                     path = MODE == TRACE_SHADOW ? (q >> 4) : q;
                     light = MODE == TRACE_SHADOW ? (q & 15u) : 0u;
                     float4 fo, fd;
+#if VKRT_RAY_LDCG
+                    ld256cg(MODE == TRACE_MIXED && any ? wp.shrec + 4 * (size_t)path : rec_ray(wp, path), fo, fd);
+#else
                     ld256(MODE == TRACE_MIXED && any ? wp.shrec + 4 * (size_t)path : rec_ray(wp, path), fo, fd);
+#endif
                     found = false; hit.kind = 0; hit.index = 0;
                     if (MODE == TRACE_SHADOW) {
                         const float4 s = wp.sh[(size_t)path * wp.n_lights + light];
@@ -336,8 +357,10 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                             float *cs = &s_cold[0][threadIdx.x];
                             cs[0] = o.x; cs[VKRT_TRACE_BLOCK] = o.y; cs[2 * VKRT_TRACE_BLOCK] = o.z;
                             cs[3 * VKRT_TRACE_BLOCK] = d.x; cs[4 * VKRT_TRACE_BLOCK] = d.y; cs[5 * VKRT_TRACE_BLOCK] = d.z;
+#if VKRT_COLD_FLOATS >= 12
                             cs[6 * VKRT_TRACE_BLOCK] = tv.sr.inv.x; cs[7 * VKRT_TRACE_BLOCK] = tv.sr.inv.y; cs[8 * VKRT_TRACE_BLOCK] = tv.sr.inv.z;
                             cs[9 * VKRT_TRACE_BLOCK] = tv.sr.oinv.x; cs[10 * VKRT_TRACE_BLOCK] = tv.sr.oinv.y; cs[11 * VKRT_TRACE_BLOCK] = tv.sr.oinv.z;
+#endif
                         }
 #endif
                     }
@@ -398,8 +421,12 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                         const float *cs = &s_cold[0][threadIdx.x];
                         const V3 co = v3(cs[0], cs[VKRT_TRACE_BLOCK], cs[2 * VKRT_TRACE_BLOCK]);
                         const V3 cd = v3(cs[3 * VKRT_TRACE_BLOCK], cs[4 * VKRT_TRACE_BLOCK], cs[5 * VKRT_TRACE_BLOCK]);
+#if VKRT_COLD_FLOATS >= 12
                         tv.sr.inv = v3(cs[6 * VKRT_TRACE_BLOCK], cs[7 * VKRT_TRACE_BLOCK], cs[8 * VKRT_TRACE_BLOCK]);
                         tv.sr.oinv = v3(cs[9 * VKRT_TRACE_BLOCK], cs[10 * VKRT_TRACE_BLOCK], cs[11 * VKRT_TRACE_BLOCK]);
+#else
+                        tv.sr = slab_setup(co, cd);      // the same operations on the same values as at the ray's start
+#endif
                         trav_leaf_step<STATS>(tv, stack, sc, co, cd, any, st);
 #else
                         trav_leaf_step<STATS>(tv, stack, sc, o, d, any, st);
@@ -441,13 +468,27 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
             if (MODE == TRACE_SHADOW) wp.occ[(size_t)path * wp.n_lights + light] = found ? 1 : 0;
             else if (MODE == TRACE_MIXED && any) {
                 if (!found) {        // unoccluded: the light's term counts (Tracer.comp:473-503)
+#if VKRT_RAY_LDCG
+                    const float4 a1 = __ldcg(wp.shrec + 4 * (size_t)path + 2);
+#else
                     const float4 a1 = wp.shrec[4 * (size_t)path + 2];
+#endif
+#if VKRT_RAY_LDCG
+                    if (light) __stcg(wp.rad + path, make_float4(a1.x, a1.y, a1.z, 0.f));
+                    else __stcg(rec_state(wp, path), a1);
+#else
                     if (light) wp.rad[path] = make_float4(a1.x, a1.y, a1.z, 0.f);
                     else rec_state(wp, path)[0] = a1;
+#endif
                 }
             } else {
+#if VKRT_RAY_LDCG
+                __stcg(&rec_ray(wp, path)[0].w, cur);
+                __stcg(&rec_ray(wp, path)[1].w, __uint_as_float(found ? ((hit.kind << 28) | hit.index) : 0u));
+#else
                 rec_ray(wp, path)[0].w = cur;
                 rec_ray(wp, path)[1].w = __uint_as_float(found ? ((hit.kind << 28) | hit.index) : 0u);
+#endif
             }
             has = false;
         }
