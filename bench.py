@@ -317,6 +317,25 @@ def run_ours(args):
     kernel_ms = statistics.mean(trav_ms)
     frame_kernels_ms = statistics.mean(trace_ms)
 
+    # the same frame with its waves one after the other on one stream (VKRT_FLAG_SERIAL_WAVES): per-launch event
+    # times without the other lane's kernels sharing the SMs -- what the serialised ncu launch list can be compared with
+    serial = None
+    if variant == V.VARIANT_WAVEFRONT:
+        try:
+            rser = make_renderer(V.FLAG_NO_RESOLVE | V.FLAG_SERIAL_WAVES)
+            s_trav, s_all = [], []
+            for i in range(min(args.steps, 3) + 1):
+                rser.set_frame_index(args.warmup + i)
+                rser.draw(frame_data_for(V, w, h, args.warmup + i))
+                ms, _, all_ms = rser.last_frame_traversal_timing()
+                if i > 0:                                  # the first frame allocates the wave buffers
+                    s_trav.append(ms); s_all.append(all_ms)
+            rser.close()
+            serial = (statistics.mean(s_trav), statistics.mean(s_all))
+        except Exception as exc:                           # a measurement aid: never fails the bench
+            sys.stderr.write("bench.py: serial-wave timing skipped: %r\n" % (exc,))
+    barrier()
+
     # -------- end-to-end through the public API with host buffers ("e2e") -----------------------
     barrier()
     t0 = time.perf_counter()
@@ -369,6 +388,15 @@ def run_ours(args):
                         "utilisation of the traversal loop (DESIGN.md section 4), the HBM fraction is the contract's reference number"
                         % (bvh.n_nodes * node_bytes / 1e6)}
 
+    if serial is not None:
+        roofline.update({"kernel_ms_per_frame_serial": serial[0], "achieved_serial": alg_bytes / (serial[0] * 1e-3) / 1e9,
+                         "frac_serial": alg_bytes / (serial[0] * 1e-3) / 1e9 / hbm_peak,
+                         "share_of_step_serial": serial[0] / max(serial[1], 1e-9),
+                         "serial_note": "the same launches with the frame's two waves back to back on one stream "
+                                        "(VKRT_FLAG_SERIAL_WAVES) instead of overlapping on two: each launch is timed alone, "
+                                        "like in the serialised ncu launch list under profiles/; `achieved` / `frac` / "
+                                        "`share_of_step` above come from the overlapped (shipping) configuration, where a "
+                                        "launch shares the SMs with the other wave's kernels and its event time is longer"})
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:

@@ -111,7 +111,10 @@ enum {
                                         reference renders every frame from scratch)       */
     VKRT_FLAG_HIT_IDS     = 1u << 1, /* write the primary nearest-hit id AOV               */
     VKRT_FLAG_STATS       = 1u << 2, /* also count BVH node visits / leaf tests            */
-    VKRT_FLAG_NO_RESOLVE  = 1u << 3  /* skip the rgba8 resolve in vkrt_draw (shard ranks)  */
+    VKRT_FLAG_NO_RESOLVE  = 1u << 3, /* skip the rgba8 resolve in vkrt_draw (shard ranks)  */
+    VKRT_FLAG_SERIAL_WAVES = 1u << 4 /* measurement aid (wavefront): the same waves and launches, but one after the other on one
+                                        stream instead of overlapping on two -- per-launch event times then belong to one kernel
+                                        alone (bench.py's *_serial roofline figures); the image is bit-identical */
 };
 
 typedef struct vkrt_create_info {

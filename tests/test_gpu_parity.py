@@ -269,6 +269,27 @@ def test_wavefront_multi_wave_equals_megakernel(vk):
     assert outs[0][0][..., 3].max() == 2 * (40 * 2 // 3 - 40 // 3)
 
 
+def test_serial_waves_flag_is_bit_identical(vk):
+    """VKRT_FLAG_SERIAL_WAVES (bench.py's measurement aid) only changes where the waves are enqueued."""
+    V = vk
+    w, h = 200, 120
+    fd = V.default_frame_data(aspect_ratio=w / h, seed=0.3)
+    scene = V.scenes.random_spheres(512)
+    out = []
+    for flags in (0, V.FLAG_SERIAL_WAVES):
+        r = V.Renderer(w, h, spp=16, max_depth=6, variant=V.VARIANT_WAVEFRONT, flags=flags)
+        r.set_scene(scene)
+        r.build_bvh()
+        r.set_seed(5)
+        for i in range(2):
+            r.set_frame_index(i)
+            r.draw(fd)
+        out.append((r.read_accum(), r.read_rgba8(), r.last_frame_traversal_timing()))
+        r.close()
+    assert bits_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert out[0][2][1] == out[1][2][1] and out[1][2][0] > 0.0          # the same traversal launches, timed
+
+
 def test_tile_and_sample_shards_recombine(vk, oracle):
     """SURVEY 8e: tile shards are disjoint pixels -> recombination is bit-identical to one GPU;
     sample shards change the summation order -> equal to the oracle's per-range sums added in order."""

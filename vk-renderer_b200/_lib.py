@@ -17,7 +17,7 @@ ERROR_NAMES = ["SUCCESS", "NO_SUITABLE_GPU", "NO_SUITABLE_SURFACE", "UNKNOWN", "
 INTEGRATOR_WHITTED, INTEGRATOR_PATH = 0, 1
 VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT = 0, 1
 SCENE_TRACER, SCENE_RAYTRACER = 0, 1
-FLAG_PROGRESSIVE, FLAG_HIT_IDS, FLAG_STATS, FLAG_NO_RESOLVE = 1, 2, 4, 8
+FLAG_PROGRESSIVE, FLAG_HIT_IDS, FLAG_STATS, FLAG_NO_RESOLVE, FLAG_SERIAL_WAVES = 1, 2, 4, 8, 16
 MAT_DIFFUSE, MAT_DIELECTRIC = 0, 1
 TILING_LINEAR, TILING_OPTIMAL = 0, 1
 SEMAPHORE_ACQUIRE, SEMAPHORE_RELEASE = 0, 1

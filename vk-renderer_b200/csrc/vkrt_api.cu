@@ -540,7 +540,8 @@ VKRT_API vkrt_error vkrt_draw(vkrt_ctx *c, const vkrt_frame_data *frame)
                 size_t per_wave = (c->spp + lanes - 1) / lanes;
                 if (per_wave > 16 / lanes) per_wave = 16 / lanes;
                 while (per_wave > 1 && slots * per_wave > ((size_t)64 << 20) / lanes) --per_wave;
-                CU(c, wave_engine_init(c->wave, slots * per_wave, lanes));
+                // VKRT_FLAG_SERIAL_WAVES: waves of the same size, one buffer set, one stream
+                CU(c, wave_engine_init(c->wave, slots * per_wave, (c->info.flags & VKRT_FLAG_SERIAL_WAVES) ? 1u : lanes));
                 c->wave_ready = true;
             }
             uint32_t nl = 0;
