@@ -32,7 +32,7 @@ def ncu_rows(path):
 
 
 # ---- bench lines ------------------------------------------------------------------------------------
-for f in ("cfg4", "cfg4_mega", "cfg3", "cfg2", "ref"):
+for f in ("cfg4", "cfg4_serial", "cfg4_mega", "cfg3", "cfg2", "ref"):
     src = G("bench_%s.json" % f)
     if os.path.exists(src) and os.path.getsize(src):
         line = open(src).read().strip().splitlines()[-1]
@@ -109,12 +109,16 @@ if os.path.exists(rep):
 # ---- summary -------------------------------------------------------------------------------------------
 with open(P("SUMMARY.md"), "w") as f:
     f.write("# Round evidence (%s), generated by tools/make_profiles.py from tools/evidence.sh run `%s`\n\n" % (rnd, tag))
-    for b in ("cfg4", "cfg4_mega", "cfg3", "cfg2", "ref"):
+    for b in ("cfg4", "cfg4_serial", "cfg4_mega", "cfg3", "cfg2", "ref"):
         try:
             d = json.loads(open(P("bench_%s.json" % b)).read())
             rf = d.get("roofline") or {}
             f.write("* `%s_bench_%s.json`: %.1f %s, %.2f ms/step, e2e %.1f, roofline frac %s, share_of_step %s\n"
                     % (rnd, b, d["value"], d["unit"], d["ms_per_step"], d["e2e"]["value"], rf.get("frac"), rf.get("share_of_step")))
+            if "share_of_step_serial" in rf:
+                f.write("  * waves serialised on one stream (each launch timed alone, comparable with the ncu launch list below): "
+                        "traversal launches %.2f ms/frame, share_of_step_serial %.3f, frac_serial %.3f\n"
+                        % (rf["kernel_ms_per_frame_serial"], rf["share_of_step_serial"], rf["frac_serial"]))
         except Exception as e:
             f.write("* %s: missing (%s)\n" % (b, e))
     f.write("\n## Kernel shares of one cfg4 frame in the ncu launch list (`%s_launches_wavefront_cfg4.csv`, serialised, cold caches)\n\n" % rnd)
@@ -123,6 +127,6 @@ with open(P("SUMMARY.md"), "w") as f:
     for k, v in sorted(share.items(), key=lambda kv: -kv[1]):
         f.write("| %s | %d | %.3f | %.1f %% |\n" % (k, cnt[k], v / 1e6, 100 * v / total))
     f.write("\nframe kernels: %d launches, %.3f ms summed; traversal kernels' share %.3f "
-            "(bench.py's live `share_of_step` must agree with this)\n" % (len(frame), total / 1e6, trace_share))
+            "(bench.py's live `share_of_step_serial` must agree with this; `share_of_step` is taken while the two waves overlap)\n" % (len(frame), total / 1e6, trace_share))
     f.write("\ndram bytes per trace launch (mean over one frame): %.1f MB -> profiles/traffic.json\n" % (traffic / 1e6))
 print(open(P("SUMMARY.md")).read())
