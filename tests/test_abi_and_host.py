@@ -48,6 +48,30 @@ def test_product_never_touches_the_oracle():
                     assert not re.search(pat, text, re.M), "%s matches %s" % (f, pat)
 
 
+def test_create_argument_checks_need_no_device(vk):
+    """vkrt_create validates its struct before it looks for a device: the same answers with and without a GPU."""
+    L = vk._lib
+    lib = L.load()
+
+    def create(**kw):
+        d = dict(struct_size=C.sizeof(L.CreateInfo), width=64, height=64, spp=1, max_depth=1, integrator=L.INTEGRATOR_PATH,
+                 variant=L.VARIANT_MEGAKERNEL, frames_in_flight=2, device_id=0)
+        d.update(kw)
+        ctx = C.c_void_p()
+        rc = lib.vkrt_create(C.byref(L.CreateInfo(**d)), C.byref(ctx))
+        assert rc != L.SUCCESS or has_gpu()
+        if rc == L.SUCCESS:
+            lib.vkrt_destroy(ctx)
+        return rc, lib.vkrt_last_error_string(None)
+
+    assert lib.vkrt_create(None, None) == L.BAD_ARG
+    for kw in (dict(struct_size=12), dict(width=0), dict(height=0), dict(width=65537), dict(width=65536, height=65536),
+               dict(integrator=2), dict(variant=2)):
+        rc, msg = create(**kw)
+        assert rc == L.BAD_ARG and msg.startswith(b"[app] - err :: "), (kw, rc, msg)
+    assert b"2^30 pixels" in create(width=65536, height=32768)[1]
+
+
 @pytest.mark.skipif(has_gpu(), reason="exercises the no-GPU failure path")
 def test_create_fails_loudly_without_gpu(vk):
     with pytest.raises(vk.VkrtError) as e:

@@ -268,6 +268,8 @@ VKRT_API vkrt_error vkrt_create(const vkrt_create_info *info, vkrt_ctx **out_ctx
     if (info->struct_size != sizeof(vkrt_create_info)) return fail(nullptr, VKRT_BAD_ARG, "vkrt_create_info.struct_size mismatch");
     if (info->width == 0 || info->height == 0 || info->width > 65536 || info->height > 65536)
         return fail(nullptr, VKRT_BAD_ARG, "bad resolution");
+    if ((uint64_t)info->width * info->height > ((uint64_t)1 << 30))
+        return fail(nullptr, VKRT_BAD_ARG, "more than 2^30 pixels (pixel and path indices are 32-bit)");
     if (info->integrator > VKRT_INTEGRATOR_PATH || info->variant > VKRT_VARIANT_WAVEFRONT)
         return fail(nullptr, VKRT_BAD_ARG, "bad integrator / variant");
     int n_dev = 0;
