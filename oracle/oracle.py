@@ -4,8 +4,9 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl refere
 import this module.  The product package (vk-renderer_b200/) never does.
 
 The oracle restates Assets/Tracer.comp and Assets/Raytracer.comp on the CPU
-(oracle/vkrt_oracle.cpp).  "Parity unpinned" by the reference: it has no tests or golden
-vectors and its shaders cannot run in this image; see vkrt_oracle.h.
+(oracle/vkrt_oracle.cpp).  The reference has no tests or golden vectors of its own; the pins are the
+outputs of its compiled shaders (Assets/Compiled/*.spv) executed by oracle/spirv_interp.py, committed as
+tests/golden/spirv_vectors.npz and checked in tests/test_spirv_pins.py; see vkrt_oracle.h.
 """
 import ctypes as C
 import os

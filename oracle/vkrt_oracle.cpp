@@ -1,5 +1,5 @@
 // CPU ORACLE -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.  See vkrt_oracle.h for the contract
-// ("parity unpinned" by the reference; what pins exist; the one stated deviation: the RNG).
+// (what pins it: the reference's compiled SPIR-V run by oracle/spirv_interp.py; the one stated deviation: the RNG).
 //
 // Every function cites the reference lines it restates (paths relative to the reference
 // root).  Arithmetic rule ("vkrt-f32"): every operation is one IEEE-754 binary32

@@ -6,12 +6,20 @@
  * and bench.py's cpu_baseline / --impl reference legs may load this; nothing under
  * vk-renderer_b200/ includes, links or calls it.
  *
- * PARITY UNPINNED BY THE REFERENCE: the reference ships no tests, golden images or
- * known-answer vectors, and its shaders cannot be executed here (no Vulkan loader, ICD
- * or SPIR-V tools in the image).  The pins that do exist are: the reference's own
- * Source/Camera.cpp compiled from where it lies (oracle/_ref, see oracle/Makefile), the
- * struct layouts of Include/GraphicsDevice.h / Include/Camera.h, and libm for the
- * transcendental routines.  Everything else is pinned by this restatement.
+ * PINS.  The reference ships no tests, golden images or known-answer vectors, and no Vulkan
+ * driver exists in this image -- but it does ship the compiled shaders its engine loads
+ * (Assets/Compiled/{Raytracer.comp,Tracer.comp,Fullscreen.frag}.spv, Source/GraphicsDevice.cpp:1086-1091).
+ * oracle/spirv_interp.py executes those binaries on the CPU; their outputs are committed as
+ * tests/golden/spirv_vectors.npz (generator: tests/golden/make_spirv_vectors.py) and this
+ * restatement is checked against them in tests/test_spirv_pins.py: the 8-bit images of both
+ * compute shaders and the primary-hit primitive ids identical, linear radiance within 1e-3
+ * relative for >= 99.9 % of the pixels (RMSE <= 1e-4), every hit / miss decision of the three
+ * intersection routines identical.  (The interpreter is this repository's, and Tracer.comp's
+ * rand() is answered with the integer RNG below while the binary runs: the pin is "the
+ * reference's compiled code under an independent IEEE executor", not a vendor's Vulkan driver.)
+ * Further pins: the reference's own Source/Camera.cpp compiled from where it lies (oracle/_ref,
+ * see oracle/Makefile), the struct layouts of Include/GraphicsDevice.h / Include/Camera.h, and
+ * libm for the transcendental routines.
  *
  * Stated deviation: rand() (Tracer.comp:221-234, an implementation-defined float hash)
  * is replaced by a counter-based integer hash (see oracle_rand_u01).

@@ -1,0 +1,193 @@
+#!/usr/bin/env python
+"""Golden vectors produced by RUNNING THE REFERENCE'S OWN COMPILED SHADERS (ref: Assets/Compiled/*.spv, the
+binaries the engine loads at Source/GraphicsDevice.cpp:1086-1091) through oracle/spirv_interp.py.
+
+    python tests/golden/make_spirv_vectors.py          # needs /root/reference; writes tests/golden/spirv_vectors.npz
+
+Contents (all float32 unless noted):
+  whitted_*   Raytracer.comp.spv main() over a 128x96 image, default camera / light (Source/Main.cpp:134-141):
+              the vec4 handed to imageStore for every pixel.
+  path_*      Tracer.comp.spv main() over a 64x48 image (SAMPLES = DEPTH = 4 as compiled in), seed 0.25, with the
+              shader's rand() replaced call site by call site by the repository's integer RNG (TracerRng): the
+              imageStore vec4, the linear radiance sum (the shader's `accum` ahead of Tracer.comp:585), and the
+              primary nearest hit (trace_ray() called on main()'s own Ray: primitive id and t).
+  present_*   Fullscreen.frag.spv over a 64x48 framebuffer sampling two 32x32 rgba8 images.
+  kat_*       calc_sphere_intersect / calc_plane_intersect / calc_tri_intersect of Tracer.comp.spv called directly
+              on 512 seeded rays each.
+"""
+import multiprocessing as mp
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+SPV = "/root/reference/Assets/Compiled"
+OUT = os.path.join(ROOT, "tests", "golden", "spirv_vectors.npz")
+
+WHITTED_WH = (128, 96)
+PATH_WH, PATH_SEED, PATH_FSEED, PATH_ASPECT = (64, 48), 7, 0.25, 1024.0 / 768.0
+PRESENT_TEX, PRESENT_WH = 32, (64, 48)
+HOST_TRIANGLE = [[(10.0, 10.0, 0.0), (0.0, 20.0, 0.0), (-10.0, 10.0, 0.0)]]      # Source/GraphicsDevice.cpp:798-803
+
+
+def frame_data(aspect, seed):
+    import vk_renderer_b200.device as D          # host-side mirror only (Main.cpp:134-141 defaults); no CUDA involved
+    return D.default_frame_data(aspect_ratio=aspect, seed=seed)
+
+
+def set_fd(S, mc, fd):
+    g = lambda a: (a.x, a.y, a.z)
+    S.set_frame_data(mc, fd.aspect_ratio, fd.seed, g(fd.light_pos), g(fd.camera.pos), g(fd.camera.dir), g(fd.camera.right), g(fd.camera.up))
+
+
+def whitted_rows(rows):
+    import spirv_interp as S
+    w, h = WHITTED_WH
+    m = S.Module(os.path.join(SPV, "Raytracer.comp.spv"))
+    mc = S.Machine(m)
+    set_fd(S, mc, frame_data(w / h, 0.0))
+    tex = S.run_compute(mc, w, h, [(x, y) for y in rows for x in range(w)])
+    return {k: v for k, v in tex.items()}
+
+
+def path_pixels(pixels):
+    """-> {(x, y): (imageStore vec4, radiance sum)} for Tracer.comp.spv with the substituted RNG."""
+    import oracle as O
+    import spirv_interp as S
+    w, h = PATH_WH
+    L = O.lib()
+    fd = frame_data(PATH_ASPECT, PATH_FSEED)
+    fkey = L.orc_frame_key(PATH_SEED, fd.seed, 0)
+    m = S.Module(os.path.join(SPV, "Tracer.comp.spv"))
+    rng = S.TracerRng(m, lambda pixel, sample, dim: L.orc_rand_u01(fkey, pixel, sample, dim))
+    mc = S.Machine(m, hooks=rng.hooks())
+    set_fd(S, mc, fd)
+    img = S.Image(w, h)
+    mc.global_by_binding(0)[0] = img
+    mc.global_by_binding(1)[0] = [[[[S.f32(float(c)) for c in v] for v in t] for t in HOST_TRIANGLE]]
+    gid = mc.global_by_builtin(28)
+    trace_ray = m.function("trace_ray(")
+    out = {}
+    for (x, y) in pixels:
+        rng.begin_pixel(y * w + x)
+        gid[0] = [x, y, 0]
+        mc.run(m.entry)
+        # the primary nearest hit: trace_ray() called directly on the Ray main() built, far bound 3000 (Tracer.comp:444)
+        isect = S.Pointer([[[[0.0] * 3, [0.0] * 3, 0.0, 0.0, 0], 3000.0, [0.0] * 3, [0.0] * 3]])
+        found = mc.run(trace_ray, [S.Pointer([rng.primary_ray]), isect])
+        out[(x, y)] = (img.texels[(x, y)], list(rng.radiance_sum), S.tracer_hit_id(found, isect.load()), isect.load()[1] if found else 0.0)
+    return out
+
+
+def path_rows(rows):
+    return path_pixels([(x, y) for y in rows for x in range(PATH_WH[0])])
+
+
+def present_inputs():
+    rs = np.random.RandomState(11)
+    t = PRESENT_TEX
+    yy, xx = np.mgrid[0:t, 0:t]
+    base = np.stack([(xx * 8) % 256, (yy * 8) % 256, ((xx + yy) * 4) % 256, np.full_like(xx, 255)], -1).astype(np.uint8)
+    a = base.copy()
+    b = base.copy()
+    b[8:20, 6:26, :3] = rs.randint(0, 256, size=(12, 20, 3))       # a region where the temporal-variance gate opens
+    a[::5, ::7, :3] = rs.randint(0, 256, size=a[::5, ::7, :3].shape)
+    return a, b
+
+
+def present_all():
+    import spirv_interp as S
+    a, b = present_inputs()
+    m = S.Module(os.path.join(SPV, "Fullscreen.frag.spv"))
+    mc = S.Machine(m)
+    mc.global_by_binding(0)[0] = S.bilinear_sampler(a.tolist())
+    mc.global_by_binding(1)[0] = S.bilinear_sampler(b.tolist())
+    uv_cell, out_cell = mc.global_cell("uv_coords"), mc.global_cell("frag_color")
+    w, h = PRESENT_WH
+    out = np.zeros((h, w, 4), np.float32)
+    for y in range(h):
+        for x in range(w):
+            # Fullscreen.vert:8-10 interpolated at the pixel centre
+            uv_cell[0] = [S._fdiv(S.f32(x + 0.5), float(w)), S._fdiv(S.f32(y + 0.5), float(h))]
+            mc.run(m.entry)
+            out[y, x] = out_cell[0]
+    return a, b, out
+
+
+def kats():
+    import spirv_interp as S
+    m = S.Module(os.path.join(SPV, "Tracer.comp.spv"))
+    mc = S.Machine(m)
+    rs = np.random.RandomState(5)
+    n = 512
+    o = rs.uniform(-60, 60, size=(n, 3)).astype(np.float32)
+    o[:, 1] = rs.uniform(1, 120, size=n).astype(np.float32)
+    mat = [[0.5, 0.5, 0.5], [0.0, 0.0, 0.0], 0.4, 0.0, 0]
+    sph = np.concatenate([rs.uniform(-50, 50, size=(n, 3)), rs.uniform(2, 25, size=(n, 1))], 1).astype(np.float32)
+    tri = rs.uniform(-30, 30, size=(n, 3, 3)).astype(np.float32)
+    # rays aimed near their sphere (offset up to 1.3 r: hits, grazing rays, misses; some origins inside) or, for the
+    # second half, at a point of their triangle's plane (barycentrics in [-0.3, 1.3]: inside and just outside)
+    tgt = sph[:, :3] + rs.normal(size=(n, 3)) * (sph[:, 3:4] * rs.uniform(0, 1.3, size=(n, 1)) / np.sqrt(3.0))
+    bu, bv = rs.uniform(-0.3, 1.3, size=(n, 1)), rs.uniform(-0.3, 1.3, size=(n, 1))
+    ttgt = tri[:, 0] + bu * (tri[:, 1] - tri[:, 0]) + bv * (tri[:, 2] - tri[:, 0])
+    tgt[n // 2:] = ttgt[n // 2:]
+    o[::9] = (sph[::9, :3] + 0.3 * sph[::9, 3:4]).astype(np.float32)          # inside the sphere: near root < 0 (Tracer.comp:326)
+    d = (tgt - o).astype(np.float64)
+    d = (d / np.sqrt((d ** 2).sum(1, keepdims=True))).astype(np.float32)
+    # Tracer.comp:348 culls back faces (det < EPSILON): turn three of four aimed-at triangles towards their ray
+    nrm = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    back = (nrm * d).sum(1) > 0
+    back[::4] = False
+    back[:n // 2] = False
+    tri[back] = tri[back][:, [0, 2, 1]]
+    pln = rs.normal(size=(n, 4)).astype(np.float32)
+    pln[:, :3] = (pln[:, :3] / np.sqrt((pln[:, :3].astype(np.float64) ** 2).sum(1, keepdims=True))).astype(np.float32)
+    pln[:, 3] = rs.uniform(-64, 128, size=n).astype(np.float32)
+    pln[::16, :3] = np.array([0, 1, 0], np.float32)                 # axis-aligned planes like the room's
+    d[8::16, 1] = 0.0                                               # ... with rays parallel to them (Tracer.comp:337)
+    f_s, f_p, f_t = m.function("calc_sphere_intersect("), m.function("calc_plane_intersect("), m.function("calc_tri_intersect(")
+    P = lambda v: S.Pointer([v])
+    F = lambda a: [float(x) for x in a]
+    t_s, t_p, t_t = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    for i in range(n):
+        ray = [F(o[i]), F(d[i])]
+        t_s[i] = mc.run(f_s, [P(ray), P([mat, F(sph[i, :3]), float(sph[i, 3])])])
+        t_p[i] = mc.run(f_p, [P(ray), P([mat, F(pln[i, :3]), float(pln[i, 3])])])
+        t_t[i] = mc.run(f_t, [P(ray), P([F(tri[i, 0]), F(tri[i, 1]), F(tri[i, 2])])])
+    return dict(kat_o=o, kat_d=d, kat_sphere=sph, kat_plane=pln, kat_tri=tri, kat_t_sphere=t_s, kat_t_plane=t_p, kat_t_tri=t_t)
+
+
+def main():
+    assert os.path.isdir(SPV), "the reference tree is not mounted"
+    import oracle as O
+    O.build()
+    n = max(1, (os.cpu_count() or 2) - 0)
+    with mp.Pool(n) as pool:
+        w, h = WHITTED_WH
+        chunks = [list(range(y, min(y + 4, h))) for y in range(0, h, 4)]
+        whitted = np.zeros((h, w, 4), np.float32)
+        for part in pool.imap_unordered(whitted_rows, chunks):
+            for (x, y), t in part.items():
+                whitted[y, x] = t
+        w, h = PATH_WH
+        chunks = [[y] for y in range(h)]
+        path_tex, path_rad = np.zeros((h, w, 4), np.float32), np.zeros((h, w, 3), np.float32)
+        path_id, path_t = np.zeros((h, w), np.uint32), np.zeros((h, w), np.float32)
+        for part in pool.imap_unordered(path_rows, chunks):
+            for (x, y), (t, r, hid, ht) in part.items():
+                path_tex[y, x], path_rad[y, x], path_id[y, x], path_t[y, x] = t, r, hid, ht
+    a, b, present = present_all()
+    k = kats()
+    np.savez_compressed(OUT, whitted_texels=whitted, path_texels=path_tex, path_radiance_sum=path_rad,
+                        path_primary_id=path_id, path_primary_t=path_t,
+                        path_seed=np.array([PATH_SEED]), path_frame_seed=np.array([PATH_FSEED], np.float32),
+                        path_aspect=np.array([PATH_ASPECT], np.float32),
+                        present_binding0=a, present_binding1=b, present_color=present, **k)
+    print("wrote", OUT, os.path.getsize(OUT), "bytes")
+
+
+if __name__ == "__main__":
+    main()

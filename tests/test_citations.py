@@ -9,7 +9,8 @@ import pytest
 from conftest import ROOT
 
 REF = "/root/reference"
-FILES = ["include/vkrt.h", "DESIGN.md", "INTEGRATION.md", "oracle/vkrt_oracle.cpp", "oracle/vkrt_oracle.h",
+FILES = ["include/vkrt.h", "DESIGN.md", "INTEGRATION.md", "oracle/vkrt_oracle.cpp", "oracle/vkrt_oracle.h", "oracle/spirv_interp.py",
+         "tests/test_spirv_pins.py", "tests/golden/make_spirv_vectors.py",
          "vk-renderer_b200/csrc/vkrt_api.cu", "vk-renderer_b200/csrc/vkrt_device.cuh", "vk-renderer_b200/csrc/vkrt_render.cu",
          "vk-renderer_b200/csrc/vkrt_wavefront.cu", "vk-renderer_b200/csrc/host/GraphicsDevice_cuda.cpp",
          "vk-renderer_b200/csrc/host/Camera.cpp", "vk-renderer_b200/csrc/host/headless_main.cpp", "vk-renderer_b200/device.py"]
