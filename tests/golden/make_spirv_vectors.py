@@ -11,6 +11,8 @@ Contents (all float32 unless noted):
               shader's rand() replaced call site by call site by the repository's integer RNG (TracerRng): the
               imageStore vec4, the linear radiance sum (the shader's `accum` ahead of Tracer.comp:585), and the
               primary nearest hit (trace_ray() called on main()'s own Ray: primitive id and t).
+  whitted2_* / path2_*  the same two shaders from a second camera (view2_camera, view2_light) that sees the host's triangle
+              front-on and the open side of the room (misses); path2 at 48x36, seed 0.75, frame index 3.
   present_*   Fullscreen.frag.spv over a 64x48 framebuffer sampling two 32x32 rgba8 images.
   kat_*       calc_sphere_intersect / calc_plane_intersect / calc_tri_intersect of Tracer.comp.spv called directly
               on 512 seeded rays each.
@@ -33,9 +35,33 @@ PRESENT_TEX, PRESENT_WH = 32, (64, 48)
 HOST_TRIANGLE = [[(10.0, 10.0, 0.0), (0.0, 20.0, 0.0), (-10.0, 10.0, 0.0)]]      # Source/GraphicsDevice.cpp:798-803
 
 
-def frame_data(aspect, seed):
+# view 2: from inside the room towards -z, where the reference's room has no wall (Tracer.comp:204-211): the host's
+# triangle front-on (Tracer.comp:348 culls its back face), three spheres, and rays that leave the scene (misses)
+VIEW2 = dict(pos=(4.0, 30.0, 58.0), dir=(-0.05, -0.18, -1.0), light=(10.0, 70.0, 20.0))
+WHITTED2_WH = (64, 48)
+PATH2_WH, PATH2_SEED, PATH2_FSEED, PATH2_ASPECT, PATH2_FRAME = (48, 36), 11, 0.75, 4.0 / 3.0, 3
+
+
+def view2_camera():
+    """pos / dir / right / up of VIEW2 as float32 (an orthonormal basis; the shaders only combine them linearly)."""
+    d = np.array(VIEW2["dir"], np.float64)
+    d /= np.sqrt((d ** 2).sum())
+    r = np.cross(d, np.array([0.0, 1.0, 0.0]))
+    r /= np.sqrt((r ** 2).sum())
+    u = np.cross(r, d)
+    return [np.array(VIEW2["pos"], np.float32), d.astype(np.float32), r.astype(np.float32), u.astype(np.float32)]
+
+
+def frame_data(aspect, seed, view2=False):
     import vk_renderer_b200.device as D          # host-side mirror only (Main.cpp:134-141 defaults); no CUDA involved
-    return D.default_frame_data(aspect_ratio=aspect, seed=seed)
+    fd = D.default_frame_data(aspect_ratio=aspect, seed=seed)
+    if view2:
+        cam = view2_camera()
+        for name, v in zip(("pos", "dir", "right", "up"), cam):
+            a = getattr(fd.camera, name)
+            a.x, a.y, a.z = float(v[0]), float(v[1]), float(v[2])
+        fd.light_pos.x, fd.light_pos.y, fd.light_pos.z = VIEW2["light"]
+    return fd
 
 
 def set_fd(S, mc, fd):
@@ -43,24 +69,32 @@ def set_fd(S, mc, fd):
     S.set_frame_data(mc, fd.aspect_ratio, fd.seed, g(fd.light_pos), g(fd.camera.pos), g(fd.camera.dir), g(fd.camera.right), g(fd.camera.up))
 
 
-def whitted_rows(rows):
+def whitted_rows(rows, view2=False):
     import spirv_interp as S
-    w, h = WHITTED_WH
+    w, h = WHITTED2_WH if view2 else WHITTED_WH
     m = S.Module(os.path.join(SPV, "Raytracer.comp.spv"))
     mc = S.Machine(m)
-    set_fd(S, mc, frame_data(w / h, 0.0))
-    tex = S.run_compute(mc, w, h, [(x, y) for y in rows for x in range(w)])
+    set_fd(S, mc, frame_data(w / h, 0.0, view2))
+    tex = S.run_compute(mc, w, h, [(x, y) for y in rows for x in range(w)], triangles=HOST_TRIANGLE if m_has_ssbo(m) else None)
     return {k: v for k, v in tex.items()}
 
 
-def path_pixels(pixels):
-    """-> {(x, y): (imageStore vec4, radiance sum)} for Tracer.comp.spv with the substituted RNG."""
+def whitted2_rows(rows):
+    return whitted_rows(rows, True)
+
+
+def m_has_ssbo(m):
+    return any(33 in m.decor.get(g, {}) and m.decor[g][33][0] == 1 for g in m.globals)
+
+
+def path_pixels(pixels, view2=False):
+    """-> {(x, y): (imageStore vec4, radiance sum, primary hit id, primary t)} for Tracer.comp.spv with the substituted RNG."""
     import oracle as O
     import spirv_interp as S
-    w, h = PATH_WH
+    w, h = PATH2_WH if view2 else PATH_WH
     L = O.lib()
-    fd = frame_data(PATH_ASPECT, PATH_FSEED)
-    fkey = L.orc_frame_key(PATH_SEED, fd.seed, 0)
+    fd = frame_data(PATH2_ASPECT, PATH2_FSEED, True) if view2 else frame_data(PATH_ASPECT, PATH_FSEED)
+    fkey = L.orc_frame_key(PATH2_SEED, fd.seed, PATH2_FRAME) if view2 else L.orc_frame_key(PATH_SEED, fd.seed, 0)
     m = S.Module(os.path.join(SPV, "Tracer.comp.spv"))
     rng = S.TracerRng(m, lambda pixel, sample, dim: L.orc_rand_u01(fkey, pixel, sample, dim))
     mc = S.Machine(m, hooks=rng.hooks())
@@ -84,6 +118,10 @@ def path_pixels(pixels):
 
 def path_rows(rows):
     return path_pixels([(x, y) for y in rows for x in range(PATH_WH[0])])
+
+
+def path2_rows(rows):
+    return path_pixels([(x, y) for y in rows for x in range(PATH2_WH[0])], True)
 
 
 def present_inputs():
@@ -179,10 +217,26 @@ def main():
         for part in pool.imap_unordered(path_rows, chunks):
             for (x, y), (t, r, hid, ht) in part.items():
                 path_tex[y, x], path_rad[y, x], path_id[y, x], path_t[y, x] = t, r, hid, ht
+        w, h = WHITTED2_WH
+        whitted2 = np.zeros((h, w, 4), np.float32)
+        for part in pool.imap_unordered(whitted2_rows, [list(range(y, min(y + 4, h))) for y in range(0, h, 4)]):
+            for (x, y), t in part.items():
+                whitted2[y, x] = t
+        w, h = PATH2_WH
+        path2_tex, path2_rad = np.zeros((h, w, 4), np.float32), np.zeros((h, w, 3), np.float32)
+        path2_id, path2_t = np.zeros((h, w), np.uint32), np.zeros((h, w), np.float32)
+        for part in pool.imap_unordered(path2_rows, [[y] for y in range(h)]):
+            for (x, y), (t, r, hid, ht) in part.items():
+                path2_tex[y, x], path2_rad[y, x], path2_id[y, x], path2_t[y, x] = t, r, hid, ht
     a, b, present = present_all()
     k = kats()
     np.savez_compressed(OUT, whitted_texels=whitted, path_texels=path_tex, path_radiance_sum=path_rad,
                         path_primary_id=path_id, path_primary_t=path_t,
+                        view2_camera=np.stack(view2_camera()), view2_light=np.array(VIEW2["light"], np.float32),
+                        whitted2_texels=whitted2, path2_texels=path2_tex, path2_radiance_sum=path2_rad,
+                        path2_primary_id=path2_id, path2_primary_t=path2_t, path2_seed=np.array([PATH2_SEED]),
+                        path2_frame_seed=np.array([PATH2_FSEED], np.float32), path2_aspect=np.array([PATH2_ASPECT], np.float32),
+                        path2_frame_index=np.array([PATH2_FRAME]),
                         path_seed=np.array([PATH_SEED]), path_frame_seed=np.array([PATH_FSEED], np.float32),
                         path_aspect=np.array([PATH_ASPECT], np.float32),
                         present_binding0=a, present_binding1=b, present_color=present, **k)

@@ -34,22 +34,29 @@ def _unorm8(a):
     return np.floor(np.clip(a, 0.0, 1.0) * np.float32(255.0) + np.float32(0.5)).astype(np.int32)
 
 
-def _frame_data(vk, aspect, seed):
-    return vk.default_frame_data(aspect_ratio=float(aspect), seed=float(seed))
+def _frame_data(vk, aspect, seed, gold=None):
+    """Default camera / light (Source/Main.cpp:134-141), or the fixture's second view when `gold` is given."""
+    fd = vk.default_frame_data(aspect_ratio=float(aspect), seed=float(seed))
+    if gold is not None:
+        for name, v in zip(("pos", "dir", "right", "up"), gold["view2_camera"]):
+            a = getattr(fd.camera, name)
+            a.x, a.y, a.z = float(v[0]), float(v[1]), float(v[2])
+        fd.light_pos.x, fd.light_pos.y, fd.light_pos.z = [float(x) for x in gold["view2_light"]]
+    return fd
 
 
-def _check_whitted(acc, rgba, gold):
-    wt = gold["whitted_texels"]
+def _check_whitted(acc, rgba, gold, key="whitted"):
+    wt = gold[key + "_texels"]
     d = np.abs(wt[..., :3] - acc[..., :3]).max(-1)
     assert d.max() <= 1e-3 and (d <= 1e-5).mean() >= 0.99, (d.max(), (d <= 1e-5).mean())   # measured: 4.4e-4, 99.7 %
     assert np.array_equal(_unorm8(wt[..., :3]), rgba[..., :3].astype(np.int32))            # the image the engine shows
     assert (wt[..., 3] == 1.0).all()
 
 
-def _check_path(acc, ids, rgba, gold):
-    pt, pr = gold["path_texels"], gold["path_radiance_sum"]
-    # primary nearest-hit primitive ids: bit-exact (BASELINE.json north_star; no grazing tie in this view)
-    assert np.array_equal(ids, gold["path_primary_id"])
+def _check_path(acc, ids, rgba, gold, key="path"):
+    pt, pr = gold[key + "_texels"], gold[key + "_radiance_sum"]
+    # primary nearest-hit primitive ids: bit-exact (BASELINE.json north_star; no grazing tie in these views)
+    assert np.array_equal(ids, gold[key + "_primary_id"])
     # the 8-bit image the engine presents: identical
     assert np.array_equal(_unorm8(pt[..., :3]), rgba[..., :3].astype(np.int32))
     # accumulated linear radiance: north_star's bar (1e-3 relative for >= 99.9 % of the pixels, RMSE <= 1e-4)
@@ -78,6 +85,23 @@ def test_oracle_path_matches_the_reference_spirv(vk, oracle, gold):
     _check_path(acc, ids, rgba, gold)
     t_ref = gold["path_primary_t"]
     assert (t_ref[gold["path_primary_id"] != 0] > 1e-3).all() and (t_ref[gold["path_primary_id"] == 0] == 0).all()
+
+
+def test_oracle_matches_the_reference_spirv_from_a_second_view(vk, oracle, gold):
+    """Both compute shaders from a camera that sees the host's triangle front-on (Tracer.comp:378-396, mirror) and the
+    room's open side (misses, Tracer.comp:445), another light position, seed and frame index."""
+    ids = gold["path2_primary_id"]
+    kinds = set((ids >> 28).ravel().tolist())
+    assert kinds == {0, 1, 2, 3}, kinds                                    # miss, triangle, spheres, planes all occur
+    h, w = gold["whitted2_texels"].shape[:2]
+    fd = _frame_data(vk, w / h, 0.0, gold)
+    acc, _, rgba, _ = oracle.Scene().use_default(oracle.SCENE_RAYTRACER).render(fd, w, h, spp=1, max_depth=2, integrator=oracle.WHITTED)
+    _check_whitted(acc, rgba, gold, "whitted2")
+    h, w = gold["path2_texels"].shape[:2]
+    fd = _frame_data(vk, gold["path2_aspect"][0], gold["path2_frame_seed"][0], gold)
+    acc, ids, rgba, _ = oracle.Scene().use_default(oracle.SCENE_TRACER).render(
+        fd, w, h, spp=4, max_depth=4, integrator=oracle.PATH, seed=int(gold["path2_seed"][0]), frame_index=int(gold["path2_frame_index"][0]))
+    _check_path(acc, ids, rgba, gold, "path2")
 
 
 def test_oracle_present_filter_matches_the_reference_spirv(oracle, gold):
@@ -139,6 +163,15 @@ def test_fixtures_are_what_the_reference_binaries_compute(gold):
         assert np.array_equal(np.asarray(t, np.float32).view(np.uint32), gold["path_texels"][y, x].view(np.uint32))
         assert np.array_equal(np.asarray(r, np.float32).view(np.uint32), gold["path_radiance_sum"][y, x].view(np.uint32))
         assert hid == gold["path_primary_id"][y, x] and np.float32(ht) == gold["path_primary_t"][y, x]
+    # the second view
+    h, w = gold["path2_texels"].shape[:2]
+    part = G.path_pixels([(x, (x * 5) % h) for x in range(0, w, 4)], True)
+    for (x, y), (t, r, hid, ht) in part.items():
+        assert np.array_equal(np.asarray(t, np.float32).view(np.uint32), gold["path2_texels"][y, x].view(np.uint32))
+        assert np.array_equal(np.asarray(r, np.float32).view(np.uint32), gold["path2_radiance_sum"][y, x].view(np.uint32))
+        assert hid == gold["path2_primary_id"][y, x]
+    for (x, y), t in G.whitted_rows([17], True).items():
+        assert np.array_equal(np.asarray(t, np.float32).view(np.uint32), gold["whitted2_texels"][y, x].view(np.uint32))
 
 
 def test_interpreter_covers_exactly_the_shipped_instruction_set():
@@ -179,3 +212,24 @@ def test_gpu_path_matches_the_reference_spirv(vk, gold, variant):
     acc, ids, rgba = r.read_accum(), r.read_hit_ids(), r.read_rgba8()
     r.close()
     _check_path(acc, ids, rgba, gold)
+
+
+@pytest.mark.gpu
+def test_gpu_matches_the_reference_spirv_from_a_second_view(vk, gold):
+    h, w = gold["whitted2_texels"].shape[:2]
+    r = vk.Renderer(w, h, spp=1, max_depth=2, integrator=vk.INTEGRATOR_WHITTED)
+    r.use_default_scene(vk.SCENE_RAYTRACER)
+    r.draw(_frame_data(vk, w / h, 0.0, gold))
+    acc, rgba = r.read_accum(), r.read_rgba8()
+    r.close()
+    _check_whitted(acc, rgba, gold, "whitted2")
+    h, w = gold["path2_texels"].shape[:2]
+    for variant in (0, 1):
+        r = vk.Renderer(w, h, spp=4, max_depth=4, variant=variant, flags=vk.FLAG_HIT_IDS)
+        r.use_default_scene(vk.SCENE_TRACER)
+        r.set_seed(int(gold["path2_seed"][0]))
+        r.set_frame_index(int(gold["path2_frame_index"][0]))
+        r.draw(_frame_data(vk, gold["path2_aspect"][0], gold["path2_frame_seed"][0], gold))
+        acc, ids, rgba = r.read_accum(), r.read_hit_ids(), r.read_rgba8()
+        r.close()
+        _check_path(acc, ids, rgba, gold, "path2")
