@@ -208,6 +208,19 @@ def test_bench_reference_arm_runs_on_cpu():
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["unit"] == "Mrays/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0
+    # under torchrun only rank 0 runs the CPU arm: the other ranks exit 0 without work or output
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=60, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_bench_product_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback: the product arm of bench.py stops with a message instead of measuring something else."""
+    if has_gpu():
+        pytest.skip("exercises the no-GPU failure path")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout) and r.stdout.strip() == ""
 
 
 # ---- the C++ host side (csrc/host): GraphicsDevice drop-in + headless frame loop ----------------------
