@@ -79,6 +79,21 @@ def whitted_rows(rows, view2=False):
     return {k: v for k, v in tex.items()}
 
 
+FULL_WH = (640, 480)                      # BASELINE.json configs[0]: Raytracer.comp, 640x480, 1 spp
+OUT_FULL = os.path.join(ROOT, "tests", "golden", "spirv_config0.npz")
+
+
+def whitted_full_rows(rows):
+    """Raytracer.comp.spv main() over rows of the full configs[0] frame -> {(x, y): [r, g, b] as unorm8 + floats}."""
+    import spirv_interp as S
+    w, h = FULL_WH
+    m = S.Module(os.path.join(SPV, "Raytracer.comp.spv"))
+    mc = S.Machine(m)
+    set_fd(S, mc, frame_data(w / h, 0.0))
+    tex = S.run_compute(mc, w, h, [(x, y) for y in rows for x in range(w)])
+    return {k: v[:3] for k, v in tex.items()}
+
+
 def whitted2_rows(rows):
     return whitted_rows(rows, True)
 
@@ -243,5 +258,20 @@ def main():
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 
 
+def main_full():
+    """python tests/golden/make_spirv_vectors.py --full : BASELINE configs[0] at its full size (a few minutes)."""
+    assert os.path.isdir(SPV), "the reference tree is not mounted"
+    w, h = FULL_WH
+    img = np.zeros((h, w, 3), np.float32)
+    with mp.Pool(os.cpu_count() or 2) as pool:
+        for part in pool.imap_unordered(whitted_full_rows, [list(range(y, min(y + 2, h))) for y in range(0, h, 2)]):
+            for (x, y), t in part.items():
+                img[y, x] = t
+    u8 = np.floor(np.clip(np.where(np.isnan(img), 0.0, img), 0.0, 1.0).astype(np.float32) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)
+    # the 8-bit image in full, the float colours as binary16 of (value * 255 - unorm8) would not compress: keep every 4th row / column exactly
+    np.savez_compressed(OUT_FULL, whitted_full_rgb8=u8, whitted_full_float_4x4=img[::4, ::4].copy())
+    print("wrote", OUT_FULL, os.path.getsize(OUT_FULL), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    main_full() if "--full" in sys.argv else main()
