@@ -418,6 +418,27 @@ def test_pack_layout_matches_host_statement(vk):
         r.close()
 
 
+def test_primary_hit_ids_config4_full_size(vk):
+    """BASELINE config 4 at its full size: the primary nearest-hit primitive id of every one of the 2,073,600 pixels is
+    bit-exact against the oracle's (tests/golden/cfg4_primary_ids.npz, made by tests/golden/make_cfg4_ids.py); the band of
+    grazing ties in which the reference's literal in-order loop would name another sphere is 2 pixels (reported)."""
+    import os
+    from conftest import ROOT
+    V = vk
+    z = np.load(os.path.join(ROOT, "tests", "golden", "cfg4_primary_ids.npz"))
+    w, h = 1920, 1080
+    scene = V.scenes.grid_spheres()
+    assert scene.digest() == str(z["scene_sha"][0]) and int(z["tie_band"][0]) == 2
+    fd = V.default_frame_data(aspect_ratio=w / h, seed=0.5)
+    for variant in (0, 1):
+        r = V.Renderer(w, h, spp=1, max_depth=1, variant=variant, flags=V.FLAG_HIT_IDS | V.FLAG_NO_RESOLVE)
+        r.set_scene(scene); r.build_bvh(); r.set_seed(2026)
+        r.draw(fd)
+        ids = r.read_hit_ids()
+        r.close()
+        assert np.array_equal(ids, z["ids"]), "variant %d: %d primary hit ids differ" % (variant, int((ids != z["ids"]).sum()))
+
+
 def test_full_size_properties_config4(vk):
     """Size-independent checks at BASELINE config 4's full size (100k spheres, 1920x1080, 16 spp, depth 8):
     the two kernel variants agree bit for bit, a second draw of the same frame index is idempotent, and

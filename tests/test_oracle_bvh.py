@@ -100,3 +100,23 @@ def test_bvh_tree_invariants(vk, oracle):
                 s = scene.spheres[rec[6].view(np.int32)]
                 rp = np.float32(s[3] * np.float32(1.001) + np.float32(0.001))
                 assert np.array_equal(lo, s[:3] - rp) and np.array_equal(hi, s[:3] + rp)
+
+
+def test_cfg4_primary_id_fixture_is_the_oracles(vk, oracle):
+    """tests/golden/cfg4_primary_ids.npz (the full-size primary-hit ids the GPU test compares with): made from the current
+    scene generator, and a centred window of it is what the oracle computes now (rule S through its LBVH)."""
+    import os
+    from conftest import ROOT
+    z = np.load(os.path.join(ROOT, "tests", "golden", "cfg4_primary_ids.npz"))
+    scene = vk.scenes.grid_spheres()
+    assert scene.digest() == str(z["scene_sha"][0])
+    assert z["ids"].shape == (1080, 1920) and int(z["tie_band"][0]) == 2        # 2 of 2,073,600 primary rays are grazing ties
+    kinds = set((z["ids"] >> 28).ravel().tolist())
+    assert kinds <= {0, 2, 3} and 2 in kinds and 3 in kinds                   # spheres and room planes (the scene has no triangle)
+    sc = apply_scene(oracle, scene, fast=True).build_bvh()
+    w, h = 1920, 1080
+    rect = (900, 500, 1020, 560)
+    fd = vk.default_frame_data(aspect_ratio=w / h, seed=0.5)
+    _, ids, _, _ = sc.render(fd, w, h, spp=1, max_depth=1, sphere_mode=oracle.S_BVH, seed=2026, rect=rect)
+    x0, y0, x1, y1 = rect
+    assert np.array_equal(ids[y0:y1, x0:x1], z["ids"][y0:y1, x0:x1])
