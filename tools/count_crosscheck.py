@@ -24,16 +24,22 @@ def main():
     path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "profiles", "r01_bench_cfg4.json")
     d = json.loads(open(path).read().strip().splitlines()[-1])
     cfg = d["config"]
-    assert cfg["workload"].startswith("synthetic 100k") and d["n_gpus"] == 1, "written for the single-GPU cfg4 line"
+    assert d["n_gpus"] == 1, "written for single-GPU lines"
     w, h, spp, depth, k, w0 = cfg["width"], cfg["height"], cfg["spp"], cfg["max_depth"], d["steps"], d["warmup"]
-    scene = scenes.grid_spheres()
+    if cfg["workload"].startswith("synthetic 100k"):          # cfg4: LBVH, rule S
+        scene, mode = scenes.grid_spheres(), O.S_BVH
+    elif cfg["workload"].startswith("reference default scene"):   # cfg2: the literal primitive loop
+        scene, mode = scenes.tracer_default(), O.LITERAL
+    else:
+        raise SystemExit("no cross-check for this workload (cfg3 would take the oracle ~10 minutes per frame)")
     assert scene.digest() == cfg["scene_sha"], "the scene generator changed since the bench line was taken"
     sc = apply_scene(O, scene, fast=True)
-    sc.build_bvh()
+    if mode == O.S_BVH:
+        sc.build_bvh()
     closest = shadow = 0
     for i in range(w0, w0 + k):
         fd = default_frame_data(aspect_ratio=float(w) / float(h), seed=float((i * 0.61803398875) % 1.0))
-        _, _, _, c = sc.render(fd, w, h, spp=spp, max_depth=depth, integrator=O.PATH, sphere_mode=O.S_BVH, seed=bench.SEED,
+        _, _, _, c = sc.render(fd, w, h, spp=spp, max_depth=depth, integrator=O.PATH, sphere_mode=mode, seed=bench.SEED,
                                frame_index=i, want_ids=False, want_rgba=False)
         closest += c.closest_rays
         shadow += c.shadow_rays
