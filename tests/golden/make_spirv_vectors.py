@@ -13,6 +13,8 @@ Contents (all float32 unless noted):
               primary nearest hit (trace_ray() called on main()'s own Ray: primitive id and t).
   whitted2_* / path2_*  the same two shaders from a second camera (view2_camera, view2_light) that sees the host's triangle
               front-on and the open side of the room (misses); path2 at 48x36, seed 0.75, frame index 3.
+  floathash_* Tracer.comp.spv with its own float-hash rand() left in place: mean radiance per pixel over 48 radiance()
+              calls on a 24x18 image -- the distribution the integer RNG has to reproduce (not the values).
   present_*   Fullscreen.frag.spv over a 64x48 framebuffer sampling two 32x32 rgba8 images.
   kat_*       calc_sphere_intersect / calc_plane_intersect / calc_tri_intersect of Tracer.comp.spv called directly
               on 512 seeded rays each.
@@ -139,6 +141,42 @@ def path2_rows(rows):
     return path_pixels([(x, y) for y in rows for x in range(PATH2_WH[0])], True)
 
 
+FH_WH, FH_SPP, FH_FSEED = (24, 18), 48, 0.37
+
+
+def floathash_rows(rows):
+    """Tracer.comp.spv with its OWN rand() (the float hash, Tracer.comp:221-234), nothing substituted: main() runs once
+    per pixel to set rand_salt / coords and build the primary Ray (its four radiance() calls are skipped), then
+    radiance() is called FH_SPP times.  -> {(x, y): mean radiance, clamped at 0}.  Column 0 is skipped: uv.y / uv.x is
+    inf or NaN there and so is every rand() (SURVEY appendix A #15)."""
+    import spirv_interp as S
+    w, h = FH_WH
+    m = S.Module(os.path.join(SPV, "Tracer.comp.spv"))
+    rad = m.function("radiance(")
+    mc = S.Machine(m)
+    set_fd(S, mc, frame_data(w / h, FH_FSEED))
+    mc.global_by_binding(0)[0] = S.Image(w, h)
+    mc.global_by_binding(1)[0] = [[[[S.f32(float(c)) for c in v] for v in t] for t in HOST_TRIANGLE]]
+    gid = mc.global_by_builtin(28)
+    cap = {}
+
+    def capture(machine, args, site):
+        cap["ray"] = args[0].load()
+        return [0.0, 0.0, 0.0]
+    mc.hooks[rad] = capture
+    out = {}
+    for y in rows:
+        for x in range(1, w):
+            gid[0] = [x, y, 0]
+            mc.run(m.entry)
+            acc = np.zeros(3)
+            for _ in range(FH_SPP):
+                r = np.array(mc.run(rad, [S.Pointer([cap["ray"]])]), np.float64)
+                acc += np.where(np.isnan(r), 0.0, np.maximum(r, 0.0))
+            out[(x, y)] = acc / FH_SPP
+    return out
+
+
 def present_inputs():
     rs = np.random.RandomState(11)
     t = PRESENT_TEX
@@ -243,6 +281,11 @@ def main():
         for part in pool.imap_unordered(path2_rows, [[y] for y in range(h)]):
             for (x, y), (t, r, hid, ht) in part.items():
                 path2_tex[y, x], path2_rad[y, x], path2_id[y, x], path2_t[y, x] = t, r, hid, ht
+        w, h = FH_WH
+        fh = np.zeros((h, w, 3), np.float32)
+        for part in pool.imap_unordered(floathash_rows, [[y] for y in range(h)]):
+            for (x, y), v in part.items():
+                fh[y, x] = v
     a, b, present = present_all()
     k = kats()
     np.savez_compressed(OUT, whitted_texels=whitted, path_texels=path_tex, path_radiance_sum=path_rad,
@@ -252,6 +295,7 @@ def main():
                         path2_primary_id=path2_id, path2_primary_t=path2_t, path2_seed=np.array([PATH2_SEED]),
                         path2_frame_seed=np.array([PATH2_FSEED], np.float32), path2_aspect=np.array([PATH2_ASPECT], np.float32),
                         path2_frame_index=np.array([PATH2_FRAME]),
+                        floathash_mean=fh, floathash_spp=np.array([FH_SPP]), floathash_frame_seed=np.array([FH_FSEED], np.float32),
                         path_seed=np.array([PATH_SEED]), path_frame_seed=np.array([PATH_FSEED], np.float32),
                         path_aspect=np.array([PATH_ASPECT], np.float32),
                         present_binding0=a, present_binding1=b, present_color=present, **k)
