@@ -686,3 +686,21 @@ def tracer_hit_id(found, intersection):
     if metalness == 1.0:                          # mirror: the triangle (N = the constant cross product) or sphere 2
         return (1 << 28) | 0 if tuple(n) == (0.0, 0.0, 200.0) else (2 << 28) | 2
     return (2 << 28) | 3                          # plastic
+
+
+def set_tracer_scene(module, spheres=None, planes=None):
+    """Tracer.comp keeps its scene in two Private arrays that main() fills from constants at its start
+    (`Sphere spheres[4] = {...}`, `Plane planes[5] = {...}`, ref: Tracer.comp:196-211).  This replaces the VALUES of those
+    two constants in the loaded module -- data only, no instruction is touched -- so the reference binary renders another
+    4-sphere / 5-plane scene.  spheres: 4 x [material, [x, y, z], r]; planes: 5 x [material, [nx, ny, nz], len];
+    material = [albedo[3], emissive[3], roughness, metalness, type]."""
+    main = module.functions[module.entry]
+    gid = {module.names.get(g): g for g in module.globals}
+    for name, value, count in (("spheres", spheres, 4), ("planes", planes, 5)):
+        if value is None:
+            continue
+        assert len(value) == count, "%s: the loop bound is compiled in (%d)" % (name, count)
+        stores = [w[1] for op, w in main["code"] if op == 62 and w[0] == gid[name]]
+        assert len(stores) == 1 and stores[0] in module.consts
+        conv = lambda v: [conv(x) for x in v] if isinstance(v, (list, tuple)) else (f32(float(v)) if isinstance(v, float) else int(v))
+        module.consts[stores[0]] = conv(value)

@@ -13,6 +13,9 @@ Contents (all float32 unless noted):
               primary nearest hit (trace_ray() called on main()'s own Ray: primitive id and t).
   whitted2_* / path2_*  the same two shaders from a second camera (view2_camera, view2_light) that sees the host's triangle
               front-on and the open side of the room (misses); path2 at 48x36, seed 0.75, frame index 3.
+  path3_* / scene3_*  Tracer.comp.spv with other scene CONSTANTS (set_tracer_scene: data only): two emissive spheres of
+              different colours, a rough dielectric, a rough metal, metallic walls; 48x36, seed 0.5, frame index 1.
+              scene3_materials rows = albedo[3], roughness, emissive[3], metalness, type (the vkrt_material order).
   floathash_* Tracer.comp.spv with its own float-hash rand() left in place: mean radiance per pixel over 48 radiance()
               calls on a 24x18 image -- the distribution the integer RNG has to reproduce (not the values).
   present_*   Fullscreen.frag.spv over a 64x48 framebuffer sampling two 32x32 rgba8 images.
@@ -52,6 +55,27 @@ def view2_camera():
     r /= np.sqrt((r ** 2).sum())
     u = np.cross(r, d)
     return [np.array(VIEW2["pos"], np.float32), d.astype(np.float32), r.astype(np.float32), u.astype(np.float32)]
+
+
+# scene 3: the reference binary with other scene constants (oracle/spirv_interp.set_tracer_scene): TWO emissive spheres of
+# different colours (the per-light loop and its RNG dimensions, Tracer.comp:458-503), a rough dielectric, a rough metal,
+# metallic / coloured walls.  material = [albedo, emissive, roughness, metalness, type]
+SCENE3_MATS = [
+    [[1.0, 1.0, 1.0], [0.0, 0.0, 0.0], 0.58, 0.0, 1],          # 0 dielectric, eta 0.58
+    [[1.0, 1.0, 1.0], [128.0, 128.0, 128.0], 0.6, 0.0, 0],     # 1 white light
+    [[0.9, 0.8, 0.3], [0.0, 0.0, 0.0], 0.15, 0.9, 0],          # 2 rough gold
+    [[0.8, 0.3, 0.2], [60.0, 20.0, 5.0], 0.5, 0.0, 0],         # 3 orange light
+    [[0.7, 0.7, 0.8], [0.0, 0.0, 0.0], 0.2, 0.3, 0],           # 4 glossy floor
+    [[0.9, 0.9, 0.9], [0.0, 0.0, 0.0], 0.8, 0.0, 0],           # 5 chalk ceiling
+    [[0.2, 0.6, 0.7], [0.0, 0.0, 0.0], 0.35, 0.1, 0],          # 6 teal wall
+    [[0.75, 0.25, 0.25], [0.0, 0.0, 0.0], 0.4, 0.0, 0],        # 7 matte red (the reference's)
+    [[0.3, 0.3, 0.3], [0.0, 0.0, 0.0], 0.05, 1.0, 0],          # 8 dark mirror wall
+    [[1.0, 0.5, 0.5], [0.0, 0.0, 0.0], 0.0, 1.0, 0],           # 9 `mirror`: what trace_ray gives every triangle (Tracer.comp:386)
+]
+SCENE3_SPHERES = [(0, (30.0, 18.0, 6.0), 18.0), (1, (0.0, 96.0, 0.0), 12.0), (2, (-28.0, 20.0, 18.0), 20.0), (3, (-30.0, 9.0, -40.0), 9.0)]
+SCENE3_PLANES = [(4, (0.0, 1.0, 0.0), 0.0), (5, (0.0, -1.0, 0.0), 128.0), (6, (1.0, 0.0, 0.0), 64.0), (7, (0.0, 0.0, -1.0), 64.0),
+                 (8, (-1.0, 0.0, 0.0), 64.0)]
+PATH3_WH, PATH3_SEED, PATH3_FSEED, PATH3_ASPECT, PATH3_FRAME = (48, 36), 23, 0.5, 4.0 / 3.0, 1
 
 
 def frame_data(aspect, seed, view2=False):
@@ -104,15 +128,22 @@ def m_has_ssbo(m):
     return any(33 in m.decor.get(g, {}) and m.decor[g][33][0] == 1 for g in m.globals)
 
 
-def path_pixels(pixels, view2=False):
+def path_pixels(pixels, view2=False, scene3=False):
     """-> {(x, y): (imageStore vec4, radiance sum, primary hit id, primary t)} for Tracer.comp.spv with the substituted RNG."""
     import oracle as O
     import spirv_interp as S
-    w, h = PATH2_WH if view2 else PATH_WH
+    w, h = PATH3_WH if scene3 else (PATH2_WH if view2 else PATH_WH)
     L = O.lib()
-    fd = frame_data(PATH2_ASPECT, PATH2_FSEED, True) if view2 else frame_data(PATH_ASPECT, PATH_FSEED)
-    fkey = L.orc_frame_key(PATH2_SEED, fd.seed, PATH2_FRAME) if view2 else L.orc_frame_key(PATH_SEED, fd.seed, 0)
+    if scene3:
+        fd = frame_data(PATH3_ASPECT, PATH3_FSEED)
+        fkey = L.orc_frame_key(PATH3_SEED, fd.seed, PATH3_FRAME)
+    else:
+        fd = frame_data(PATH2_ASPECT, PATH2_FSEED, True) if view2 else frame_data(PATH_ASPECT, PATH_FSEED)
+        fkey = L.orc_frame_key(PATH2_SEED, fd.seed, PATH2_FRAME) if view2 else L.orc_frame_key(PATH_SEED, fd.seed, 0)
     m = S.Module(os.path.join(SPV, "Tracer.comp.spv"))
+    if scene3:
+        S.set_tracer_scene(m, [[SCENE3_MATS[i], list(p), r] for i, p, r in SCENE3_SPHERES],
+                           [[SCENE3_MATS[i], list(n), l] for i, n, l in SCENE3_PLANES])
     rng = S.TracerRng(m, lambda pixel, sample, dim: L.orc_rand_u01(fkey, pixel, sample, dim))
     mc = S.Machine(m, hooks=rng.hooks())
     set_fd(S, mc, fd)
@@ -129,12 +160,17 @@ def path_pixels(pixels, view2=False):
         # the primary nearest hit: trace_ray() called directly on the Ray main() built, far bound 3000 (Tracer.comp:444)
         isect = S.Pointer([[[[0.0] * 3, [0.0] * 3, 0.0, 0.0, 0], 3000.0, [0.0] * 3, [0.0] * 3]])
         found = mc.run(trace_ray, [S.Pointer([rng.primary_ray]), isect])
-        out[(x, y)] = (img.texels[(x, y)], list(rng.radiance_sum), S.tracer_hit_id(found, isect.load()), isect.load()[1] if found else 0.0)
+        hid = 0 if scene3 else S.tracer_hit_id(found, isect.load())       # tracer_hit_id knows the default scene's materials only
+        out[(x, y)] = (img.texels[(x, y)], list(rng.radiance_sum), hid, isect.load()[1] if found else 0.0)
     return out
 
 
 def path_rows(rows):
     return path_pixels([(x, y) for y in rows for x in range(PATH_WH[0])])
+
+
+def path3_rows(rows):
+    return path_pixels([(x, y) for y in rows for x in range(PATH3_WH[0])], scene3=True)
 
 
 def path2_rows(rows):
@@ -281,6 +317,11 @@ def main():
         for part in pool.imap_unordered(path2_rows, [[y] for y in range(h)]):
             for (x, y), (t, r, hid, ht) in part.items():
                 path2_tex[y, x], path2_rad[y, x], path2_id[y, x], path2_t[y, x] = t, r, hid, ht
+        w, h = PATH3_WH
+        path3_tex, path3_rad, path3_t = np.zeros((h, w, 4), np.float32), np.zeros((h, w, 3), np.float32), np.zeros((h, w), np.float32)
+        for part in pool.imap_unordered(path3_rows, [[y] for y in range(h)]):
+            for (x, y), (t, r, _, ht) in part.items():
+                path3_tex[y, x], path3_rad[y, x], path3_t[y, x] = t, r, ht
         w, h = FH_WH
         fh = np.zeros((h, w, 3), np.float32)
         for part in pool.imap_unordered(floathash_rows, [[y] for y in range(h)]):
@@ -295,6 +336,14 @@ def main():
                         path2_primary_id=path2_id, path2_primary_t=path2_t, path2_seed=np.array([PATH2_SEED]),
                         path2_frame_seed=np.array([PATH2_FSEED], np.float32), path2_aspect=np.array([PATH2_ASPECT], np.float32),
                         path2_frame_index=np.array([PATH2_FRAME]),
+                        path3_texels=path3_tex, path3_radiance_sum=path3_rad, path3_primary_t=path3_t, path3_seed=np.array([PATH3_SEED]),
+                        path3_frame_seed=np.array([PATH3_FSEED], np.float32), path3_aspect=np.array([PATH3_ASPECT], np.float32),
+                        path3_frame_index=np.array([PATH3_FRAME]),
+                        scene3_materials=np.array([m[0] + [m[2]] + m[1] + [m[3], float(m[4])] for m in SCENE3_MATS], np.float32),
+                        scene3_spheres=np.array([list(p) + [r] for _, p, r in SCENE3_SPHERES], np.float32),
+                        scene3_sphere_mat=np.array([i for i, _, _ in SCENE3_SPHERES], np.uint32),
+                        scene3_planes=np.array([list(n) + [l] for _, n, l in SCENE3_PLANES], np.float32),
+                        scene3_plane_mat=np.array([i for i, _, _ in SCENE3_PLANES], np.uint32),
                         floathash_mean=fh, floathash_spp=np.array([FH_SPP]), floathash_frame_seed=np.array([FH_FSEED], np.float32),
                         path_seed=np.array([PATH_SEED]), path_frame_seed=np.array([PATH_FSEED], np.float32),
                         path_aspect=np.array([PATH_ASPECT], np.float32),
