@@ -16,6 +16,8 @@ Contents (all float32 unless noted):
   path3_* / scene3_*  Tracer.comp.spv with other scene CONSTANTS (set_tracer_scene: data only): two emissive spheres of
               different colours, a rough dielectric, a rough metal, metallic walls; 48x36, seed 0.5, frame index 1.
               scene3_materials rows = albedo[3], roughness, emissive[3], metalness, type (the vkrt_material order).
+  path4_* / scene4_*  the same with TIES: two coincident spheres and one 5e-4 behind another's front -- the later sphere wins
+              (t < cur + EPSILON, Tracer.comp:402); 40x30.  Planes as in scene 3.
   floathash_* Tracer.comp.spv with its own float-hash rand() left in place: mean radiance per pixel over 48 radiance()
               calls on a 24x18 image -- the distribution the integer RNG has to reproduce (not the values).
   present_*   Fullscreen.frag.spv over a 64x48 framebuffer sampling two 32x32 rgba8 images.
@@ -76,6 +78,13 @@ SCENE3_SPHERES = [(0, (30.0, 18.0, 6.0), 18.0), (1, (0.0, 96.0, 0.0), 12.0), (2,
 SCENE3_PLANES = [(4, (0.0, 1.0, 0.0), 0.0), (5, (0.0, -1.0, 0.0), 128.0), (6, (1.0, 0.0, 0.0), 64.0), (7, (0.0, 0.0, -1.0), 64.0),
                  (8, (-1.0, 0.0, 0.0), 64.0)]
 PATH3_WH, PATH3_SEED, PATH3_FSEED, PATH3_ASPECT, PATH3_FRAME = (48, 36), 23, 0.5, 4.0 / 3.0, 1
+# scene 4: ties.  trace_ray accepts a sphere when t < cur + EPSILON (Tracer.comp:402): a LATER sphere within 1e-3 overrides a
+# nearer one.  Spheres 0 and 2 coincide (the later, gold one must win), sphere 3 sits 5e-4 behind sphere 1's front (it wins
+# too, although it is farther); the default scene's materials otherwise.
+SCENE4_SPHERES = [(7, (20.0, 20.0, 0.0), 14.0), (6, (-20.0, 20.0, 0.0), 14.0), (2, (20.0, 20.0, 0.0), 14.0), (3, (-20.0, 20.0, -0.0005), 14.0)]
+SCENE4_MATS = SCENE3_MATS[:6] + [[[0.25, 0.75, 0.25], [0.0, 0.0, 0.0], 0.4, 0.0, 0], [[0.25, 0.25, 0.75], [0.0, 0.0, 0.0], 0.4, 0.0, 0]] + SCENE3_MATS[8:]
+SCENE4_SPHERES = [(7, (20.0, 20.0, 0.0), 14.0), (6, (-20.0, 20.0, 0.0), 14.0), (2, (20.0, 20.0, 0.0), 14.0), (1, (-20.0, 20.0, -0.0005), 14.0)]
+PATH4_WH, PATH4_SEED, PATH4_FSEED = (40, 30), 31, 0.125
 
 
 def frame_data(aspect, seed, view2=False):
@@ -128,13 +137,16 @@ def m_has_ssbo(m):
     return any(33 in m.decor.get(g, {}) and m.decor[g][33][0] == 1 for g in m.globals)
 
 
-def path_pixels(pixels, view2=False, scene3=False):
+def path_pixels(pixels, view2=False, scene3=False, scene4=False):
     """-> {(x, y): (imageStore vec4, radiance sum, primary hit id, primary t)} for Tracer.comp.spv with the substituted RNG."""
     import oracle as O
     import spirv_interp as S
-    w, h = PATH3_WH if scene3 else (PATH2_WH if view2 else PATH_WH)
+    w, h = PATH4_WH if scene4 else (PATH3_WH if scene3 else (PATH2_WH if view2 else PATH_WH))
     L = O.lib()
-    if scene3:
+    if scene4:
+        fd = frame_data(w / h, PATH4_FSEED)
+        fkey = L.orc_frame_key(PATH4_SEED, fd.seed, 0)
+    elif scene3:
         fd = frame_data(PATH3_ASPECT, PATH3_FSEED)
         fkey = L.orc_frame_key(PATH3_SEED, fd.seed, PATH3_FRAME)
     else:
@@ -144,6 +156,9 @@ def path_pixels(pixels, view2=False, scene3=False):
     if scene3:
         S.set_tracer_scene(m, [[SCENE3_MATS[i], list(p), r] for i, p, r in SCENE3_SPHERES],
                            [[SCENE3_MATS[i], list(n), l] for i, n, l in SCENE3_PLANES])
+    if scene4:
+        S.set_tracer_scene(m, [[SCENE4_MATS[i], list(p), r] for i, p, r in SCENE4_SPHERES],
+                           [[SCENE4_MATS[i], list(n), l] for i, n, l in SCENE3_PLANES])
     rng = S.TracerRng(m, lambda pixel, sample, dim: L.orc_rand_u01(fkey, pixel, sample, dim))
     mc = S.Machine(m, hooks=rng.hooks())
     set_fd(S, mc, fd)
@@ -160,7 +175,7 @@ def path_pixels(pixels, view2=False, scene3=False):
         # the primary nearest hit: trace_ray() called directly on the Ray main() built, far bound 3000 (Tracer.comp:444)
         isect = S.Pointer([[[[0.0] * 3, [0.0] * 3, 0.0, 0.0, 0], 3000.0, [0.0] * 3, [0.0] * 3]])
         found = mc.run(trace_ray, [S.Pointer([rng.primary_ray]), isect])
-        hid = 0 if scene3 else S.tracer_hit_id(found, isect.load())       # tracer_hit_id knows the default scene's materials only
+        hid = 0 if (scene3 or scene4) else S.tracer_hit_id(found, isect.load())       # tracer_hit_id knows the default scene's materials only
         out[(x, y)] = (img.texels[(x, y)], list(rng.radiance_sum), hid, isect.load()[1] if found else 0.0)
     return out
 
@@ -171,6 +186,10 @@ def path_rows(rows):
 
 def path3_rows(rows):
     return path_pixels([(x, y) for y in rows for x in range(PATH3_WH[0])], scene3=True)
+
+
+def path4_rows(rows):
+    return path_pixels([(x, y) for y in rows for x in range(PATH4_WH[0])], scene4=True)
 
 
 def path2_rows(rows):
@@ -322,6 +341,11 @@ def main():
         for part in pool.imap_unordered(path3_rows, [[y] for y in range(h)]):
             for (x, y), (t, r, _, ht) in part.items():
                 path3_tex[y, x], path3_rad[y, x], path3_t[y, x] = t, r, ht
+        w, h = PATH4_WH
+        path4_tex, path4_rad = np.zeros((h, w, 4), np.float32), np.zeros((h, w, 3), np.float32)
+        for part in pool.imap_unordered(path4_rows, [[y] for y in range(h)]):
+            for (x, y), (t, r, _, _) in part.items():
+                path4_tex[y, x], path4_rad[y, x] = t, r
         w, h = FH_WH
         fh = np.zeros((h, w, 3), np.float32)
         for part in pool.imap_unordered(floathash_rows, [[y] for y in range(h)]):
@@ -344,6 +368,11 @@ def main():
                         scene3_sphere_mat=np.array([i for i, _, _ in SCENE3_SPHERES], np.uint32),
                         scene3_planes=np.array([list(n) + [l] for _, n, l in SCENE3_PLANES], np.float32),
                         scene3_plane_mat=np.array([i for i, _, _ in SCENE3_PLANES], np.uint32),
+                        path4_texels=path4_tex, path4_radiance_sum=path4_rad, path4_seed=np.array([PATH4_SEED]),
+                        path4_frame_seed=np.array([PATH4_FSEED], np.float32),
+                        scene4_materials=np.array([m[0] + [m[2]] + m[1] + [m[3], float(m[4])] for m in SCENE4_MATS], np.float32),
+                        scene4_spheres=np.array([list(p) + [r] for _, p, r in SCENE4_SPHERES], np.float32),
+                        scene4_sphere_mat=np.array([i for i, _, _ in SCENE4_SPHERES], np.uint32),
                         floathash_mean=fh, floathash_spp=np.array([FH_SPP]), floathash_frame_seed=np.array([FH_FSEED], np.float32),
                         path_seed=np.array([PATH_SEED]), path_frame_seed=np.array([PATH_FSEED], np.float32),
                         path_aspect=np.array([PATH_ASPECT], np.float32),

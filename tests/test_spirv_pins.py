@@ -184,6 +184,51 @@ def test_gpu_two_light_scene_matches_the_reference_spirv(vk, gold, variant):
     _check_path3(acc, rgba, gold)
 
 
+def _scene4(vk, gold):
+    g = gold["scene4_materials"]
+    mats = np.zeros((len(g), 12), np.float32)
+    mats[:, :8] = g[:, :8]
+    mats.view(np.uint32)[:, 8] = g[:, 8].astype(np.uint32)
+    tri = np.zeros((1, 12), np.float32)
+    tri[0, 0:3], tri[0, 4:7], tri[0, 8:11] = (10, 10, 0), (0, 20, 0), (-10, 10, 0)
+    return vk.scenes.Scene("scene4", mats, gold["scene4_spheres"], gold["scene4_sphere_mat"], gold["scene3_planes"],
+                           gold["scene3_plane_mat"], tri, 9)
+
+
+def _check_path4(rgba, gold):
+    d = np.abs(_unorm8(gold["path4_texels"][..., :3]) - rgba[..., :3].astype(np.int32)).max(-1)
+    assert d.max() <= 1 and (d == 0).mean() >= 0.995, (d.max(), (d == 0).mean())       # measured: 99.75 % identical, rest 1 LSB
+
+
+def test_oracle_literal_tie_rule_matches_the_reference_spirv(vk, oracle, gold):
+    """Ties: coincident spheres and a sphere 5e-4 behind another's front.  The reference's in-order loop lets the LATER
+    sphere win (t < cur + EPSILON, Tracer.comp:402); the oracle's literal mode -- what every scene without a BVH uses --
+    must do the same, and rule S (BVH scenes only) is seen to differ here, which is why it is a stated rule."""
+    from helpers import apply_scene
+    scene = _scene4(vk, gold)
+    h, w = gold["path4_texels"].shape[:2]
+    fd = _frame_data(vk, w / h, gold["path4_frame_seed"][0])
+    kw = dict(spp=4, max_depth=4, integrator=oracle.PATH, seed=int(gold["path4_seed"][0]))
+    _, ids, rgba, _ = apply_scene(oracle, scene).render(fd, w, h, sphere_mode=oracle.LITERAL, **kw)
+    _check_path4(rgba, gold)
+    assert ((ids >> 28) == 2).any() and ((ids & 0x0FFFFFFF)[(ids >> 28) == 2] == 2).any()      # the later coincident sphere wins
+    _, ids_s, rgba_s, _ = apply_scene(oracle, scene).render(fd, w, h, sphere_mode=oracle.S_LINEAR, **kw)
+    assert ((ids_s & 0x0FFFFFFF)[(ids_s >> 28) == 2] == 0).any() and not np.array_equal(rgba_s, rgba)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", [0, 1])
+def test_gpu_literal_tie_rule_matches_the_reference_spirv(vk, gold, variant):
+    h, w = gold["path4_texels"].shape[:2]
+    r = vk.Renderer(w, h, spp=4, max_depth=4, variant=variant)
+    r.set_scene(_scene4(vk, gold))
+    r.set_seed(int(gold["path4_seed"][0]))
+    r.draw(_frame_data(vk, w / h, gold["path4_frame_seed"][0]))
+    rgba = r.read_rgba8()
+    r.close()
+    _check_path4(rgba, gold)
+
+
 def test_integer_rng_reproduces_the_float_hash_distribution(vk, oracle, gold):
     """The one stated deviation, checked as a distribution: Tracer.comp.spv ran with its OWN float-hash rand()
     (nothing substituted) for 48 radiance() calls per pixel; the oracle with the integer RNG, over 12 independent seeds,
