@@ -3,7 +3,7 @@
 TEST INFRASTRUCTURE (like everything under oracle/): only tests/ and the fixture generator
 tests/golden/make_spirv_vectors.py use it.  The reference ships the binaries its engine loads
 (ref: Assets/Compiled/Tracer.comp.spv, loaded at Source/GraphicsDevice.cpp:1091; Raytracer.comp.spv;
-Fullscreen.frag.spv, :1086), produced by glslangValidator from Assets/*.comp (ref: Assets/Compile.sh).  No Vulkan
+Fullscreen.frag.spv, Fullscreen.vert.spv, :1086), produced by glslangValidator from Assets/*.comp (ref: Assets/Compile.sh).  No Vulkan
 driver exists in this image, so this module is the one way to *run the reference itself* here: it walks the
 unoptimised, structured SPIR-V glslang emits, one invocation at a time.
 
@@ -14,7 +14,7 @@ contract (which fuses a few multiply-adds and uses its own polynomials), so comp
 stated tolerance, and identity where the reference's arithmetic leaves no freedom (hit / miss decisions away
 from ties, integer results, control flow).
 
-Supported: exactly the instruction subset that occurs in the three binaries (checked at load time).
+Supported: exactly the instruction subset that occurs in the four binaries (checked at load time).
 Functions can be called individually by their OpName (e.g. "trace_ray(struct-Ray-vf3-vf31;struct-Intersect-...;")
 and calls to a named function can be intercepted (`hooks`), which is how the fixture generator substitutes the
 repository's integer RNG for the shader's float hash rand() (DESIGN.md "RNG").
@@ -480,6 +480,13 @@ class Machine:
                     v[w[1]] = _map1(lambda y: conv(y if isinstance(y, int) else _I.unpack(_F.pack(y))[0]), x)
                 else:
                     v[w[1]] = _map1(lambda y: _F.unpack(_I.pack(_u32(y)))[0] if isinstance(y, int) else y, x)
+            elif op in (194, 195, 196, 197, 198, 199):                # shifts and bitwise ops (Fullscreen.vert.spv)
+                t = m.types[w[0]]
+                et = m.types[t[1]] if t[0] == "vector" else t
+                wrap = _s32 if et[2] else _u32
+                fn = {194: lambda x, y: _u32(x) >> (y & 31), 195: lambda x, y: _s32(x) >> (y & 31), 196: lambda x, y: x << (y & 31),
+                      197: lambda x, y: x | y, 198: lambda x, y: x ^ y, 199: lambda x, y: x & y}[op]
+                v[w[1]] = _map1(wrap, _map2(fn, val(w[2]), val(w[3])))
             elif op == 68:                                            # OpArrayLength
                 v[w[1]] = len(val(w[2]).load()[w[3]])
             elif op == 104:                                           # OpImageQuerySize

@@ -339,6 +339,28 @@ def test_random_poses_live(oracle):
     assert sum(o["p_bad"] for o in out) <= 2 and max(o["w_max"] for o in out) <= 1e-3
 
 
+@pytest.mark.skipif(not os.path.isdir(SPV), reason="the reference tree is not mounted here")
+def test_fullscreen_triangle_uv_convention():
+    """Fullscreen.vert.spv: the three vertices carry uv (0,0), (2,0), (0,2) and position uv * 2 - 1, so the interpolated
+    uv at the centre of framebuffer pixel (x, y) is ((x + 0.5) / W, (y + 0.5) / H), row 0 on top -- what the oracle's
+    present filter and the Fullscreen.frag.spv vectors assume (Fullscreen.frag:16 then flips v)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import spirv_interp as S
+    m = S.Module(os.path.join(SPV, "Fullscreen.vert.spv"))
+    mc = S.Machine(m)
+    vi, uv = mc.global_by_builtin(42), mc.global_cell("uv_coords")
+    per_vertex = [g for g, (sc, tid, _) in m.globals.items() if sc == 3 and m.types[tid][0] == "struct"][0]
+    got = []
+    for i in range(3):
+        vi[0] = i
+        mc.run(m.entry)
+        got.append((tuple(uv[0]), tuple(mc.g[per_vertex][0][0])))
+    assert [g[0] for g in got] == [(0.0, 0.0), (2.0, 0.0), (0.0, 2.0)]
+    assert [g[1] for g in got] == [(-1.0, -1.0, 0.0, 1.0), (3.0, -1.0, 0.0, 1.0), (-1.0, 3.0, 0.0, 1.0)]
+    # position = uv * 2 - 1 is affine, so uv interpolates to (ndc + 1) / 2 = ((x + 0.5) / W, (y + 0.5) / H) at a pixel centre
+
+
 def test_interpreter_covers_exactly_the_shipped_instruction_set():
     """oracle/spirv_interp.py is not a general SPIR-V implementation: it must refuse what it does not model."""
     import sys
