@@ -1,7 +1,7 @@
 """A small SPIR-V interpreter: executes the reference's OWN compiled shaders on the CPU.
 
-TEST INFRASTRUCTURE (like everything under oracle/): only tests/ and the fixture generator
-tests/golden/make_spirv_vectors.py use it.  The reference ships the binaries its engine loads
+TEST INFRASTRUCTURE (like everything under oracle/): only tests/ uses it (the pin tests, the fixture generator
+tests/golden/make_spirv_vectors.py and the verification scripts under tests/tools/).  The reference ships the binaries its engine loads
 (ref: Assets/Compiled/Tracer.comp.spv, loaded at Source/GraphicsDevice.cpp:1091; Raytracer.comp.spv;
 Fullscreen.frag.spv, Fullscreen.vert.spv, :1086), produced by glslangValidator from Assets/*.comp (ref: Assets/Compile.sh).  No Vulkan
 driver exists in this image, so this module is the one way to *run the reference itself* here: it walks the

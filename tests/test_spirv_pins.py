@@ -329,10 +329,10 @@ def test_fixtures_are_what_the_reference_binaries_compute(gold):
 
 @pytest.mark.skipif(not os.path.isdir(SPV), reason="the reference tree is not mounted here")
 def test_random_poses_live(oracle):
-    """tools/spirv_fuzz.py on 16 random cameras / lights / aspect ratios / seeds (24 random pixels each, both shaders): ids
+    """tests/tools/spirv_fuzz.py on 16 random cameras / lights / aspect ratios / seeds (24 random pixels each, both shaders): ids
     identical, whitted within one 8-bit step, at most a stray path pixel off (profiles/r01_spirv_fuzz.txt: 2 of 15,360)."""
     import sys
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    sys.path.insert(0, os.path.join(ROOT, "tests", "tools"))
     import spirv_fuzz as F
     out = [F.work(k) for k in range(200, 216)]
     assert sum(o["id_bad"] for o in out) == 0 and sum(o["w_bad"] for o in out) == 0

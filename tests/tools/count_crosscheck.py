@@ -4,13 +4,13 @@ nearest-hit and shadow rays of its K timed full-size frames (frame indices warmu
 bench.frame_data_for); this script renders the same frames with the oracle and compares the totals.  Ray counts are a
 sensitive fingerprint of the whole computation -- one different Russian-roulette decision or hit / miss changes them.
 
-    python tools/count_crosscheck.py [profiles/r01_bench_cfg4.json]      # ~25 s per frame on 8 cores
+    python tests/tools/count_crosscheck.py [profiles/r01_bench_cfg4.json]      # ~25 s per frame on 8 cores
 """
 import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 

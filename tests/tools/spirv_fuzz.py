@@ -3,7 +3,7 @@
 lights, aspect ratios and seeds, 24 random pixels each are run through Raytracer.comp.spv and Tracer.comp.spv
 (oracle/spirv_interp.py; Tracer's rand() answered by the integer RNG) and through the oracle.
 
-    python tools/spirv_fuzz.py [N=64]      # ~10 s per 64 poses on 8 cores
+    python tests/tools/spirv_fuzz.py [N=64]      # ~10 s per 64 poses on 8 cores
 
 Expected (measured with N = 640, profiles/r01_spirv_fuzz.txt): every primary-hit id identical, every whitted pixel within
 one 8-bit step, and a path pixel in ~10,000 off by more than that -- a last-bit difference between two legal executions
@@ -16,7 +16,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for _p in (ROOT, os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests', 'golden')):
     sys.path.insert(0, _p)
 W,H=40,30
