@@ -72,6 +72,23 @@ def test_create_argument_checks_need_no_device(vk):
     assert b"2^30 pixels" in create(width=65536, height=32768)[1]
 
 
+def test_only_the_allowed_places_use_the_oracle():
+    """Outside tests/, only bench.py (its cpu_baseline / --impl reference leg) and __graft_entry__ (build + smoke) may
+    import the oracle; tools/ and the product package never do."""
+    users = []
+    for dirpath, dirs, files in os.walk(ROOT):
+        dirs[:] = [d for d in dirs if d not in (".git", "build", "gpurun_out", "__pycache__", "tests", "oracle", "baseline", ".pytest_cache")]
+        for f in files:
+            if f.endswith((".py", ".sh")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                if re.search(r"^\s*(import|from)\s+(oracle|spirv_interp)\b", text, re.M):
+                    users.append(os.path.relpath(os.path.join(dirpath, f), ROOT))
+    assert sorted(users) == ["__graft_entry__.py", "bench.py"], users
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    # ... and inside bench.py only the CPU arm's function does
+    assert bench.count("import oracle") == 1 and bench.split("import oracle")[0].rsplit("\ndef ", 1)[1].startswith("cpu_render(")
+
+
 @pytest.mark.skipif(has_gpu(), reason="exercises the no-GPU failure path")
 def test_create_fails_loudly_without_gpu(vk):
     with pytest.raises(vk.VkrtError) as e:
