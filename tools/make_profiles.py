@@ -129,4 +129,14 @@ with open(P("SUMMARY.md"), "w") as f:
     f.write("\nframe kernels: %d launches, %.3f ms summed; traversal kernels' share %.3f "
             "(bench.py's live `share_of_step_serial` must agree with this; `share_of_step` is taken while the two waves overlap)\n" % (len(frame), total / 1e6, trace_share))
     f.write("\ndram bytes per trace launch (mean over one frame): %.1f MB -> profiles/traffic.json\n" % (traffic / 1e6))
+# other evidence files of the round, when present
+extra = [("sweeps.txt", "tuning sweeps (one bench line per compile-time variant)"),
+         ("ray_count_crosscheck.txt", "the CPU oracle's ray counts of the bench's full-size frames against the device counters (no GPU needed)"),
+         ("spirv_fuzz.txt", "random-pose fuzz of the oracle against the reference's compiled shaders")]
+with open(P("SUMMARY.md"), "a") as f:
+    have = [(n, d) for n, d in extra if os.path.exists(P(n))]
+    if have:
+        f.write("\n## Other evidence\n\n")
+        for n, d in have:
+            f.write("* `%s_%s`: %s\n" % (rnd, n, d))
 print(open(P("SUMMARY.md")).read())
