@@ -41,7 +41,7 @@ enum {
     VKRT_NO_SUITABLE_SURFACE = 2, /* never produced; kept for value parity */
     VKRT_UNKNOWN             = 3,
     VKRT_CUDA_ERROR          = 4,
-    VKRT_NCCL_ERROR          = 5, /* reserved for the in-library collective */
+    VKRT_NCCL_ERROR          = 5, /* the multi-GPU frame exchange failed (a peer did not deliver its frame in time) */
     VKRT_BAD_ARG             = 6
 };
 
@@ -112,9 +112,11 @@ enum {
     VKRT_FLAG_HIT_IDS     = 1u << 1, /* write the primary nearest-hit id AOV               */
     VKRT_FLAG_STATS       = 1u << 2, /* also count BVH node visits / leaf tests            */
     VKRT_FLAG_NO_RESOLVE  = 1u << 3, /* skip the rgba8 resolve in vkrt_draw (shard ranks)  */
-    VKRT_FLAG_SERIAL_WAVES = 1u << 4 /* measurement aid (wavefront): the same waves and launches, but one after the other on one
+    VKRT_FLAG_SERIAL_WAVES = 1u << 4, /* measurement aid (wavefront): the same waves and launches, but one after the other on one
                                         stream instead of overlapping on two -- per-launch event times then belong to one kernel
-                                        alone (bench.py's *_serial roofline figures); the image is bit-identical */
+                                        alone (bench.py's roofline figures); the image is bit-identical */
+    VKRT_FLAG_LAUNCH_TIMING = 1u << 5 /* measurement aid (wavefront): bracket every kernel launch with a CUDA-event pair
+                                        (vkrt_last_frame_traversal_timing, vkrt_debug_dump_timeline); off = no event in the hot path */
 };
 
 typedef struct vkrt_create_info {
@@ -133,6 +135,13 @@ typedef struct vkrt_create_info {
      * [sample_shard_rank*spp/count, (sample_shard_rank+1)*spp/count) of each frame */
     uint32_t sample_shard_rank, sample_shard_count;
     void    *stream;             /* cudaStream_t to launch on; NULL = library-owned stream */
+    /* In-library multi-GPU (ref: the reference is single-GPU, Source/VulkanState.h:52-55; GraphicsDevice::Draw stays ONE call):
+     * n_devices > 1 makes this one context render every frame on the CUDA devices device_ids[0 .. n_devices), sharded by
+     * interleaved screen tiles; device_ids[0] gathers (every other GPU stores its pixels straight into its memory over
+     * NVLink, "frame exchange" below) and owns the outputs.  n_devices <= 1: device_id is used, as before.  The shard
+     * fields above must then be 0 / 1 -- the library shards by itself. */
+    uint32_t n_devices;
+    int32_t  device_ids[8];
 } vkrt_create_info;
 
 typedef struct vkrt_ctx vkrt_ctx;
@@ -247,10 +256,12 @@ VKRT_API vkrt_error vkrt_debug_bind_array_target(vkrt_ctx *ctx, uint32_t slot);
 /* The two vkCmdPipelineBarriers become one semaphore pair per slot, exported by the engine with vkGetSemaphoreFdKHR
  * (OPAQUE_FD; binary or timeline):
  *   VKRT_SEMAPHORE_ACQUIRE  signalled by the engine in the last submit that samples image `slot` before the
- *                           library's next write to it; the n-th resolve into the slot (n >= 2) waits for it
+ *                           library's next write to it; the n-th frame drawn into the slot (n >= 2) waits for it
  *                           (timeline: for value n - 1) before it writes -- replaces the barrier at :1234-1252;
- *   VKRT_SEMAPHORE_RELEASE  signalled by the library on its stream after the n-th resolve into the slot (timeline:
+ *   VKRT_SEMAPHORE_RELEASE  signalled by the library on its stream after the n-th frame drawn into the slot (timeline:
  *                           to value n); the engine's submit that samples the image waits for it -- :1268-1284.
+ * n counts the vkrt_draw calls that targeted the slot since its FIRST semaphore was imported (import both before
+ * drawing); an explicit vkrt_resolve of the same frame neither waits nor signals.
  * Without semaphores the caller orders the two APIs itself (vkrt_wait_idle / a fence).  Like the image's, the
  * descriptor stays the caller's. */
 enum { VKRT_SEMAPHORE_ACQUIRE = 0, VKRT_SEMAPHORE_RELEASE = 1 };
@@ -324,6 +335,32 @@ VKRT_API vkrt_error vkrt_shard_floats(vkrt_ctx *ctx, uint32_t tile_rank, size_t 
  * full accumulator; add = 0 overwrites, add = 1 sums (sample shards, applied in call order). */
 VKRT_API vkrt_error vkrt_unpack_shard(vkrt_ctx *ctx, const float *dev_packed, uint32_t tile_rank,
                                       uint32_t tile_count, int add);
+
+/* ------------------------------------------------------------------------- */
+/* Frame exchange over peer memory (NVLink / NVSwitch) -- SURVEY.md 8(e)      */
+/* ------------------------------------------------------------------------- */
+/* With an exchange attached the sharded contexts of one frame (tile_shard_* x sample_shard_*, one per GPU, in one or in
+ * several processes) need no pack / gather / unpack step: the last kernel of every context's vkrt_draw stores the pixels
+ * it owns directly into a frame target in the memory of the GATHERING context's GPU (tile rank 0, sample rank 0), through
+ * a peer mapping, and publishes a frame counter there; the gathering context's vkrt_draw waits for the counters of all
+ * ranks on the device, adds the sample groups in rank order into its accumulator and resolves.  Everything is ordered on
+ * the device (no host synchronisation, no collective call), frames stay two deep in flight.  Every context must draw
+ * the same sequence of frames.  VKRT_FLAG_PROGRESSIVE is applied by the gathering context.
+ *   vkrt_exchange_create  gathering context: allocates the exchange block and returns a handle (CUDA IPC) for it
+ *   vkrt_exchange_open    a context in ANOTHER process: maps the block from the handle (cudaIpcOpenMemHandle)
+ *   vkrt_exchange_attach  a context in the SAME process: maps it through cudaDeviceEnablePeerAccess
+ *   vkrt_exchange_close   detaches (waits for the frames in flight) */
+typedef struct vkrt_exchange_handle {
+    uint8_t  ipc[64];            /* cudaIpcMemHandle_t */
+    uint64_t bytes;
+    uint32_t width, height;
+    uint32_t tile_shard_count, sample_shard_count;
+    uint32_t magic, _pad;
+} vkrt_exchange_handle;
+VKRT_API vkrt_error vkrt_exchange_create(vkrt_ctx *ctx, vkrt_exchange_handle *out);
+VKRT_API vkrt_error vkrt_exchange_open(vkrt_ctx *ctx, const vkrt_exchange_handle *handle);
+VKRT_API vkrt_error vkrt_exchange_attach(vkrt_ctx *ctx, vkrt_ctx *gathering_ctx);
+VKRT_API vkrt_error vkrt_exchange_close(vkrt_ctx *ctx);
 
 /* Microbenchmarks for the roofline denominators that MEASURED_PEAKS.json lacks. */
 VKRT_API vkrt_error vkrt_measure_fp32_peak(int device_id, float *tflops);

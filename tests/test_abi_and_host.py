@@ -66,7 +66,7 @@ def test_create_argument_checks_need_no_device(vk):
 
     assert lib.vkrt_create(None, None) == L.BAD_ARG
     for kw in (dict(struct_size=12), dict(width=0), dict(height=0), dict(width=65537), dict(width=65536, height=65536),
-               dict(integrator=2), dict(variant=2)):
+               dict(integrator=2), dict(variant=2), dict(max_depth=256), dict(max_depth=257), dict(spp=(1 << 24) + 1)):
         rc, msg = create(**kw)
         assert rc == L.BAD_ARG and msg.startswith(b"[app] - err :: "), (kw, rc, msg)
     assert b"2^30 pixels" in create(width=65536, height=32768)[1]

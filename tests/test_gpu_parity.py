@@ -276,7 +276,7 @@ def test_serial_waves_flag_is_bit_identical(vk):
     fd = V.default_frame_data(aspect_ratio=w / h, seed=0.3)
     scene = V.scenes.random_spheres(512)
     out = []
-    for flags in (0, V.FLAG_SERIAL_WAVES):
+    for flags in (V.FLAG_LAUNCH_TIMING, V.FLAG_SERIAL_WAVES | V.FLAG_LAUNCH_TIMING, 0):
         r = V.Renderer(w, h, spp=16, max_depth=6, variant=V.VARIANT_WAVEFRONT, flags=flags)
         r.set_scene(scene)
         r.build_bvh()
@@ -284,9 +284,15 @@ def test_serial_waves_flag_is_bit_identical(vk):
         for i in range(2):
             r.set_frame_index(i)
             r.draw(fd)
-        out.append((r.read_accum(), r.read_rgba8(), r.last_frame_traversal_timing()))
+        if flags:
+            out.append((r.read_accum(), r.read_rgba8(), r.last_frame_traversal_timing()))
+        else:                        # without VKRT_FLAG_LAUNCH_TIMING the hot path records no per-launch events
+            with pytest.raises(V.VkrtError):
+                r.last_frame_traversal_timing()
+            out.append((r.read_accum(), r.read_rgba8(), None))
         r.close()
     assert bits_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert bits_equal(out[0][0], out[2][0]) and np.array_equal(out[0][1], out[2][1])
     assert out[0][2][1] == out[1][2][1] and out[1][2][0] > 0.0          # the same traversal launches, timed
 
 

@@ -1,0 +1,268 @@
+// Design experiment (test infrastructure, CPU only): counts node visits / box tests / leaf tests of candidate
+// traversal schemes on the oracle's LBVH, for synthetic secondary and shadow rays of the cfg4 scene.
+//   usage: trav_sim spheres.bin nodes.bin n_rays
+// spheres.bin: n x {cx,cy,cz,r} float32;  nodes.bin: (n-1) x 16 float32 (orc_scene_read_bvh layout)
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <vector>
+
+struct V3 { float x, y, z; };
+static inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+static inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+static inline V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+static inline float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static inline V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+static inline V3 norm(V3 a) { return a * (1.0f / std::sqrt(dot(a, a))); }
+
+struct Sphere { float cx, cy, cz, r; };
+struct Child { float lo[3], hi[3]; int index, kind; };
+struct Node { Child c[2]; };
+
+struct Box { float lo[3], hi[3]; };
+static inline float area(const Box &b)
+{
+    const float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
+    return dx * dy + dy * dz + dz * dx;
+}
+struct WChild { Box b; int ref; };          // ref >= 0 wide node, < 0 ~sphere
+struct WNode { std::vector<WChild> c; };
+
+static std::vector<Sphere> sph;
+static std::vector<Node> nodes;
+
+struct Ray { V3 o, d, inv, oinv; float B; bool any; };
+static inline float sinv(float d) { return 1.0f / (std::fabs(d) > 1e-20f ? d : std::copysign(1e-20f, d)); }
+static inline void setup(Ray &r) { r.inv = {sinv(r.d.x), sinv(r.d.y), sinv(r.d.z)}; r.oinv = {r.o.x * r.inv.x, r.o.y * r.inv.y, r.o.z * r.inv.z}; }
+static inline bool slab(const Ray &r, const float *lo, const float *hi, float &tn, float &tf)
+{
+    const float t0x = lo[0] * r.inv.x - r.oinv.x, t1x = hi[0] * r.inv.x - r.oinv.x;
+    const float t0y = lo[1] * r.inv.y - r.oinv.y, t1y = hi[1] * r.inv.y - r.oinv.y;
+    const float t0z = lo[2] * r.inv.z - r.oinv.z, t1z = hi[2] * r.inv.z - r.oinv.z;
+    tn = std::max(std::max(std::min(t0x, t1x), std::min(t0y, t1y)), std::min(t0z, t1z));
+    tf = std::min(std::min(std::max(t0x, t1x), std::max(t0y, t1y)), std::max(t0z, t1z));
+    return tn <= tf && tf >= 0.0f;
+}
+static inline float isect(const Ray &r, const Sphere &s)
+{
+    const V3 oc = r.o - V3{s.cx, s.cy, s.cz};
+    const float b = 2.0f * dot(oc, r.d), c = dot(oc, oc) - s.r * s.r, h = b * b - 4.0f * c;
+    if (h < 0.0f) return -1.0f;
+    return (-b - std::sqrt(h)) * 0.5f;
+}
+struct Best { float t; int idx; };
+static inline void leaf(const Ray &r, int si, Best &best, uint64_t &leaves)
+{
+    const Sphere &s = sph[si];
+    const float rp = s.r * 1.001f + 0.001f;
+    const float lo[3] = {s.cx - rp, s.cy - rp, s.cz - rp}, hi[3] = {s.cx + rp, s.cy + rp, s.cz + rp};
+    float tn, tf;
+    if (!slab(r, lo, hi, tn, tf) || !(tn <= best.t)) return;
+    ++leaves;
+    const float t = isect(r, s);
+    if (!(t > 1e-3f) || !(tn <= t)) return;
+    if (best.idx < 0) { if (t < r.B) { best.t = t; best.idx = si; } }
+    else if (t < best.t || (t == best.t && si < best.idx)) { best.t = t; best.idx = si; }
+}
+
+struct Cnt { uint64_t visits = 0, boxes = 0, leaves = 0, stale = 0, pushes = 0, maxsp = 0, popcull = 0; };
+
+// (a) the shipping binary walk; cull_pop: the entry's own tn travels with it and is re-checked at the pop
+static Best trav_binary(const Ray &r, bool cull_pop, int trunc_bits, Cnt &c)
+{
+    Best best{r.B, -1};
+    struct E { int ref; float tn; };
+    E stack[256]; int sp = 0;
+    int node = 0;
+    for (;;) {
+        if (node < 0) {
+            leaf(r, ~node, best, c.leaves);
+            if (r.any && best.idx >= 0) return best;
+        } else {
+            const Node &n = nodes[node];
+            ++c.visits; c.boxes += 2;
+            float tn0, tn1, tf;
+            const bool h0 = slab(r, n.c[0].lo, n.c[0].hi, tn0, tf) && tn0 <= best.t;
+            const bool h1 = slab(r, n.c[1].lo, n.c[1].hi, tn1, tf) && tn1 <= best.t;
+            const int c0 = n.c[0].kind ? ~n.c[0].index : n.c[0].index, c1 = n.c[1].kind ? ~n.c[1].index : n.c[1].index;
+            if (!h0 && !h1) ++c.stale;
+            const bool take1 = h1 && (!h0 || tn1 < tn0);
+            if (h0 && h1) { stack[sp++] = {take1 ? c0 : c1, take1 ? tn0 : tn1}; ++c.pushes; c.maxsp = std::max<uint64_t>(c.maxsp, sp); }
+            if (h0 || h1) { node = take1 ? c1 : c0; continue; }
+        }
+        for (;;) {
+            if (sp == 0) return best;
+            const E e = stack[--sp];
+            if (cull_pop) {
+                float tn = e.tn;
+                if (trunc_bits) { uint32_t u; memcpy(&u, &tn, 4); if (tn > 0) { u &= ~((1u << (23 - trunc_bits)) - 1u); memcpy(&tn, &u, 4); } else tn = 0.f; }
+                if (tn > best.t) { ++c.popcull; continue; }
+            }
+            node = e.ref; break;
+        }
+    }
+}
+
+// (c) k-wide collapse of the binary tree: open the inner child of largest area until k slots are used
+static std::vector<WNode> wide;
+static int build_wide(int bnode, int k)
+{
+    const int id = (int)wide.size();
+    wide.emplace_back();
+    std::vector<std::pair<Box, int>> slots;     // ref: >= 0 binary inner node, < 0 ~sphere
+    for (int j = 0; j < 2; ++j) {
+        const Child &ch = nodes[bnode].c[j];
+        Box b; memcpy(b.lo, ch.lo, 12); memcpy(b.hi, ch.hi, 12);
+        slots.push_back({b, ch.kind ? ~ch.index : ch.index});
+    }
+    while ((int)slots.size() < k) {
+        int pick = -1; float best = -1.f;
+        for (int j = 0; j < (int)slots.size(); ++j) if (slots[j].second >= 0 && area(slots[j].first) > best) { best = area(slots[j].first); pick = j; }
+        if (pick < 0) break;
+        const int bn = slots[pick].second;
+        slots.erase(slots.begin() + pick);
+        for (int j = 0; j < 2; ++j) {
+            const Child &ch = nodes[bn].c[j];
+            Box b; memcpy(b.lo, ch.lo, 12); memcpy(b.hi, ch.hi, 12);
+            slots.push_back({b, ch.kind ? ~ch.index : ch.index});
+        }
+    }
+    std::vector<WChild> cs;
+    for (auto &s : slots) cs.push_back({s.first, s.second});
+    for (auto &ch : cs) if (ch.ref >= 0) ch.ref = build_wide(ch.ref, k);
+    wide[id].c = cs;
+    return id;
+}
+// mode 0: hits sorted by tn, nearest first; mode 1: stored order (no sort); cull_pop as above
+static Best trav_wide(const Ray &r, int mode, bool cull_pop, Cnt &c)
+{
+    Best best{r.B, -1};
+    struct E { int ref; float tn; };
+    E stack[512]; int sp = 0;
+    int node = 0;
+    for (;;) {
+        if (node < 0) {
+            leaf(r, ~node, best, c.leaves);
+            if (r.any && best.idx >= 0) return best;
+        } else {
+            const WNode &n = wide[node];
+            ++c.visits; c.boxes += n.c.size();
+            E hit[16]; int nh = 0;
+            for (const WChild &ch : n.c) {
+                float tn, tf;
+                if (slab(r, ch.b.lo, ch.b.hi, tn, tf) && tn <= best.t) hit[nh++] = {ch.ref, tn};
+            }
+            if (nh == 0) ++c.stale;
+            if (mode == 0) std::sort(hit, hit + nh, [](const E &a, const E &b) { return a.tn < b.tn; });
+            for (int j = nh - 1; j >= 1; --j) { stack[sp++] = hit[j]; ++c.pushes; }
+            c.maxsp = std::max<uint64_t>(c.maxsp, sp);
+            if (nh) { node = hit[0].ref; continue; }
+        }
+        for (;;) {
+            if (sp == 0) return best;
+            const E e = stack[--sp];
+            if (cull_pop && e.tn > best.t) { ++c.popcull; continue; }
+            node = e.ref; break;
+        }
+    }
+}
+
+int main(int argc, char **argv)
+{
+    if (argc < 4) return 1;
+    {
+        FILE *f = fopen(argv[1], "rb"); fseek(f, 0, SEEK_END); const long n = ftell(f) / 16; fseek(f, 0, SEEK_SET);
+        sph.resize(n); if (fread(sph.data(), 16, n, f) != (size_t)n) return 2; fclose(f);
+    }
+    {
+        FILE *f = fopen(argv[2], "rb"); fseek(f, 0, SEEK_END); const long n = ftell(f) / 64; fseek(f, 0, SEEK_SET);
+        std::vector<float> raw(n * 16); if (fread(raw.data(), 64, n, f) != (size_t)n) return 2; fclose(f);
+        nodes.resize(n);
+        for (long i = 0; i < n; ++i)
+            for (int k = 0; k < 2; ++k) {
+                const float *p = raw.data() + i * 16 + k * 8;
+                Child &c = nodes[i].c[k];
+                c.lo[0] = p[0]; c.lo[1] = p[1]; c.lo[2] = p[2]; c.hi[0] = p[3]; c.hi[1] = p[4]; c.hi[2] = p[5];
+                memcpy(&c.index, p + 6, 4); memcpy(&c.kind, p + 7, 4);
+            }
+    }
+    const int n_rays = atoi(argv[3]);
+    std::mt19937 rng(12345);
+    std::uniform_real_distribution<float> U(0.f, 1.f);
+    std::vector<Ray> rays;
+    const V3 light{0.f, 96.f, 0.f};
+    for (int i = 0; i < n_rays; ++i) {
+        // origin: a point on a random sphere (70 %) or on a wall / floor (30 %); bounce = cosine lobe about the normal
+        V3 P, N;
+        if (U(rng) < 0.7f) {
+            const Sphere &s = sph[1 + (size_t)(U(rng) * (sph.size() - 1)) % (sph.size() - 1)];
+            const float z = 2.f * U(rng) - 1.f, ph = 6.2831853f * U(rng), rr = std::sqrt(std::max(0.f, 1.f - z * z));
+            N = {rr * std::cos(ph), z, rr * std::sin(ph)};
+            P = V3{s.cx, s.cy, s.cz} + N * s.r;
+        } else {
+            const int w = (int)(U(rng) * 5.f) % 5;
+            const float a = -60.f + 120.f * U(rng), b = -60.f + 120.f * U(rng), h = 128.f * U(rng);
+            if (w == 0) { P = {a, 0.f, b}; N = {0, 1, 0}; }
+            else if (w == 1) { P = {a, 128.f, b}; N = {0, -1, 0}; }
+            else if (w == 2) { P = {-64.f, h, b}; N = {1, 0, 0}; }
+            else if (w == 3) { P = {a, h, 64.f}; N = {0, 0, -1}; }
+            else { P = {64.f, h, b}; N = {-1, 0, 0}; }
+        }
+        Ray r;
+        r.o = P;
+        if (i & 1) {      // shadow ray towards the light sphere
+            const V3 L = light - P;
+            const float dist = std::sqrt(dot(L, L));
+            r.d = norm(L + V3{U(rng) - .5f, U(rng) - .5f, U(rng) - .5f} * 8.f);
+            if (dot(r.d, N) <= 0.f) { --i; continue; }      // zero-term rays are not traced
+            r.B = dist - 12.f + 1e-3f; r.any = true;
+        } else {
+            const V3 w = N, u = norm(cross(std::fabs(w.x) > .5f ? V3{0, 1, 0} : V3{1, 0, 0}, w)), v = cross(w, u);
+            const float r2 = U(rng), ph = 6.2831853f * U(rng), s = std::sqrt(r2), cz = std::sqrt(1.f - r2);
+            r.d = norm(u * (s * std::cos(ph)) + v * (s * std::sin(ph)) + w * cz);
+            const int depth = 1 + (int)(U(rng) * U(rng) * 7.f);
+            r.B = 3000.f / ((depth + 1.f) * (depth + 1.f)) + 1e-3f; r.any = false;
+        }
+        setup(r);
+        rays.push_back(r);
+    }
+    auto report = [&](const char *name, const Cnt &c, int kind) {
+        const double n = rays.size() / 2.0;
+        printf("%-34s %s  visits %6.2f  boxes %6.2f  leaves %5.2f  stale %5.2f  pushes %5.2f  popcull %5.2f  maxsp %d\n", name,
+               kind ? "shadow " : "nearest", c.visits / n, c.boxes / n, c.leaves / n, c.stale / n, c.pushes / n, c.popcull / n, (int)c.maxsp);
+    };
+    std::vector<Best> ref(rays.size());
+    for (int kind = 0; kind < 2; ++kind) {
+        Cnt c;
+        for (size_t i = kind; i < rays.size(); i += 2) ref[i] = trav_binary(rays[i], false, 0, c);
+        report("binary (shipping)", c, kind);
+    }
+    for (int kind = 0; kind < 2; ++kind) {
+        Cnt c;
+        for (size_t i = kind; i < rays.size(); i += 2) { const Best b = trav_binary(rays[i], true, 0, c); if (!rays[i].any && (b.idx != ref[i].idx)) printf("MISMATCH\n"); }
+        report("binary + tn on stack", c, kind);
+    }
+    for (int kind = 0; kind < 2; ++kind) {
+        Cnt c;
+        for (size_t i = kind; i < rays.size(); i += 2) trav_binary(rays[i], true, 5, c);
+        report("binary + 5-bit tn on stack", c, kind);
+    }
+    for (int k : {4, 8}) {
+        wide.clear();
+        build_wide(0, k);
+        double fill = 0; for (auto &w : wide) fill += w.c.size();
+        printf("-- %d-wide: %zu nodes, mean fill %.2f\n", k, wide.size(), fill / wide.size());
+        for (int mode = 0; mode < 2; ++mode)
+            for (int cp = 0; cp < 2; ++cp)
+                for (int kind = 0; kind < 2; ++kind) {
+                    Cnt c;
+                    for (size_t i = kind; i < rays.size(); i += 2) { const Best b = trav_wide(rays[i], mode, cp, c); if (!rays[i].any && (b.idx != ref[i].idx)) printf("MISMATCH\n"); }
+                    char nm[64]; snprintf(nm, sizeof nm, "%d-wide %s%s", k, mode ? "unsorted" : "sorted", cp ? " + tn on stack" : "");
+                    report(nm, c, kind);
+                }
+    }
+    return 0;
+}

@@ -5,7 +5,7 @@ import vk_renderer_b200 as V
 shard = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 scene = V.scenes.grid_spheres()
 w, h = 1920, 1080
-r = V.Renderer(w, h, spp=16, max_depth=8, variant=1, tile_shard=(0, shard))
+r = V.Renderer(w, h, spp=16, max_depth=8, variant=1, tile_shard=(0, shard), flags=V.FLAG_LAUNCH_TIMING)
 r.set_scene(scene); r.build_bvh(); r.set_seed(1)
 fd = V.default_frame_data(aspect_ratio=w / h)
 for i in range(6):

@@ -4,7 +4,7 @@ import vk_renderer_b200 as V
 scene = V.scenes.grid_spheres()
 for (w, h) in ((64, 64), (256, 256), (680, 384)):
     for variant in (1, 0):
-        r = V.Renderer(w, h, spp=16, max_depth=8, variant=variant)
+        r = V.Renderer(w, h, spp=16, max_depth=8, variant=variant, flags=V.FLAG_LAUNCH_TIMING)
         r.set_scene(scene); r.build_bvh(); r.set_seed(1)
         fd = V.default_frame_data(aspect_ratio=w / h)
         for i in range(3): r.draw(fd)

@@ -5,7 +5,7 @@ the host-side mirror of the reference's engine interface (device.py).  No CPU fa
 `_lib` builds/loads the CUDA library or raises.
 """
 from . import _lib
-from ._lib import (FLAG_HIT_IDS, FLAG_NO_RESOLVE, FLAG_PROGRESSIVE, FLAG_SERIAL_WAVES, FLAG_STATS, INTEGRATOR_PATH, INTEGRATOR_WHITTED,
+from ._lib import (FLAG_HIT_IDS, FLAG_LAUNCH_TIMING, FLAG_NO_RESOLVE, FLAG_PROGRESSIVE, FLAG_SERIAL_WAVES, FLAG_STATS, INTEGRATOR_PATH, INTEGRATOR_WHITTED,
                    SCENE_RAYTRACER, SCENE_TRACER, SEMAPHORE_ACQUIRE, SEMAPHORE_RELEASE, TILING_LINEAR, TILING_OPTIMAL,
                    VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT, FrameData, VkrtError)
 from .device import Camera, GraphicsDevice, default_camera, default_frame_data

@@ -17,7 +17,7 @@ ERROR_NAMES = ["SUCCESS", "NO_SUITABLE_GPU", "NO_SUITABLE_SURFACE", "UNKNOWN", "
 INTEGRATOR_WHITTED, INTEGRATOR_PATH = 0, 1
 VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT = 0, 1
 SCENE_TRACER, SCENE_RAYTRACER = 0, 1
-FLAG_PROGRESSIVE, FLAG_HIT_IDS, FLAG_STATS, FLAG_NO_RESOLVE, FLAG_SERIAL_WAVES = 1, 2, 4, 8, 16
+FLAG_PROGRESSIVE, FLAG_HIT_IDS, FLAG_STATS, FLAG_NO_RESOLVE, FLAG_SERIAL_WAVES, FLAG_LAUNCH_TIMING = 1, 2, 4, 8, 16, 32
 MAT_DIFFUSE, MAT_DIELECTRIC = 0, 1
 TILING_LINEAR, TILING_OPTIMAL = 0, 1
 SEMAPHORE_ACQUIRE, SEMAPHORE_RELEASE = 0, 1
@@ -50,7 +50,13 @@ class CreateInfo(C.Structure):
                 ("spp", C.c_uint32), ("max_depth", C.c_uint32), ("integrator", C.c_uint32),
                 ("variant", C.c_uint32), ("frames_in_flight", C.c_uint32), ("device_id", C.c_int32),
                 ("flags", C.c_uint32), ("tile_shard_rank", C.c_uint32), ("tile_shard_count", C.c_uint32),
-                ("sample_shard_rank", C.c_uint32), ("sample_shard_count", C.c_uint32), ("stream", C.c_void_p)]
+                ("sample_shard_rank", C.c_uint32), ("sample_shard_count", C.c_uint32), ("stream", C.c_void_p),
+                ("n_devices", C.c_uint32), ("device_ids", C.c_int32 * 8)]
+
+
+class ExchangeHandle(C.Structure):  # include/vkrt.h: the frame-exchange block of the gathering context (CUDA IPC)
+    _fields_ = [("ipc", C.c_uint8 * 64), ("bytes", C.c_uint64), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("tile_shard_count", C.c_uint32), ("sample_shard_count", C.c_uint32), ("magic", C.c_uint32), ("_pad", C.c_uint32)]
 
 
 class Counters(C.Structure):
@@ -69,7 +75,7 @@ class ExternalImage(C.Structure):  # include/vkrt.h: one exported traced image (
                 ("tiling", C.c_uint32), ("row_pitch", C.c_uint32), ("dedicated", C.c_uint32), ("_pad", C.c_uint32)]
 
 
-assert C.sizeof(ExternalImage) == 40
+assert C.sizeof(ExternalImage) == 40 and C.sizeof(ExchangeHandle) == 96
 assert C.sizeof(CameraData) == 64 and C.sizeof(FrameData) == 96 and C.sizeof(Triangle) == 48
 assert C.sizeof(Material) == 48
 assert FrameData.seed.offset == 4 and FrameData.light_pos.offset == 16 and FrameData.camera.offset == 32
@@ -123,6 +129,10 @@ SIGNATURES = {
     "vkrt_pack_shard_into": ([_vp, _vp, _sz], C.c_int8),
     "vkrt_shard_floats": ([_vp, _u32, _P(_sz)], C.c_int8),
     "vkrt_unpack_shard": ([_vp, _vp, _u32, _u32, _i32], C.c_int8),
+    "vkrt_exchange_create": ([_vp, _P(ExchangeHandle)], C.c_int8),
+    "vkrt_exchange_open": ([_vp, _P(ExchangeHandle)], C.c_int8),
+    "vkrt_exchange_attach": ([_vp, _vp], C.c_int8),
+    "vkrt_exchange_close": ([_vp], C.c_int8),
     "vkrt_measure_fp32_peak": ([_i32, _P(C.c_float)], C.c_int8),
     "vkrt_measure_l2_bandwidth": ([_i32, _P(C.c_float)], C.c_int8),
     "vkrt_last_error_string": ([_vp], C.c_char_p),

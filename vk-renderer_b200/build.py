@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libvkrt_cuda.so")
 OBJ = os.path.join(HERE, "..", "build")
-SOURCES = ["vkrt_render.cu", "vkrt_wavefront.cu", "vkrt_bvh.cu", "vkrt_api.cu", "vkrt_micro.cu"]
+SOURCES = ["vkrt_render.cu", "vkrt_wavefront.cu", "vkrt_bvh.cu", "vkrt_api.cu", "vkrt_exchange.cu", "vkrt_micro.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -44,7 +44,7 @@ struct ExtSlot {
     cudaSurfaceObject_t surf = 0;
     uchar4 *ptr = nullptr; size_t pitch = 0;  // kind 1
     cudaExternalSemaphore_t sem[2] = {nullptr, nullptr};
-    uint64_t resolves = 0;                    // resolves into this slot since its semaphores were imported
+    uint64_t frames = 0;                      // frames (per-draw resolves) written into this slot since its first semaphore was imported
 };
 
 struct vkrt_ctx {
@@ -96,6 +96,16 @@ struct vkrt_ctx {
     bool pending_join = false;     // the last frame ended on a lane stream that `stream` has not waited for yet
     bool timing_valid = false;
     uint32_t last_launches = 0;
+
+    // frame exchange (include/vkrt.h, csrc/vkrt_exchange.cu): the block in the gathering GPU's memory as this context sees it
+    struct Exchange {
+        char *base = nullptr; size_t bytes = 0;
+        bool owner = false, ipc = false;
+        uint32_t T = 1, S = 1, rank = 0;          // rank = sample_rank * T + tile_rank
+        uint64_t frame = 0;                        // frames drawn since the exchange was attached
+    } xch;
+    // in-library multi-GPU: this context is the gathering one, the children render the other tile shards
+    std::vector<vkrt_ctx *> children;
 };
 
 namespace {
@@ -216,7 +226,7 @@ void ext_release_target(ExtSlot &e)
 void ext_release_semaphores(ExtSlot &e)
 {
     for (auto &sm : e.sem) { if (sm) cudaDestroyExternalSemaphore(sm); sm = nullptr; }
-    e.resolves = 0;
+    e.frames = 0;
 }
 // The library never consumes the caller's descriptor: it imports a duplicate.  A successful import hands the
 // duplicate to the CUDA driver; after a failed one it is closed here unless the driver already did.
@@ -232,26 +242,55 @@ vkrt_error make_idle(vkrt_ctx *c)
 
 // The resolve of the frame into the current target (Tracer.comp:585-592), bracketed by the slot's semaphores: what
 // the reference's two vkCmdPipelineBarriers around the dispatch do (Source/GraphicsDevice.cpp:1234-1252, :1268-1284).
-vkrt_error resolve_current(vkrt_ctx *c, const RenderParams &rp, cudaStream_t st)
+// `frame` = this is the resolve of a new frame (vkrt_draw); an explicit re-resolve of the same frame (vkrt_resolve,
+// e.g. after a shard gather) rewrites the image the engine already owns for this frame and neither waits nor signals:
+// the engine never signals ACQUIRE twice for one frame, and a binary RELEASE must not be signalled twice.
+vkrt_error resolve_current(vkrt_ctx *c, const RenderParams &rp, cudaStream_t st, bool frame)
 {
     ExtSlot &e = c->ext[c->cur_target];
     ResolveTarget tg{c->d_rgba[c->cur_target], (size_t)c->info.width * 4u, 0};
     if (e.kind == 1) { tg.ptr = e.ptr; tg.pitch = e.pitch; }
     else if (e.kind == 2) { tg.ptr = nullptr; tg.surf = e.surf; }
-    ++e.resolves;
-    if (e.sem[VKRT_SEMAPHORE_ACQUIRE] && e.resolves >= 2) {
+    const bool sync = frame && (e.sem[VKRT_SEMAPHORE_ACQUIRE] || e.sem[VKRT_SEMAPHORE_RELEASE]);
+    if (sync) ++e.frames;
+    if (sync && e.sem[VKRT_SEMAPHORE_ACQUIRE] && e.frames >= 2) {
         cudaExternalSemaphoreWaitParams wp{};
-        wp.params.fence.value = e.resolves - 1;          // timeline semaphores; a binary semaphore ignores the value
+        wp.params.fence.value = e.frames - 1;            // timeline semaphores; a binary semaphore ignores the value
         CU(c, cudaWaitExternalSemaphoresAsync(&e.sem[VKRT_SEMAPHORE_ACQUIRE], &wp, 1, st));
     }
     CU(c, launch_resolve(rp, c->info.integrator, tg, st));
-    if (e.sem[VKRT_SEMAPHORE_RELEASE]) {
+    if (sync && e.sem[VKRT_SEMAPHORE_RELEASE]) {
         cudaExternalSemaphoreSignalParams sp{};
-        sp.params.fence.value = e.resolves;
+        sp.params.fence.value = e.frames;
         CU(c, cudaSignalExternalSemaphoresAsync(&e.sem[VKRT_SEMAPHORE_RELEASE], &sp, 1, st));
     }
     return VKRT_SUCCESS;
 }
+
+unsigned long long *x_done(vkrt_ctx *c, uint32_t r) { return reinterpret_cast<unsigned long long *>(c->xch.base) + (size_t)r * X_FLAG_STRIDE; }
+unsigned long long *x_consumed(vkrt_ctx *c) { return reinterpret_cast<unsigned long long *>(c->xch.base + X_OFF_CONSUMED); }
+uint32_t *x_error(vkrt_ctx *c) { return reinterpret_cast<uint32_t *>(c->xch.base + X_OFF_ERROR); }
+float4 *x_target(vkrt_ctx *c, uint64_t frame, uint32_t sample_group)
+{
+    const size_t n_px = (size_t)c->info.width * c->info.height;
+    return reinterpret_cast<float4 *>(c->xch.base + X_OFF_TARGETS) + ((size_t)(frame & 1u) * c->xch.S + sample_group) * n_px;
+}
+const uint32_t X_MAGIC = 0x58524b56u;     // "VKRX"
+
+// a context on one device (the shard fields of `info` say which part of the frame it renders)
+vkrt_error create_single(const vkrt_create_info *info, vkrt_ctx **out_ctx);
+
+// applies a call to the other devices' contexts of an in-library multi-GPU context
+template <class F>
+vkrt_error for_children(vkrt_ctx *c, F f)
+{
+    for (vkrt_ctx *ch : c->children) {
+        const vkrt_error r = f(ch);
+        if (r != VKRT_SUCCESS) return fail(c, r, "device " + std::to_string(ch->info.device_id) + ": " + ch->err);
+    }
+    return VKRT_SUCCESS;
+}
+#define FWD(c, call) do { if (!(c)->children.empty()) { const vkrt_error _r = for_children((c), [&](vkrt_ctx *ch) { return call; }); if (_r != VKRT_SUCCESS) return _r; } } while (0)
 
 } // namespace
 
@@ -266,12 +305,60 @@ VKRT_API vkrt_error vkrt_create(const vkrt_create_info *info, vkrt_ctx **out_ctx
     if (!info || !out_ctx) return fail(nullptr, VKRT_BAD_ARG, "null argument");
     *out_ctx = nullptr;
     if (info->struct_size != sizeof(vkrt_create_info)) return fail(nullptr, VKRT_BAD_ARG, "vkrt_create_info.struct_size mismatch");
+    if (info->n_devices <= 1) {
+        vkrt_create_info one = *info;
+        if (info->n_devices == 1) one.device_id = info->device_ids[0];
+        one.n_devices = 0;
+        return create_single(&one, out_ctx);
+    }
+    // in-library multi-GPU: one context per device, interleaved tile shards, frame exchange into device_ids[0]
+    const uint32_t n = info->n_devices;
+    if (n > 8) return fail(nullptr, VKRT_BAD_ARG, "n_devices > 8");
+    if (info->tile_shard_count > 1 || info->sample_shard_count > 1 || info->tile_shard_rank || info->sample_shard_rank)
+        return fail(nullptr, VKRT_BAD_ARG, "n_devices > 1: the library shards the frame by itself, leave the shard fields 0");
+    if (info->flags & VKRT_FLAG_NO_RESOLVE) return fail(nullptr, VKRT_BAD_ARG, "n_devices > 1 with VKRT_FLAG_NO_RESOLVE");
+    for (uint32_t i = 0; i < n; ++i)
+        for (uint32_t j = 0; j < i; ++j)
+            if (info->device_ids[i] == info->device_ids[j]) return fail(nullptr, VKRT_BAD_ARG, "device_ids must be distinct");
+    vkrt_ctx *parent = nullptr;
+    vkrt_create_info one = *info;
+    one.n_devices = 0; one.device_id = info->device_ids[0]; one.tile_shard_rank = 0; one.tile_shard_count = n;
+    vkrt_error r = create_single(&one, &parent);
+    if (r != VKRT_SUCCESS) return r;
+    vkrt_exchange_handle h;
+    r = vkrt_exchange_create(parent, &h);
+    if (r != VKRT_SUCCESS) { g_create_error = parent->err; vkrt_destroy(parent); return r; }
+    for (uint32_t i = 1; i < n; ++i) {
+        vkrt_ctx *ch = nullptr;
+        one.device_id = info->device_ids[i]; one.tile_shard_rank = i; one.stream = nullptr;
+        one.flags = (info->flags | VKRT_FLAG_NO_RESOLVE) & ~(uint32_t)VKRT_FLAG_PROGRESSIVE;
+        r = create_single(&one, &ch);
+        if (r == VKRT_SUCCESS) {
+            parent->children.push_back(ch);
+            r = vkrt_exchange_attach(ch, parent);
+            if (r != VKRT_SUCCESS) g_create_error = ch->err;
+        }
+        if (r != VKRT_SUCCESS) { vkrt_destroy(parent); return r; }
+    }
+    *out_ctx = parent;
+    return VKRT_SUCCESS;
+}
+
+} // extern "C"
+
+namespace {
+vkrt_error create_single(const vkrt_create_info *info, vkrt_ctx **out_ctx)
+{
     if (info->width == 0 || info->height == 0 || info->width > 65536 || info->height > 65536)
         return fail(nullptr, VKRT_BAD_ARG, "bad resolution");
     if ((uint64_t)info->width * info->height > ((uint64_t)1 << 30))
         return fail(nullptr, VKRT_BAD_ARG, "more than 2^30 pixels (pixel and path indices are 32-bit)");
     if (info->integrator > VKRT_INTEGRATOR_PATH || info->variant > VKRT_VARIANT_WAVEFRONT)
         return fail(nullptr, VKRT_BAD_ARG, "bad integrator / variant");
+    // the same ranges as vkrt_set_sampling (0 = the shader's default): the wavefront keeps one counter set per depth
+    // (C_SETS) and packs the depth into 8 bits of the path record, the sample index into 24
+    if (info->spp > (1u << 24) || info->max_depth > 255)
+        return fail(nullptr, VKRT_BAD_ARG, "spp / max_depth out of range (spp <= 2^24, max_depth <= 255)");
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
         cudaGetLastError();
@@ -327,12 +414,19 @@ VKRT_API vkrt_error vkrt_create(const vkrt_create_info *info, vkrt_ctx **out_ctx
     *out_ctx = c;
     return VKRT_SUCCESS;
 }
+} // namespace
+
+extern "C" {
 
 VKRT_API vkrt_error vkrt_destroy(vkrt_ctx *c)
 {
     if (!c) return VKRT_BAD_ARG;
+    if (!c->children.empty()) vkrt_wait_idle(c);       // the devices wait for each other's frame counters
+    for (vkrt_ctx *ch : c->children) vkrt_destroy(ch);
+    c->children.clear();
     DeviceGuard g(c->info.device_id);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->xch.base) vkrt_exchange_close(c);
     cudaFree(c->d_spheres); cudaFree(c->d_sphere_mat); cudaFree(c->d_mats); cudaFree(c->d_tris);
     cudaFree(c->bvh.nodes); cudaFree(c->bvh.nodes4); cudaFree(c->bvh.qnodes); cudaFree(c->d_accum); cudaFree(c->d_hit_ids);
     for (auto p : c->d_rgba) cudaFree(p);
@@ -354,10 +448,23 @@ VKRT_API vkrt_error vkrt_set_sampling(vkrt_ctx *c, uint32_t spp, uint32_t max_de
     if (!c) return VKRT_BAD_ARG;
     if (spp == 0 || max_depth == 0 || spp > (1u << 24) || max_depth > 255) return fail(c, VKRT_BAD_ARG, "spp / max_depth out of range");
     c->spp = spp; c->max_depth = max_depth;
+    FWD(c, vkrt_set_sampling(ch, spp, max_depth));
     return VKRT_SUCCESS;
 }
-VKRT_API vkrt_error vkrt_set_seed(vkrt_ctx *c, uint64_t seed) { if (!c) return VKRT_BAD_ARG; c->seed = seed; return VKRT_SUCCESS; }
-VKRT_API vkrt_error vkrt_set_frame_index(vkrt_ctx *c, uint32_t i) { if (!c) return VKRT_BAD_ARG; c->frame_index = i; return VKRT_SUCCESS; }
+VKRT_API vkrt_error vkrt_set_seed(vkrt_ctx *c, uint64_t seed)
+{
+    if (!c) return VKRT_BAD_ARG;
+    c->seed = seed;
+    FWD(c, vkrt_set_seed(ch, seed));
+    return VKRT_SUCCESS;
+}
+VKRT_API vkrt_error vkrt_set_frame_index(vkrt_ctx *c, uint32_t i)
+{
+    if (!c) return VKRT_BAD_ARG;
+    c->frame_index = i;
+    FWD(c, vkrt_set_frame_index(ch, i));
+    return VKRT_SUCCESS;
+}
 VKRT_API vkrt_error vkrt_reset_accum(vkrt_ctx *c)
 {
     if (!c) return VKRT_BAD_ARG;
@@ -373,12 +480,14 @@ VKRT_API vkrt_error vkrt_set_triangles(vkrt_ctx *c, const vkrt_triangle *t, uint
 {
     if (!c || (n && !t)) return VKRT_BAD_ARG;
     c->tris.assign(t, t + n); c->scene_dirty = true;
+    FWD(c, vkrt_set_triangles(ch, t, n));
     return VKRT_SUCCESS;
 }
 VKRT_API vkrt_error vkrt_set_triangle_material(vkrt_ctx *c, uint32_t mat_id)
 {
     if (!c) return VKRT_BAD_ARG;
     c->tri_mat = mat_id; c->scene_dirty = true;
+    FWD(c, vkrt_set_triangle_material(ch, mat_id));
     return VKRT_SUCCESS;
 }
 VKRT_API vkrt_error vkrt_set_materials(vkrt_ctx *c, const vkrt_material *m, uint32_t n)
@@ -386,6 +495,7 @@ VKRT_API vkrt_error vkrt_set_materials(vkrt_ctx *c, const vkrt_material *m, uint
     if (!c || (n && !m)) return VKRT_BAD_ARG;
     for (uint32_t i = 0; i < n; ++i) if (m[i].type > 1u) return fail(c, VKRT_BAD_ARG, "unknown material type");
     c->mats.assign(m, m + n); c->scene_dirty = true;
+    FWD(c, vkrt_set_materials(ch, m, n));
     return VKRT_SUCCESS;
 }
 VKRT_API vkrt_error vkrt_set_spheres(vkrt_ctx *c, const vkrt_sphere *s, const uint32_t *mat_id, uint32_t n)
@@ -394,6 +504,7 @@ VKRT_API vkrt_error vkrt_set_spheres(vkrt_ctx *c, const vkrt_sphere *s, const ui
     c->spheres.assign(s, s + n); c->sphere_mat.assign(mat_id, mat_id + n);
     c->use_bvh = false;                       // a new sphere list invalidates the tree
     c->scene_dirty = true;
+    FWD(c, vkrt_set_spheres(ch, s, mat_id, n));
     return VKRT_SUCCESS;
 }
 VKRT_API vkrt_error vkrt_set_planes(vkrt_ctx *c, const vkrt_plane *p, const uint32_t *mat_id, uint32_t n)
@@ -401,6 +512,7 @@ VKRT_API vkrt_error vkrt_set_planes(vkrt_ctx *c, const vkrt_plane *p, const uint
     if (!c || (n && (!p || !mat_id))) return VKRT_BAD_ARG;
     if (n > MAX_PLANES) return fail(c, VKRT_BAD_ARG, "more than 16 planes");
     c->planes.assign(p, p + n); c->plane_mat.assign(mat_id, mat_id + n); c->scene_dirty = true;
+    FWD(c, vkrt_set_planes(ch, p, mat_id, n));
     return VKRT_SUCCESS;
 }
 
@@ -459,12 +571,14 @@ VKRT_API vkrt_error vkrt_build_bvh(vkrt_ctx *c)
     CU(c, build_lbvh(c->d_spheres, (uint32_t)c->spheres.size(), c->bvh, c->stream));
     c->use_bvh = true;
     c->scene_dirty = true;
+    FWD(c, vkrt_build_bvh(ch));                // the build is deterministic: every device gets the identical tree
     return VKRT_SUCCESS;
 }
 VKRT_API vkrt_error vkrt_clear_bvh(vkrt_ctx *c)
 {
     if (!c) return VKRT_BAD_ARG;
     c->use_bvh = false; c->scene_dirty = true;
+    FWD(c, vkrt_clear_bvh(ch));
     return VKRT_SUCCESS;
 }
 VKRT_API vkrt_error vkrt_get_bvh_info(vkrt_ctx *c, vkrt_bvh_info *out)
@@ -504,6 +618,7 @@ VKRT_API vkrt_error vkrt_read_bvh_qnodes(vkrt_ctx *c, uint32_t *host, size_t byt
 VKRT_API vkrt_error vkrt_draw(vkrt_ctx *c, const vkrt_frame_data *frame)
 {
     if (!c || !frame) return VKRT_BAD_ARG;
+    FWD(c, vkrt_draw(ch, frame));                 // the other devices' shards of this frame first: they only enqueue
     DeviceGuard g(c->info.device_id);
     vkrt_error r = upload_scene(c);
     if (r != VKRT_SUCCESS) return r;
@@ -517,6 +632,16 @@ VKRT_API vkrt_error vkrt_draw(vkrt_ctx *c, const vkrt_frame_data *frame)
     rp.accumulate = (progressive && c->accum_valid) ? 1u : 0u;
     const bool stats = (c->info.flags & VKRT_FLAG_STATS) != 0;
     uint32_t launches = 0;
+    // frame exchange: this frame's pixels go straight into the frame target in the gathering GPU's memory.  The target
+    // was last read by the collect of frame f - 2; the kernels that overwrite it are ordered behind ev_consumed below.
+    const bool exchange = c->xch.base != nullptr;
+    const uint64_t xf = c->xch.frame;
+    if (exchange) {
+        CU(c, join(c));
+        if (!c->xch.owner && xf >= 2) { CU(c, launch_xwait(x_consumed(c), 1, 0, xf - 1, x_error(c), c->stream)); ++launches; }
+        rp.accum = x_target(c, xf, c->info.sample_shard_rank);
+        rp.accumulate = 0;                          // VKRT_FLAG_PROGRESSIVE is applied by the gathering context's collect
+    }
 
     // everything enqueued on the stream so far may still read the previous frame's accumulator / AOVs / image, and
     // so may that frame's own resolve on its lane stream: the stream joins the previous frame first (that does not
@@ -534,7 +659,7 @@ VKRT_API vkrt_error vkrt_draw(vkrt_ctx *c, const vkrt_frame_data *frame)
         if (c->info.integrator == VKRT_INTEGRATOR_WHITTED) {
             CU(c, launch_whitted(c->dev, rp, c->use_bvh, stats, c->stream)); ++launches;
         } else if (wavefront) {
-            if (!c->wave_ready) {
+            {
                 // two lanes of up to 8 samples of every owned pixel each (one lane when spp == 1), at most
                 // 32 Mi path records per lane (~3.5 GB of HBM)
                 const size_t slots = (size_t)c->owned_tiles * TILE_PX;
@@ -543,11 +668,26 @@ VKRT_API vkrt_error vkrt_draw(vkrt_ctx *c, const vkrt_frame_data *frame)
                 if (per_wave > 16 / lanes) per_wave = 16 / lanes;
                 while (per_wave > 1 && slots * per_wave > ((size_t)64 << 20) / lanes) --per_wave;
                 // VKRT_FLAG_SERIAL_WAVES: waves of the same size, one buffer set, one stream
-                CU(c, wave_engine_init(c->wave, slots * per_wave, (c->info.flags & VKRT_FLAG_SERIAL_WAVES) ? 1u : lanes));
-                c->wave_ready = true;
+                const uint32_t eng_lanes = (c->info.flags & VKRT_FLAG_SERIAL_WAVES) ? 1u : lanes;
+                const size_t cap = slots * per_wave;
+                if (cap >= ((size_t)1 << 28))
+                    return fail(c, VKRT_BAD_ARG, "the wavefront variant holds at most 2^28 path records per wave: this context owns too many "
+                                                 "pixels (shard the frame by tiles, or use the megakernel variant)");
+                // sized from the sampling in force: vkrt_set_sampling may have changed it since the last draw
+                if (c->wave_ready && (c->wave.n_lanes != eng_lanes || c->wave.lane[0].capacity != cap)) {
+                    CU(c, cudaDeviceSynchronize());
+                    wave_engine_free(c->wave);
+                    c->wave_ready = false;
+                    c->pending_join = false;
+                }
+                if (!c->wave_ready) {
+                    CU(c, wave_engine_init(c->wave, cap, eng_lanes));
+                    c->wave_ready = true;
+                }
             }
             uint32_t nl = 0;
-            CU(c, launch_path_wavefront(c->dev, rp, c->wave, c->use_bvh, stats, c->sm_count, c->stream, c->ev_consumed,
+            CU(c, launch_path_wavefront(c->dev, rp, c->wave, c->use_bvh, stats, (c->info.flags & VKRT_FLAG_LAUNCH_TIMING) != 0,
+                                        c->sm_count, c->stream, c->ev_consumed,
                                         c->ev_begin, &tail, &nl));
             launches += nl;
         } else {
@@ -558,11 +698,24 @@ VKRT_API vkrt_error vkrt_draw(vkrt_ctx *c, const vkrt_frame_data *frame)
         CU(c, cudaEventRecord(c->ev_begin, c->stream));
     }
     CU(c, cudaEventRecord(c->ev_trace1, tail));
+    if (exchange) {
+        // publish "frame xf of this rank is complete" next to the pixels; the gathering context then waits (on the
+        // device) for every rank, adds the sample groups in rank order and frees the target for frame xf + 2
+        CU(c, launch_xsignal(x_done(c, c->xch.rank), xf + 1, tail)); ++launches;
+        if (c->xch.owner) {
+            CU(c, launch_xwait(x_done(c, 0), c->xch.T * c->xch.S, X_FLAG_STRIDE, xf + 1, x_error(c), tail)); ++launches;
+            CU(c, launch_xcollect(c->d_accum, x_target(c, xf, 0), (size_t)c->info.width * c->info.height, c->xch.S,
+                                  (progressive && c->accum_valid) ? 1 : 0, tail)); ++launches;
+            CU(c, launch_xsignal(x_consumed(c), xf + 1, tail)); ++launches;
+        }
+        rp.accum = c->d_accum;
+        ++c->xch.frame;
+    }
     // frame k targets traced_images[k % FRAMES_IN_FLIGHT] (state.currentFrame, :1234 / :1341); cur_target stays on the
     // most recent frame's slot afterwards, which is what the read-backs return
     c->cur_target = (c->cur_target + 1) % (uint32_t)c->d_rgba.size();
-    if (!(c->info.flags & VKRT_FLAG_NO_RESOLVE)) {
-        r = resolve_current(c, rp, tail); ++launches;
+    if (!(c->info.flags & VKRT_FLAG_NO_RESOLVE) && !(exchange && !c->xch.owner)) {     // only the gathering rank has the whole frame
+        r = resolve_current(c, rp, tail, true); ++launches;
         if (r != VKRT_SUCCESS) return r;
     }
     CU(c, cudaEventRecord(c->ev_end, tail));
@@ -582,7 +735,7 @@ VKRT_API vkrt_error vkrt_resolve(vkrt_ctx *c)
     CU(c, join(c));
     RenderParams rp;
     fill_params(c, rp);
-    return resolve_current(c, rp, c->stream);
+    return resolve_current(c, rp, c->stream, false);
 }
 
 VKRT_API vkrt_error vkrt_wait_idle(vkrt_ctx *c)
@@ -591,6 +744,12 @@ VKRT_API vkrt_error vkrt_wait_idle(vkrt_ctx *c)
     DeviceGuard g(c->info.device_id);
     CU(c, join(c));
     CU(c, cudaStreamSynchronize(c->stream));
+    FWD(c, vkrt_wait_idle(ch));
+    if (c->xch.base) {
+        uint32_t err = 0;
+        CU(c, cudaMemcpy(&err, x_error(c), sizeof err, cudaMemcpyDeviceToHost));
+        if (err) return fail(c, VKRT_NCCL_ERROR, "frame exchange: a rank did not deliver its frame within the time limit");
+    }
     return VKRT_SUCCESS;
 }
 
@@ -692,6 +851,14 @@ VKRT_API vkrt_error vkrt_get_counters(vkrt_ctx *c, vkrt_counters *out)
     out->closest_rays = h[CNT_CLOSEST]; out->shadow_rays = h[CNT_SHADOW]; out->node_visits = h[CNT_NODES];
     out->leaf_tests = h[CNT_LEAVES]; out->paths = h[CNT_PATHS]; out->frames = c->frames;
     out->shared_primary_rays = h[CNT_SHARED]; out->zero_term_shadow_rays = h[CNT_SKIPPED];
+    for (vkrt_ctx *ch : c->children) {           // one frame, several devices: the rays add up, the frames do not
+        vkrt_counters o;
+        const vkrt_error r = vkrt_get_counters(ch, &o);
+        if (r != VKRT_SUCCESS) return fail(c, r, ch->err);
+        out->closest_rays += o.closest_rays; out->shadow_rays += o.shadow_rays; out->node_visits += o.node_visits;
+        out->leaf_tests += o.leaf_tests; out->paths += o.paths;
+        out->shared_primary_rays += o.shared_primary_rays; out->zero_term_shadow_rays += o.zero_term_shadow_rays;
+    }
     return VKRT_SUCCESS;
 }
 VKRT_API vkrt_error vkrt_reset_counters(vkrt_ctx *c)
@@ -701,6 +868,7 @@ VKRT_API vkrt_error vkrt_reset_counters(vkrt_ctx *c)
     CU(c, join(c));
     CU(c, cudaMemsetAsync(c->d_counters, 0, CNT_N * sizeof(unsigned long long), c->stream));
     c->frames = 0;
+    FWD(c, vkrt_reset_counters(ch));
     return VKRT_SUCCESS;
 }
 VKRT_API vkrt_error vkrt_last_frame_timing(vkrt_ctx *c, float *trace_ms, float *total_ms, uint32_t *n_launches)
@@ -726,6 +894,8 @@ VKRT_API vkrt_error vkrt_last_frame_traversal_timing(vkrt_ctx *c, float *travers
     CU(c, cudaEventSynchronize(c->ev_end));
     float sum = 0.f, all = 0.f; uint32_t n = 0;
     if (c->info.integrator == VKRT_INTEGRATOR_PATH && c->info.variant == VKRT_VARIANT_WAVEFRONT && c->wave_ready) {
+        if (!(c->info.flags & VKRT_FLAG_LAUNCH_TIMING))
+            return fail(c, VKRT_BAD_ARG, "per-launch timing needs a context created with VKRT_FLAG_LAUNCH_TIMING");
         for (uint32_t l = 0; l < c->wave.n_lanes; ++l)
             for (uint32_t i = 0; i + 1 < c->wave.lane[l].n_ev; i += 2) {
                 const uint8_t tag = c->wave.lane[l].ev_tag[i / 2];
@@ -751,6 +921,7 @@ VKRT_API vkrt_error vkrt_debug_dump_timeline(vkrt_ctx *c, const char *path)
 {
     if (!c || !path) return VKRT_BAD_ARG;
     if (!c->timing_valid || !c->wave_ready) return fail(c, VKRT_BAD_ARG, "no wavefront frame drawn yet");
+    if (!(c->info.flags & VKRT_FLAG_LAUNCH_TIMING)) return fail(c, VKRT_BAD_ARG, "the timeline needs a context created with VKRT_FLAG_LAUNCH_TIMING");
     DeviceGuard g(c->info.device_id);
     CU(c, cudaEventSynchronize(c->ev_end));
     FILE *f = std::fopen(path, "w");
@@ -917,9 +1088,11 @@ VKRT_API vkrt_error vkrt_import_vk_semaphore(vkrt_ctx *c, uint32_t slot, uint32_
     const cudaError_t ce = cudaImportExternalSemaphore(&sem, &sd);
     if (ce != cudaSuccess) { cudaGetLastError(); close_if_open(own); return cuda_fail(c, ce, "cudaImportExternalSemaphore"); }
     ExtSlot &e = c->ext[slot];
+    // the frame count both timelines are derived from starts with the slot's FIRST semaphore; importing the second
+    // one (or replacing one) later does not move it back
+    if (!e.sem[VKRT_SEMAPHORE_ACQUIRE] && !e.sem[VKRT_SEMAPHORE_RELEASE]) e.frames = 0;
     if (e.sem[which]) cudaDestroyExternalSemaphore(e.sem[which]);
     e.sem[which] = sem;
-    e.resolves = 0;
     return VKRT_SUCCESS;
 }
 
@@ -979,6 +1152,102 @@ VKRT_API vkrt_error vkrt_unpack_shard(vkrt_ctx *c, const float *dev_packed, uint
     CU(c, join(c));
     CU(c, launch_unpack(c->d_accum, (const float4 *)dev_packed, c->info.width, c->info.height, tile_rank, tile_count, add, c->stream));
     c->accum_valid = true;
+    return VKRT_SUCCESS;
+}
+
+// ---- frame exchange over peer memory (csrc/vkrt_exchange.cu) ---------------------------------------
+static vkrt_error exchange_bind(vkrt_ctx *c, char *base, size_t bytes, bool owner, bool ipc)
+{
+    c->xch = vkrt_ctx::Exchange{};
+    c->xch.base = base; c->xch.bytes = bytes; c->xch.owner = owner; c->xch.ipc = ipc;
+    c->xch.T = c->info.tile_shard_count; c->xch.S = c->info.sample_shard_count;
+    c->xch.rank = c->info.sample_shard_rank * c->info.tile_shard_count + c->info.tile_shard_rank;
+    return VKRT_SUCCESS;
+}
+static size_t exchange_bytes(const vkrt_ctx *c)
+{
+    return (size_t)X_OFF_TARGETS + (size_t)2 * c->info.sample_shard_count * c->info.width * c->info.height * sizeof(float4);
+}
+VKRT_API vkrt_error vkrt_exchange_create(vkrt_ctx *c, vkrt_exchange_handle *out)
+{
+    if (!c || !out) return VKRT_BAD_ARG;
+    if (c->info.tile_shard_rank != 0 || c->info.sample_shard_rank != 0)
+        return fail(c, VKRT_BAD_ARG, "the exchange block belongs to the gathering context (tile rank 0, sample rank 0)");
+    if ((uint64_t)c->info.tile_shard_count * c->info.sample_shard_count > X_MAX_RANKS) return fail(c, VKRT_BAD_ARG, "more than 64 ranks");
+    if (c->xch.base) return fail(c, VKRT_BAD_ARG, "an exchange is already attached");
+    DeviceGuard g(c->info.device_id);
+    vkrt_error r = make_idle(c);
+    if (r != VKRT_SUCCESS) return r;
+    const size_t bytes = exchange_bytes(c);
+    char *base = nullptr;
+    CU(c, cudaMalloc((void **)&base, bytes));
+    cudaError_t e = cudaMemset(base, 0, bytes);
+    std::memset(out, 0, sizeof *out);
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) <= sizeof(out->ipc), "cudaIpcMemHandle_t is 64 bytes");
+    // the handle is only needed by other processes; a device without IPC support still serves vkrt_exchange_attach
+    if (e == cudaSuccess && cudaIpcGetMemHandle(&h, base) == cudaSuccess) std::memcpy(out->ipc, &h, sizeof h);
+    else cudaGetLastError();
+    if (e != cudaSuccess) { cudaFree(base); return cuda_fail(c, e, "cudaMemset(exchange block)"); }
+    out->bytes = bytes; out->width = c->info.width; out->height = c->info.height;
+    out->tile_shard_count = c->info.tile_shard_count; out->sample_shard_count = c->info.sample_shard_count; out->magic = X_MAGIC;
+    return exchange_bind(c, base, bytes, true, false);
+}
+static vkrt_error exchange_check_peer(vkrt_ctx *c, uint32_t w, uint32_t h, uint32_t T, uint32_t S)
+{
+    if (c->xch.base) return fail(c, VKRT_BAD_ARG, "an exchange is already attached");
+    if (w != c->info.width || h != c->info.height || T != c->info.tile_shard_count || S != c->info.sample_shard_count)
+        return fail(c, VKRT_BAD_ARG, "the exchange block was made for another frame size / shard layout");
+    if (c->info.tile_shard_rank == 0 && c->info.sample_shard_rank == 0)
+        return fail(c, VKRT_BAD_ARG, "rank (0, 0) is the gathering context: it creates the exchange block");
+    if ((c->info.flags & VKRT_FLAG_PROGRESSIVE) != 0) return fail(c, VKRT_BAD_ARG, "VKRT_FLAG_PROGRESSIVE belongs to the gathering context only");
+    return VKRT_SUCCESS;
+}
+VKRT_API vkrt_error vkrt_exchange_open(vkrt_ctx *c, const vkrt_exchange_handle *hd)
+{
+    if (!c || !hd) return VKRT_BAD_ARG;
+    if (hd->magic != X_MAGIC) return fail(c, VKRT_BAD_ARG, "not an exchange handle");
+    vkrt_error r = exchange_check_peer(c, hd->width, hd->height, hd->tile_shard_count, hd->sample_shard_count);
+    if (r != VKRT_SUCCESS) return r;
+    if (hd->bytes != exchange_bytes(c)) return fail(c, VKRT_BAD_ARG, "exchange block size mismatch");
+    DeviceGuard g(c->info.device_id);
+    r = make_idle(c);
+    if (r != VKRT_SUCCESS) return r;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, hd->ipc, sizeof h);
+    void *base = nullptr;
+    CU(c, cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    return exchange_bind(c, (char *)base, (size_t)hd->bytes, false, true);
+}
+VKRT_API vkrt_error vkrt_exchange_attach(vkrt_ctx *c, vkrt_ctx *owner)
+{
+    if (!c || !owner) return VKRT_BAD_ARG;
+    if (!owner->xch.base || !owner->xch.owner) return fail(c, VKRT_BAD_ARG, "the gathering context has no exchange block (vkrt_exchange_create)");
+    vkrt_error r = exchange_check_peer(c, owner->info.width, owner->info.height, owner->info.tile_shard_count, owner->info.sample_shard_count);
+    if (r != VKRT_SUCCESS) return r;
+    DeviceGuard g(c->info.device_id);
+    r = make_idle(c);
+    if (r != VKRT_SUCCESS) return r;
+    if (c->info.device_id != owner->info.device_id) {
+        int can = 0;
+        CU(c, cudaDeviceCanAccessPeer(&can, c->info.device_id, owner->info.device_id));
+        if (!can) return fail(c, VKRT_NO_SUITABLE_GPU, "no peer access between the devices (NVLink / PCIe P2P)");
+        const cudaError_t e = cudaDeviceEnablePeerAccess(owner->info.device_id, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(c, e, "cudaDeviceEnablePeerAccess");
+        cudaGetLastError();
+    }
+    return exchange_bind(c, owner->xch.base, owner->xch.bytes, false, false);
+}
+VKRT_API vkrt_error vkrt_exchange_close(vkrt_ctx *c)
+{
+    if (!c) return VKRT_BAD_ARG;
+    if (!c->xch.base) return VKRT_SUCCESS;
+    DeviceGuard g(c->info.device_id);
+    cudaDeviceSynchronize();
+    cudaGetLastError();
+    if (c->xch.owner) cudaFree(c->xch.base);
+    else if (c->xch.ipc) cudaIpcCloseMemHandle(c->xch.base);
+    c->xch = vkrt_ctx::Exchange{};
     return VKRT_SUCCESS;
 }
 

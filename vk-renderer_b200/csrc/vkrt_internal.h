@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <vector>
 #include "../../include/vkrt.h"
 
 namespace vkrt {
@@ -58,10 +59,11 @@ struct WaveBuffers {
     uint8_t *occ;                 // their any-hit results
     uint32_t *queue_shadow;       // (path << 4 | light) items that still need the sphere any-hit query
     uint32_t shadow_lights;
-    // CUDA-event pairs around every traversal-kernel launch of the last frame (roofline timing)
-    cudaEvent_t ev[128];
-    uint8_t ev_tag[64];           // kernel of pair k = (ev[2k], ev[2k+1]): 0 generate 1 extend 2 classify 3 shadow 4 shade 5 reduce
-    uint32_t n_ev, ev_created;
+    // VKRT_FLAG_LAUNCH_TIMING: CUDA-event pairs around every kernel launch of the last frame (roofline timing); the pool
+    // grows with the number of launches, nothing is dropped
+    std::vector<cudaEvent_t> ev;
+    std::vector<uint8_t> ev_tag;  // kernel of pair k = (ev[2k], ev[2k+1]): 0 generate 1 extend 2 classify 3 shadow 4 shade 5 reduce
+    uint32_t n_ev;                // events recorded by the last frame
 };
 cudaError_t wave_alloc(WaveBuffers &wb, size_t capacity);
 void wave_free(WaveBuffers &wb);
@@ -81,7 +83,7 @@ void wave_engine_free(WaveEngine &eng);
 // previous frame has been enqueued; only the kernels that overwrite those wait for it, so the bulk of a frame
 // overlaps the tail (and the read-back / gather) of the frame before -- two frames in flight, like the
 // reference's FRAMES_IN_FLIGHT (Source/Main.cpp:110).  *tail = the stream the frame's last kernel went to.
-cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, WaveEngine &eng, bool bvh, bool stats,
+cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, WaveEngine &eng, bool bvh, bool stats, bool timing,
                                   int sm_count, cudaStream_t st, cudaEvent_t ev_consumed, cudaEvent_t ev_begin,
                                   cudaStream_t *tail, uint32_t *n_launches);
 
@@ -96,6 +98,12 @@ struct BvhBuild {
     uint32_t launches = 0;
 };
 cudaError_t build_lbvh(const float4 *d_spheres, uint32_t n, BvhBuild &out, cudaStream_t st);
+
+// vkrt_exchange.cu: device-side synchronisation and collection of the multi-GPU frame exchange
+enum { X_MAX_RANKS = 64, X_FLAG_STRIDE = 16 /* uint64s = 128 bytes */, X_OFF_CONSUMED = 8192, X_OFF_ERROR = 8320, X_OFF_TARGETS = 16384 };
+cudaError_t launch_xwait(const unsigned long long *flags, uint32_t n, uint32_t stride, unsigned long long need, uint32_t *error, cudaStream_t st);
+cudaError_t launch_xsignal(unsigned long long *flag, unsigned long long value, cudaStream_t st);
+cudaError_t launch_xcollect(float4 *accum, const float4 *targets, size_t n_px, uint32_t S, int add, cudaStream_t st);
 
 // vkrt_micro.cu
 cudaError_t measure_fp32_peak(float *tflops);

@@ -85,6 +85,7 @@ namespace vkrt {
 // one counter set per depth iteration (no reset launches): paths entering the depth, the material bins, the
 // shadow-ray queue and the two work-fetch heads; survivors are counted in the NEXT depth's set
 enum { C_ACTIVE = 0, C_DIEL = 2, C_DIFF = 3, C_SHADOW = 4, C_HEAD_EXTEND = 5, C_HEAD_SHADOW = 6, C_ZERO = 7, C_N = 8, C_SETS = 257 };
+static_assert(C_SETS >= 255 + 2, "one counter set per depth 0..max_depth (max_depth <= 255, checked by vkrt_create / vkrt_set_sampling)");
 
 struct WaveParams {
     float4 *rec, *sh, *term, *rad;   // rec: 4 float4 per path (see the top of the file)
@@ -902,7 +903,7 @@ void wave_free(WaveBuffers &wb)
     cudaFree(wb.rec); cudaFree(wb.sample_rad);
     cudaFree(wb.queue[0]); cudaFree(wb.queue[1]); cudaFree(wb.queue_mat[0]); cudaFree(wb.queue_mat[1]); cudaFree(wb.counts);
     cudaFree(wb.shadow); cudaFree(wb.occ); cudaFree(wb.queue_shadow); cudaFree(wb.term); cudaFree(wb.shrec);
-    for (uint32_t i = 0; i < wb.ev_created; ++i) cudaEventDestroy(wb.ev[i]);
+    for (cudaEvent_t e : wb.ev) cudaEventDestroy(e);
     wb = WaveBuffers{};
 }
 
@@ -918,9 +919,6 @@ static cudaError_t lane_prepare(WaveBuffers &wb, uint32_t nl)
         if ((e = cudaMalloc((void **)&wb.occ, wb.capacity * nl)) != cudaSuccess) return e;
         if ((e = cudaMalloc((void **)&wb.queue_shadow, wb.capacity * nl * sizeof(uint32_t))) != cudaSuccess) return e;
         wb.shadow_lights = nl;
-    }
-    if (!wb.ev_created) {
-        for (uint32_t i = 0; i < 128; ++i) if ((e = cudaEventCreate(&wb.ev[i])) != cudaSuccess) return e; else wb.ev_created = i + 1;
     }
     wb.n_ev = 0;
     return cudaSuccess;
@@ -958,7 +956,7 @@ void wave_engine_free(WaveEngine &eng)
 // sets on two streams, so the launch gaps and the drain tails of one wave's ~34 small kernels are filled by the
 // other wave's kernels (this matters most when a GPU owns only 1/8 of the tiles); the per-pixel sums are still
 // formed in sample order because the `reduce` launches are chained with events, wave after wave.
-cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, WaveEngine &eng, bool bvh, bool stats,
+cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, WaveEngine &eng, bool bvh, bool stats, bool timing,
                                   int sm_count, cudaStream_t st, cudaEvent_t ev_consumed, cudaEvent_t ev_begin,
                                   cudaStream_t *tail, uint32_t *n_launches)
 {
@@ -1017,9 +1015,16 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
             if (fork && rp.hit_ids && (e = cudaStreamWaitEvent(ls, ev_consumed, 0)) != cudaSuccess) return e;
             if ((e = cudaEventRecord(ev_begin, ls)) != cudaSuccess) return e;
         }
-        // every launch of the wave is bracketed by timing events (roofline timing, vkrt_debug_dump_timeline)
-        auto ev_open = [&](uint8_t tag) { if (wb.n_ev + 1 < 128) { wb.ev_tag[wb.n_ev / 2] = tag; cudaEventRecord(wb.ev[wb.n_ev++], ls); } };
-        auto ev_close = [&]() { if (wb.n_ev < 128 && (wb.n_ev & 1u)) cudaEventRecord(wb.ev[wb.n_ev++], ls); };
+        // VKRT_FLAG_LAUNCH_TIMING: every launch of the wave is bracketed by timing events (roofline timing,
+        // vkrt_debug_dump_timeline); without the flag the hot path records none
+        cudaError_t ev_err = cudaSuccess;
+        auto ev_rec = [&]() {
+            if (wb.n_ev == wb.ev.size()) { cudaEvent_t n; const cudaError_t ce = cudaEventCreate(&n); if (ce != cudaSuccess) { ev_err = ce; return; } wb.ev.push_back(n); }
+            const cudaError_t ce = cudaEventRecord(wb.ev[wb.n_ev++], ls);
+            if (ce != cudaSuccess) ev_err = ce;
+        };
+        auto ev_open = [&](uint8_t tag) { if (!timing) return; if (wb.ev_tag.size() <= wb.n_ev / 2) wb.ev_tag.resize(wb.n_ev / 2 + 1); wb.ev_tag[wb.n_ev / 2] = tag; ev_rec(); };
+        auto ev_close = [&]() { if (timing && (wb.n_ev & 1u)) ev_rec(); };
         WaveParams wp{};
         wp.rec = wb.rec; wp.shrec = wb.shrec; wp.sh = wb.shadow; wp.term = wb.term; wp.rad = wb.sample_rad;
         wp.q_active[0] = wb.queue[0]; wp.q_active[1] = wb.queue[1]; wp.q_diel = wb.queue_mat[0]; wp.q_diff = wb.queue_mat[1];
@@ -1102,6 +1107,7 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
             eng.prev_reduce_lane = lane; eng.have_prev_reduce = true;
         }
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (ev_err != cudaSuccess) return ev_err;
     }
     if (tail) *tail = ls;
     if (n_launches) *n_launches = launches;

@@ -25,13 +25,20 @@ def pack_materials(albedo, roughness, emissive, metalness, mtype):
 
 class Renderer:
     def __init__(self, width, height, spp=4, max_depth=0, integrator=L.INTEGRATOR_PATH, variant=L.VARIANT_MEGAKERNEL,
-                 flags=0, device_id=0, frames_in_flight=2, tile_shard=(0, 1), sample_shard=(0, 1), stream=None):
+                 flags=0, device_id=0, frames_in_flight=2, tile_shard=(0, 1), sample_shard=(0, 1), stream=None, device_ids=None):
+        """device_ids: in-library multi-GPU -- ONE context renders every frame on these CUDA devices (interleaved tile
+        shards, frame exchange over peer memory into device_ids[0]); tile_shard / sample_shard stay at their defaults."""
         self.lib = L.load()
         info = L.CreateInfo(struct_size=C.sizeof(L.CreateInfo), width=width, height=height, spp=spp, max_depth=max_depth,
                             integrator=integrator, variant=variant, frames_in_flight=frames_in_flight,
                             device_id=device_id, flags=flags, tile_shard_rank=tile_shard[0],
                             tile_shard_count=tile_shard[1], sample_shard_rank=sample_shard[0],
                             sample_shard_count=sample_shard[1], stream=stream)
+        if device_ids is not None:
+            info.n_devices = len(device_ids)
+            for i, d in enumerate(device_ids):
+                info.device_ids[i] = d
+            device_id = device_ids[0]
         ctx = C.c_void_p()
         rc = self.lib.vkrt_create(C.byref(info), C.byref(ctx))
         L.check(self.lib, None, rc)
@@ -239,6 +246,23 @@ class Renderer:
 
     def unpack_shard(self, dev_ptr, tile_rank, tile_count, add=False):
         self._ck(self.lib.vkrt_unpack_shard(self.ctx, C.c_void_p(dev_ptr), tile_rank, tile_count, 1 if add else 0))
+
+    # ---- frame exchange over peer memory ------------------------------------------------------------
+    def exchange_create(self):
+        """Gathering context (tile rank 0, sample rank 0): -> the handle (bytes) the other processes open."""
+        h = L.ExchangeHandle()
+        self._ck(self.lib.vkrt_exchange_create(self.ctx, C.byref(h)))
+        return bytes(h)
+
+    def exchange_open(self, handle_bytes):
+        h = L.ExchangeHandle.from_buffer_copy(handle_bytes)
+        self._ck(self.lib.vkrt_exchange_open(self.ctx, C.byref(h)))
+
+    def exchange_attach(self, gathering_renderer):
+        self._ck(self.lib.vkrt_exchange_attach(self.ctx, gathering_renderer.ctx))
+
+    def exchange_close(self):
+        self._ck(self.lib.vkrt_exchange_close(self.ctx))
 
 
 def measure_fp32_peak(device_id=0):

@@ -4,6 +4,10 @@ exchange step of the path -- the gather of every rank's owned accumulator tiles 
 single-GPU render; sample shards are summed on rank 0 in rank order (deterministic).
 
 Rank layout for world = T * S: tile_rank = rank % T, sample_rank = rank // T.
+
+Two exchange modes: `PeerExchange` (default in bench.py) -- every rank's last kernel stores its pixels straight into
+rank 0's memory over NVLink (csrc/vkrt_exchange.cu); torch.distributed only carries the 96-byte CUDA-IPC handle once.
+`FrameGather` -- pack -> NCCL gather -> unpack, the plain-collective form of the same step.
 """
 import numpy as np
 import torch
@@ -70,3 +74,24 @@ class FrameGather:
                 for src, buf in enumerate(bufs):
                     (tile_rank, tiles), (sample_rank, _) = shard_layout(src, self.world, self.samples)
                     self.r.unpack_shard(buf.data_ptr(), tile_rank, tiles, add=(sample_rank > 0))
+
+
+class PeerExchange:
+    """Frame exchange over peer memory: rank 0 creates the exchange block, the other ranks map it (CUDA IPC).  After
+    attach(), renderer.draw() on every rank IS the exchange: no further call is needed, rank 0's accumulator and
+    rgba8 image hold the whole frame."""
+
+    def __init__(self, renderer, rank, world, group=None):
+        self.r, self.rank, self.world = renderer, rank, world
+        box = [renderer.exchange_create() if rank == 0 else None]
+        if world > 1:
+            dist.broadcast_object_list(box, src=0, group=group)
+            if rank != 0:
+                renderer.exchange_open(box[0])
+            dist.barrier(group=group)
+
+    def close(self):
+        self.r.wait_idle()
+        if self.world > 1:
+            dist.barrier()
+        self.r.exchange_close()
