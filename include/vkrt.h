@@ -310,6 +310,8 @@ typedef struct vkrt_bvh_info {
     uint32_t node_bytes;
     float    build_ms;      /* device time of the last vkrt_build_bvh */
     uint32_t build_launches;
+    uint32_t depth;         /* inner-node levels on the longest root-to-leaf chain; <= 64 by construction (distinct 64-bit
+                               (Morton code, index) keys), and the bound of the kernels' traversal stacks (128 entries) */
 } vkrt_bvh_info;
 VKRT_API vkrt_error vkrt_get_bvh_info(vkrt_ctx *ctx, vkrt_bvh_info *out);
 /* Copies the packed nodes (n_nodes * 16 floats) to the host. */

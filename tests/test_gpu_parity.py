@@ -156,6 +156,36 @@ def test_bvh_duplicate_centres(vk, oracle):
 
 
 @pytest.mark.parametrize("variant", [0, 1])
+def test_degenerate_scene_100k_coincident_centres(vk, oracle, variant):
+    """Worst case for the hierarchy: 100,000 spheres around ONE centre (every Morton code equal, every box overlaps every
+    other).  The Karras tree is then the radix tree of the indices: its depth stays far below the 128-entry traversal
+    stacks (vkrt_bvh_info.depth <= 64 for ANY scene, enforced by vkrt_build_bvh), every ray that meets the cluster
+    visits all of it, and the answer is still rule S's, bit for bit."""
+    V = vk
+    n = 100000
+    scene = V.scenes.random_spheres(8)
+    scene.spheres = np.zeros((n + 1, 4), dtype=np.float32)
+    scene.spheres[0] = (0.0, 96.0, 0.0, 12.0)                                       # the light keeps its place
+    scene.spheres[1:, :3] = (10.0, 40.0, 20.0)
+    scene.spheres[1:, 3] = 8.0 + np.arange(n, dtype=np.float32) * np.float32(1e-5)
+    scene.sphere_mat = np.concatenate([np.array([7], dtype=np.uint32), 8 + (np.arange(n, dtype=np.uint32) % 8)])
+    w, h = 48, 32
+    fd = V.default_frame_data(aspect_ratio=w / h, seed=0.4)
+    r = V.Renderer(w, h, spp=2, max_depth=3, variant=variant, flags=V.FLAG_HIT_IDS)
+    r.set_scene(scene)
+    info = r.build_bvh()
+    assert 17 <= info.depth <= 64, info.depth
+    r.set_seed(3)
+    r.draw(fd)
+    acc, ids = r.read_accum(), r.read_hit_ids()
+    r.close()
+    sc = apply_scene(oracle, scene, fast=True).build_bvh()
+    oacc, oids, _, _ = sc.render(fd, w, h, spp=2, max_depth=3, sphere_mode=oracle.S_BVH, seed=3)
+    assert np.array_equal(ids, oids)
+    assert bits_equal(acc, oacc), mismatch_report(acc, oacc)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
 def test_path_random_spheres_bvh_bit_exact(vk, oracle, variant):
     """BASELINE config 3's scene (1,024 random spheres, device LBVH) at a size the oracle finishes in
     seconds: the GPU's LBVH traversal must equal both the oracle's own BVH traversal and the oracle's

@@ -67,7 +67,7 @@ class Counters(C.Structure):
 
 class BvhInfo(C.Structure):
     _fields_ = [("n_spheres", C.c_uint32), ("n_nodes", C.c_uint32), ("node_bytes", C.c_uint32),
-                ("build_ms", C.c_float), ("build_launches", C.c_uint32)]
+                ("build_ms", C.c_float), ("build_launches", C.c_uint32), ("depth", C.c_uint32)]
 
 
 class ExternalImage(C.Structure):  # include/vkrt.h: one exported traced image (ref: Source/GraphicsDevice.cpp:664-699)

@@ -89,7 +89,10 @@ struct GraphicsDevice final
 
 	// --- headless extras (not in the reference) -------------------------------------------------------
 	// the shader's compile-time constants / the swapchain extent, to be set before Construct
-	struct Options { unsigned spp = 4, max_depth = 4, extent_w = 1024, extent_h = 768; int device = 0; bool wavefront = false; };
+	// n_devices > 1: the ONE Draw call renders on devices[0 .. n_devices) (vkrt_create_info.device_ids, tile shards
+	// exchanged over peer memory into devices[0]) -- the engine code does not change
+	struct Options { unsigned spp = 4, max_depth = 4, extent_w = 1024, extent_h = 768; int device = 0; bool wavefront = false;
+	                 unsigned n_devices = 0; int devices[8] = {0, 1, 2, 3, 4, 5, 6, 7}; };
 	static Options & options();
 	// copies the most recent traced image (rgba8, row 0 = bottom like the shader's imageStore) to the host
 	bool ReadImage(unsigned char * rgba8, unsigned long long bytes);

@@ -48,6 +48,8 @@ GraphicsDevice::Error GraphicsDevice::Construct(const CreateInfo & info)
 	ci.variant          = o.wavefront ? VKRT_VARIANT_WAVEFRONT : VKRT_VARIANT_MEGAKERNEL;
 	ci.frames_in_flight = info.framesInFlight;
 	ci.device_id        = o.device;
+	ci.n_devices        = o.n_devices;                       // > 1: one Draw, several GPUs (the reference is single-GPU)
+	for (unsigned i = 0; i < 8; ++i) ci.device_ids[i] = o.devices[i];
 
 	if (const vkrt_error e = vkrt_create(&ci, &state.ctx); e != VKRT_SUCCESS)
 	{

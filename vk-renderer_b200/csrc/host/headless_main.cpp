@@ -2,7 +2,7 @@
 // scripted camera path (the reference moves the camera from WASD/mouse callbacks, Main.cpp:23-83).
 //
 //   vkrt_headless [--frames N] [--res R] [--spp S] [--depth D] [--wavefront] [--seed K] [--sleep] [--out img.ppm]
-//                 [--print-camera]
+//                 [--print-camera] [--devices 0,1,...]
 //
 // --seed K calls srand(K) after Construct so that the seeds Draw draws from rand() are reproducible
 // (the reference seeds with time(0)); --sleep keeps the 12 ms sleep of Main.cpp:195.
@@ -50,6 +50,18 @@ int main(int argc, char ** argv)
 		else if (a == "--sleep") do_sleep = true;
 		else if (a == "--out") out = next();
 		else if (a == "--print-camera") print_camera = true;
+		else if (a == "--devices")
+		{
+			// one Draw call per frame on several GPUs (vkrt_create_info.device_ids)
+			GraphicsDevice::Options & o = GraphicsDevice::options();
+			o.n_devices = 0;
+			for (const char * p = next(); *p && o.n_devices < 8; )
+			{
+				o.devices[o.n_devices++] = std::atoi(p);
+				while (*p && *p != ',') ++p;
+				if (*p == ',') ++p;
+			}
+		}
 	}
 
 	// Main.cpp:134-139

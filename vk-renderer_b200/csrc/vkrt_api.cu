@@ -3,6 +3,7 @@
 // Mirrors the ownership model of the reference's GraphicsDevice (Source/GraphicsDevice.cpp:40-43:
 // the library owns every GPU object; the caller owns FrameData, copied inside Draw at :1258).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fcntl.h>
 #include <unistd.h>
@@ -569,6 +570,10 @@ VKRT_API vkrt_error vkrt_build_bvh(vkrt_ctx *c)
     vkrt_error r = upload_scene(c);
     if (r != VKRT_SUCCESS) return r;
     CU(c, build_lbvh(c->d_spheres, (uint32_t)c->spheres.size(), c->bvh, c->stream));
+    // the traversal stacks (BVH_STACK entries of thread-local memory, unchecked in the kernels) hold at most one entry
+    // per tree level; the LBVH cannot be deeper than 64 levels, and this is where that is enforced
+    if (c->bvh.depth + 2 > (int)BVH_STACK)
+        return fail(c, VKRT_BAD_ARG, "the LBVH is " + std::to_string(c->bvh.depth) + " levels deep: deeper than the traversal stack");
     c->use_bvh = true;
     c->scene_dirty = true;
     FWD(c, vkrt_build_bvh(ch));                // the build is deterministic: every device gets the identical tree
@@ -589,6 +594,7 @@ VKRT_API vkrt_error vkrt_get_bvh_info(vkrt_ctx *c, vkrt_bvh_info *out)
     out->node_bytes = 64;
     out->build_ms = c->bvh.build_ms;
     out->build_launches = c->bvh.launches;
+    out->depth = c->use_bvh ? (uint32_t)c->bvh.depth : 0;
     return VKRT_SUCCESS;
 }
 VKRT_API vkrt_error vkrt_read_bvh_nodes(vkrt_ctx *c, float *host, size_t bytes)
@@ -663,7 +669,11 @@ VKRT_API vkrt_error vkrt_draw(vkrt_ctx *c, const vkrt_frame_data *frame)
                 // two lanes of up to 8 samples of every owned pixel each (one lane when spp == 1), at most
                 // 32 Mi path records per lane (~3.5 GB of HBM)
                 const size_t slots = (size_t)c->owned_tiles * TILE_PX;
-                const uint32_t lanes = c->spp >= 2 ? VKRT_WAVE_LANES : 1;
+                uint32_t lanes = c->spp >= 2 ? VKRT_WAVE_LANES : 1;
+                if (const char *ev = std::getenv("VKRT_TUNE_LANES")) {          // tuning aid: 1..4 lanes (the image does not depend on it)
+                    const int v = std::atoi(ev);
+                    if (v >= 1 && v <= 4 && (uint32_t)v <= c->spp) lanes = (uint32_t)v;
+                }
                 size_t per_wave = (c->spp + lanes - 1) / lanes;
                 if (per_wave > 16 / lanes) per_wave = 16 / lanes;
                 while (per_wave > 1 && slots * per_wave > ((size_t)64 << 20) / lanes) --per_wave;

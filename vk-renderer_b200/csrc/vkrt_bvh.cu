@@ -244,6 +244,18 @@ __global__ void __launch_bounds__(256) k_refit(const float4 *__restrict__ sph, c
     }
 }
 
+// depth of the tree = the longest leaf-to-root chain.  The traversal stacks hold one entry per level at most (the
+// near-first binary walk pushes the far child and descends), so this bounds them; it cannot exceed 64: the Karras
+// hierarchy is the radix tree of the DISTINCT 64-bit keys (Morton code, index), every level fixes at least one more bit.
+__global__ void __launch_bounds__(256) k_tree_depth(const int *__restrict__ parent_inner, const int *__restrict__ parent_leaf, int n, int *depth)
+{
+    const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+    int d = 0;
+    if (leaf < n) for (int node = parent_leaf[leaf]; node >= 0; node = parent_inner[node]) ++d;
+    d = __reduce_max_sync(0xffffffffu, d);
+    if ((threadIdx.x & 31) == 0) atomicMax(depth, d);
+}
+
 __global__ void k_single_leaf(const float4 *__restrict__ sph, float4 *__restrict__ nodes)
 {
     float lo[3], hi[3];
@@ -343,7 +355,8 @@ cudaError_t build_lbvh(const float4 *d_spheres, uint32_t n, BvhBuild &out, cudaS
     if (out.nodes4) { cudaFree(out.nodes4); out.nodes4 = nullptr; }
     if (out.qnodes) { cudaFree(out.qnodes); out.qnodes = nullptr; }
     float *grid = nullptr;
-    out.n_nodes = 0; out.build_ms = 0.f; out.launches = 0;
+    int *d_depth = nullptr;
+    out.n_nodes = 0; out.build_ms = 0.f; out.launches = 0; out.depth = 0;
     if (n == 0) return cudaSuccess;
 
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -394,6 +407,10 @@ cudaError_t build_lbvh(const float4 *d_spheres, uint32_t n, BvhBuild &out, cudaS
         k_refit<<<(n + 255u) / 256u, 256, 0, st>>>(d_spheres, vals[cur], (int)n, children, parent_inner, parent_leaf, arrivals,
                                                    box_lo, box_hi, out.nodes); ++launches;
         CK(cudaGetLastError());
+        CK(cudaMalloc(&d_depth, sizeof(int)));
+        CK(cudaMemsetAsync(d_depth, 0, sizeof(int), st));
+        k_tree_depth<<<(n + 255u) / 256u, 256, 0, st>>>(parent_inner, parent_leaf, (int)n, d_depth); ++launches;
+        CK(cudaGetLastError());
     }
     k_collapse4<<<(n_inner + 255u) / 256u, 256, 0, st>>>(out.nodes, n_inner, out.nodes4); ++launches;
     CK(cudaGetLastError());
@@ -402,6 +419,8 @@ cudaError_t build_lbvh(const float4 *d_spheres, uint32_t n, BvhBuild &out, cudaS
     CK(cudaGetLastError());
     CK(cudaEventRecord(e1, st));
     CK(cudaMemcpyAsync(out.qgrid, grid, 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (d_depth) CK(cudaMemcpyAsync(&out.depth, d_depth, sizeof(int), cudaMemcpyDeviceToHost, st));
+    else out.depth = 1;
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&out.build_ms, e0, e1));
     out.n_nodes = n_inner;
@@ -411,7 +430,7 @@ done:
     if (e1) cudaEventDestroy(e1);
     cudaFree(bounds); cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); cudaFree(hist);
     cudaFree(children); cudaFree(parent_inner); cudaFree(parent_leaf); cudaFree(arrivals); cudaFree(box_lo); cudaFree(box_hi);
-    cudaFree(grid);
+    cudaFree(grid); cudaFree(d_depth);
     if (err != cudaSuccess) { cudaFree(out.nodes); cudaFree(out.nodes4); cudaFree(out.qnodes); out.nodes = nullptr; out.nodes4 = nullptr; out.qnodes = nullptr; }
     return err;
 }

@@ -12,6 +12,9 @@
 
 namespace vkrt {
 
+// BVH_STACK: entries of the per-thread traversal stacks.  The near-first binary walk holds at most one entry per tree
+// level and the LBVH has at most 64 levels (vkrt_bvh.cu::k_tree_depth; vkrt_build_bvh refuses a deeper tree), so the
+// kernels push without a bound check.
 enum { MAX_PLANES = 16, BVH_STACK = 128 };
 enum { KIND_TRI = 1, KIND_SPHERE = 2, KIND_PLANE = 3 };
 

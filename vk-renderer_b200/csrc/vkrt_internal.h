@@ -59,6 +59,9 @@ struct WaveBuffers {
     uint8_t *occ;                 // their any-hit results
     uint32_t *queue_shadow;       // (path << 4 | light) items that still need the sphere any-hit query
     uint32_t shadow_lights;
+    // dense fused pipeline (scenes with <= 1 light): ping-pong ray / state arrays, nearest-hit results, shadow records
+    float4 *d_ray[2], *d_st[2], *d_shr;
+    float2 *d_hit;
     // VKRT_FLAG_LAUNCH_TIMING: CUDA-event pairs around every kernel launch of the last frame (roofline timing); the pool
     // grows with the number of launches, nothing is dropped
     std::vector<cudaEvent_t> ev;
@@ -94,6 +97,7 @@ struct BvhBuild {
     uint4 *qnodes = nullptr;      // 32-byte traversal nodes: two 16-byte child records on the 16-bit grid below
     float qgrid[6] = {0, 0, 0, 0, 0, 0};   // per axis: scale s[3], offset b2[3]; coordinate of code q = (2^23 + q) * s + b2
     uint32_t n_nodes = 0;
+    int depth = 0;                // levels of inner nodes on the longest root-to-leaf chain (<= 64, see k_tree_depth)
     float build_ms = 0.f;
     uint32_t launches = 0;
 };

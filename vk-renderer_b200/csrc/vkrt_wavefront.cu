@@ -73,6 +73,9 @@
 #ifndef VKRT_BLOCK_PUSH
 #define VKRT_BLOCK_PUSH 1          // classify / shade: one queue-counter atomicAdd per block instead of per warp
 #endif
+#ifndef VKRT_DENSE
+#define VKRT_DENSE 1               // fused pipeline: survivors of a depth are written DENSELY (ping-pong ray / state arrays, position =
+#endif                             //                 queue index): no path-id indirection, every record access is a contiguous stream
 #ifndef VKRT_SHADE_BLOCK
 #define VKRT_SHADE_BLOCK 256
 #endif
@@ -96,6 +99,14 @@ struct WaveParams {
     uint32_t s0, S;          // first sample of the wave, samples per pixel in the wave
     uint32_t n_slots;        // = RenderParams.n_work
     uint32_t n_lights;
+    // dense fused pipeline (VKRT_DENSE): the arrays of the depth being processed (x_*) and of the next depth (n_*).
+    //   ray   2 float4 per path  {o.xyz - | d.xyz -}
+    //   state 2 float4 per path  {acc.xyz slot | mask.xyz sample<<8|depth}
+    //   hit   float2 per path    {t_hit, hit id}            written by trace, read by logic
+    //   shr   4 float4 per shadow ray {P.xyz t | L.xyz dst | acc_if_visible.xyz slot | -}; dst = index of the path's state in
+    //         the NEXT depth's arrays, or 0x80000000 | index into rad when the path ended at this bounce
+    const float4 *x_ray; float4 *x_st, *n_ray, *n_st, *x_shr;
+    float2 *x_hit;
 };
 
 VKRT_DEV void ld256(const float4 *p, float4 &a, float4 &b)
@@ -288,7 +299,9 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ Dev
 // MODE 0: nearest-hit items only.  MODE 2: ONE launch traces the nearest-hit rays of depth d and the shadow rays of
 // depth d-1 -- item i < n_ext is a nearest-hit item, the rest are shadow items (the longer rays go first); lanes of
 // one warp may hold either kind, the traversal is the same code.
-enum { TRACE_EXTEND = 0, TRACE_SHADOW = 1, TRACE_MIXED = 2 };
+// MODE 3 (dense fused pipeline): like MODE 2, but item i IS ray i of the depth's dense ray array and shadow item k is
+//                   shadow record k -- no queues; the nearest hit goes to hit[i]
+enum { TRACE_EXTEND = 0, TRACE_SHADOW = 1, TRACE_MIXED = 2, TRACE_DENSE = 3 };
 template <int MODE, bool BVH, bool STATS>
 __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_trace(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
                                                                 const __grid_constant__ WaveParams wp, const uint32_t *__restrict__ queue,
@@ -296,11 +309,12 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                                                                 const uint32_t *__restrict__ n_sh_ptr, uint32_t *head, uint32_t depth)
 {
     const unsigned full = 0xffffffffu, lane = threadIdx.x & 31u;
+    constexpr bool MIX = MODE == TRACE_MIXED || MODE == TRACE_DENSE, DENSE = MODE == TRACE_DENSE;
     Stats st; stats_zero(st);
     const uint32_t n_ext = MODE == TRACE_SHADOW ? 0u : *n_items_ptr;
-    const uint32_t n_items = MODE == TRACE_SHADOW ? *n_items_ptr : (MODE == TRACE_MIXED ? n_ext + *n_sh_ptr : n_ext);
+    const uint32_t n_items = MODE == TRACE_SHADOW ? *n_items_ptr : (MIX ? n_ext + *n_sh_ptr : n_ext);
     bool any = MODE == TRACE_SHADOW;
-    static_assert(MODE != TRACE_MIXED || VKRT_LEAF_BATCH != 0, "the mixed trace kernel needs the phase-split traversal");
+    static_assert(!MIX || VKRT_LEAF_BATCH != 0, "the mixed trace kernel needs the phase-split traversal");
     const float EPS = 1e-3f;
     const float tmax = path_tmax(depth);       // every ray of one extend launch is at the same depth (:444)
 
@@ -359,28 +373,33 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                 if (item >= n_items) drained = true;
                 else {
                     has = true;
-                    if (MODE == TRACE_MIXED) any = item >= n_ext;
-#if VKRT_RAY_LDCG
-                    const uint32_t q = __ldcg((MODE == TRACE_MIXED && any) ? queue_sh + (item - n_ext) : queue + item);
-#else
-                    const uint32_t q = (MODE == TRACE_MIXED && any) ? queue_sh[item - n_ext] : queue[item];
-#endif
-                    path = MODE == TRACE_SHADOW ? (q >> 4) : q;
-                    light = MODE == TRACE_SHADOW ? (q & 15u) : 0u;
+                    if (MIX) any = item >= n_ext;
                     float4 fo, fd;
+                    if (DENSE) {
+                        path = any ? item - n_ext : item;              // the item's own index: there is no queue
+                        ld256cg(any ? wp.x_shr + 4 * (size_t)path : wp.x_ray + 2 * (size_t)path, fo, fd);
+                    } else {
 #if VKRT_RAY_LDCG
-                    ld256cg(MODE == TRACE_MIXED && any ? wp.shrec + 4 * (size_t)path : rec_ray(wp, path), fo, fd);
+                        const uint32_t q = __ldcg((MIX && any) ? queue_sh + (item - n_ext) : queue + item);
 #else
-                    ld256(MODE == TRACE_MIXED && any ? wp.shrec + 4 * (size_t)path : rec_ray(wp, path), fo, fd);
+                        const uint32_t q = (MIX && any) ? queue_sh[item - n_ext] : queue[item];
 #endif
+                        path = MODE == TRACE_SHADOW ? (q >> 4) : q;
+                        light = MODE == TRACE_SHADOW ? (q & 15u) : 0u;
+#if VKRT_RAY_LDCG
+                        ld256cg(MIX && any ? wp.shrec + 4 * (size_t)path : rec_ray(wp, path), fo, fd);
+#else
+                        ld256(MIX && any ? wp.shrec + 4 * (size_t)path : rec_ray(wp, path), fo, fd);
+#endif
+                    }
                     found = false; hit.kind = 0; hit.index = 0;
                     if (MODE == TRACE_SHADOW) {
                         const float4 s = wp.sh[(size_t)path * wp.n_lights + light];
                         o = madd3(fo.w, xyz(fd), xyz(fo));           // the hit point P (== surface_of's P)
                         d = xyz(s); cur = s.w;
-                    } else if (MODE == TRACE_MIXED && any) {
-                        o = xyz(fo); d = xyz(fd); cur = fo.w;        // shrec: {P.xyz t | L.xyz dead}
-                        light = __float_as_uint(fd.w);               // "the path ended at this bounce"
+                    } else if (MIX && any) {
+                        o = xyz(fo); d = xyz(fd); cur = fo.w;        // shrec: {P.xyz t | L.xyz dead}   (dense: {P.xyz t | L.xyz dst})
+                        light = __float_as_uint(fd.w);               // "the path ended at this bounce"  (dense: where acc_if_visible goes)
                     } else {
                         o = xyz(fo); d = xyz(fd);
                         cur = tmax;
@@ -509,7 +528,15 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                 }
             }
             if (MODE == TRACE_SHADOW) wp.occ[(size_t)path * wp.n_lights + light] = found ? 1 : 0;
-            else if (MODE == TRACE_MIXED && any) {
+            else if (DENSE && any) {
+                if (!found) {        // unoccluded: the light's term counts (Tracer.comp:473-503)
+                    const float4 a1 = __ldcg(wp.x_shr + 4 * (size_t)path + 2);
+                    if (light & 0x80000000u) __stcg(wp.rad + (light & 0x7fffffffu), make_float4(a1.x, a1.y, a1.z, 0.f));
+                    else __stcg(wp.x_st + 2 * (size_t)light, a1);
+                }
+            } else if (DENSE) {
+                __stcg(wp.x_hit + path, make_float2(cur, __uint_as_float(found ? ((hit.kind << 28) | hit.index) : 0u)));
+            } else if (MIX && any) {
                 if (!found) {        // unoccluded: the light's term counts (Tracer.comp:473-503)
 #if VKRT_RAY_LDCG
                     const float4 a1 = __ldcg(wp.shrec + 4 * (size_t)path + 2);
@@ -736,27 +763,37 @@ struct LightsDeferred {
         return v3(0.0f);          // shade as if occluded; the visible outcome is formed by the caller
     }
 };
-// one path after its nearest hit is final (`found`, `hit` include the plane loop; ps.acc is already clamped, :441)
-VKRT_DEV void logic_path(const DevScene &sc, const RenderParams &rp, const WaveParams &wp, V3 cam_pos, uint32_t path, PathState &ps,
-                         const Hit &hit, bool found, uint32_t pix, uint32_t sl, Stats &st, bool &alive, bool &need_ray)
+// one path after its nearest hit is final (`found`, `hit` include the plane loop; ps.acc is already clamped, :441):
+// shades it as if the light sample were occluded (ps: the next ray, mask, accumulator) and, when a shadow ray is
+// needed, returns that ray {P, L, t} and the accumulator for the other outcome (acc_v)
+struct ShadowOut { V3 P, L, acc_v; float t; };
+VKRT_DEV void logic_compute(const DevScene &sc, const RenderParams &rp, const WaveParams &wp, V3 cam_pos, PathState &ps,
+                            const Hit &hit, bool found, uint32_t pix, uint32_t sl, Stats &st, bool &alive, bool &need_ray, ShadowOut &so)
 {
     alive = false; need_ray = false;
     if (found) {
         const uint32_t skey = sample_key(rp.fkey, pix, wp.s0 + sl);
-        const V3 acc_b = ps.acc, mask_b = ps.mask, P = madd3(hit.t, ps.d, ps.o);    // P == surface_of's P
-        V3 L = v3(0.0f), term = v3(0.0f), emis = v3(0.0f);
-        float t = 0.0f;
-        const LightsDeferred lights{sc, cam_pos, skey, ps.depth * DIMS_PER_BOUNCE, st, &need_ray, &L, &term, &t};
+        const V3 acc_b = ps.acc, mask_b = ps.mask;
+        so.P = madd3(hit.t, ps.d, ps.o);                                                // P == surface_of's P
+        V3 term = v3(0.0f), emis = v3(0.0f);
+        so.L = v3(0.0f); so.t = 0.0f;
+        const LightsDeferred lights{sc, cam_pos, skey, ps.depth * DIMS_PER_BOUNCE, st, &need_ray, &so.L, &term, &so.t};
         alive = path_shade(sc, cam_pos, rp.max_depth, skey, ps, hit, lights, &emis);
-        if (need_ray) {
-            const V3 acc_v = acc_b + mask_b * (emis + (v3(0.0f) + term));
-            float4 *sr = wp.shrec + 4 * (size_t)path;
-            st256(sr, make_float4(P.x, P.y, P.z, t), make_float4(L.x, L.y, L.z, __uint_as_float(alive ? 0u : 1u)));
-            sr[2] = make_float4(acc_v.x, acc_v.y, acc_v.z, __uint_as_float(pix));
-        }
-        if (alive) store_path(wp, path, ps, pix, sl);
+        if (need_ray) so.acc_v = acc_b + mask_b * (emis + (v3(0.0f) + term));
     }
-    if (!alive) wp.rad[path] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, 0.f);               // miss (:445) or the path ended
+}
+VKRT_DEV void logic_path(const DevScene &sc, const RenderParams &rp, const WaveParams &wp, V3 cam_pos, uint32_t path, PathState &ps,
+                         const Hit &hit, bool found, uint32_t pix, uint32_t sl, Stats &st, bool &alive, bool &need_ray)
+{
+    ShadowOut so;
+    logic_compute(sc, rp, wp, cam_pos, ps, hit, found, pix, sl, st, alive, need_ray, so);
+    if (need_ray) {
+        float4 *sr = wp.shrec + 4 * (size_t)path;
+        st256(sr, make_float4(so.P.x, so.P.y, so.P.z, so.t), make_float4(so.L.x, so.L.y, so.L.z, __uint_as_float(alive ? 0u : 1u)));
+        sr[2] = make_float4(so.acc_v.x, so.acc_v.y, so.acc_v.z, __uint_as_float(pix));
+    }
+    if (alive) store_path(wp, path, ps, pix, sl);
+    else wp.rad[path] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, 0.f);               // miss (:445) or the path ended
 }
 __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wf_logic(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
                                                       const __grid_constant__ WaveParams wp, const uint32_t *__restrict__ queue,
@@ -863,6 +900,145 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wf_g
     wf_flush(st, rp.counters, STATS);
 }
 
+// ---- dense fused pipeline (VKRT_DENSE) ---------------------------------------------------------------------
+// The same two kernels per depth, but the survivors of a depth are written densely: the block reserves its
+// range of the next depth's arrays with one atomicAdd (reserve_block) and every thread stores its path's ray and
+// state at its position there.  Item i of a depth is ray i / state i / hit i -- no path-id queues, no indirection:
+// `logic` reads and writes contiguous streams, the trace kernel fetches its ray records from a contiguous array.
+// A shadow record carries where its "visible" accumulator has to go (the path's state in the next depth's array, or
+// the finished radiance of (sample, slot) when the path ended).
+template <int NQ>
+VKRT_DEV void reserve_block(uint32_t *const (&count)[NQ], const bool (&want)[NQ], uint32_t (&pos)[NQ])
+{
+    __shared__ uint32_t s_cnt[NQ][32];
+    __shared__ uint32_t s_base[NQ];
+    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31u) >> 5;
+    unsigned m[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        m[q] = __ballot_sync(full, want[q]);
+        if (lane == 0) s_cnt[q][warp] = (uint32_t)__popc(m[q]);
+    }
+    __syncthreads();
+    if (threadIdx.x < NQ) {
+        uint32_t tot = 0;
+        for (unsigned w = 0; w < n_warps; ++w) { const uint32_t c = s_cnt[threadIdx.x][w]; s_cnt[threadIdx.x][w] = tot; tot += c; }
+        s_base[threadIdx.x] = tot ? atomicAdd(count[threadIdx.x], tot) : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) pos[q] = s_base[q] + s_cnt[q][warp] + (uint32_t)__popc(m[q] & ((1u << lane) - 1u));
+    __syncthreads();      // s_cnt / s_base are reused by the next call
+}
+// stores what logic_compute produced for one path: the next depth's ray / state at position j, the shadow record at
+// position k, or the finished radiance of (sample, slot)
+VKRT_DEV void dense_store(const WaveParams &wp, const PathState &ps, const ShadowOut &so, bool alive, bool need_ray, uint32_t j, uint32_t k,
+                          uint32_t slot, uint32_t sl)
+{
+    const uint32_t rad_i = sl * wp.n_slots + slot;
+    if (alive) {
+        st256(wp.n_ray + 2 * (size_t)j, make_float4(ps.o.x, ps.o.y, ps.o.z, 0.f), make_float4(ps.d.x, ps.d.y, ps.d.z, 0.f));
+        st256(wp.n_st + 2 * (size_t)j, make_float4(ps.acc.x, ps.acc.y, ps.acc.z, __uint_as_float(slot)),
+              make_float4(ps.mask.x, ps.mask.y, ps.mask.z, __uint_as_float((sl << 8) | ps.depth)));
+    } else {
+        wp.rad[rad_i] = make_float4(ps.acc.x, ps.acc.y, ps.acc.z, 0.f);                          // miss (:445) or the path ended
+    }
+    if (need_ray) {
+        float4 *sr = wp.x_shr + 4 * (size_t)k;
+        st256(sr, make_float4(so.P.x, so.P.y, so.P.z, so.t), make_float4(so.L.x, so.L.y, so.L.z, __uint_as_float(alive ? j : (0x80000000u | rad_i))));
+        sr[2] = make_float4(so.acc_v.x, so.acc_v.y, so.acc_v.z, __uint_as_float(slot));
+    }
+}
+__global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wfd_logic(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
+                                                       const __grid_constant__ WaveParams wp, const uint32_t *__restrict__ n_ptr)
+{
+    Stats st; stats_zero(st);
+    const uint32_t n = *n_ptr;
+    const V3 cam_pos = v3(rp.fd.camera.pos.x, rp.fd.camera.pos.y, rp.fd.camera.pos.z);
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        bool alive = false, need_ray = false;
+        PathState ps; ShadowOut so;
+        uint32_t slot = 0, sl = 0;
+        if (i < n) {
+            float4 fo, fd, fa, fm;
+            ld256cg(wp.x_ray + 2 * (size_t)i, fo, fd);
+            ld256cg(wp.x_st + 2 * (size_t)i, fa, fm);
+            const float2 h = __ldcg(wp.x_hit + i);
+            ps.o = xyz(fo); ps.d = xyz(fd); ps.acc = xyz(fa); ps.mask = xyz(fm);
+            const uint32_t sd = __float_as_uint(fm.w);
+            ps.depth = sd & 255u; sl = sd >> 8;
+            slot = __float_as_uint(fa.w);
+            uint32_t px, py;
+            slot_to_pixel_w(rp, slot, px, py);
+            const uint32_t pix = py * rp.width + px;
+            const uint32_t id0 = __float_as_uint(h.y);
+            Hit hit{h.x, id0 >> 28, id0 & 0x0fffffffu};
+            ps.acc = clamp3(ps.acc, 0.0f, 1.0f);                                                        // :441
+            float cur = hit.t;
+            const bool found = trace_planes<true>(sc, ps.o, ps.d, cur, hit) || id0 != 0u;             // :414-428
+            hit.t = cur;
+            logic_compute(sc, rp, wp, cam_pos, ps, hit, found, pix, sl, st, alive, need_ray, so);
+        }
+        uint32_t *const cs[2] = {wp.cnt_next + C_ACTIVE, wp.cnt + C_SHADOW};
+        const bool ws[2] = {alive, need_ray};
+        uint32_t pos[2];
+        reserve_block<2>(cs, ws, pos);
+        if (i < n) dense_store(wp, ps, so, alive, need_ray, pos[0], pos[1], slot, sl);
+    }
+    wf_flush(st, rp.counters, false);
+}
+// generate + logic of depth 0, dense: like k_wf_generate_logic, the survivors go to the depth-1 arrays
+template <bool BVH, bool STATS>
+__global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wfd_generate_logic(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
+                                                                                       const __grid_constant__ WaveParams wp)
+{
+    Stats st; stats_zero(st);
+    const V3 cam_pos = v3(rp.fd.camera.pos.x, rp.fd.camera.pos.y, rp.fd.camera.pos.z);
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t px = 0, py = 0;
+    const bool valid = slot < wp.n_slots && slot_to_pixel_w(rp, slot, px, py);
+    V3 o = v3(0.f), d = v3(0.f);
+    Hit hit{0.f, 0, 0};
+    bool found = false;
+    uint32_t pix = 0;
+    if (valid) {
+        primary_ray(rp.fd, rp.width, rp.height, px, py, o, d);
+        float cur = path_tmax(0);
+        found = trace_tris<true>(sc, o, d, cur, hit);
+        if (BVH) {
+            const SBest b = bvh_query<false, STATS>(sc, o, d, 1e-3f, sphere_bound<true>(cur), st);
+            if (b.idx >= 0) { cur = b.t; hit.kind = KIND_SPHERE; hit.index = (uint32_t)b.idx; found = true; }
+        } else {
+            for (uint32_t i = 0; i < sc.n_spheres; ++i) {                         // literal loop, Tracer.comp:398-412
+                const float t = sphere_intersect(o, d, __ldg(sc.spheres + i));
+                if ((t > 1e-3f) && (t < cur + 1e-3f)) { cur = t; hit.kind = KIND_SPHERE; hit.index = i; found = true; }
+            }
+        }
+        found = trace_planes<true>(sc, o, d, cur, hit) || found;                 // :414-428
+        hit.t = cur;
+        pix = py * rp.width + px;
+        if (rp.hit_ids && wp.s0 == rp.s_begin) rp.hit_ids[pix] = found ? ((hit.kind << 28) | hit.index) : 0u;
+        st.closest += wp.S;
+        st.shared += wp.S - 1u;
+        st.paths += wp.S;
+    }
+    for (uint32_t sl = 0; sl < wp.S; ++sl) {
+        bool alive = false, need_ray = false;
+        PathState ps; ShadowOut so;
+        if (valid) {
+            path_begin(ps, o, d);                   // acc = 0: the firefly clamp of :441 leaves it unchanged
+            logic_compute(sc, rp, wp, cam_pos, ps, hit, found, pix, sl, st, alive, need_ray, so);
+        }
+        uint32_t *const cs[2] = {wp.cnt_next + C_ACTIVE, wp.cnt + C_SHADOW};
+        const bool ws[2] = {alive, need_ray};
+        uint32_t pos[2];
+        reserve_block<2>(cs, ws, pos);
+        if (valid) dense_store(wp, ps, so, alive, need_ray, pos[0], pos[1], slot, sl);
+    }
+    wf_flush(st, rp.counters, STATS);
+}
+
 // ---- reduce: per pixel, add the wave's samples in sample order -------------------------------------
 __global__ void __launch_bounds__(256) k_wf_reduce(const __grid_constant__ RenderParams rp, const __grid_constant__ WaveParams wp,
                                                     float4 *__restrict__ frame_sum, uint32_t first_wave, uint32_t last_wave)
@@ -887,12 +1063,8 @@ cudaError_t wave_alloc(WaveBuffers &wb, size_t capacity)
     wb.capacity = capacity;
     cudaError_t e;
 #define A(ptr, bytes) do { e = cudaMalloc((void **)&(ptr), (bytes)); if (e != cudaSuccess) { wave_free(wb); return e; } } while (0)
-    A(wb.rec, capacity * 4 * sizeof(float4));
+    // the path-record arrays depend on the pipeline the scene takes (lane_prepare)
     A(wb.sample_rad, capacity * sizeof(float4));
-    A(wb.queue[0], capacity * sizeof(uint32_t));
-    A(wb.queue[1], capacity * sizeof(uint32_t));
-    A(wb.queue_mat[0], capacity * sizeof(uint32_t));
-    A(wb.queue_mat[1], capacity * sizeof(uint32_t));
     A(wb.counts, (size_t)C_SETS * C_N * sizeof(uint32_t));
 #undef A
     return cudaSuccess;
@@ -903,14 +1075,31 @@ void wave_free(WaveBuffers &wb)
     cudaFree(wb.rec); cudaFree(wb.sample_rad);
     cudaFree(wb.queue[0]); cudaFree(wb.queue[1]); cudaFree(wb.queue_mat[0]); cudaFree(wb.queue_mat[1]); cudaFree(wb.counts);
     cudaFree(wb.shadow); cudaFree(wb.occ); cudaFree(wb.queue_shadow); cudaFree(wb.term); cudaFree(wb.shrec);
+    cudaFree(wb.d_ray[0]); cudaFree(wb.d_ray[1]); cudaFree(wb.d_st[0]); cudaFree(wb.d_st[1]); cudaFree(wb.d_hit); cudaFree(wb.d_shr);
     for (cudaEvent_t e : wb.ev) cudaEventDestroy(e);
     wb = WaveBuffers{};
 }
 
-// lazily sizes the per-scene buffers of one lane
-static cudaError_t lane_prepare(WaveBuffers &wb, uint32_t nl)
+// lazily sizes the per-scene buffers of one lane: the dense arrays of the fused pipeline, or the indexed path records,
+// queues and per-light shadow arrays of the four-kernel one
+static cudaError_t lane_prepare(WaveBuffers &wb, uint32_t nl, bool dense, bool fused)
 {
     cudaError_t e;
+    wb.n_ev = 0;
+#define A(ptr, bytes) do { if (!(ptr) && (e = cudaMalloc((void **)&(ptr), (bytes))) != cudaSuccess) return e; } while (0)
+    if (dense) {
+        for (int k = 0; k < 2; ++k) { A(wb.d_ray[k], wb.capacity * 2 * sizeof(float4)); A(wb.d_st[k], wb.capacity * 2 * sizeof(float4)); }
+        A(wb.d_hit, wb.capacity * sizeof(float2));
+        A(wb.d_shr, wb.capacity * 4 * sizeof(float4));
+        return cudaSuccess;
+    }
+    A(wb.rec, wb.capacity * 4 * sizeof(float4));
+    A(wb.queue[0], wb.capacity * sizeof(uint32_t));
+    A(wb.queue[1], wb.capacity * sizeof(uint32_t));
+    A(wb.queue_mat[0], wb.capacity * sizeof(uint32_t));
+    A(wb.queue_mat[1], wb.capacity * sizeof(uint32_t));
+    if (fused) A(wb.shrec, wb.capacity * 4 * sizeof(float4));
+#undef A
     if (wb.shadow_lights < nl) {
         cudaFree(wb.shadow); cudaFree(wb.occ); cudaFree(wb.queue_shadow); cudaFree(wb.term);
         wb.shadow = nullptr; wb.occ = nullptr; wb.queue_shadow = nullptr; wb.term = nullptr;
@@ -920,7 +1109,6 @@ static cudaError_t lane_prepare(WaveBuffers &wb, uint32_t nl)
         if ((e = cudaMalloc((void **)&wb.queue_shadow, wb.capacity * nl * sizeof(uint32_t))) != cudaSuccess) return e;
         wb.shadow_lights = nl;
     }
-    wb.n_ev = 0;
     return cudaSuccess;
 }
 
@@ -971,10 +1159,10 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
     if (S > spp) S = spp;
     if (n_lanes > 1 && spp >= n_lanes && S > (spp + n_lanes - 1) / n_lanes) S = (spp + n_lanes - 1) / n_lanes;
     const uint32_t n_waves = (spp + S - 1) / S;
-    for (uint32_t l = 0; l < n_lanes; ++l) if ((e = lane_prepare(eng.lane[l], nl)) != cudaSuccess) return e;
-    if (VKRT_FUSED != 0 && VKRT_LEAF_BATCH != 0 && sc.n_lights == 1)
-        for (uint32_t l = 0; l < n_lanes; ++l)
-            if (!eng.lane[l].shrec && (e = cudaMalloc((void **)&eng.lane[l].shrec, eng.lane[l].capacity * 4 * sizeof(float4))) != cudaSuccess) return e;
+    // scenes with at most one light take the fused pipeline (logic + mixed trace), the others the four-kernel one
+    const bool fused = VKRT_FUSED != 0 && VKRT_LEAF_BATCH != 0 && sc.n_lights <= 1;
+    const bool dense = fused && VKRT_DENSE != 0 && VKRT_FUSED_GENERATE != 0;
+    for (uint32_t l = 0; l < n_lanes; ++l) if ((e = lane_prepare(eng.lane[l], nl, dense, fused && sc.n_lights == 1)) != cudaSuccess) return e;
     if (n_waves > 1 && !eng.frame_sum) {
         if ((e = cudaMalloc((void **)&eng.frame_sum, (size_t)rp.n_work * sizeof(float4))) != cudaSuccess) return e;
     }
@@ -986,12 +1174,13 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
                                              : (stats ? k_wf_trace<TRACE_SHADOW, false, true> : k_wf_trace<TRACE_SHADOW, false, false>);
         if (mode == TRACE_MIXED) return bvh ? (stats ? k_wf_trace<TRACE_MIXED, true, true> : k_wf_trace<TRACE_MIXED, true, false>)
                                             : (stats ? k_wf_trace<TRACE_MIXED, false, true> : k_wf_trace<TRACE_MIXED, false, false>);
+        if (mode == TRACE_DENSE) return bvh ? (stats ? k_wf_trace<TRACE_DENSE, true, true> : k_wf_trace<TRACE_DENSE, true, false>)
+                                            : (stats ? k_wf_trace<TRACE_DENSE, false, true> : k_wf_trace<TRACE_DENSE, false, false>);
         return bvh ? (stats ? k_wf_trace<TRACE_EXTEND, true, true> : k_wf_trace<TRACE_EXTEND, true, false>)
                    : (stats ? k_wf_trace<TRACE_EXTEND, false, true> : k_wf_trace<TRACE_EXTEND, false, false>);
     };
-    // scenes with at most one light take the fused pipeline (logic + mixed trace), the others the four-kernel one
-    const bool fused = VKRT_FUSED != 0 && VKRT_LEAF_BATCH != 0 && sc.n_lights <= 1;
-    trace_fn k_extend = pick_trace((fused && sc.n_lights) ? TRACE_MIXED : TRACE_EXTEND), k_shadow = pick_trace(fused ? TRACE_MIXED : TRACE_SHADOW);
+    trace_fn k_extend = pick_trace(dense ? TRACE_DENSE : (fused && sc.n_lights) ? TRACE_MIXED : TRACE_EXTEND),
+             k_shadow = pick_trace(dense ? TRACE_DENSE : fused ? TRACE_MIXED : TRACE_SHADOW);
     int occ_e = 0, occ_s = 0;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_extend, VKRT_TRACE_BLOCK, 0)) != cudaSuccess) return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_shadow, VKRT_TRACE_BLOCK, 0)) != cudaSuccess) return e;
@@ -1035,7 +1224,35 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
         wp.n_slots = rp.n_work;
         wp.n_lights = sc.n_lights;
         if ((e = cudaMemsetAsync(wb.counts, 0, (size_t)(rp.max_depth + 1) * C_N * sizeof(uint32_t), ls)) != cudaSuccess) return e;
-        if (fused && VKRT_FUSED_GENERATE) {
+        if (dense) {
+            // depth 0 inside generate; per depth d >= 1: trace (rays of d + shadow rays of d - 1) -> logic; the last depth's
+            // shadow rays at the end.  Arrays of depth d: parity d & 1.
+            void (*k_gen)(const DevScene, const RenderParams, const WaveParams) =
+                bvh ? (stats ? k_wfd_generate_logic<true, true> : k_wfd_generate_logic<true, false>)
+                    : (stats ? k_wfd_generate_logic<false, true> : k_wfd_generate_logic<false, false>);
+            wp.x_hit = wb.d_hit; wp.x_shr = wb.d_shr;
+            wp.cnt = wb.counts; wp.cnt_next = wb.counts + C_N;
+            wp.n_ray = wb.d_ray[1]; wp.n_st = wb.d_st[1];
+            ev_open(0);
+            k_gen<<<(wp.n_slots + VKRT_SHADE_BLOCK - 1u) / VKRT_SHADE_BLOCK, VKRT_SHADE_BLOCK, 0, ls>>>(sc, rp, wp); ++launches;
+            ev_close();
+            for (uint32_t depth = 1; depth <= rp.max_depth; ++depth) {
+                const uint32_t cur = depth & 1u, nxt = cur ^ 1u;
+                wp.cnt = wb.counts + (size_t)depth * C_N;
+                wp.cnt_next = wp.cnt + C_N;
+                wp.x_ray = wb.d_ray[cur]; wp.x_st = wb.d_st[cur]; wp.n_ray = wb.d_ray[nxt]; wp.n_st = wb.d_st[nxt];
+                const bool last = depth == rp.max_depth;          // no rays of this depth exist: only the shadow rays of depth - 1
+                if (last && !sc.n_lights) break;
+                ev_open(last ? 3 : 1);
+                k_extend<<<grid_e, VKRT_TRACE_BLOCK, 0, ls>>>(sc, rp, wp, nullptr, last ? wp.cnt + C_ZERO : wp.cnt + C_ACTIVE, nullptr,
+                                                               wp.cnt - C_N + C_SHADOW, wp.cnt + C_HEAD_EXTEND, depth); ++launches;
+                ev_close();
+                if (last) break;
+                ev_open(2);
+                k_wfd_logic<<<grid_shade, VKRT_SHADE_BLOCK, 0, ls>>>(sc, rp, wp, wp.cnt + C_ACTIVE); ++launches;
+                ev_close();
+            }
+        } else if (fused && VKRT_FUSED_GENERATE) {
             void (*k_gen)(const DevScene, const RenderParams, const WaveParams) =
                 bvh ? (stats ? k_wf_generate_logic<true, true> : k_wf_generate_logic<true, false>)
                     : (stats ? k_wf_generate_logic<false, true> : k_wf_generate_logic<false, false>);
@@ -1051,7 +1268,7 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
             k_gen<<<(wp.n_slots + 255u) / 256u, 256, 0, ls>>>(sc, rp, wp); ++launches;
             ev_close();
         }
-        for (uint32_t depth = 0; depth < rp.max_depth; ++depth) {
+        for (uint32_t depth = 0; depth < rp.max_depth && !dense; ++depth) {
             const uint32_t cur = depth & 1u, nxt = cur ^ 1u;
             wp.cnt = wb.counts + (size_t)depth * C_N;
             wp.cnt_next = wp.cnt + C_N;
