@@ -179,6 +179,14 @@ VKRT_API vkrt_error vkrt_reset_accum(vkrt_ctx *ctx);
 VKRT_API vkrt_error vkrt_set_triangles(vkrt_ctx *ctx, const vkrt_triangle *tris, uint32_t n);
 /* All triangles share one material: `mirror` in Tracer.comp:386, materials[1] in Raytracer.comp:116. */
 VKRT_API vkrt_error vkrt_set_triangle_material(vkrt_ctx *ctx, uint32_t mat_id);
+/* Per-triangle materials (new: meshes; ref: the TODO at Raytracer.comp:10): one material id per triangle of the list set
+ * last, or n = 0 to return to the single shared material. */
+VKRT_API vkrt_error vkrt_set_triangle_materials(vkrt_ctx *ctx, const uint32_t *mat_ids, uint32_t n);
+/* Minimal mesh loader: reads the `v` / `f` records of a Wavefront OBJ file into the reference's 48-byte Triangle layout
+ * (polygons are fanned; xform = optional row-major 3x4 matrix applied to every vertex, or NULL).  Writes at most `capacity`
+ * triangles and always reports the number the file holds. */
+VKRT_API vkrt_error vkrt_load_obj(const char *path, const float xform[12], vkrt_triangle *out, uint32_t capacity,
+                                  uint32_t *n_triangles);
 VKRT_API vkrt_error vkrt_set_materials(vkrt_ctx *ctx, const vkrt_material *mats, uint32_t n);
 VKRT_API vkrt_error vkrt_set_spheres(vkrt_ctx *ctx, const vkrt_sphere *spheres,
                                      const uint32_t *mat_id, uint32_t n);
@@ -189,7 +197,9 @@ VKRT_API vkrt_error vkrt_set_planes(vkrt_ctx *ctx, const vkrt_plane *planes,
 VKRT_API vkrt_error vkrt_use_default_scene(vkrt_ctx *ctx, uint32_t which);
 /* Builds the LBVH over the spheres on the device (Morton codes -> radix sort -> Karras
  * hierarchy -> bottom-up refit) and switches sphere queries from the literal in-order
- * loop (Tracer.comp:398-412) to the order-independent nearest-hit rule (DESIGN.md "S rule"). */
+ * loop (Tracer.comp:398-412) to the order-independent nearest-hit rule (DESIGN.md "S rule").
+ * The triangles of the scene get a second tree of the same kind over their padded boxes and are queried by the
+ * analogous rule T instead of the in-order loop of Tracer.comp:378-396 (DESIGN.md "Rule T"). */
 VKRT_API vkrt_error vkrt_build_bvh(vkrt_ctx *ctx);
 VKRT_API vkrt_error vkrt_clear_bvh(vkrt_ctx *ctx);
 
@@ -312,6 +322,10 @@ typedef struct vkrt_bvh_info {
     uint32_t build_launches;
     uint32_t depth;         /* inner-node levels on the longest root-to-leaf chain; <= 64 by construction (distinct 64-bit
                                (Morton code, index) keys), and the bound of the kernels' traversal stacks (128 entries) */
+    uint32_t n_triangles;   /* the triangles' own tree (rule T): triangles, inner nodes, depth, device build time */
+    uint32_t n_tri_nodes;
+    uint32_t tri_depth;
+    float    tri_build_ms;
 } vkrt_bvh_info;
 VKRT_API vkrt_error vkrt_get_bvh_info(vkrt_ctx *ctx, vkrt_bvh_info *out);
 /* Copies the packed nodes (n_nodes * 16 floats) to the host. */

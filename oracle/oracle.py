@@ -60,6 +60,7 @@ def _load(fast):
     lib.orc_scene_set_spheres.argtypes = [vp, vp, vp, C.c_uint32]
     lib.orc_scene_set_planes.argtypes = [vp, vp, vp, C.c_uint32]
     lib.orc_scene_set_triangles.argtypes = [vp, vp, C.c_uint32, C.c_uint32]
+    lib.orc_scene_set_triangle_materials.argtypes = [vp, vp, C.c_uint32]
     lib.orc_scene_use_default.argtypes = [vp, C.c_uint32]
     lib.orc_scene_build_bvh.argtypes = [vp]
     lib.orc_scene_bvh_nodes.argtypes = [vp]
@@ -145,6 +146,10 @@ class Scene:
     def set_triangles(self, tris, mat_id):  # (n, 12) float32 (3 x vec3 padded to 16 B)
         tris = np.ascontiguousarray(tris, dtype=np.float32).reshape(-1, 12)
         assert self.l.orc_scene_set_triangles(self.h, _ptr(tris), tris.shape[0], mat_id) == 0
+
+    def set_triangle_materials(self, mat_ids):  # one material id per triangle (None / empty: all use set_triangles' mat_id)
+        m = np.ascontiguousarray(mat_ids if mat_ids is not None else [], dtype=np.uint32)
+        assert self.l.orc_scene_set_triangle_materials(self.h, _ptr(m), m.shape[0]) == 0
 
     def build_bvh(self):
         assert self.l.orc_scene_build_bvh(self.h) == 0

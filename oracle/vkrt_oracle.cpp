@@ -204,6 +204,7 @@ struct orc_scene {
     std::vector<uint32_t> plane_mat;
     std::vector<orc_triangle> tris;
     uint32_t tri_mat = 0;
+    std::vector<uint32_t> tri_mats;      // per-triangle material ids (empty: every triangle uses tri_mat, Tracer.comp:386)
     std::vector<uint32_t> lights;        // indices of spheres with emissive != 0 (Tracer.comp:462), ascending
     std::vector<BvhNode> bvh;
     bool has_bvh = false;
@@ -368,6 +369,41 @@ inline SBest s_query_bvh(const orc_scene &sc, const Ray &ray, float eps, float B
     return best;
 }
 
+// Rule T (new, like rule S): triangles of a scene that has a hierarchy.  Triangle j is a CANDIDATE iff its padded box
+//   [min(v) - p, max(v) + p],  p = 0.001 + 0.001 * (largest extent of the unpadded box),
+// passes the slab test and t_j = tri_intersect (Tracer.comp:340-372, back-face culled) satisfies eps < t_j < B and
+// tn <= t_j; the nearest hit is the candidate with the smallest (t_j, j).  Order-independent, so any hierarchy over the
+// padded boxes traversed in any order gives the same answer as this linear scan.  (The reference's in-order loop with
+// its +EPSILON chain rule, :378-396, picks the LATER triangle among hits within 1e-3 -- the same kind of tie band as
+// for spheres; scenes without a hierarchy keep that literal loop.)
+inline void tri_box(const orc_triangle &t, V3 &lo, V3 &hi)
+{
+    const V3 a = from3a(t.v0), b = from3a(t.v1), c = from3a(t.v2);
+    lo = {mn(mn(a.x, b.x), c.x), mn(mn(a.y, b.y), c.y), mn(mn(a.z, b.z), c.z)};
+    hi = {mx(mx(a.x, b.x), c.x), mx(mx(a.y, b.y), c.y), mx(mx(a.z, b.z), c.z)};
+    const float p = 0.001f + 0.001f * mx(mx(hi.x - lo.x, hi.y - lo.y), hi.z - lo.z);
+    lo = {lo.x - p, lo.y - p, lo.z - p};
+    hi = {hi.x + p, hi.y + p, hi.z + p};
+}
+inline SBest t_query_linear(const orc_scene &sc, const Ray &ray, float eps, float B, bool any, Stats &st)
+{
+    SBest best{B, -1};
+    const SlabRay sr = slab_setup(ray);
+    for (size_t j = 0; j < sc.tris.size(); ++j) {
+        V3 lo, hi; tri_box(sc.tris[j], lo, hi);
+        float tn, tf;
+        if (!slab_test(sr, lo, hi, tn, tf)) continue;
+        if (!(tn <= best.t)) continue;
+        ++st.leaves;
+        const float t = tri_intersect(ray, sc.tris[j], eps);
+        if (!(t > eps) || !(tn <= t)) continue;
+        if (best.idx < 0) { if (t < B) { best.t = t; best.idx = (int)j; } }
+        else if (t < best.t || (t == best.t && (int)j < best.idx)) { best.t = t; best.idx = (int)j; }
+        if (any && best.idx >= 0) break;
+    }
+    return best;
+}
+
 // literal in-order loop with the chain rule (Tracer.comp:398-412): returns the LAST accepted sphere
 inline int literal_spheres_tracer(const orc_scene &sc, const Ray &ray, float eps, float &cur)
 {
@@ -390,6 +426,12 @@ inline bool trace_ray(const orc_scene &sc, uint32_t mode, const Ray &ray, Hit &h
     if (shadow) ++st.shadow; else ++st.closest;
     bool found = false;
     float cur = hit.t;
+    if (mode != ORC_SPHERES_LITERAL && !sc.tris.empty()) {
+        // scenes with a hierarchy: rule T (the same exclusive bound as the literal loop's first acceptance)
+        const SBest b = t_query_linear(sc, ray, EPS, TRACER_RULES ? cur + EPS : cur, shadow, st);
+        if (b.idx >= 0) { cur = b.t; hit.kind = KIND_TRI; hit.index = (uint32_t)b.idx; found = true; }
+        if (shadow && found) { hit.t = cur; return true; }
+    } else
     for (size_t i = 0; i < sc.tris.size(); ++i) {
         const float t = tri_intersect(ray, sc.tris[i], EPS);
         const bool acc = TRACER_RULES ? ((t > EPS) && (t < cur + EPS)) : (t > EPS && t < cur);
@@ -432,7 +474,7 @@ inline Surface surface_of(const orc_scene &sc, const Ray &ray, const Hit &hit)
         const orc_triangle &t = sc.tris[hit.index];
         const V3 u = from3a(t.v1) - from3a(t.v0), v = from3a(t.v2) - from3a(t.v0);
         s.N = cross3(u, v);                                   // unnormalised, as in the shader
-        s.mat = &sc.mats[sc.tri_mat];
+        s.mat = &sc.mats[sc.tri_mats.empty() ? sc.tri_mat : sc.tri_mats[hit.index]];
     } else if (hit.kind == KIND_SPHERE) {
         const orc_sphere &sp = sc.spheres[hit.index];
         s.N = (s.P - V3{sp.cx, sp.cy, sp.cz}) / sp.r;
@@ -692,6 +734,13 @@ int orc_scene_set_triangles(orc_scene *s, const orc_triangle *t, uint32_t n, uin
 {
     s->tris.assign(t, t + n);
     s->tri_mat = mat_id;
+    s->tri_mats.clear();
+    return 0;
+}
+int orc_scene_set_triangle_materials(orc_scene *s, const uint32_t *mat_ids, uint32_t n)
+{
+    if (n != s->tris.size() && n != 0) return 6;
+    s->tri_mats.assign(mat_ids, mat_ids + n);
     return 0;
 }
 
@@ -882,6 +931,7 @@ int orc_render(const orc_scene *sc, const orc_params *pp, const orc_frame_data *
     for (uint32_t m : sc->sphere_mat) if (m >= sc->mats.size()) return 6;
     for (uint32_t m : sc->plane_mat) if (m >= sc->mats.size()) return 6;
     if (!sc->tris.empty() && sc->tri_mat >= sc->mats.size()) return 6;
+    for (uint32_t m : sc->tri_mats) if (m >= sc->mats.size()) return 6;
     const uint32_t x0 = p.x0, y0 = p.y0;
     const uint32_t x1 = (p.x1 == 0 && p.x0 == 0) ? p.width : p.x1, y1 = (p.y1 == 0 && p.y0 == 0) ? p.height : p.y1;
     const uint32_t s0 = p.sample_begin, s1 = (p.sample_end == 0 && p.sample_begin == 0) ? p.spp : p.sample_end;

@@ -48,6 +48,8 @@ enum { ORC_WHITTED = 0, ORC_PATH = 1 };
 enum { ORC_SPHERES_LITERAL  = 0,  /* in-order loop with the +EPSILON chain rule (Tracer.comp:398-412) */
        ORC_SPHERES_S_LINEAR = 1,  /* order-independent rule "S", evaluated by a linear scan          */
        ORC_SPHERES_S_BVH    = 2 };/* rule "S", evaluated by traversing the oracle's own CPU LBVH     */
+/* In the two S modes (scenes with a hierarchy) triangles follow the analogous order-independent rule "T", evaluated by
+ * a linear scan over all triangles; in LITERAL mode they keep the reference's in-order loop (Tracer.comp:378-396). */
 
 typedef struct orc_scene orc_scene;
 
@@ -76,6 +78,8 @@ int  orc_scene_set_materials(orc_scene *, const orc_material *, uint32_t n);
 int  orc_scene_set_spheres(orc_scene *, const orc_sphere *, const uint32_t *mat_id, uint32_t n);
 int  orc_scene_set_planes(orc_scene *, const orc_plane *, const uint32_t *mat_id, uint32_t n);
 int  orc_scene_set_triangles(orc_scene *, const orc_triangle *, uint32_t n, uint32_t mat_id);
+/* per-triangle materials (n = number of triangles, or 0 to go back to the single mat_id of set_triangles) */
+int  orc_scene_set_triangle_materials(orc_scene *, const uint32_t *mat_ids, uint32_t n);
 int  orc_scene_use_default(orc_scene *, uint32_t which /* 0 Tracer.comp, 1 Raytracer.comp */);
 int  orc_scene_build_bvh(orc_scene *);          /* CPU LBVH (Morton / sort / Karras / refit) */
 uint32_t orc_scene_bvh_nodes(const orc_scene *);

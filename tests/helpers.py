@@ -38,4 +38,6 @@ def apply_scene(oracle_mod, scene, fast=False):
     sc.set_spheres(scene.spheres, scene.sphere_mat)
     sc.set_planes(scene.planes, scene.plane_mat)
     sc.set_triangles(scene.triangles, scene.tri_mat)
+    if getattr(scene, "tri_mats", None) is not None:
+        sc.set_triangle_materials(scene.tri_mats)
     return sc

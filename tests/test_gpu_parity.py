@@ -79,6 +79,56 @@ def test_path_config2_full_size_subrect(vk, oracle):
     r.close()
 
 
+def test_path_config3_full_size_subrect(vk, oracle):
+    """BASELINE configs[2] at its full size (1,024 spheres, 3840x2160, 64 spp, depth 8, device LBVH, wavefront): the
+    oracle renders two windows of the same frame and those must match the GPU frame bit for bit."""
+    V = vk
+    w, h = 3840, 2160
+    scene = V.scenes.random_spheres(1024)
+    fd = V.default_frame_data(aspect_ratio=w / h, seed=0.5)
+    r = V.Renderer(w, h, spp=64, max_depth=8, variant=V.VARIANT_WAVEFRONT, flags=V.FLAG_HIT_IDS | V.FLAG_NO_RESOLVE)
+    r.set_scene(scene); r.build_bvh(); r.set_seed(7)
+    r.draw(fd)
+    acc, ids, cnt = r.read_accum(), r.read_hit_ids(), r.counters()
+    r.close()
+    sc = apply_scene(oracle, scene, fast=True).build_bvh()
+    for rect in ((1900, 1060, 1948, 1092), (3808, 2136, 3840, 2160)):
+        oacc, oids, _, _ = sc.render(fd, w, h, spp=64, max_depth=8, sphere_mode=oracle.S_BVH, seed=7, rect=rect, want_rgba=False)
+        x0, y0, x1, y1 = rect
+        assert np.array_equal(ids[y0:y1, x0:x1], oids[y0:y1, x0:x1])
+        assert bits_equal(acc[y0:y1, x0:x1], oacc[y0:y1, x0:x1]), mismatch_report(acc[y0:y1, x0:x1], oacc[y0:y1, x0:x1])
+    assert np.all(acc[..., 3] == 64.0) and cnt.paths == w * h * 64
+
+
+def test_path_config5_tile_shard_of_the_full_frame(vk, oracle):
+    """BASELINE configs[4] (100k spheres, 7680x4320, 256 spp, depth 8): one interleaved tile shard (1 of 256, the way a
+    rank of the multi-GPU run holds it) of the full-size frame on the GPU; the oracle renders one of its 32x32 tiles
+    near the image centre and a 128-sample half of it (the sample shard of configs[4]) -- bit-identical."""
+    V = vk
+    w, h = 7680, 4320
+    tiles_x = w // 32
+    tile = (h // 64) * tiles_x + tiles_x // 2          # a tile in the middle of the frame
+    count = 256
+    rank = tile % count
+    tx, ty = tile % tiles_x, tile // tiles_x
+    rect = (tx * 32, ty * 32, tx * 32 + 32, ty * 32 + 32)
+    scene = V.scenes.grid_spheres()
+    fd = V.default_frame_data(aspect_ratio=w / h, seed=0.5)
+    sc = apply_scene(oracle, scene, fast=True).build_bvh()
+    for samp, srange in (((0, 1), (0, 256)), ((1, 2), (128, 256))):
+        r = V.Renderer(w, h, spp=256, max_depth=8, variant=V.VARIANT_WAVEFRONT, flags=V.FLAG_NO_RESOLVE,
+                       tile_shard=(rank, count), sample_shard=samp)
+        r.set_scene(scene); r.build_bvh(); r.set_seed(2026)
+        r.draw(fd)
+        acc = r.read_accum()
+        r.close()
+        oacc, _, _, _ = sc.render(fd, w, h, spp=256, max_depth=8, sphere_mode=oracle.S_BVH, seed=2026, rect=rect, samples=srange,
+                                  want_ids=False, want_rgba=False)
+        x0, y0, x1, y1 = rect
+        assert np.all(acc[y0:y1, x0:x1, 3] == float(srange[1] - srange[0]))
+        assert bits_equal(acc[y0:y1, x0:x1], oacc[y0:y1, x0:x1]), mismatch_report(acc[y0:y1, x0:x1], oacc[y0:y1, x0:x1])
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 17, 1024])
 def test_bvh_tree_matches_oracle_tree(vk, oracle, n):
     V = vk
@@ -277,26 +327,28 @@ def test_progressive_accumulation(vk, oracle):
 
 
 def test_wavefront_multi_wave_equals_megakernel(vk):
-    """40 spp needs three waves of <= 16 samples: the running per-pixel sum must still be formed in
-    sample order, i.e. be bit-identical to the megakernel; also with tile + sample shards and with
-    progressive accumulation."""
+    """A frame of more than 16 spp is cut into waves of <= 16 samples (53 spp: 16 + 16 + 16 + 5): the running per-pixel sum
+    must still be formed in sample order, i.e. be bit-identical to the megakernel, the later waves reuse the first wave's
+    primary hits; also one wave per frame (13 of 40 spp), tile + sample shards, progressive accumulation, three frames
+    back to back (the lanes alternate between frames)."""
     V = vk
     w, h = 96, 72
     scene = V.scenes.random_spheres(200)
     fd = V.default_frame_data(aspect_ratio=w / h, seed=0.9)
-    outs = []
-    for variant in (0, 1):
-        r = V.Renderer(w, h, spp=40, max_depth=5, variant=variant, flags=V.FLAG_PROGRESSIVE | V.FLAG_HIT_IDS,
-                       tile_shard=(1, 2), sample_shard=(1, 3))
-        r.set_scene(scene); r.build_bvh(); r.set_seed(5)
-        r.draw(fd); r.draw(fd)
-        c = r.counters()
-        outs.append((r.read_accum(), r.read_hit_ids(), (c.closest_rays, c.shadow_rays, c.paths)))
-        r.close()
-    assert bits_equal(outs[0][0], outs[1][0]), mismatch_report(outs[0][0], outs[1][0])
-    assert np.array_equal(outs[0][1], outs[1][1])
-    assert outs[0][2] == outs[1][2]
-    assert outs[0][0][..., 3].max() == 2 * (40 * 2 // 3 - 40 // 3)
+    for spp, tile, samp, n_expect in ((40, (1, 2), (1, 3), 40 * 2 // 3 - 40 // 3), (53, (0, 1), (0, 1), 53), (35, (1, 3), (0, 1), 35)):
+        outs = []
+        for variant in (0, 1):
+            r = V.Renderer(w, h, spp=spp, max_depth=5, variant=variant, flags=V.FLAG_PROGRESSIVE | V.FLAG_HIT_IDS,
+                           tile_shard=tile, sample_shard=samp)
+            r.set_scene(scene); r.build_bvh(); r.set_seed(5)
+            r.draw(fd); r.draw(fd); r.draw(fd)
+            c = r.counters()
+            outs.append((r.read_accum(), r.read_hit_ids(), (c.closest_rays, c.shadow_rays, c.paths)))
+            r.close()
+        assert bits_equal(outs[0][0], outs[1][0]), mismatch_report(outs[0][0], outs[1][0])
+        assert np.array_equal(outs[0][1], outs[1][1])
+        assert outs[0][2] == outs[1][2]
+        assert outs[0][0][..., 3].max() == 3 * n_expect
 
 
 def test_serial_waves_flag_is_bit_identical(vk):

@@ -9,8 +9,8 @@ from ._lib import (FLAG_HIT_IDS, FLAG_LAUNCH_TIMING, FLAG_NO_RESOLVE, FLAG_PROGR
                    SCENE_RAYTRACER, SCENE_TRACER, SEMAPHORE_ACQUIRE, SEMAPHORE_RELEASE, TILING_LINEAR, TILING_OPTIMAL,
                    VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT, FrameData, VkrtError)
 from .device import Camera, GraphicsDevice, default_camera, default_frame_data
-from .renderer import Renderer, measure_fp32_peak, measure_l2_bandwidth, pack_materials
+from .renderer import Renderer, load_obj, measure_fp32_peak, measure_l2_bandwidth, pack_materials
 from . import scenes
 
 __all__ = ["Renderer", "GraphicsDevice", "Camera", "FrameData", "default_camera", "default_frame_data", "scenes",
-           "VkrtError", "pack_materials", "measure_fp32_peak", "measure_l2_bandwidth"]
+           "VkrtError", "pack_materials", "load_obj", "measure_fp32_peak", "measure_l2_bandwidth"]

@@ -67,7 +67,8 @@ class Counters(C.Structure):
 
 class BvhInfo(C.Structure):
     _fields_ = [("n_spheres", C.c_uint32), ("n_nodes", C.c_uint32), ("node_bytes", C.c_uint32),
-                ("build_ms", C.c_float), ("build_launches", C.c_uint32), ("depth", C.c_uint32)]
+                ("build_ms", C.c_float), ("build_launches", C.c_uint32), ("depth", C.c_uint32),
+                ("n_triangles", C.c_uint32), ("n_tri_nodes", C.c_uint32), ("tri_depth", C.c_uint32), ("tri_build_ms", C.c_float)]
 
 
 class ExternalImage(C.Structure):  # include/vkrt.h: one exported traced image (ref: Source/GraphicsDevice.cpp:664-699)
@@ -96,6 +97,8 @@ SIGNATURES = {
     "vkrt_reset_accum": ([_vp], C.c_int8),
     "vkrt_set_triangles": ([_vp, _vp, _u32], C.c_int8),
     "vkrt_set_triangle_material": ([_vp, _u32], C.c_int8),
+    "vkrt_set_triangle_materials": ([_vp, _vp, _u32], C.c_int8),
+    "vkrt_load_obj": ([C.c_char_p, _P(C.c_float), _vp, _u32, _P(_u32)], C.c_int8),
     "vkrt_set_materials": ([_vp, _vp, _u32], C.c_int8),
     "vkrt_set_spheres": ([_vp, _vp, _vp, _u32], C.c_int8),
     "vkrt_set_planes": ([_vp, _vp, _vp, _u32], C.c_int8),

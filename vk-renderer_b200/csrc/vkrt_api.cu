@@ -62,11 +62,13 @@ struct vkrt_ctx {
     std::vector<vkrt_plane> planes;
     std::vector<uint32_t> plane_mat;
     std::vector<vkrt_triangle> tris;
+    std::vector<uint32_t> tri_mats;       // per-triangle material ids (empty: every triangle uses tri_mat)
     uint32_t tri_mat = 0;
     bool scene_dirty = true;
     float4 *d_spheres = nullptr, *d_mats = nullptr, *d_tris = nullptr;
-    uint32_t *d_sphere_mat = nullptr;
+    uint32_t *d_sphere_mat = nullptr, *d_tri_mats = nullptr;
     BvhBuild bvh;
+    TriBvhBuild tbvh;                      // the triangles' own tree (built by vkrt_build_bvh when the scene has triangles)
     bool use_bvh = false;
     DevScene dev{};
 
@@ -146,6 +148,8 @@ vkrt_error upload_scene(vkrt_ctx *c)
     for (uint32_t m : c->sphere_mat) if (m >= c->mats.size()) return fail(c, VKRT_BAD_ARG, "sphere material id out of range");
     for (uint32_t m : c->plane_mat) if (m >= c->mats.size()) return fail(c, VKRT_BAD_ARG, "plane material id out of range");
     if (!c->tris.empty() && c->tri_mat >= c->mats.size()) return fail(c, VKRT_BAD_ARG, "triangle material id out of range");
+    if (!c->tri_mats.empty() && c->tri_mats.size() != c->tris.size()) return fail(c, VKRT_BAD_ARG, "per-triangle materials: one id per triangle");
+    for (uint32_t m : c->tri_mats) if (m >= c->mats.size()) return fail(c, VKRT_BAD_ARG, "triangle material id out of range");
     for (const vkrt_material &m : c->mats) if (m.type > 1u) return fail(c, VKRT_BAD_ARG, "unknown material type");
 
     // the emissive-sphere list of Tracer.comp:458-462, in sphere order
@@ -167,6 +171,7 @@ vkrt_error upload_scene(vkrt_ctx *c)
     CU(c, up(&c->d_sphere_mat, c->sphere_mat.data(), c->sphere_mat.size() * sizeof(uint32_t)));
     CU(c, up(&c->d_mats, c->mats.data(), c->mats.size() * sizeof(vkrt_material)));
     CU(c, up(&c->d_tris, c->tris.data(), c->tris.size() * sizeof(vkrt_triangle)));
+    CU(c, up(&c->d_tri_mats, c->tri_mats.data(), c->tri_mats.size() * sizeof(uint32_t)));
     CU(c, cudaStreamSynchronize(c->stream));
 
     DevScene &d = c->dev;
@@ -177,6 +182,9 @@ vkrt_error upload_scene(vkrt_ctx *c)
     d.qbvh = c->use_bvh ? c->bvh.qnodes : nullptr;
     for (int k = 0; k < 3; ++k) { d.qs[k] = c->bvh.qgrid[k]; d.qb2[k] = c->bvh.qgrid[3 + k]; }
     d.n_nodes = c->use_bvh ? c->bvh.n_nodes : 0;
+    d.tbvh = (c->use_bvh && c->tbvh.n_nodes) ? c->tbvh.nodes : nullptr;
+    d.n_tnodes = d.tbvh ? c->tbvh.n_nodes : 0;
+    d.tri_mats = c->d_tri_mats;
     d.n_spheres = (uint32_t)c->spheres.size(); d.n_tris = (uint32_t)c->tris.size(); d.tri_mat = c->tri_mat;
     d.n_planes = (uint32_t)c->planes.size(); d.n_mats = (uint32_t)c->mats.size();
     for (size_t i = 0; i < c->planes.size(); ++i) {
@@ -428,7 +436,8 @@ VKRT_API vkrt_error vkrt_destroy(vkrt_ctx *c)
     DeviceGuard g(c->info.device_id);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->xch.base) vkrt_exchange_close(c);
-    cudaFree(c->d_spheres); cudaFree(c->d_sphere_mat); cudaFree(c->d_mats); cudaFree(c->d_tris);
+    cudaFree(c->d_spheres); cudaFree(c->d_sphere_mat); cudaFree(c->d_mats); cudaFree(c->d_tris); cudaFree(c->d_tri_mats);
+    cudaFree(c->tbvh.nodes);
     cudaFree(c->bvh.nodes); cudaFree(c->bvh.nodes4); cudaFree(c->bvh.qnodes); cudaFree(c->d_accum); cudaFree(c->d_hit_ids);
     for (auto p : c->d_rgba) cudaFree(p);
     for (auto &e : c->ext) { ext_release_target(e); ext_release_semaphores(e); }
@@ -481,6 +490,8 @@ VKRT_API vkrt_error vkrt_set_triangles(vkrt_ctx *c, const vkrt_triangle *t, uint
 {
     if (!c || (n && !t)) return VKRT_BAD_ARG;
     c->tris.assign(t, t + n); c->scene_dirty = true;
+    c->tri_mats.clear();                       // a new triangle list: back to the one shared material
+    c->tbvh.n_nodes = 0;                       // ... and its tree is gone (vkrt_build_bvh makes a new one)
     FWD(c, vkrt_set_triangles(ch, t, n));
     return VKRT_SUCCESS;
 }
@@ -489,6 +500,14 @@ VKRT_API vkrt_error vkrt_set_triangle_material(vkrt_ctx *c, uint32_t mat_id)
     if (!c) return VKRT_BAD_ARG;
     c->tri_mat = mat_id; c->scene_dirty = true;
     FWD(c, vkrt_set_triangle_material(ch, mat_id));
+    return VKRT_SUCCESS;
+}
+VKRT_API vkrt_error vkrt_set_triangle_materials(vkrt_ctx *c, const uint32_t *mat_ids, uint32_t n)
+{
+    if (!c || (n && !mat_ids)) return VKRT_BAD_ARG;
+    if (n != 0 && n != c->tris.size()) return fail(c, VKRT_BAD_ARG, "per-triangle materials: one id per triangle (set the triangles first)");
+    c->tri_mats.assign(mat_ids, mat_ids + n); c->scene_dirty = true;
+    FWD(c, vkrt_set_triangle_materials(ch, mat_ids, n));
     return VKRT_SUCCESS;
 }
 VKRT_API vkrt_error vkrt_set_materials(vkrt_ctx *c, const vkrt_material *m, uint32_t n)
@@ -574,6 +593,10 @@ VKRT_API vkrt_error vkrt_build_bvh(vkrt_ctx *c)
     // per tree level; the LBVH cannot be deeper than 64 levels, and this is where that is enforced
     if (c->bvh.depth + 2 > (int)BVH_STACK)
         return fail(c, VKRT_BAD_ARG, "the LBVH is " + std::to_string(c->bvh.depth) + " levels deep: deeper than the traversal stack");
+    // triangles get a tree of their own (rule T); a scene without triangles keeps none
+    CU(c, build_tri_lbvh(c->d_tris, (uint32_t)c->tris.size(), c->tbvh, c->stream));
+    if (c->tbvh.depth + 2 > (int)BVH_STACK)
+        return fail(c, VKRT_BAD_ARG, "the triangle LBVH is " + std::to_string(c->tbvh.depth) + " levels deep: deeper than the traversal stack");
     c->use_bvh = true;
     c->scene_dirty = true;
     FWD(c, vkrt_build_bvh(ch));                // the build is deterministic: every device gets the identical tree
@@ -595,6 +618,10 @@ VKRT_API vkrt_error vkrt_get_bvh_info(vkrt_ctx *c, vkrt_bvh_info *out)
     out->build_ms = c->bvh.build_ms;
     out->build_launches = c->bvh.launches;
     out->depth = c->use_bvh ? (uint32_t)c->bvh.depth : 0;
+    out->n_triangles = (uint32_t)c->tris.size();
+    out->n_tri_nodes = c->use_bvh ? c->tbvh.n_nodes : 0;
+    out->tri_depth = c->use_bvh ? (uint32_t)c->tbvh.depth : 0;
+    out->tri_build_ms = c->use_bvh ? c->tbvh.build_ms : 0.f;
     return VKRT_SUCCESS;
 }
 VKRT_API vkrt_error vkrt_read_bvh_nodes(vkrt_ctx *c, float *host, size_t bytes)
@@ -666,17 +693,23 @@ VKRT_API vkrt_error vkrt_draw(vkrt_ctx *c, const vkrt_frame_data *frame)
             CU(c, launch_whitted(c->dev, rp, c->use_bvh, stats, c->stream)); ++launches;
         } else if (wavefront) {
             {
-                // two lanes of up to 8 samples of every owned pixel each (one lane when spp == 1), at most
-                // 32 Mi path records per lane (~3.5 GB of HBM)
+                // two lanes (buffer set + stream) of up to 16 samples of every owned pixel each, at most 48 Mi path records
+                // per lane (~10 GB of the 180 GB).  A frame of <= 16 spp is ONE wave: the lanes then alternate between
+                // consecutive frames (two frames in flight, like the reference's FRAMES_IN_FLIGHT), every launch is as
+                // large as the frame allows and one frame's thin deep bounces run next to the next frame's fat early ones
+                // (measured on cfg4: 28.5 -> 28.3 ms/frame, and 4.44 -> 3.96 ms for the 1/8 tile shard of an 8-GPU run)
                 const size_t slots = (size_t)c->owned_tiles * TILE_PX;
-                uint32_t lanes = c->spp >= 2 ? VKRT_WAVE_LANES : 1;
+                uint32_t lanes = VKRT_WAVE_LANES;
                 if (const char *ev = std::getenv("VKRT_TUNE_LANES")) {          // tuning aid: 1..4 lanes (the image does not depend on it)
                     const int v = std::atoi(ev);
-                    if (v >= 1 && v <= 4 && (uint32_t)v <= c->spp) lanes = (uint32_t)v;
+                    if (v >= 1 && v <= 4) lanes = (uint32_t)v;
                 }
-                size_t per_wave = (c->spp + lanes - 1) / lanes;
-                if (per_wave > 16 / lanes) per_wave = 16 / lanes;
-                while (per_wave > 1 && slots * per_wave > ((size_t)64 << 20) / lanes) --per_wave;
+                size_t per_wave = c->spp < 16u ? c->spp : 16u;
+                if (const char *ev = std::getenv("VKRT_TUNE_WAVE_SPP")) {       // tuning aid: samples per wave (the image does not depend on it)
+                    const int v = std::atoi(ev);
+                    if (v >= 1 && (uint32_t)v <= c->spp) per_wave = (size_t)v;
+                }
+                while (per_wave > 1 && slots * per_wave > ((size_t)48 << 20)) --per_wave;
                 // VKRT_FLAG_SERIAL_WAVES: waves of the same size, one buffer set, one stream
                 const uint32_t eng_lanes = (c->info.flags & VKRT_FLAG_SERIAL_WAVES) ? 1u : lanes;
                 const size_t cap = slots * per_wave;
@@ -1162,6 +1195,62 @@ VKRT_API vkrt_error vkrt_unpack_shard(vkrt_ctx *c, const float *dev_packed, uint
     CU(c, join(c));
     CU(c, launch_unpack(c->d_accum, (const float4 *)dev_packed, c->info.width, c->info.height, tile_rank, tile_count, add, c->stream));
     c->accum_valid = true;
+    return VKRT_SUCCESS;
+}
+
+// ---- mesh loading (ref: the TODO at Assets/Raytracer.comp:10, "Load mesh data off of disk and upload ... triangle lists") ----
+// Wavefront OBJ, the subset a triangle list needs: `v x y z` and `f a b c ...` (1-based or negative indices, an optional
+// /vt/vn suffix per corner is ignored, polygons are fanned around their first corner).  Context-free: the engine hands
+// the triangles to vkrt_set_triangles like the reference hands its one triangle to the SSBO (Source/GraphicsDevice.cpp:796-822).
+VKRT_API vkrt_error vkrt_load_obj(const char *path, const float xform[12], vkrt_triangle *out, uint32_t capacity, uint32_t *n_triangles)
+{
+    if (!path || !n_triangles) return VKRT_BAD_ARG;
+    *n_triangles = 0;
+    FILE *f = std::fopen(path, "r");
+    if (!f) return fail(nullptr, VKRT_BAD_ARG, std::string("cannot open ") + path);
+    std::vector<float> v;
+    uint32_t n = 0;
+    char line[1024];
+    bool bad = false;
+    while (std::fgets(line, sizeof line, f)) {
+        if (line[0] == 'v' && (line[1] == ' ' || line[1] == '\t')) {
+            float x, y, z;
+            if (std::sscanf(line + 2, "%f %f %f", &x, &y, &z) != 3) { bad = true; break; }
+            if (xform) {                       // row-major 3x4: p' = M p + t
+                const float X = xform[0] * x + xform[1] * y + xform[2] * z + xform[3];
+                const float Y = xform[4] * x + xform[5] * y + xform[6] * z + xform[7];
+                const float Z = xform[8] * x + xform[9] * y + xform[10] * z + xform[11];
+                x = X; y = Y; z = Z;
+            }
+            v.push_back(x); v.push_back(y); v.push_back(z);
+        } else if (line[0] == 'f' && (line[1] == ' ' || line[1] == '\t')) {
+            long idx[64]; int k = 0;
+            const long nv = (long)(v.size() / 3);
+            for (char *p = line + 2; *p && k < 64; ) {
+                while (*p == ' ' || *p == '\t') ++p;
+                if (!*p || *p == '\n' || *p == '\r') break;
+                char *end = nullptr;
+                long i = std::strtol(p, &end, 10);
+                if (end == p) { bad = true; break; }
+                i = i < 0 ? nv + i : i - 1;
+                if (i < 0 || i >= nv) { bad = true; break; }
+                idx[k++] = i;
+                p = end;
+                while (*p && *p != ' ' && *p != '\t' && *p != '\n' && *p != '\r') ++p;      // skip /vt/vn
+            }
+            if (bad || k < 3) { bad = true; break; }
+            for (int j = 1; j + 1 < k; ++j, ++n) {
+                if (out && n < capacity) {
+                    const long t3[3] = {idx[0], idx[j], idx[j + 1]};
+                    vkrt_vec3a *dst[3] = {&out[n].v0, &out[n].v1, &out[n].v2};
+                    for (int q = 0; q < 3; ++q) { dst[q]->x = v[3 * t3[q]]; dst[q]->y = v[3 * t3[q] + 1]; dst[q]->z = v[3 * t3[q] + 2]; dst[q]->_pad = 0.f; }
+                }
+            }
+        }
+    }
+    std::fclose(f);
+    if (bad) return fail(nullptr, VKRT_BAD_ARG, std::string("malformed OBJ: ") + path);
+    *n_triangles = n;                          // the number in the file: call again with a larger buffer if it exceeds `capacity`
     return VKRT_SUCCESS;
 }
 

@@ -11,6 +11,35 @@
 
 namespace vkrt {
 
+// The builder works on any primitive list that can name a centroid (Morton code) and a padded leaf box (refit):
+// the spheres (rule S, vkrt_device.cuh) and the triangles of the SSBO (rule T).
+struct PrimSpheres {
+    const float4 *s;
+    __device__ __forceinline__ void centroid(uint32_t i, float *c) const { const float4 v = s[i]; c[0] = v.x; c[1] = v.y; c[2] = v.z; }
+    __device__ __forceinline__ void box(uint32_t i, float *lo, float *hi) const
+    {
+        const float4 v = s[i];
+        const float rp = sphere_pad_radius(v.w);
+        lo[0] = v.x - rp; lo[1] = v.y - rp; lo[2] = v.z - rp;
+        hi[0] = v.x + rp; hi[1] = v.y + rp; hi[2] = v.z + rp;
+    }
+};
+struct PrimTris {
+    const float4 *t;      // 3 float4 per triangle (the reference's SSBO layout, Tracer.comp:127-132)
+    __device__ __forceinline__ void box(uint32_t i, float *lo, float *hi) const
+    {
+        V3 l, h;
+        tri_padded_box(xyz(t[3 * i]), xyz(t[3 * i + 1]), xyz(t[3 * i + 2]), l, h);
+        lo[0] = l.x; lo[1] = l.y; lo[2] = l.z; hi[0] = h.x; hi[1] = h.y; hi[2] = h.z;
+    }
+    __device__ __forceinline__ void centroid(uint32_t i, float *c) const
+    {
+        float lo[3], hi[3];
+        box(i, lo, hi);
+        c[0] = 0.5f * (lo[0] + hi[0]); c[1] = 0.5f * (lo[1] + hi[1]); c[2] = 0.5f * (lo[2] + hi[2]);
+    }
+};
+
 // float <-> order-preserving int, for atomicMin/atomicMax on floats
 __device__ __forceinline__ int f2ord(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
@@ -21,13 +50,15 @@ __global__ void k_bounds_init(int *b)
     else if (threadIdx.x < 6) b[threadIdx.x] = (int)0x80000000; // max
 }
 
-__global__ void __launch_bounds__(256) k_bounds(const float4 *__restrict__ sph, uint32_t n, int *b)
+template <class P>
+__global__ void __launch_bounds__(256) k_bounds(const P prim, uint32_t n, int *b)
 {
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 s = sph[i];
-        lo[0] = fminf(lo[0], s.x); lo[1] = fminf(lo[1], s.y); lo[2] = fminf(lo[2], s.z);
-        hi[0] = fmaxf(hi[0], s.x); hi[1] = fmaxf(hi[1], s.y); hi[2] = fmaxf(hi[2], s.z);
+        float c[3];
+        prim.centroid(i, c);
+        lo[0] = fminf(lo[0], c[0]); lo[1] = fminf(lo[1], c[1]); lo[2] = fminf(lo[2], c[2]);
+        hi[0] = fmaxf(hi[0], c[0]); hi[1] = fmaxf(hi[1], c[1]); hi[2] = fmaxf(hi[2], c[2]);
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -53,7 +84,8 @@ __device__ __forceinline__ uint32_t quant10(float c, float cmin, float scale)
     return (uint32_t)q;
 }
 
-__global__ void __launch_bounds__(256) k_morton(const float4 *__restrict__ sph, uint32_t n, const int *__restrict__ b,
+template <class P>
+__global__ void __launch_bounds__(256) k_morton(const P prim, uint32_t n, const int *__restrict__ b,
                                                  uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -61,9 +93,10 @@ __global__ void __launch_bounds__(256) k_morton(const float4 *__restrict__ sph, 
     const float cminx = ord2f(b[0]), cminy = ord2f(b[1]), cminz = ord2f(b[2]);
     const float ex = ord2f(b[3]) - cminx, ey = ord2f(b[4]) - cminy, ez = ord2f(b[5]) - cminz;
     const float sx = ex > 0.0f ? 1024.0f / ex : 0.0f, sy = ey > 0.0f ? 1024.0f / ey : 0.0f, sz = ez > 0.0f ? 1024.0f / ez : 0.0f;
-    const float4 s = sph[i];
-    keys[i] = (expand_bits(quant10(s.x, cminx, sx)) << 2) | (expand_bits(quant10(s.y, cminy, sy)) << 1) |
-              expand_bits(quant10(s.z, cminz, sz));
+    float c[3];
+    prim.centroid(i, c);
+    keys[i] = (expand_bits(quant10(c[0], cminx, sx)) << 2) | (expand_bits(quant10(c[1], cminy, sy)) << 1) |
+              expand_bits(quant10(c[2], cminz, sz));
     vals[i] = i;
 }
 
@@ -199,14 +232,8 @@ __device__ __forceinline__ void write_child(float4 *node, int k, bool leaf, int 
     node[2 * k] = make_float4(lo[0], lo[1], lo[2], hi[0]);
     node[2 * k + 1] = make_float4(hi[1], hi[2], __int_as_float(index), __int_as_float(leaf ? 1 : 0));
 }
-__device__ __forceinline__ void leaf_box(float4 s, float *lo, float *hi)
-{
-    const float rp = sphere_pad_radius(s.w);
-    lo[0] = s.x - rp; lo[1] = s.y - rp; lo[2] = s.z - rp;
-    hi[0] = s.x + rp; hi[1] = s.y + rp; hi[2] = s.z + rp;
-}
-
-__global__ void __launch_bounds__(256) k_refit(const float4 *__restrict__ sph, const uint32_t *__restrict__ sorted_idx, int n,
+template <class P>
+__global__ void __launch_bounds__(256) k_refit(const P prim, const uint32_t *__restrict__ sorted_idx, int n,
                                                 const int2 *__restrict__ children, const int *__restrict__ parent_inner,
                                                 const int *__restrict__ parent_leaf, int *__restrict__ arrivals,
                                                 float4 *__restrict__ box_lo, float4 *__restrict__ box_hi,
@@ -229,7 +256,7 @@ __global__ void __launch_bounds__(256) k_refit(const float4 *__restrict__ sph, c
             is_leaf[k] = ch < 0;
             if (is_leaf[k]) {
                 idx[k] = (int)sorted_idx[~ch];
-                leaf_box(sph[idx[k]], lo[k], hi[k]);
+                prim.box((uint32_t)idx[k], lo[k], hi[k]);
             } else {
                 idx[k] = ch;
                 const volatile float4 *pl = box_lo + ch, *ph = box_hi + ch;
@@ -256,10 +283,11 @@ __global__ void __launch_bounds__(256) k_tree_depth(const int *__restrict__ pare
     if ((threadIdx.x & 31) == 0) atomicMax(depth, d);
 }
 
-__global__ void k_single_leaf(const float4 *__restrict__ sph, float4 *__restrict__ nodes)
+template <class P>
+__global__ void k_single_leaf(const P prim, float4 *__restrict__ nodes)
 {
     float lo[3], hi[3];
-    leaf_box(sph[0], lo, hi);
+    prim.box(0u, lo, hi);
     write_child(nodes, 0, true, 0, lo, hi);
     write_child(nodes, 1, true, 0, lo, hi);
 }
@@ -348,34 +376,20 @@ __global__ void __launch_bounds__(256) k_quantize(const float4 *__restrict__ nod
 
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { err = _e; goto done; } } while (0)
 
-cudaError_t build_lbvh(const float4 *d_spheres, uint32_t n, BvhBuild &out, cudaStream_t st)
+// the hierarchy itself: `nodes` = (n > 1 ? n - 1 : 1) exact 64-byte nodes (caller-allocated), depth, launch count
+template <class P>
+static cudaError_t build_tree(const P prim, uint32_t n, float4 *nodes, int *depth_out, uint32_t *launches_out, cudaStream_t st)
 {
     cudaError_t err = cudaSuccess;
-    if (out.nodes) { cudaFree(out.nodes); out.nodes = nullptr; }
-    if (out.nodes4) { cudaFree(out.nodes4); out.nodes4 = nullptr; }
-    if (out.qnodes) { cudaFree(out.qnodes); out.qnodes = nullptr; }
-    float *grid = nullptr;
-    int *d_depth = nullptr;
-    out.n_nodes = 0; out.build_ms = 0.f; out.launches = 0; out.depth = 0;
-    if (n == 0) return cudaSuccess;
-
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    int *bounds = nullptr, *parent_inner = nullptr, *parent_leaf = nullptr, *arrivals = nullptr;
+    int *bounds = nullptr, *parent_inner = nullptr, *parent_leaf = nullptr, *arrivals = nullptr, *d_depth = nullptr;
     uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr}, *hist = nullptr;
     int2 *children = nullptr;
     float4 *box_lo = nullptr, *box_hi = nullptr;
-    const uint32_t n_inner = n > 1 ? n - 1 : 1;
     const uint32_t n_blocks = (n + RS_TILE - 1) / RS_TILE;
     uint32_t launches = 0;
-
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    CK(cudaMalloc(&out.nodes, (size_t)n_inner * 64));
-    CK(cudaMalloc(&out.nodes4, (size_t)n_inner * 128));
-    CK(cudaMalloc(&out.qnodes, (size_t)n_inner * 32));
-    CK(cudaMalloc(&grid, 6 * sizeof(float)));
-    CK(cudaEventRecord(e0, st));
+    *depth_out = 1;
     if (n == 1) {
-        k_single_leaf<<<1, 1, 0, st>>>(d_spheres, out.nodes); ++launches;
+        k_single_leaf<P><<<1, 1, 0, st>>>(prim, nodes); ++launches;
         CK(cudaGetLastError());
     } else {
         CK(cudaMalloc(&bounds, 6 * sizeof(int)));
@@ -387,14 +401,16 @@ cudaError_t build_lbvh(const float4 *d_spheres, uint32_t n, BvhBuild &out, cudaS
         CK(cudaMalloc(&arrivals, (size_t)(n - 1) * sizeof(int)));
         CK(cudaMalloc(&box_lo, (size_t)(n - 1) * sizeof(float4)));
         CK(cudaMalloc(&box_hi, (size_t)(n - 1) * sizeof(float4)));
+        CK(cudaMalloc(&d_depth, sizeof(int)));
         CK(cudaMemsetAsync(arrivals, 0, (size_t)(n - 1) * sizeof(int), st));
+        CK(cudaMemsetAsync(d_depth, 0, sizeof(int), st));
 
         k_bounds_init<<<1, 32, 0, st>>>(bounds); ++launches;
         {
             unsigned g = (n + 255u) / 256u; if (g > 592u) g = 592u;   // 4 x 148 SMs
-            k_bounds<<<g, 256, 0, st>>>(d_spheres, n, bounds); ++launches;
+            k_bounds<P><<<g, 256, 0, st>>>(prim, n, bounds); ++launches;
         }
-        k_morton<<<(n + 255u) / 256u, 256, 0, st>>>(d_spheres, n, bounds, keys[0], vals[0]); ++launches;
+        k_morton<P><<<(n + 255u) / 256u, 256, 0, st>>>(prim, n, bounds, keys[0], vals[0]); ++launches;
         int cur = 0;
         for (int pass = 0; pass < 4; ++pass) {
             const int shift = pass * 8;
@@ -404,14 +420,43 @@ cudaError_t build_lbvh(const float4 *d_spheres, uint32_t n, BvhBuild &out, cudaS
             cur ^= 1;
         }
         k_karras<<<(n - 1 + 255u) / 256u, 256, 0, st>>>(keys[cur], (int)n, children, parent_inner, parent_leaf); ++launches;
-        k_refit<<<(n + 255u) / 256u, 256, 0, st>>>(d_spheres, vals[cur], (int)n, children, parent_inner, parent_leaf, arrivals,
-                                                   box_lo, box_hi, out.nodes); ++launches;
+        k_refit<P><<<(n + 255u) / 256u, 256, 0, st>>>(prim, vals[cur], (int)n, children, parent_inner, parent_leaf, arrivals,
+                                                      box_lo, box_hi, nodes); ++launches;
         CK(cudaGetLastError());
-        CK(cudaMalloc(&d_depth, sizeof(int)));
-        CK(cudaMemsetAsync(d_depth, 0, sizeof(int), st));
         k_tree_depth<<<(n + 255u) / 256u, 256, 0, st>>>(parent_inner, parent_leaf, (int)n, d_depth); ++launches;
         CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(depth_out, d_depth, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));       // the temporaries below are freed when this returns
     }
+    *launches_out += launches;
+done:
+    cudaFree(bounds); cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); cudaFree(hist);
+    cudaFree(children); cudaFree(parent_inner); cudaFree(parent_leaf); cudaFree(arrivals); cudaFree(box_lo); cudaFree(box_hi);
+    cudaFree(d_depth);
+    return err;
+}
+
+cudaError_t build_lbvh(const float4 *d_spheres, uint32_t n, BvhBuild &out, cudaStream_t st)
+{
+    cudaError_t err = cudaSuccess;
+    if (out.nodes) { cudaFree(out.nodes); out.nodes = nullptr; }
+    if (out.nodes4) { cudaFree(out.nodes4); out.nodes4 = nullptr; }
+    if (out.qnodes) { cudaFree(out.qnodes); out.qnodes = nullptr; }
+    float *grid = nullptr;
+    out.n_nodes = 0; out.build_ms = 0.f; out.launches = 0; out.depth = 0;
+    if (n == 0) return cudaSuccess;
+
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const uint32_t n_inner = n > 1 ? n - 1 : 1;
+    uint32_t launches = 0;
+
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaMalloc(&out.nodes, (size_t)n_inner * 64));
+    CK(cudaMalloc(&out.nodes4, (size_t)n_inner * 128));
+    CK(cudaMalloc(&out.qnodes, (size_t)n_inner * 32));
+    CK(cudaMalloc(&grid, 6 * sizeof(float)));
+    CK(cudaEventRecord(e0, st));
+    CK(build_tree(PrimSpheres{d_spheres}, n, out.nodes, &out.depth, &launches, st));
     k_collapse4<<<(n_inner + 255u) / 256u, 256, 0, st>>>(out.nodes, n_inner, out.nodes4); ++launches;
     CK(cudaGetLastError());
     k_qgrid<<<1, 32, 0, st>>>(out.nodes, grid); ++launches;
@@ -419,8 +464,6 @@ cudaError_t build_lbvh(const float4 *d_spheres, uint32_t n, BvhBuild &out, cudaS
     CK(cudaGetLastError());
     CK(cudaEventRecord(e1, st));
     CK(cudaMemcpyAsync(out.qgrid, grid, 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (d_depth) CK(cudaMemcpyAsync(&out.depth, d_depth, sizeof(int), cudaMemcpyDeviceToHost, st));
-    else out.depth = 1;
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&out.build_ms, e0, e1));
     out.n_nodes = n_inner;
@@ -428,10 +471,32 @@ cudaError_t build_lbvh(const float4 *d_spheres, uint32_t n, BvhBuild &out, cudaS
 done:
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
-    cudaFree(bounds); cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); cudaFree(hist);
-    cudaFree(children); cudaFree(parent_inner); cudaFree(parent_leaf); cudaFree(arrivals); cudaFree(box_lo); cudaFree(box_hi);
-    cudaFree(grid); cudaFree(d_depth);
+    cudaFree(grid);
     if (err != cudaSuccess) { cudaFree(out.nodes); cudaFree(out.nodes4); cudaFree(out.qnodes); out.nodes = nullptr; out.nodes4 = nullptr; out.qnodes = nullptr; }
+    return err;
+}
+
+// the triangles' own hierarchy (rule T): the same builder over the padded triangle boxes; exact 64-byte nodes only
+cudaError_t build_tri_lbvh(const float4 *d_tris, uint32_t n, TriBvhBuild &out, cudaStream_t st)
+{
+    cudaError_t err = cudaSuccess;
+    if (out.nodes) { cudaFree(out.nodes); out.nodes = nullptr; }
+    out.n_nodes = 0; out.depth = 0; out.build_ms = 0.f; out.launches = 0;
+    if (n == 0) return cudaSuccess;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const uint32_t n_inner = n > 1 ? n - 1 : 1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaMalloc(&out.nodes, (size_t)n_inner * 64));
+    CK(cudaEventRecord(e0, st));
+    CK(build_tree(PrimTris{d_tris}, n, out.nodes, &out.depth, &out.launches, st));
+    CK(cudaEventRecord(e1, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&out.build_ms, e0, e1));
+    out.n_nodes = n_inner;
+done:
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (err != cudaSuccess) { cudaFree(out.nodes); out.nodes = nullptr; }
     return err;
 }
 

@@ -34,7 +34,9 @@ struct DevScene {
     const uint4 *qbvh;            // 32-byte traversal nodes (two child records with 16-bit box coordinates)
     const float4 *tris;
     const float4 *mats;
-    uint32_t n_spheres, n_tris, tri_mat, n_planes, n_lights, n_nodes, n_mats, _pad;
+    const float4 *tbvh;           // the triangles' own binary 64-byte nodes (rule T), or null: literal triangle loop
+    const uint32_t *tri_mats;     // per-triangle material ids, or null: every triangle uses tri_mat (Tracer.comp:386)
+    uint32_t n_spheres, n_tris, tri_mat, n_planes, n_lights, n_nodes, n_mats, n_tnodes;
     float4 planes[MAX_PLANES];
     uint32_t plane_mat[MAX_PLANES];
     uint32_t lights[MAX_LIGHTS];
@@ -124,6 +126,15 @@ VKRT_DEV bool slab_test(const SlabRay &s, V3 lo, V3 hi, float &tn, float &tf)
     return tn <= tf && tf >= 0.0f;
 }
 VKRT_DEV float sphere_pad_radius(float r) { return r * 1.001f + 0.001f; }
+// rule T: the padded box of a triangle, [min(v) - p, max(v) + p] with p = 0.001 + 0.001 * (largest extent)
+VKRT_DEV void tri_padded_box(V3 a, V3 b, V3 c, V3 &lo, V3 &hi)
+{
+    lo = v3(fminf(fminf(a.x, b.x), c.x), fminf(fminf(a.y, b.y), c.y), fminf(fminf(a.z, b.z), c.z));
+    hi = v3(fmaxf(fmaxf(a.x, b.x), c.x), fmaxf(fmaxf(a.y, b.y), c.y), fmaxf(fmaxf(a.z, b.z), c.z));
+    const float p = 0.001f + 0.001f * fmaxf(fmaxf(hi.x - lo.x, hi.y - lo.y), hi.z - lo.z);
+    lo = v3(lo.x - p, lo.y - p, lo.z - p);
+    hi = v3(hi.x + p, hi.y + p, hi.z + p);
+}
 
 struct SBest { float t; int idx; };
 
@@ -164,6 +175,22 @@ VKRT_DEV void trav_init(Trav &tv, const DevScene &sc, V3 o, V3 d, float eps, flo
     tv.node = sc.n_nodes ? 0 : -1;
 }
 // the exact rule-S leaf test: the sphere's own padded box, then the reference's intersection formula
+// the rule-T leaf test: the triangle's padded box, then the reference's Moeller-Trumbore routine (Tracer.comp:340-372)
+template <bool STATS>
+VKRT_DEV void tri_leaf_test(Trav &tv, const DevScene &sc, V3 o, V3 d, int ti, Stats &st)
+{
+    const V3 v0 = xyz(__ldg(sc.tris + 3 * ti)), v1 = xyz(__ldg(sc.tris + 3 * ti + 1)), v2 = xyz(__ldg(sc.tris + 3 * ti + 2));
+    V3 lo, hi;
+    tri_padded_box(v0, v1, v2, lo, hi);
+    float tn, tf;
+    if (slab_test(tv.sr, lo, hi, tn, tf) && tn <= tv.best.t) {
+        if (STATS) ++st.leaves;
+        const float t = tri_intersect(o, d, v0, v1, v2, tv.eps);
+        if (!(t > tv.eps) || !(tn <= t)) return;
+        if (tv.best.idx < 0) { if (t < tv.B) { tv.best.t = t; tv.best.idx = ti; } }
+        else if (t < tv.best.t || (t == tv.best.t && ti < tv.best.idx)) { tv.best.t = t; tv.best.idx = ti; }
+    }
+}
 template <bool STATS>
 VKRT_DEV void leaf_test(Trav &tv, const DevScene &sc, V3 o, V3 d, int si, Stats &st)
 {
@@ -183,10 +210,11 @@ VKRT_DEV void cswap(float &ta, int &ia, float &tb, int &ib)
     const int i = s ? ib : ia; ib = s ? ia : ib; ia = i;
 }
 
-template <bool ANY, bool STATS>
+template <bool ANY, bool STATS, bool TRI = false>
 VKRT_DEV void trav_step(Trav &tv, int *__restrict__ stack, const DevScene &sc, V3 o, V3 d, Stats &st)
 {
 #if VKRT_BVH4
+    static_assert(!TRI, "the 4-wide option has no triangle tree");
     // one 128-byte node = four child records {lo.xyz hi.x | hi.yz index kind} = four 256-bit loads in flight at once
     const float4 *np = sc.bvh4 + 8 * (size_t)tv.node;
     float4 a[4], b[4];
@@ -220,7 +248,7 @@ VKRT_DEV void trav_step(Trav &tv, int *__restrict__ stack, const DevScene &sc, V
     if (c > 0) tv.node = idx[0];
     else tv.node = tv.sp ? stack[--tv.sp] : -1;
 #else
-    const float4 *np = sc.bvh + 4 * (size_t)tv.node;
+    const float4 *np = (TRI ? sc.tbvh : sc.bvh) + 4 * (size_t)tv.node;
     float4 a0, b0, a1, b1;
     ldg256(np, a0, b0);
     ldg256(np + 2, a1, b1);
@@ -229,8 +257,8 @@ VKRT_DEV void trav_step(Trav &tv, int *__restrict__ stack, const DevScene &sc, V
     bool h0 = slab_test(tv.sr, v3(a0.x, a0.y, a0.z), v3(a0.w, b0.x, b0.y), tn0, tf) && tn0 <= tv.best.t;
     bool h1 = slab_test(tv.sr, v3(a1.x, a1.y, a1.z), v3(a1.w, b1.x, b1.y), tn1, tf) && tn1 <= tv.best.t;
     const int i0 = __float_as_int(b0.z), i1 = __float_as_int(b1.z);
-    if (h0 && __float_as_int(b0.w) != 0) { leaf_test<STATS>(tv, sc, o, d, i0, st); h0 = false; }
-    if (h1 && __float_as_int(b1.w) != 0) { leaf_test<STATS>(tv, sc, o, d, i1, st); h1 = false; }
+    if (h0 && __float_as_int(b0.w) != 0) { if (TRI) tri_leaf_test<STATS>(tv, sc, o, d, i0, st); else leaf_test<STATS>(tv, sc, o, d, i0, st); h0 = false; }
+    if (h1 && __float_as_int(b1.w) != 0) { if (TRI) tri_leaf_test<STATS>(tv, sc, o, d, i1, st); else leaf_test<STATS>(tv, sc, o, d, i1, st); h1 = false; }
     if (ANY && tv.best.idx >= 0) { tv.node = -1; return; }
     const bool both = h0 && h1;
     const bool take1 = both ? (tn1 < tn0) : h1;
@@ -433,13 +461,34 @@ VKRT_DEV SBest bvh_query(const DevScene &sc, V3 o, V3 d, float eps, float B, Sta
     while (tv.node >= 0) trav_step<ANY, STATS>(tv, stack, sc, o, d, st);
     return tv.best;
 }
+// the same walk through the triangles' tree (rule T)
+template <bool ANY>
+VKRT_DEV SBest tri_bvh_query(const DevScene &sc, V3 o, V3 d, float eps, float B)
+{
+    Trav tv;
+    int stack[BVH_STACK];
+    Stats st;
+    trav_init(tv, sc, o, d, eps, B);
+    tv.node = sc.n_tnodes ? 0 : -1;
+    while (tv.node >= 0) trav_step<ANY, false, true>(tv, stack, sc, o, d, st);
+    return tv.best;
+}
 
 // ---- trace_ray: Tracer.comp:374-431 (TRACER = true) / Raytracer.comp:224-278 (false) ----------
 // SHADOW queries only need the boolean, so they may leave early.
-template <bool TRACER>
+// Scenes with a hierarchy (vkrt_build_bvh) hold their triangles in a tree of their own and query it by the
+// order-independent rule T (same exclusive bound as the literal loop's first acceptance); ANY = a shadow query, which
+// may stop at the first hit.  Scenes without one run the reference's literal loop.
+template <bool TRACER, bool ANY = false>
 VKRT_DEV bool trace_tris(const DevScene &sc, V3 o, V3 d, float &cur, Hit &hit)
 {
     const float EPS = TRACER ? 1e-3f : 0.01f;
+    if (sc.tbvh) {
+        const SBest b = tri_bvh_query<ANY>(sc, o, d, EPS, TRACER ? cur + EPS : cur);
+        if (b.idx < 0) return false;
+        cur = b.t; hit.kind = KIND_TRI; hit.index = (uint32_t)b.idx;
+        return true;
+    }
     bool found = false;
     for (uint32_t i = 0; i < sc.n_tris; ++i) {
         const V3 v0 = xyz(__ldg(sc.tris + 3 * i)), v1 = xyz(__ldg(sc.tris + 3 * i + 1)), v2 = xyz(__ldg(sc.tris + 3 * i + 2));
@@ -510,7 +559,7 @@ VKRT_DEV Surface surface_of(const DevScene &sc, V3 o, V3 d, const Hit &hit)
         const V3 v0 = xyz(__ldg(sc.tris + 3 * hit.index)), v1 = xyz(__ldg(sc.tris + 3 * hit.index + 1)),
                  v2 = xyz(__ldg(sc.tris + 3 * hit.index + 2));
         s.N = cross3(v1 - v0, v2 - v0);      // unnormalised (Tracer.comp:389-392)
-        s.mat = sc.tri_mat;
+        s.mat = sc.tri_mats ? __ldg(sc.tri_mats + hit.index) : sc.tri_mat;
     } else if (hit.kind == KIND_SPHERE) {
         const float4 sp = __ldg(sc.spheres + hit.index);
         s.N = (s.P - xyz(sp)) / sp.w;         // Tracer.comp:408

@@ -75,7 +75,12 @@ struct WaveEngine {
     WaveBuffers lane[4];
     cudaStream_t stream[4];
     cudaEvent_t ev_fork, ev_reduce[4];
+    cudaEvent_t ev_stage[4];      // staggered lanes: "the wave on this lane has reached the stagger depth"
+    uint32_t stage_lane; bool have_stage;
     float4 *frame_sum;            // running per-slot sum across the waves of a frame
+    float2 *prim[2];              // per-slot primary hit {t, id} of the frame being launched / the frame before (frames overlap)
+    uint32_t prim_flip;
+    cudaEvent_t ev_prim;          // the first wave's generate kernel has stored the primary hits
     uint32_t n_lanes;
     uint32_t wave_seq;            // waves launched so far: lanes alternate across frame boundaries too
     uint32_t prev_reduce_lane; bool have_prev_reduce;
@@ -102,6 +107,14 @@ struct BvhBuild {
     uint32_t launches = 0;
 };
 cudaError_t build_lbvh(const float4 *d_spheres, uint32_t n, BvhBuild &out, cudaStream_t st);
+struct TriBvhBuild {
+    float4 *nodes = nullptr;      // binary 64-byte nodes over the padded triangle boxes (rule T)
+    uint32_t n_nodes = 0;
+    int depth = 0;
+    float build_ms = 0.f;
+    uint32_t launches = 0;
+};
+cudaError_t build_tri_lbvh(const float4 *d_tris, uint32_t n, TriBvhBuild &out, cudaStream_t st);
 
 // vkrt_exchange.cu: device-side synchronisation and collection of the multi-GPU frame exchange
 enum { X_MAX_RANKS = 64, X_FLAG_STRIDE = 16 /* uint64s = 128 bytes */, X_OFF_CONSUMED = 8192, X_OFF_ERROR = 8320, X_OFF_TARGETS = 16384 };

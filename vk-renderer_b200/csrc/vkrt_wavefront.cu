@@ -22,6 +22,8 @@
 //
 // and a wave ends with `reduce`, which adds the per-sample radiances of every pixel IN SAMPLE ORDER,
 // so the result is bit-identical to the megakernel and to the oracle whatever the scheduling was.
+#include <cstdlib>
+
 #include "vkrt_device.cuh"
 #include "vkrt_internal.h"
 
@@ -76,6 +78,9 @@
 #ifndef VKRT_DENSE
 #define VKRT_DENSE 1               // fused pipeline: survivors of a depth are written DENSELY (ping-pong ray / state arrays, position =
 #endif                             //                 queue index): no path-id indirection, every record access is a contiguous stream
+#ifndef VKRT_STAGGER
+#define VKRT_STAGGER 0             // > 0: a wave starts when the wave before it has launched this depth's logic (staggered lanes)
+#endif
 #ifndef VKRT_SHADE_BLOCK
 #define VKRT_SHADE_BLOCK 256
 #endif
@@ -107,6 +112,9 @@ struct WaveParams {
     //         the NEXT depth's arrays, or 0x80000000 | index into rad when the path ended at this bounce
     const float4 *x_ray; float4 *x_st, *n_ray, *n_st, *x_shr;
     float2 *x_hit;
+    // every sample of a pixel starts from the same primary hit (Tracer.comp:574-581): the frame's first wave stores it
+    // per pixel slot (prim_mode 1), the later waves of the frame load it instead of traversing again (prim_mode 2)
+    float2 *prim; uint32_t prim_mode;
 };
 
 VKRT_DEV void ld256(const float4 *p, float4 &a, float4 &b)
@@ -318,6 +326,15 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
     const float EPS = 1e-3f;
     const float tmax = path_tmax(depth);       // every ray of one extend launch is at the same depth (:444)
 
+    // items a warp reserves per atomicAdd on the queue head: VKRT_FETCH_CHUNK when there is plenty of work, smaller when
+    // the launch has fewer items than that per warp -- a thin launch (deep bounces, small tile shards) is then spread over
+    // all SMs in many partly filled warps instead of a few full ones, and ends after about one ray's latency
+    uint32_t chunk = (uint32_t)VKRT_FETCH_CHUNK;
+    {
+        const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+        while (chunk > 8u && n_items < chunk * n_warps) chunk >>= 1;
+    }
+    const uint32_t refill_at = chunk < (uint32_t)VKRT_REFILL ? chunk : (uint32_t)VKRT_REFILL;
     bool has = false, drained = false;
     uint32_t res_base = 0, res_left = 0;       // this warp's current reservation of queue items (warp-uniform)
     uint32_t path = 0, light = 0;
@@ -357,18 +374,20 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
         if (m) {
             // the warp reserves ray indices VKRT_FETCH_CHUNK at a time (one atomicAdd by one lane, broadcast
             // with __shfl_sync) and hands them to the lanes that need work from that reservation
-            const uint32_t cnt = (uint32_t)__popc(m);
+            // (a thin launch hands out at most one chunk per round: the other idle lanes stay idle for other warps' sake)
+            const uint32_t idle = (uint32_t)__popc(m);
+            const uint32_t cnt = idle < chunk ? idle : chunk;
             uint32_t new_base = 0;
             if (res_left < cnt) {
                 const int leader = __ffs(m) - 1;
-                if ((int)lane == leader) new_base = atomicAdd(head, (uint32_t)VKRT_FETCH_CHUNK);
+                if ((int)lane == leader) new_base = atomicAdd(head, chunk);
                 new_base = __shfl_sync(full, new_base, leader);
             }
             const uint32_t rank = (uint32_t)__popc(m & ((1u << lane) - 1u));
             const uint32_t my_item = rank < res_left ? res_base + rank : new_base + (rank - res_left);
-            if (res_left < cnt) { res_base = new_base + (cnt - res_left); res_left = (uint32_t)VKRT_FETCH_CHUNK - (cnt - res_left); }
+            if (res_left < cnt) { res_base = new_base + (cnt - res_left); res_left = chunk - (cnt - res_left); }
             else { res_base += cnt; res_left -= cnt; }
-            if (need) {
+            if (need && rank < cnt) {
                 const uint32_t item = my_item;
                 if (item >= n_items) drained = true;
                 else {
@@ -443,7 +462,7 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                 const bool trav = has && (tv.node != FIN || pend != FIN);
                 const unsigned tm = __ballot_sync(full, trav);
                 if (tm == 0) break;
-                if (__popc(tm) < VKRT_REFILL && __any_sync(full, !drained && !trav)) break;
+                if (__popc(tm) < (int)refill_at && __any_sync(full, !drained && !trav)) break;
                 const unsigned im = __ballot_sync(full, trav && tv.node >= 0);
                 const unsigned pm = __ballot_sync(full, trav && pend != FIN);
                 if (im == 0 || __popc(pm) >= VKRT_LEAF_BATCH) {
@@ -471,7 +490,7 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                 const bool trav = has && tv.node != FIN;
                 const unsigned tm = __ballot_sync(full, trav);
                 if (tm == 0) break;
-                if (__popc(tm) < VKRT_REFILL && __any_sync(full, !drained && !trav)) break;
+                if (__popc(tm) < (int)refill_at && __any_sync(full, !drained && !trav)) break;
                 // lanes whose next item is a scheduled leaf wait until VKRT_LEAF_BATCH of them can run the leaf test
                 // together (or nobody has an inner node left); everybody else keeps visiting inner nodes
                 const unsigned im = __ballot_sync(full, trav && tv.node >= 0);
@@ -509,7 +528,7 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                 const bool trav = has && tv.node >= 0;
                 const unsigned tm = __ballot_sync(full, trav);
                 if (tm == 0) break;
-                if (__popc(tm) < VKRT_REFILL && __any_sync(full, !drained && !trav)) break;
+                if (__popc(tm) < (int)refill_at && __any_sync(full, !drained && !trav)) break;
 #pragma unroll
                 for (int u = 0; u < VKRT_TRAV_UNROLL; ++u)     // the warp votes above cost ~10 instructions: amortise them
                     if (has && tv.node >= 0) trav_step<MODE == TRACE_SHADOW, STATS>(tv, stack, sc, o, d, st);
@@ -1004,23 +1023,30 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wfd_
     uint32_t pix = 0;
     if (valid) {
         primary_ray(rp.fd, rp.width, rp.height, px, py, o, d);
-        float cur = path_tmax(0);
-        found = trace_tris<true>(sc, o, d, cur, hit);
-        if (BVH) {
-            const SBest b = bvh_query<false, STATS>(sc, o, d, 1e-3f, sphere_bound<true>(cur), st);
-            if (b.idx >= 0) { cur = b.t; hit.kind = KIND_SPHERE; hit.index = (uint32_t)b.idx; found = true; }
+        if (wp.prim_mode == 2u) {                   // a later wave of the frame: the pixel's primary hit is known
+            const float2 ph = __ldcg(wp.prim + slot);
+            const uint32_t id = __float_as_uint(ph.y);
+            hit.t = ph.x; hit.kind = id >> 28; hit.index = id & 0x0fffffffu; found = id != 0u;
         } else {
-            for (uint32_t i = 0; i < sc.n_spheres; ++i) {                         // literal loop, Tracer.comp:398-412
-                const float t = sphere_intersect(o, d, __ldg(sc.spheres + i));
-                if ((t > 1e-3f) && (t < cur + 1e-3f)) { cur = t; hit.kind = KIND_SPHERE; hit.index = i; found = true; }
+            float cur = path_tmax(0);
+            found = trace_tris<true>(sc, o, d, cur, hit);
+            if (BVH) {
+                const SBest b = bvh_query<false, STATS>(sc, o, d, 1e-3f, sphere_bound<true>(cur), st);
+                if (b.idx >= 0) { cur = b.t; hit.kind = KIND_SPHERE; hit.index = (uint32_t)b.idx; found = true; }
+            } else {
+                for (uint32_t i = 0; i < sc.n_spheres; ++i) {                         // literal loop, Tracer.comp:398-412
+                    const float t = sphere_intersect(o, d, __ldg(sc.spheres + i));
+                    if ((t > 1e-3f) && (t < cur + 1e-3f)) { cur = t; hit.kind = KIND_SPHERE; hit.index = i; found = true; }
+                }
             }
+            found = trace_planes<true>(sc, o, d, cur, hit) || found;                 // :414-428
+            hit.t = cur;
+            if (wp.prim_mode == 1u) __stcg(wp.prim + slot, make_float2(cur, __uint_as_float(found ? ((hit.kind << 28) | hit.index) : 0u)));
         }
-        found = trace_planes<true>(sc, o, d, cur, hit) || found;                 // :414-428
-        hit.t = cur;
         pix = py * rp.width + px;
         if (rp.hit_ids && wp.s0 == rp.s_begin) rp.hit_ids[pix] = found ? ((hit.kind << 28) | hit.index) : 0u;
         st.closest += wp.S;
-        st.shared += wp.S - 1u;
+        st.shared += wp.S - (wp.prim_mode == 2u ? 0u : 1u);
         st.paths += wp.S;
     }
     for (uint32_t sl = 0; sl < wp.S; ++sl) {
@@ -1125,6 +1151,9 @@ cudaError_t wave_engine_init(WaveEngine &eng, size_t lane_capacity, uint32_t n_l
         }
     }
     if (n_lanes > 1 && (e = cudaEventCreateWithFlags(&eng.ev_fork, cudaEventDisableTiming)) != cudaSuccess) { wave_engine_free(eng); return e; }
+    if (n_lanes > 1 && (e = cudaEventCreateWithFlags(&eng.ev_prim, cudaEventDisableTiming)) != cudaSuccess) { wave_engine_free(eng); return e; }
+    for (uint32_t l = 0; l < n_lanes && n_lanes > 1; ++l)
+        if ((e = cudaEventCreateWithFlags(&eng.ev_stage[l], cudaEventDisableTiming)) != cudaSuccess) { wave_engine_free(eng); return e; }
     return cudaSuccess;
 }
 
@@ -1134,9 +1163,11 @@ void wave_engine_free(WaveEngine &eng)
         wave_free(eng.lane[l]);
         if (eng.stream[l]) { cudaStreamSynchronize(eng.stream[l]); cudaStreamDestroy(eng.stream[l]); }
         if (eng.ev_reduce[l]) cudaEventDestroy(eng.ev_reduce[l]);
+        if (eng.ev_stage[l]) cudaEventDestroy(eng.ev_stage[l]);
     }
     if (eng.ev_fork) cudaEventDestroy(eng.ev_fork);
-    cudaFree(eng.frame_sum);
+    if (eng.ev_prim) cudaEventDestroy(eng.ev_prim);
+    cudaFree(eng.frame_sum); cudaFree(eng.prim[0]); cudaFree(eng.prim[1]);
     eng = WaveEngine{};
 }
 
@@ -1157,7 +1188,8 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
     uint32_t S = (uint32_t)(eng.lane[0].capacity / rp.n_work);
     if (S == 0 || eng.lane[0].capacity >= ((size_t)1 << 28)) return cudaErrorMemoryAllocation;   // shadow items pack path << 4
     if (S > spp) S = spp;
-    if (n_lanes > 1 && spp >= n_lanes && S > (spp + n_lanes - 1) / n_lanes) S = (spp + n_lanes - 1) / n_lanes;
+    // (a lane large enough for the whole frame means ONE wave per frame: the lanes then alternate between consecutive frames)
+    if (n_lanes > 1 && spp >= n_lanes && S < spp && S > (spp + n_lanes - 1) / n_lanes) S = (spp + n_lanes - 1) / n_lanes;
     const uint32_t n_waves = (spp + S - 1) / S;
     // scenes with at most one light take the fused pipeline (logic + mixed trace), the others the four-kernel one
     const bool fused = VKRT_FUSED != 0 && VKRT_LEAF_BATCH != 0 && sc.n_lights <= 1;
@@ -1166,6 +1198,11 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
     if (n_waves > 1 && !eng.frame_sum) {
         if ((e = cudaMalloc((void **)&eng.frame_sum, (size_t)rp.n_work * sizeof(float4))) != cudaSuccess) return e;
     }
+    // the per-pixel primary hit travels from the frame's first wave to its later ones (two copies: consecutive frames overlap)
+    const bool share_prim = dense && n_waves > 1;
+    for (int k = 0; k < 2 && share_prim; ++k)
+        if (!eng.prim[k] && (e = cudaMalloc((void **)&eng.prim[k], (size_t)rp.n_work * sizeof(float2))) != cudaSuccess) return e;
+    if (share_prim) eng.prim_flip ^= 1u;
 
     typedef void (*trace_fn)(const DevScene, const RenderParams, const WaveParams, const uint32_t *, const uint32_t *, const uint32_t *,
                              const uint32_t *, uint32_t *, uint32_t);
@@ -1194,6 +1231,8 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
 
     // with lanes the waves never wait for `st` as a whole (that would serialise consecutive frames): see ev_consumed
     const bool fork = n_lanes > 1;
+    static const uint32_t stagger_env = []() { const char *v = std::getenv("VKRT_TUNE_STAGGER"); return v ? (uint32_t)std::atoi(v) : (uint32_t)VKRT_STAGGER; }();
+    const uint32_t stagger = (dense && rp.max_depth > 2) ? (stagger_env < rp.max_depth - 1 ? stagger_env : rp.max_depth - 2) : 0u;
     cudaStream_t ls = st;
     for (uint32_t wv = 0; wv < n_waves; ++wv) {
         const uint32_t lane = fork ? (eng.wave_seq++ % n_lanes) : 0u;
@@ -1223,6 +1262,13 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
         wp.S = (wp.s0 + S <= rp.s_end) ? S : (rp.s_end - wp.s0);
         wp.n_slots = rp.n_work;
         wp.n_lights = sc.n_lights;
+        // staggered lanes: this wave starts when the wave before it (on another lane) has reached depth `stagger`, so one
+        // lane's thin, latency-bound deep bounces run next to the other lane's fat early ones instead of next to its own kind
+        if (fork && stagger && eng.have_stage && (e = cudaStreamWaitEvent(ls, eng.ev_stage[eng.stage_lane], 0)) != cudaSuccess) return e;
+        wp.prim = share_prim ? eng.prim[eng.prim_flip] : nullptr;
+        wp.prim_mode = share_prim ? (wv == 0 ? 1u : 2u) : 0u;
+        // the later waves run on other streams than the first: they wait for its generate kernel (ev_prim below)
+        if (share_prim && wv > 0 && fork && (e = cudaStreamWaitEvent(ls, eng.ev_prim, 0)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(wb.counts, 0, (size_t)(rp.max_depth + 1) * C_N * sizeof(uint32_t), ls)) != cudaSuccess) return e;
         if (dense) {
             // depth 0 inside generate; per depth d >= 1: trace (rays of d + shadow rays of d - 1) -> logic; the last depth's
@@ -1236,6 +1282,7 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
             ev_open(0);
             k_gen<<<(wp.n_slots + VKRT_SHADE_BLOCK - 1u) / VKRT_SHADE_BLOCK, VKRT_SHADE_BLOCK, 0, ls>>>(sc, rp, wp); ++launches;
             ev_close();
+            if (share_prim && wv == 0 && fork && (e = cudaEventRecord(eng.ev_prim, ls)) != cudaSuccess) return e;
             for (uint32_t depth = 1; depth <= rp.max_depth; ++depth) {
                 const uint32_t cur = depth & 1u, nxt = cur ^ 1u;
                 wp.cnt = wb.counts + (size_t)depth * C_N;
@@ -1251,6 +1298,10 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
                 ev_open(2);
                 k_wfd_logic<<<grid_shade, VKRT_SHADE_BLOCK, 0, ls>>>(sc, rp, wp, wp.cnt + C_ACTIVE); ++launches;
                 ev_close();
+                if (fork && stagger && (depth == stagger || (depth + 1 == rp.max_depth && depth < stagger))) {
+                    if ((e = cudaEventRecord(eng.ev_stage[lane], ls)) != cudaSuccess) return e;
+                    eng.stage_lane = lane; eng.have_stage = true;
+                }
             }
         } else if (fused && VKRT_FUSED_GENERATE) {
             void (*k_gen)(const DevScene, const RenderParams, const WaveParams) =

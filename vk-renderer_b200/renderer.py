@@ -87,12 +87,19 @@ class Renderer:
         if mat_id is not None:
             self._ck(self.lib.vkrt_set_triangle_material(self.ctx, mat_id))
 
+    def set_triangle_materials(self, mat_ids):
+        """One material id per triangle (None / empty: every triangle uses the shared material again)."""
+        m = np.ascontiguousarray(mat_ids if mat_ids is not None else [], dtype=np.uint32)
+        self._ck(self.lib.vkrt_set_triangle_materials(self.ctx, _ptr(m), m.shape[0]))
+
     def set_scene(self, scene):
         """scene: scenes.Scene (materials / spheres / planes / triangles as numpy arrays)."""
         self.set_materials(scene.materials)
         self.set_spheres(scene.spheres, scene.sphere_mat)
         self.set_planes(scene.planes, scene.plane_mat)
         self.set_triangles(scene.triangles, scene.tri_mat)
+        if getattr(scene, "tri_mats", None) is not None:
+            self.set_triangle_materials(scene.tri_mats)
         return self
 
     def build_bvh(self):
@@ -277,3 +284,18 @@ def measure_l2_bandwidth(device_id=0):
     v = C.c_float()
     L.check(lib, None, lib.vkrt_measure_l2_bandwidth(device_id, C.byref(v)))
     return v.value
+
+
+def load_obj(path, xform=None):
+    """vkrt_load_obj: the triangles of a Wavefront OBJ file as an (n, 12) float32 array in the reference's 48-byte
+    Triangle layout (xform: optional 3x4 row-major matrix applied to every vertex)."""
+    lib = L.load()
+    n = C.c_uint32()
+    m = None
+    if xform is not None:
+        m = (C.c_float * 12)(*[float(x) for x in np.asarray(xform, dtype=np.float32).reshape(12)])
+    L.check(lib, None, lib.vkrt_load_obj(path.encode(), m, None, 0, C.byref(n)))
+    out = np.zeros((n.value, 12), dtype=np.float32)
+    if n.value:
+        L.check(lib, None, lib.vkrt_load_obj(path.encode(), m, _ptr(out), n.value, C.byref(n)))
+    return out

@@ -24,6 +24,7 @@ class Scene:
     plane_mat: np.ndarray   # (n,) uint32
     triangles: np.ndarray   # (n, 12) float32, 3 x vec3 padded to 16 B
     tri_mat: int
+    tri_mats: np.ndarray = None   # optional (n,) uint32: per-triangle material ids (meshes); None = every triangle uses tri_mat
 
     def digest(self):
         """sha256 over every array: the scene hash quoted next to benchmark numbers."""
@@ -31,6 +32,8 @@ class Scene:
         for a in (self.materials, self.spheres, self.sphere_mat, self.planes, self.plane_mat, self.triangles):
             h.update(np.ascontiguousarray(a).tobytes())
         h.update(str(self.tri_mat).encode())
+        if self.tri_mats is not None:
+            h.update(np.ascontiguousarray(self.tri_mats).tobytes())
         return h.hexdigest()[:16]
 
 
@@ -154,3 +157,50 @@ def grid_spheres(nx=50, ny=40, nz=50, seed=None):
     cz = -60.0 + (iz + 0.5) * cell[2] + (2.0 * _u01(seed, i, 2) - 1.0) * amp[2]
     return _assemble("grid_spheres_%d" % n, seed, np.stack([cx, cy, cz], axis=1).astype(np.float32),
                      np.full(n, r, dtype=np.float32))
+
+
+# ---- triangle meshes (ref: the TODO at Assets/Raytracer.comp:10) ---------------------
+def torus_triangles(centre=(0.0, 40.0, 10.0), major=20.0, minor=7.0, n_major=36, n_minor=18, tilt=0.6):
+    """A closed torus as (n, 12) float32 triangles in the reference's SSBO layout, counter-clockwise seen from outside
+    (tri_intersect culls back faces, Tracer.comp:348), tilted about the x axis."""
+    u = np.arange(n_major + 1, dtype=np.float64) * (2.0 * np.pi / n_major)
+    v = np.arange(n_minor + 1, dtype=np.float64) * (2.0 * np.pi / n_minor)
+    uu, vv = np.meshgrid(u, v, indexing="ij")
+    x = (major + minor * np.cos(vv)) * np.cos(uu)
+    z = (major + minor * np.cos(vv)) * np.sin(uu)
+    y = minor * np.sin(vv)
+    ct, st = np.cos(tilt), np.sin(tilt)
+    y, z = ct * y - st * z, st * y + ct * z
+    p = np.stack([x + centre[0], y + centre[1], z + centre[2]], axis=-1)
+    tris = []
+    for i in range(n_major):
+        for j in range(n_minor):
+            a, b, c, d = p[i, j], p[i + 1, j], p[i + 1, j + 1], p[i, j + 1]
+            tris.append((a, c, b))
+            tris.append((a, d, c))
+    t = np.zeros((len(tris), 12), dtype=np.float32)
+    for k, (a, b, c) in enumerate(tris):
+        t[k, 0:3], t[k, 4:7], t[k, 8:11] = a, b, c
+    return t
+
+
+def write_obj(path, triangles):
+    """Writes a triangle list as a Wavefront OBJ file (one `v` per corner, %.9g: float32 round-trips exactly)."""
+    with open(path, "w") as f:
+        f.write("# vk-renderer_b200 triangle list\n")
+        for t in triangles:
+            for k in range(3):
+                f.write("v %.9g %.9g %.9g\n" % tuple(float(x) for x in t[4 * k:4 * k + 3]))
+        for i in range(len(triangles)):
+            f.write("f %d %d %d\n" % (3 * i + 1, 3 * i + 2, 3 * i + 3))
+
+
+def mesh_scene(triangles, n_spheres=300, seed=77):
+    """A triangle mesh with per-triangle materials (diffuse / mirror / glass / plastic by triangle index) among
+    `n_spheres` random spheres, Tracer.comp's light and planes."""
+    s = random_spheres(n_spheres, seed=seed)
+    k = np.arange(triangles.shape[0], dtype=np.uint32)
+    # materials 0..7 are Tracer.comp's: 1 matte_red, 5 mirror, 6 glass, 4 plastic
+    tri_mats = np.array([1, 5, 4, 6, 2, 5], dtype=np.uint32)[(k // 7) % 6]
+    return Scene("mesh_%d+%s" % (triangles.shape[0], s.name), s.materials, s.spheres, s.sphere_mat, s.planes, s.plane_mat,
+                 np.ascontiguousarray(triangles, dtype=np.float32), 5, tri_mats)
