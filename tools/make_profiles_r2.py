@@ -99,9 +99,6 @@ def limiters(ms):
             "l2_throughput_pct": f("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
             "dram_throughput_pct": f("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
             "l2_bytes_per_launch": sum(m.get("lts__t_bytes.sum", 0.0) for m in ms) / max(len(ms), 1),
-            "global_load_inst": sum(m.get("sass__inst_executed_global_loads", 0.0) for m in ms),
-            "local_load_inst": sum(m.get("sass__inst_executed_local_loads", 0.0) for m in ms),
-            "local_store_inst": sum(m.get("sass__inst_executed_local_stores", 0.0) for m in ms),
             "ms_summed": w / 1e6, "launches": len(ms)}
 
 
@@ -196,6 +193,6 @@ with open(P("SUMMARY.md"), "w") as f:
     for k in ("alu_pipe_pct", "issue_active_pct", "lsu_wavefronts_pct", "fma_pipe_pct", "lanes_per_instruction", "warps_active_pct", "l1_hit_pct",
               "l2_hit_pct", "l2_throughput_pct", "dram_throughput_pct"):
         f.write("* %s = %.1f\n" % (k, L[k]))
-    f.write("* instructions: %.0f global loads, %.0f local loads, %.0f local stores (warp level, one frame)\n" % (L["global_load_inst"], L["local_load_inst"], L["local_store_inst"]))
+    f.write("* local / global load-store instruction counts: see the full captures (`%s_ncu_full_*.txt`, sass__inst_executed_*)\n" % rnd)
     f.write("* dram bytes per traversal launch: %.1f MB\n" % (ev["cfg4_wavefront"]["dram_bytes_per_launch"] / 1e6))
 print(open(P("SUMMARY.md")).read())
