@@ -326,6 +326,34 @@ def test_progressive_accumulation(vk, oracle):
     r.close()
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+def test_progressive_64_frames_config2_full_size(vk, oracle, variant):
+    """BASELINE configs[1] as bench.py's `cfg2` runs it: Raytracer.comp's geometry (+ the light sphere) through the path
+    integrator at 1920x1080, 16 spp, depth 8, **64 progressively accumulated frames** (frame index = seed of the frame).
+    The oracle accumulates the same 64 frames over two windows of the full-size image: bit-identical sums."""
+    V = vk
+    w, h, frames = 1920, 1080, 64
+    scene = V.scenes.raytracer_default(with_emitter=True)
+    fd = V.default_frame_data(aspect_ratio=w / h, seed=0.5)
+    r = V.Renderer(w, h, spp=16, max_depth=8, variant=variant, flags=V.FLAG_PROGRESSIVE | V.FLAG_NO_RESOLVE)
+    r.set_scene(scene)
+    r.set_seed(2026)
+    for f in range(frames):                        # enqueued back to back: two frames in flight
+        r.set_frame_index(f)
+        r.draw(fd)
+    acc = r.read_accum()
+    r.close()
+    assert np.all(acc[..., 3] == 16.0 * frames)
+    sc = apply_scene(oracle, scene, fast=True)
+    for rect in ((940, 520, 972, 544), (0, 0, 24, 16)):
+        oacc = None
+        for f in range(frames):
+            oacc, _, _, _ = sc.render(fd, w, h, spp=16, max_depth=8, seed=2026, frame_index=f, rect=rect, accum=oacc,
+                                      want_ids=False, want_rgba=False)
+        x0, y0, x1, y1 = rect
+        assert bits_equal(acc[y0:y1, x0:x1], oacc[y0:y1, x0:x1]), mismatch_report(acc[y0:y1, x0:x1], oacc[y0:y1, x0:x1])
+
+
 def test_wavefront_multi_wave_equals_megakernel(vk):
     """A frame of more than 16 spp is cut into waves of <= 16 samples (53 spp: 16 + 16 + 16 + 5): the running per-pixel sum
     must still be formed in sample order, i.e. be bit-identical to the megakernel, the later waves reuse the first wave's

@@ -78,6 +78,11 @@
 #ifndef VKRT_DENSE
 #define VKRT_DENSE 1               // fused pipeline: survivors of a depth are written DENSELY (ping-pong ray / state arrays, position =
 #endif                             //                 queue index): no path-id indirection, every record access is a contiguous stream
+#ifndef VKRT_GEN_PER_SAMPLE
+#define VKRT_GEN_PER_SAMPLE 0      // 1: dense pipeline, depth 0 by one thread per (pixel, sample) behind a primary-hit kernel (one thread
+#endif                             // per pixel): the S samples of a pixel become neighbours in the depth-1 arrays (shared origin).  Exact;
+                                   // measured on cfg4: the traversal launches gain 4.7 % (20.70 -> 19.73 ms) from the coherence, but depth 0
+                                   // costs 4.2 ms instead of 1.95 (every thread redoes what the per-pixel loop hoists): 29.4 vs 28.2 ms -- off
 #ifndef VKRT_STAGGER
 #define VKRT_STAGGER 0             // > 0: a wave starts when the wave before it has launched this depth's logic (staggered lanes)
 #endif
@@ -1065,6 +1070,67 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wfd_
     wf_flush(st, rp.counters, STATS);
 }
 
+// depth 0 split in two (VKRT_GEN_PER_SAMPLE): the primary hit of every owned pixel, one thread per pixel slot ...
+template <bool BVH, bool STATS>
+__global__ void __launch_bounds__(256) k_wfd_primary(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
+                                                      const __grid_constant__ WaveParams wp)
+{
+    Stats st; stats_zero(st);
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t px = 0, py = 0;
+    if (slot < wp.n_slots && slot_to_pixel_w(rp, slot, px, py)) {
+        V3 o, d;
+        primary_ray(rp.fd, rp.width, rp.height, px, py, o, d);
+        Hit hit{0.f, 0, 0};
+        float cur = path_tmax(0);
+        bool found = trace_tris<true>(sc, o, d, cur, hit);
+        if (BVH) {
+            const SBest b = bvh_query<false, STATS>(sc, o, d, 1e-3f, sphere_bound<true>(cur), st);
+            if (b.idx >= 0) { cur = b.t; hit.kind = KIND_SPHERE; hit.index = (uint32_t)b.idx; found = true; }
+        } else {
+            for (uint32_t i = 0; i < sc.n_spheres; ++i) {                         // literal loop, Tracer.comp:398-412
+                const float t = sphere_intersect(o, d, __ldg(sc.spheres + i));
+                if ((t > 1e-3f) && (t < cur + 1e-3f)) { cur = t; hit.kind = KIND_SPHERE; hit.index = i; found = true; }
+            }
+        }
+        found = trace_planes<true>(sc, o, d, cur, hit) || found;                 // :414-428
+        const uint32_t id = found ? ((hit.kind << 28) | hit.index) : 0u;
+        wp.prim[slot] = make_float2(cur, __uint_as_float(id));
+        if (rp.hit_ids) rp.hit_ids[py * rp.width + px] = id;
+    }
+    wf_flush(st, rp.counters, STATS);
+}
+// ... and the shading of depth 0, one thread per (pixel slot, sample of the wave): thread = slot * S + sample
+__global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wfd_generate_ps(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
+                                                                                    const __grid_constant__ WaveParams wp)
+{
+    Stats st; stats_zero(st);
+    const V3 cam_pos = v3(rp.fd.camera.pos.x, rp.fd.camera.pos.y, rp.fd.camera.pos.z);
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t slot = tid / wp.S, sl = tid - slot * wp.S;
+    uint32_t px = 0, py = 0;
+    const bool valid = slot < wp.n_slots && slot_to_pixel_w(rp, slot, px, py);
+    bool alive = false, need_ray = false;
+    PathState ps; ShadowOut so;
+    if (valid) {
+        V3 o, d;
+        primary_ray(rp.fd, rp.width, rp.height, px, py, o, d);
+        const float2 ph = __ldg(wp.prim + slot);
+        const uint32_t id = __float_as_uint(ph.y);
+        const Hit hit{ph.x, id >> 28, id & 0x0fffffffu};
+        path_begin(ps, o, d);                   // acc = 0: the firefly clamp of :441 leaves it unchanged
+        logic_compute(sc, rp, wp, cam_pos, ps, hit, id != 0u, py * rp.width + px, sl, st, alive, need_ray, so);
+        ++st.closest; ++st.paths;
+        if (sl != 0u || wp.prim_mode == 2u) ++st.shared;      // every sample but the frame's first reuses the pixel's one query
+    }
+    uint32_t *const cs[2] = {wp.cnt_next + C_ACTIVE, wp.cnt + C_SHADOW};
+    const bool ws[2] = {alive, need_ray};
+    uint32_t pos[2];
+    reserve_block<2>(cs, ws, pos);
+    if (valid) dense_store(wp, ps, so, alive, need_ray, pos[0], pos[1], slot, sl);
+    wf_flush(st, rp.counters, false);
+}
+
 // ---- reduce: per pixel, add the wave's samples in sample order -------------------------------------
 __global__ void __launch_bounds__(256) k_wf_reduce(const __grid_constant__ RenderParams rp, const __grid_constant__ WaveParams wp,
                                                     float4 *__restrict__ frame_sum, uint32_t first_wave, uint32_t last_wave)
@@ -1199,7 +1265,8 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
         if ((e = cudaMalloc((void **)&eng.frame_sum, (size_t)rp.n_work * sizeof(float4))) != cudaSuccess) return e;
     }
     // the per-pixel primary hit travels from the frame's first wave to its later ones (two copies: consecutive frames overlap)
-    const bool share_prim = dense && n_waves > 1;
+    const bool per_sample = dense && VKRT_GEN_PER_SAMPLE != 0;
+    const bool share_prim = dense && (n_waves > 1 || per_sample);
     for (int k = 0; k < 2 && share_prim; ++k)
         if (!eng.prim[k] && (e = cudaMalloc((void **)&eng.prim[k], (size_t)rp.n_work * sizeof(float2))) != cudaSuccess) return e;
     if (share_prim) eng.prim_flip ^= 1u;
@@ -1279,9 +1346,24 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
             wp.x_hit = wb.d_hit; wp.x_shr = wb.d_shr;
             wp.cnt = wb.counts; wp.cnt_next = wb.counts + C_N;
             wp.n_ray = wb.d_ray[1]; wp.n_st = wb.d_st[1];
+            if (per_sample) {
+                if (wv == 0) {
+                    void (*k_prim)(const DevScene, const RenderParams, const WaveParams) =
+                        bvh ? (stats ? k_wfd_primary<true, true> : k_wfd_primary<true, false>)
+                            : (stats ? k_wfd_primary<false, true> : k_wfd_primary<false, false>);
+                    ev_open(0);
+                    k_prim<<<(wp.n_slots + 255u) / 256u, 256, 0, ls>>>(sc, rp, wp); ++launches;
+                    ev_close();
+                }
+                const unsigned long long n_thr = (unsigned long long)wp.n_slots * wp.S;
+                ev_open(0);
+                k_wfd_generate_ps<<<(unsigned)((n_thr + VKRT_SHADE_BLOCK - 1u) / VKRT_SHADE_BLOCK), VKRT_SHADE_BLOCK, 0, ls>>>(sc, rp, wp); ++launches;
+                ev_close();
+            } else {
             ev_open(0);
             k_gen<<<(wp.n_slots + VKRT_SHADE_BLOCK - 1u) / VKRT_SHADE_BLOCK, VKRT_SHADE_BLOCK, 0, ls>>>(sc, rp, wp); ++launches;
             ev_close();
+            }
             if (share_prim && wv == 0 && fork && (e = cudaEventRecord(eng.ev_prim, ls)) != cudaSuccess) return e;
             for (uint32_t depth = 1; depth <= rp.max_depth; ++depth) {
                 const uint32_t cur = depth & 1u, nxt = cur ^ 1u;
