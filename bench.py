@@ -42,7 +42,7 @@ WORKLOADS = {
     "cfg2": dict(desc="Raytracer.comp geometry (:98-127) through the path integrator: diffuse -> albedo, reflective -> metalness 1 / "
                       "roughness 0, else metalness 0 / roughness 0.4, + Tracer.comp's light sphere (SURVEY 8d); 1920x1080, 16 spp, depth 8, "
                       "64-frame progressive accumulation (BASELINE configs[1])",
-                 w=1920, h=1080, spp=16, depth=8, integrator="path", scene="raytracer+light", variant="mega", progressive=64),
+                 w=1920, h=1080, spp=16, depth=8, integrator="path", scene="raytracer+light", variant="wavefront", progressive=64),
     "cfg2t": dict(desc="reference default scene of Tracer.comp (:186-211), 1920x1080, 16 spp, depth 8, literal primitive loop",
                   w=1920, h=1080, spp=16, depth=8, integrator="path", scene="tracer", variant="mega"),
     "cfg3": dict(desc="synthetic 1,024 random spheres (mixed lambertian/metal/dielectric + light + 5 planes), 3840x2160, 64 spp, depth 8, device LBVH (BASELINE configs[2])",
@@ -254,6 +254,9 @@ def run_reference(args):
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": r["note"]}
+    band = tie_band(args.workload, r["scene_sha"])
+    if band is not None:
+        line["config"]["primary_hit_tie_band"] = band      # the same `config` object as the product arm prints
     print(json.dumps(line))
     return 0
 
