@@ -479,16 +479,21 @@ VKRT_DEV SBest tri_bvh_query(const DevScene &sc, V3 o, V3 d, float eps, float B)
 // Scenes with a hierarchy (vkrt_build_bvh) hold their triangles in a tree of their own and query it by the
 // order-independent rule T (same exclusive bound as the literal loop's first acceptance); ANY = a shadow query, which
 // may stop at the first hit.  Scenes without one run the reference's literal loop.
-template <bool TRACER, bool ANY = false>
+// TB = the kernel was instantiated for scenes that MAY hold a triangle tree: the hot kernels exist in both forms and
+// scenes without one (every BASELINE configuration) run the form that does not carry the tree walk's registers, spills
+// and second stack (measured: 1.8 % of the cfg4 frame, 7 % of the megakernel on the default scene).
+template <bool TRACER, bool ANY = false, bool TB = true>
 VKRT_DEV bool trace_tris(const DevScene &sc, V3 o, V3 d, float &cur, Hit &hit)
 {
     const float EPS = TRACER ? 1e-3f : 0.01f;
-    if (sc.tbvh) {
+#ifndef VKRT_NO_TRI_BVH      // (measurement aid: the hot kernels without the triangle tree's code)
+    if (TB && sc.tbvh) {
         const SBest b = tri_bvh_query<ANY>(sc, o, d, EPS, TRACER ? cur + EPS : cur);
         if (b.idx < 0) return false;
         cur = b.t; hit.kind = KIND_TRI; hit.index = (uint32_t)b.idx;
         return true;
     }
+#endif
     bool found = false;
     for (uint32_t i = 0; i < sc.n_tris; ++i) {
         const V3 v0 = xyz(__ldg(sc.tris + 3 * i)), v1 = xyz(__ldg(sc.tris + 3 * i + 1)), v2 = xyz(__ldg(sc.tris + 3 * i + 2));
@@ -531,7 +536,7 @@ VKRT_DEV bool trace_ray(const DevScene &sc, V3 o, V3 d, Hit &hit, Stats &st)
     const float EPS = trace_eps<TRACER>();
     if (SHADOW) ++st.shadow; else ++st.closest;
     float cur = hit.t;
-    bool found = trace_tris<TRACER>(sc, o, d, cur, hit);
+    bool found = trace_tris<TRACER, SHADOW, BVH>(sc, o, d, cur, hit);      // a triangle tree only exists next to the spheres' (vkrt_build_bvh)
     if (SHADOW && found) return true;
     if (BVH) {
         const SBest b = bvh_query<SHADOW, STATS>(sc, o, d, EPS, sphere_bound<TRACER>(cur), st);

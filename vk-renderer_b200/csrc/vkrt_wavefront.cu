@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ Dev
 // MODE 3 (dense fused pipeline): like MODE 2, but item i IS ray i of the depth's dense ray array and shadow item k is
 //                   shadow record k -- no queues; the nearest hit goes to hit[i]
 enum { TRACE_EXTEND = 0, TRACE_SHADOW = 1, TRACE_MIXED = 2, TRACE_DENSE = 3 };
-template <int MODE, bool BVH, bool STATS>
+template <int MODE, bool BVH, bool STATS, bool TB = true>
 __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_trace(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
                                                                 const __grid_constant__ WaveParams wp, const uint32_t *__restrict__ queue,
                                                                 const uint32_t *__restrict__ n_items_ptr, const uint32_t *__restrict__ queue_sh,
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                         o = xyz(fo); d = xyz(fd);
                         cur = tmax;
                         ++st.closest;
-                        found = trace_tris<true>(sc, o, d, cur, hit);
+                        found = trace_tris<true, false, TB && BVH>(sc, o, d, cur, hit);
                     }
                     if (BVH) {
                         trav_init(tv, sc, o, d, EPS, sphere_bound<true>(cur)); if (tv.node < 0) tv.node = FIN;
@@ -768,6 +768,7 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_SHADE_MINBLOCKS) k_wf_s
 // The firefly clamp of the next iteration (:441) reads the accumulator after that launch, so every value is formed
 // by the same operations in the same order as in radiance(); per depth the wave costs two launches instead of four
 // and one pass over the path records instead of two.
+template <bool TB>
 struct LightsDeferred {
     const DevScene &sc; V3 cam_pos; uint32_t skey, dim0; Stats &st;
     bool *need_ray; V3 *L, *term; float *t;
@@ -781,7 +782,7 @@ struct LightsDeferred {
         if (occluded) ++st.skipped;
         Hit h{td, 0, 0};
         float cur = td;
-        if (!occluded) occluded = trace_tris<true>(sc, sf.P, Ld, cur, h);
+        if (!occluded) occluded = trace_tris<true, true, TB>(sc, sf.P, Ld, cur, h);
         if (!occluded) { cur = td; occluded = trace_planes<true>(sc, sf.P, Ld, cur, h); }
         *need_ray = !occluded; *L = Ld; *term = tm; *t = td;
         return v3(0.0f);          // shade as if occluded; the visible outcome is formed by the caller
@@ -791,6 +792,7 @@ struct LightsDeferred {
 // shades it as if the light sample were occluded (ps: the next ray, mask, accumulator) and, when a shadow ray is
 // needed, returns that ray {P, L, t} and the accumulator for the other outcome (acc_v)
 struct ShadowOut { V3 P, L, acc_v; float t; };
+template <bool TB = true>
 VKRT_DEV void logic_compute(const DevScene &sc, const RenderParams &rp, const WaveParams &wp, V3 cam_pos, PathState &ps,
                             const Hit &hit, bool found, uint32_t pix, uint32_t sl, Stats &st, bool &alive, bool &need_ray, ShadowOut &so)
 {
@@ -801,7 +803,7 @@ VKRT_DEV void logic_compute(const DevScene &sc, const RenderParams &rp, const Wa
         so.P = madd3(hit.t, ps.d, ps.o);                                                // P == surface_of's P
         V3 term = v3(0.0f), emis = v3(0.0f);
         so.L = v3(0.0f); so.t = 0.0f;
-        const LightsDeferred lights{sc, cam_pos, skey, ps.depth * DIMS_PER_BOUNCE, st, &need_ray, &so.L, &term, &so.t};
+        const LightsDeferred<TB> lights{sc, cam_pos, skey, ps.depth * DIMS_PER_BOUNCE, st, &need_ray, &so.L, &term, &so.t};
         alive = path_shade(sc, cam_pos, rp.max_depth, skey, ps, hit, lights, &emis);
         if (need_ray) so.acc_v = acc_b + mask_b * (emis + (v3(0.0f) + term));
     }
@@ -973,6 +975,7 @@ VKRT_DEV void dense_store(const WaveParams &wp, const PathState &ps, const Shado
         sr[2] = make_float4(so.acc_v.x, so.acc_v.y, so.acc_v.z, __uint_as_float(slot));
     }
 }
+template <bool TB>
 __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wfd_logic(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
                                                        const __grid_constant__ WaveParams wp, const uint32_t *__restrict__ n_ptr)
 {
@@ -1002,7 +1005,7 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wfd_
             float cur = hit.t;
             const bool found = trace_planes<true>(sc, ps.o, ps.d, cur, hit) || id0 != 0u;             // :414-428
             hit.t = cur;
-            logic_compute(sc, rp, wp, cam_pos, ps, hit, found, pix, sl, st, alive, need_ray, so);
+            logic_compute<TB>(sc, rp, wp, cam_pos, ps, hit, found, pix, sl, st, alive, need_ray, so);
         }
         uint32_t *const cs[2] = {wp.cnt_next + C_ACTIVE, wp.cnt + C_SHADOW};
         const bool ws[2] = {alive, need_ray};
@@ -1013,7 +1016,7 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wfd_
     wf_flush(st, rp.counters, false);
 }
 // generate + logic of depth 0, dense: like k_wf_generate_logic, the survivors go to the depth-1 arrays
-template <bool BVH, bool STATS>
+template <bool BVH, bool STATS, bool TB>
 __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wfd_generate_logic(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
                                                                                        const __grid_constant__ WaveParams wp)
 {
@@ -1034,7 +1037,7 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wfd_
             hit.t = ph.x; hit.kind = id >> 28; hit.index = id & 0x0fffffffu; found = id != 0u;
         } else {
             float cur = path_tmax(0);
-            found = trace_tris<true>(sc, o, d, cur, hit);
+            found = trace_tris<true, false, TB && BVH>(sc, o, d, cur, hit);
             if (BVH) {
                 const SBest b = bvh_query<false, STATS>(sc, o, d, 1e-3f, sphere_bound<true>(cur), st);
                 if (b.idx >= 0) { cur = b.t; hit.kind = KIND_SPHERE; hit.index = (uint32_t)b.idx; found = true; }
@@ -1059,7 +1062,7 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wfd_
         PathState ps; ShadowOut so;
         if (valid) {
             path_begin(ps, o, d);                   // acc = 0: the firefly clamp of :441 leaves it unchanged
-            logic_compute(sc, rp, wp, cam_pos, ps, hit, found, pix, sl, st, alive, need_ray, so);
+            logic_compute<TB && BVH>(sc, rp, wp, cam_pos, ps, hit, found, pix, sl, st, alive, need_ray, so);
         }
         uint32_t *const cs[2] = {wp.cnt_next + C_ACTIVE, wp.cnt + C_SHADOW};
         const bool ws[2] = {alive, need_ray};
@@ -1278,8 +1281,11 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
                                              : (stats ? k_wf_trace<TRACE_SHADOW, false, true> : k_wf_trace<TRACE_SHADOW, false, false>);
         if (mode == TRACE_MIXED) return bvh ? (stats ? k_wf_trace<TRACE_MIXED, true, true> : k_wf_trace<TRACE_MIXED, true, false>)
                                             : (stats ? k_wf_trace<TRACE_MIXED, false, true> : k_wf_trace<TRACE_MIXED, false, false>);
-        if (mode == TRACE_DENSE) return bvh ? (stats ? k_wf_trace<TRACE_DENSE, true, true> : k_wf_trace<TRACE_DENSE, true, false>)
-                                            : (stats ? k_wf_trace<TRACE_DENSE, false, true> : k_wf_trace<TRACE_DENSE, false, false>);
+        if (mode == TRACE_DENSE) {
+            if (bvh && sc.tbvh) return stats ? k_wf_trace<TRACE_DENSE, true, true, true> : k_wf_trace<TRACE_DENSE, true, false, true>;
+            return bvh ? (stats ? k_wf_trace<TRACE_DENSE, true, true, false> : k_wf_trace<TRACE_DENSE, true, false, false>)
+                       : (stats ? k_wf_trace<TRACE_DENSE, false, true, false> : k_wf_trace<TRACE_DENSE, false, false, false>);
+        }
         return bvh ? (stats ? k_wf_trace<TRACE_EXTEND, true, true> : k_wf_trace<TRACE_EXTEND, true, false>)
                    : (stats ? k_wf_trace<TRACE_EXTEND, false, true> : k_wf_trace<TRACE_EXTEND, false, false>);
     };
@@ -1340,9 +1346,12 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
         if (dense) {
             // depth 0 inside generate; per depth d >= 1: trace (rays of d + shadow rays of d - 1) -> logic; the last depth's
             // shadow rays at the end.  Arrays of depth d: parity d & 1.
+            const bool tb = bvh && sc.tbvh != nullptr;       // scenes with a triangle tree run the kernels that carry its walk
             void (*k_gen)(const DevScene, const RenderParams, const WaveParams) =
-                bvh ? (stats ? k_wfd_generate_logic<true, true> : k_wfd_generate_logic<true, false>)
-                    : (stats ? k_wfd_generate_logic<false, true> : k_wfd_generate_logic<false, false>);
+                tb ? (stats ? k_wfd_generate_logic<true, true, true> : k_wfd_generate_logic<true, false, true>)
+                   : bvh ? (stats ? k_wfd_generate_logic<true, true, false> : k_wfd_generate_logic<true, false, false>)
+                         : (stats ? k_wfd_generate_logic<false, true, false> : k_wfd_generate_logic<false, false, false>);
+            void (*k_logic)(const DevScene, const RenderParams, const WaveParams, const uint32_t *) = tb ? k_wfd_logic<true> : k_wfd_logic<false>;
             wp.x_hit = wb.d_hit; wp.x_shr = wb.d_shr;
             wp.cnt = wb.counts; wp.cnt_next = wb.counts + C_N;
             wp.n_ray = wb.d_ray[1]; wp.n_st = wb.d_st[1];
@@ -1378,7 +1387,7 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
                 ev_close();
                 if (last) break;
                 ev_open(2);
-                k_wfd_logic<<<grid_shade, VKRT_SHADE_BLOCK, 0, ls>>>(sc, rp, wp, wp.cnt + C_ACTIVE); ++launches;
+                k_logic<<<grid_shade, VKRT_SHADE_BLOCK, 0, ls>>>(sc, rp, wp, wp.cnt + C_ACTIVE); ++launches;
                 ev_close();
                 if (fork && stagger && (depth == stagger || (depth + 1 == rp.max_depth && depth < stagger))) {
                     if ((e = cudaEventRecord(eng.ev_stage[lane], ls)) != cudaSuccess) return e;
