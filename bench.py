@@ -176,7 +176,7 @@ def tie_band(workload, scene_sha):
 
 def ncu_evidence(key):
     """What the committed ncu capture of the dominant kernel says (profiles/ncu_limiters.json, written by
-    tools/make_profiles.py from an `ncu --set full` run of this same command): DRAM bytes per launch and the units
+    tools/make_profiles_r2.py from ncu runs of this same command (tools/evidence_r2.sh)): DRAM bytes per launch and the units
     that bound the kernel.  Not measured by this run -- a profiler cannot run inside a timed bench -- so the entry
     carries the commit and file it came from."""
     try:

@@ -70,6 +70,15 @@ def test_create_argument_checks_need_no_device(vk):
         rc, msg = create(**kw)
         assert rc == L.BAD_ARG and msg.startswith(b"[app] - err :: "), (kw, rc, msg)
     assert b"2^30 pixels" in create(width=65536, height=32768)[1]
+    # in-library multi-GPU (device_ids / n_devices): the argument checks also come before any device is touched
+    ids8 = (C.c_int32 * 8)(0, 1, 2, 3, 4, 5, 6, 7)
+    dup = (C.c_int32 * 8)(0, 1, 1, 3, 4, 5, 6, 7)
+    for kw, what in ((dict(n_devices=9, device_ids=ids8), b"n_devices > 8"),
+                     (dict(n_devices=3, device_ids=dup), b"distinct"),
+                     (dict(n_devices=2, device_ids=ids8, tile_shard_count=2), b"shards the frame by itself"),
+                     (dict(n_devices=2, device_ids=ids8, flags=L.FLAG_NO_RESOLVE), b"NO_RESOLVE")):
+        rc, msg = create(**kw)
+        assert rc == L.BAD_ARG and what in msg, (kw, rc, msg)
 
 
 def test_only_the_allowed_places_use_the_oracle():

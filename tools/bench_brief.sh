@@ -1,7 +1,7 @@
 #!/bin/bash
 # usage: tools/bench_brief.sh <label> [bench.py args...]  -> one short line per run
 label=$1; shift
-python bench.py --no-cpu-baseline "$@" 2>gpurun_out/err_$label.txt | tail -1 | python -c "
+python bench.py --no-cpu-baseline --no-extras "$@" 2>gpurun_out/err_$label.txt | tail -1 | python -c "
 import sys, json
 try:
     d = json.loads(sys.stdin.read())
