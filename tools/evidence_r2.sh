@@ -5,7 +5,8 @@
 # logic kernels, full captures of both, and the compute-bound small scenes.
 T=${1:-ev2}; O=gpurun_out; mkdir -p $O
 t0=$(date +%s); el() { echo "[$(( $(date +%s) - t0 )) s] $*"; }
-timeout 600 python -m pytest tests -m gpu -q -rs > $O/${T}_pytest.log 2>&1; el "pytest rc=$? $(tail -1 $O/${T}_pytest.log)"
+timeout 300 python __graft_entry__.py --smoke > $O/${T}_smoke.log 2>&1; el "smoke rc=$? $(tail -1 $O/${T}_smoke.log)"
+timeout 900 python -m pytest tests -m gpu -q -rs > $O/${T}_pytest.log 2>&1; el "pytest rc=$? $(tail -1 $O/${T}_pytest.log)"
 timeout 900 python bench.py --steps 20 --warmup 5 --micro > $O/${T}_bench.json 2> $O/${T}_bench.err; el bench
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $O/${T}_bench_ref.json 2> $O/${T}_bench_ref.err; el reference
 timeout 300 python bench.py --variant mega --no-cpu-baseline --no-extras > $O/${T}_bench_mega.json 2> $O/${T}_bench_mega.err; el mega
