@@ -503,11 +503,41 @@ VKRT_DEV bool trace_tris(const DevScene &sc, V3 o, V3 d, float &cur, Hit &hit)
     }
     return found;
 }
+#ifndef VKRT_PLANE_ILP
+#define VKRT_PLANE_ILP 0
+#endif
 template <bool TRACER>
 VKRT_DEV bool trace_planes(const DevScene &sc, V3 o, V3 d, float &cur, Hit &hit)
 {
     const float EPS = TRACER ? 1e-3f : 0.01f;
     bool found = false;
+#if VKRT_PLANE_ILP
+    // the same tests on the same values, four planes at a time: the two dot products of a plane do not depend on `cur`,
+    // so the constant-bank loads and FMA chains of four planes overlap; only the acceptance chain stays sequential
+    for (uint32_t i0 = 0; i0 < sc.n_planes; i0 += 4u) {
+        float dn[4], num[4];
+#pragma unroll
+        for (uint32_t k = 0; k < 4u; ++k) {
+            const uint32_t i = i0 + k < sc.n_planes ? i0 + k : sc.n_planes - 1u;
+            const float4 p = sc.planes[i];
+            const V3 N = xyz(p);
+            dn[k] = dot3(d, N);
+            num[k] = -(p.w + dot3(o, N));
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < 4u; ++k) {
+            if (i0 + k >= sc.n_planes) break;
+            const bool same_sign = (num[k] > 0.0f && dn[k] > 0.0f) || (num[k] < 0.0f && dn[k] < 0.0f);
+            if (same_sign && gl_abs(num[k]) > (cur * gl_abs(dn[k])) * 1.000001f) continue;
+            if (!same_sign && num[k] == num[k] && dn[k] == dn[k]) continue;
+            float t;
+            if (TRACER) t = gl_abs(gl_sign(dn[k] - 0.0f)) * gl_max(num[k] / dn[k], 0.0f);      // plane_intersect_tracer on the same dn, num
+            else t = dn[k] == 0.0f ? 0.0f : gl_max(num[k] / dn[k], 0.0f);                          // plane_intersect_raytracer
+            const bool acc = TRACER ? ((t > EPS) && (t < cur - EPS)) : (t > EPS && t < cur);
+            if (acc) { cur = t; hit.kind = KIND_PLANE; hit.index = i0 + k; found = true; }
+        }
+    }
+#else
     for (uint32_t i = 0; i < sc.n_planes; ++i) {
         // t = -(len + o.N) / (d.N) clamped at 0 is accepted iff EPS < t < cur (-EPS).  Two rejections need no
         // IEEE division and are exact: (a) the quotient's sign is the XOR of the operands' signs, so unless
@@ -524,6 +554,7 @@ VKRT_DEV bool trace_planes(const DevScene &sc, V3 o, V3 d, float &cur, Hit &hit)
         const bool acc = TRACER ? ((t > EPS) && (t < cur - EPS)) : (t > EPS && t < cur);
         if (acc) { cur = t; hit.kind = KIND_PLANE; hit.index = i; found = true; }
     }
+#endif
     return found;
 }
 // upper bound handed to the sphere query after the triangle loop (rule S: exclusive)

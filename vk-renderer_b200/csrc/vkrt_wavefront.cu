@@ -86,6 +86,9 @@
 #ifndef VKRT_STAGGER
 #define VKRT_STAGGER 0             // > 0: a wave starts when the wave before it has launched this depth's logic (staggered lanes)
 #endif
+#ifndef VKRT_WARP_RESERVE
+#define VKRT_WARP_RESERVE 0        // dense pipeline: 1 = a warp (not the block) reserves its survivors' range of the next depth's arrays
+#endif
 #ifndef VKRT_SHADE_BLOCK
 #define VKRT_SHADE_BLOCK 256
 #endif
@@ -443,8 +446,10 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
                             float *cs = &s_cold[0][threadIdx.x];
                             cs[0] = o.x; cs[VKRT_TRACE_BLOCK] = o.y; cs[2 * VKRT_TRACE_BLOCK] = o.z;
                             cs[3 * VKRT_TRACE_BLOCK] = d.x; cs[4 * VKRT_TRACE_BLOCK] = d.y; cs[5 * VKRT_TRACE_BLOCK] = d.z;
-#if VKRT_COLD_FLOATS >= 12
+#if VKRT_COLD_FLOATS >= 9
                             cs[6 * VKRT_TRACE_BLOCK] = tv.sr.inv.x; cs[7 * VKRT_TRACE_BLOCK] = tv.sr.inv.y; cs[8 * VKRT_TRACE_BLOCK] = tv.sr.inv.z;
+#endif
+#if VKRT_COLD_FLOATS >= 12
                             cs[9 * VKRT_TRACE_BLOCK] = tv.sr.oinv.x; cs[10 * VKRT_TRACE_BLOCK] = tv.sr.oinv.y; cs[11 * VKRT_TRACE_BLOCK] = tv.sr.oinv.z;
 #endif
                         }
@@ -510,6 +515,9 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
 #if VKRT_COLD_FLOATS >= 12
                         tv.sr.inv = v3(cs[6 * VKRT_TRACE_BLOCK], cs[7 * VKRT_TRACE_BLOCK], cs[8 * VKRT_TRACE_BLOCK]);
                         tv.sr.oinv = v3(cs[9 * VKRT_TRACE_BLOCK], cs[10 * VKRT_TRACE_BLOCK], cs[11 * VKRT_TRACE_BLOCK]);
+#elif VKRT_COLD_FLOATS >= 9
+                        tv.sr.inv = v3(cs[6 * VKRT_TRACE_BLOCK], cs[7 * VKRT_TRACE_BLOCK], cs[8 * VKRT_TRACE_BLOCK]);
+                        tv.sr.oinv = co * tv.sr.inv;     // the same three multiplications as slab_setup
 #else
                         tv.sr = slab_setup(co, cd);      // the same operations on the same values as at the ray's start
 #endif
@@ -936,6 +944,19 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wf_g
 template <int NQ>
 VKRT_DEV void reserve_block(uint32_t *const (&count)[NQ], const bool (&want)[NQ], uint32_t (&pos)[NQ])
 {
+#if VKRT_WARP_RESERVE
+    // one atomicAdd per warp and output: no block-wide barrier, so a warp never waits for the slowest warp of its block
+    // (the barrier of the block-wide form was 14 % of the logic kernels' stall samples); the L2 atomic unit takes about
+    // one same-address operation per cycle, a launch issues one per 32 paths
+    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        const unsigned m = __ballot_sync(full, want[q]);
+        uint32_t b = 0;
+        if (lane == 0 && m) b = atomicAdd(count[q], (uint32_t)__popc(m));
+        pos[q] = __shfl_sync(full, b, 0) + (uint32_t)__popc(m & ((1u << lane) - 1u));
+    }
+#else
     __shared__ uint32_t s_cnt[NQ][32];
     __shared__ uint32_t s_base[NQ];
     const unsigned full = 0xffffffffu, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31u) >> 5;
@@ -955,6 +976,7 @@ VKRT_DEV void reserve_block(uint32_t *const (&count)[NQ], const bool (&want)[NQ]
 #pragma unroll
     for (int q = 0; q < NQ; ++q) pos[q] = s_base[q] + s_cnt[q][warp] + (uint32_t)__popc(m[q] & ((1u << lane) - 1u));
     __syncthreads();      // s_cnt / s_base are reused by the next call
+#endif
 }
 // stores what logic_compute produced for one path: the next depth's ray / state at position j, the shadow record at
 // position k, or the finished radiance of (sample, slot)
