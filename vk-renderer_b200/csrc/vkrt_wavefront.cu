@@ -86,6 +86,10 @@
 #ifndef VKRT_STAGGER
 #define VKRT_STAGGER 0             // > 0: a wave starts when the wave before it has launched this depth's logic (staggered lanes)
 #endif
+#ifndef VKRT_GEN_PIXEL_MAJOR
+#define VKRT_GEN_PIXEL_MAJOR 1     // dense pipeline, depth 0: 1 = a pixel's surviving samples are adjacent in the depth-1 arrays (the Russian
+#endif                             //   roulette outcome of every sample is known ahead of the shading: one hash per sample), 0 = sample-major
+                                   //   (measured: cfg4 27.85 -> 26.97 ms/frame, traversal launches alone 20.78 -> 19.84 ms)
 #ifndef VKRT_WARP_RESERVE
 #define VKRT_WARP_RESERVE 0        // dense pipeline: 1 = a warp (not the block) reserves its survivors' range of the next depth's arrays
 #endif
@@ -978,6 +982,28 @@ VKRT_DEV void reserve_block(uint32_t *const (&count)[NQ], const bool (&want)[NQ]
     __syncthreads();      // s_cnt / s_base are reused by the next call
 #endif
 }
+// every thread asks for `c` consecutive positions; the block reserves the sum with one atomicAdd and hands out
+// the ranges in thread order
+VKRT_DEV uint32_t reserve_block_ranges(uint32_t *count, uint32_t c)
+{
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_b;
+    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31u) >> 5;
+    uint32_t x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(full, x, o); if ((int)lane >= o) x += y; }
+    if (lane == 31u) s_w[warp] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (unsigned w = 0; w < n_warps; ++w) { const uint32_t t = s_w[w]; s_w[w] = tot; tot += t; }
+        s_b = tot ? atomicAdd(count, tot) : 0u;
+    }
+    __syncthreads();
+    const uint32_t r = s_b + s_w[warp] + x - c;
+    __syncthreads();
+    return r;
+}
 // stores what logic_compute produced for one path: the next depth's ray / state at position j, the shadow record at
 // position k, or the finished radiance of (sample, slot)
 VKRT_DEV void dense_store(const WaveParams &wp, const PathState &ps, const ShadowOut &so, bool alive, bool need_ray, uint32_t j, uint32_t k,
@@ -1079,6 +1105,42 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wfd_
         st.shared += wp.S - (wp.prim_mode == 2u ? 0u : 1u);
         st.paths += wp.S;
     }
+#if VKRT_GEN_PIXEL_MAJOR
+    // Whether sample sl of this pixel survives depth 0 is known ahead of its shading: path_shade's Russian roulette compares
+    // u01(sample key, SLOT_RR) with max3(mask * albedo), mask = (1, 1, 1), of the pixel's one primary hit (Tracer.comp:547).
+    // So a thread can reserve one contiguous range for all its surviving samples: the depth-1 rays of a pixel -- same
+    // origin -- are then neighbours in the dense arrays, hence in the warps of the traversal kernel and of `logic`.
+    float p_rr = 0.f;
+    bool can_live = false;
+    if (valid && found) {
+        const Surface sf = surface_of(sc, o, d, hit);
+        const Material mat = load_material(sc, sf.mat);
+        p_rr = max3(v3(1.0f) * mat.albedo);
+        can_live = 1u < rp.max_depth;
+    }
+    for (uint32_t g0 = 0; g0 < wp.S; g0 += 32u) {
+        const uint32_t gn = wp.S - g0 < 32u ? wp.S - g0 : 32u;
+        uint32_t amask = 0;
+        if (can_live)
+            for (uint32_t k = 0; k < gn; ++k)
+                if (!(u01(sample_key(rp.fkey, pix, wp.s0 + g0 + k), SLOT_RR) > p_rr)) amask |= 1u << k;
+        const uint32_t j0 = reserve_block_ranges(wp.cnt_next + C_ACTIVE, (uint32_t)__popc(amask));
+        for (uint32_t k = 0; k < gn; ++k) {
+            const uint32_t sl = g0 + k;
+            bool alive = false, need_ray = false;
+            PathState ps; ShadowOut so;
+            if (valid) {
+                path_begin(ps, o, d);                   // acc = 0: the firefly clamp of :441 leaves it unchanged
+                logic_compute<TB && BVH>(sc, rp, wp, cam_pos, ps, hit, found, pix, sl, st, alive, need_ray, so);
+            }
+            uint32_t *const cs[1] = {wp.cnt + C_SHADOW};
+            const bool ws[1] = {need_ray};
+            uint32_t pos[1];
+            reserve_block<1>(cs, ws, pos);
+            if (valid) dense_store(wp, ps, so, alive, need_ray, j0 + (uint32_t)__popc(amask & ((1u << k) - 1u)), pos[0], slot, sl);
+        }
+    }
+#else
     for (uint32_t sl = 0; sl < wp.S; ++sl) {
         bool alive = false, need_ray = false;
         PathState ps; ShadowOut so;
@@ -1092,6 +1154,7 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wfd_
         reserve_block<2>(cs, ws, pos);
         if (valid) dense_store(wp, ps, so, alive, need_ray, pos[0], pos[1], slot, sl);
     }
+#endif
     wf_flush(st, rp.counters, STATS);
 }
 
