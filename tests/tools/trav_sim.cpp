@@ -1,6 +1,9 @@
 // Design experiment (test infrastructure, CPU only): counts node visits / box tests / leaf tests of candidate
 // traversal schemes on the oracle's LBVH, for synthetic secondary and shadow rays of the cfg4 scene.
-//   usage: trav_sim spheres.bin nodes.bin n_rays
+//   usage: trav_sim spheres.bin nodes.bin n_rays [sah | p<radius>]
+// The optional fourth argument replaces the LBVH by another hierarchy over the same spheres before the walks are
+// counted: `sah` = top-down full-sweep SAH, `p16` = PLOC (locally-ordered clustering along the Morton order, search
+// radius 16).  Any hierarchy with exact union boxes gives rule S's answer; the question is how many visits it costs.
 // spheres.bin: n x {cx,cy,cz,r} float32;  nodes.bin: (n-1) x 16 float32 (orc_scene_read_bvh layout)
 #include <algorithm>
 #include <cmath>
@@ -66,6 +69,114 @@ static inline void leaf(const Ray &r, int si, Best &best, uint64_t &leaves)
     if (!(t > 1e-3f) || !(tn <= t)) return;
     if (best.idx < 0) { if (t < r.B) { best.t = t; best.idx = si; } }
     else if (t < best.t || (t == best.t && si < best.idx)) { best.t = t; best.idx = si; }
+}
+
+
+// ---- tree-quality experiments: other hierarchies over the same spheres (exact padded leaf boxes, exact unions) ----
+static Box leafbox(int si)
+{
+    const Sphere &s = sph[si];
+    const float rp = s.r * 1.001f + 0.001f;
+    return Box{{s.cx - rp, s.cy - rp, s.cz - rp}, {s.cx + rp, s.cy + rp, s.cz + rp}};
+}
+static Box uni(const Box &a, const Box &b)
+{
+    Box r;
+    for (int k = 0; k < 3; ++k) { r.lo[k] = std::min(a.lo[k], b.lo[k]); r.hi[k] = std::max(a.hi[k], b.hi[k]); }
+    return r;
+}
+static Node make_node(const Box &b0, int r0, const Box &b1, int r1)      // ref: >= 0 inner node, < 0 ~sphere
+{
+    Node nd;
+    memcpy(nd.c[0].lo, b0.lo, 12); memcpy(nd.c[0].hi, b0.hi, 12); nd.c[0].kind = r0 < 0; nd.c[0].index = r0 < 0 ? ~r0 : r0;
+    memcpy(nd.c[1].lo, b1.lo, 12); memcpy(nd.c[1].hi, b1.hi, 12); nd.c[1].kind = r1 < 0; nd.c[1].index = r1 < 0 ? ~r1 : r1;
+    return nd;
+}
+// (1) top-down, full-sweep surface-area heuristic over the three centroid orders
+static std::vector<Node> sahn;
+static int sah_build(std::vector<int> &ids, int b, int e, Box &out)
+{
+    if (e - b == 1) { out = leafbox(ids[b]); return ~ids[b]; }
+    const int n = e - b;
+    float bestc = 1e30f; int bax = 0, bsplit = b + n / 2;
+    std::vector<float> la(n);
+    auto by_axis = [&](int ax) {
+        std::sort(ids.begin() + b, ids.begin() + e, [&](int x, int y) {
+            const float cx = (&sph[x].cx)[ax], cy = (&sph[y].cx)[ax];
+            return cx < cy || (cx == cy && x < y);
+        });
+    };
+    for (int ax = 0; ax < 3; ++ax) {
+        by_axis(ax);
+        Box acc = leafbox(ids[b]);
+        for (int i = 0; i < n - 1; ++i) { acc = uni(acc, leafbox(ids[b + i])); la[i] = area(acc) * (i + 1); }
+        acc = leafbox(ids[e - 1]);
+        for (int i = n - 1; i >= 1; --i) {
+            acc = uni(acc, leafbox(ids[b + i]));
+            const float c = la[i - 1] + area(acc) * (n - i);
+            if (c < bestc) { bestc = c; bax = ax; bsplit = b + i; }
+        }
+    }
+    by_axis(bax);
+    const int id = (int)sahn.size();
+    sahn.emplace_back();
+    Box b0, b1;
+    const int r0 = sah_build(ids, b, bsplit, b0), r1 = sah_build(ids, bsplit, e, b1);
+    sahn[id] = make_node(b0, r0, b1, r1);
+    out = uni(b0, b1);
+    return id;
+}
+// (2) PLOC: clusters in the LBVH's leaf (Morton) order; every cluster looks `R` neighbours to each side for the partner
+// with the smallest merged box, mutual choices merge, repeat until one cluster is left
+static void leaf_order(int n, std::vector<int> &out)
+{
+    for (int j = 0; j < 2; ++j) { const Child &c = nodes[n].c[j]; if (c.kind) out.push_back(c.index); else leaf_order(c.index, out); }
+}
+static void ploc_build(int R)
+{
+    std::vector<int> order;
+    leaf_order(0, order);
+    struct Cl { Box b; int ref; };
+    std::vector<Cl> cur;
+    for (int si : order) cur.push_back({leafbox(si), ~si});
+    std::vector<Node> out;
+    while (cur.size() > 1) {
+        const int n = (int)cur.size();
+        std::vector<int> nn(n);
+        for (int i = 0; i < n; ++i) {
+            float best = 1e30f; int bj = -1;
+            for (int j = std::max(0, i - R); j <= std::min(n - 1, i + R); ++j) {
+                if (j == i) continue;
+                const float a = area(uni(cur[i].b, cur[j].b));
+                if (a < best) { best = a; bj = j; }
+            }
+            nn[i] = bj;
+        }
+        std::vector<Cl> nxt;
+        for (int i = 0; i < n; ++i) {
+            const int j = nn[i];
+            if (nn[j] != i) { nxt.push_back(cur[i]); continue; }
+            if (i > j) continue;
+            out.push_back(make_node(cur[i].b, cur[i].ref, cur[j].b, cur[j].ref));
+            nxt.push_back({uni(cur[i].b, cur[j].b), (int)out.size() - 1});
+        }
+        cur.swap(nxt);
+    }
+    const int N = (int)out.size();                 // the root was created last: renumber so that it is node 0
+    std::vector<Node> ren(N);
+    for (int i = 0; i < N; ++i) {
+        Node nd = out[i];
+        for (int j = 0; j < 2; ++j) if (!nd.c[j].kind) nd.c[j].index = N - 1 - nd.c[j].index;
+        ren[N - 1 - i] = nd;
+    }
+    nodes = ren;
+}
+static double sum_child_area(const std::vector<Node> &t)
+{
+    double s = 0;
+    for (const Node &n : t)
+        for (int j = 0; j < 2; ++j) { Box b; memcpy(b.lo, n.c[j].lo, 12); memcpy(b.hi, n.c[j].hi, 12); s += area(b); }
+    return s;
 }
 
 struct Cnt { uint64_t visits = 0, boxes = 0, leaves = 0, stale = 0, pushes = 0, maxsp = 0, popcull = 0; };
@@ -190,6 +301,18 @@ int main(int argc, char **argv)
             }
     }
     const int n_rays = atoi(argv[3]);
+    printf("LBVH: %zu nodes, sum of child box areas %.4g\n", nodes.size(), sum_child_area(nodes));
+    if (argc > 4 && argv[4][0] == 'p') {
+        ploc_build(atoi(argv[4] + 1));
+        printf("PLOC radius %d: %zu nodes, sum of child box areas %.4g\n", atoi(argv[4] + 1), nodes.size(), sum_child_area(nodes));
+    } else if (argc > 4) {
+        std::vector<int> ids(sph.size());
+        for (size_t i = 0; i < ids.size(); ++i) ids[i] = (int)i;
+        Box rb;
+        sah_build(ids, 0, (int)ids.size(), rb);
+        nodes = sahn;
+        printf("sweep SAH: %zu nodes, sum of child box areas %.4g\n", nodes.size(), sum_child_area(nodes));
+    }
     std::mt19937 rng(12345);
     std::uniform_real_distribution<float> U(0.f, 1.f);
     std::vector<Ray> rays;

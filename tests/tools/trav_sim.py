@@ -1,7 +1,8 @@
 """Design experiment behind DESIGN.md section 4 ("what was measured and rejected", wide BVHs): dumps the cfg4 scene and the
 oracle's LBVH, builds tests/tools/trav_sim.cpp and prints node visits / box tests / leaf tests per ray of the candidate
 traversal schemes (binary near-first, + entry distance on the stack, 4- and 8-wide collapses, sorted / unsorted).
-CPU only; test infrastructure (it uses the oracle's tree).   python tests/tools/trav_sim.py [n_rays]"""
+CPU only; test infrastructure (it uses the oracle's tree).   python tests/tools/trav_sim.py [n_rays] [sah | p16]
+(the second argument swaps the LBVH for a sweep-SAH or a PLOC hierarchy over the same spheres: tree-quality experiment)"""
 import os
 import subprocess
 import sys
@@ -23,4 +24,4 @@ sc.spheres.astype(np.float32).tofile(os.path.join(d, "spheres.bin"))
 np.ascontiguousarray(o.bvh_nodes()).tofile(os.path.join(d, "nodes.bin"))
 exe = os.path.join(d, "trav_sim")
 subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "tools", "trav_sim.cpp")], check=True)
-subprocess.run([exe, os.path.join(d, "spheres.bin"), os.path.join(d, "nodes.bin"), n_rays], check=True)
+subprocess.run([exe, os.path.join(d, "spheres.bin"), os.path.join(d, "nodes.bin"), n_rays] + sys.argv[2:], check=True)

@@ -167,6 +167,29 @@ for rep_name, out_name, what in (("full_trace.ncu-rep", "ncu_full_k_wf_trace_cfg
                 if w in hdr:
                     f.write("%s = %s %s\n" % (w, r[hdr.index(w)], units[hdr.index(w)]))
 
+# ---- where the traversal kernel's issue slots go (tools/ncu_phases.py on the full capture's source page) -----
+phases_txt = ""
+try:
+    import tempfile
+    tmp = tempfile.mkdtemp()
+    subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "vk-renderer_b200", "libvkrt_cuda.so")], cwd=tmp,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    sass = os.path.join(tmp, "wf.sass")
+    open(sass, "w").write(subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, "vkrt_wavefront.sm_100a.cubin")],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout)
+    srcp = os.path.join(tmp, "trace_src.csv")
+    open(srcp, "w").write(subprocess.run(["ncu", "-i", G("full_trace.ncu-rep"), "--page", "source", "--csv", "--print-kernel-base", "mangled"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout)
+    for which in (0, 1, 2):
+        phases_txt += subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_phases.py"), srcp, sass, str(which)],
+                                     stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout + "\n"
+    with open(P("trace_phases.txt"), "w") as f:
+        f.write("# tools/ncu_phases.py on %s_full_trace.ncu-rep (ncu --set full --import-source on, the first three traversal launches of a cfg4 frame),\n"
+                "# library built from commit %s: executed warp instructions, stall samples and active lanes per phase of k_wf_trace\n" % (tag, head()))
+        f.write(phases_txt)
+except Exception as e:
+    print("trace_phases.txt skipped:", e)
+
 # ---- summary -------------------------------------------------------------------------------------------
 with open(P("SUMMARY.md"), "w") as f:
     f.write("# Round evidence (%s), generated by tools/make_profiles_r2.py from tools/evidence_r2.sh run `%s` (commit %s)\n\n" % (rnd, tag, head()))
