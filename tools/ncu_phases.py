@@ -72,8 +72,11 @@ def main():
     which = int(sys.argv[3]) if len(sys.argv) > 3 else 1
     rows = list(csv.reader(open(src_csv)))
     starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    # ncu prints every launch twice (one table per source view): keep one of each pair
+    if len(starts) % 2 == 0 and all(rows[starts[i] + 2][:8] == rows[starts[i + 1] + 2][:8] for i in range(0, len(starts), 2)):
+        starts = starts[0::2]
     s = starts[which]
-    e = starts[which + 1] if which + 1 < len(starts) else len(rows)
+    e = next((i for i in range(s + 1, len(rows)) if rows[i] and rows[i][0] == "Kernel Name"), len(rows))
     kernel = rows[s][1]
     block = rows[s:e]
     hdr_i = next(i for i, r in enumerate(block) if r and r[0] == "Address")
