@@ -39,6 +39,10 @@
 #ifndef VKRT_LEAF_BATCH
 #define VKRT_LEAF_BATCH 8    // run a leaf phase once this many lanes wait at a leaf (0: leaf tests inside the node step)
 #endif
+#ifndef VKRT_FAST_INNER
+#define VKRT_FAST_INNER 20    // lanes at inner nodes from which the node loop skips its other votes (0 = never; 12..25 measured, 19-20 best:
+                              // cfg4 26.98 -> 26.64 ms/frame)
+#endif
 #ifndef VKRT_TRACE_BLOCK
 #define VKRT_TRACE_BLOCK 128
 #endif
@@ -501,15 +505,23 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
             }
 #elif VKRT_LEAF_BATCH
             for (;;) {
-                const bool trav = has && tv.node != FIN;
-                const unsigned tm = __ballot_sync(full, trav);
-                if (tm == 0) break;
-                if (__popc(tm) < (int)refill_at && __any_sync(full, !drained && !trav)) break;
-                // lanes whose next item is a scheduled leaf wait until VKRT_LEAF_BATCH of them can run the leaf test
-                // together (or nobody has an inner node left); everybody else keeps visiting inner nodes
-                const unsigned im = __ballot_sync(full, trav && tv.node >= 0);
-                if (im == 0 || __popc(tm & ~im) >= VKRT_LEAF_BATCH) {
-                    if (trav && tv.node < 0) {
+                // lanes at inner nodes (a lane without a ray holds FIN, a lane at a scheduled leaf ~sphere: both negative)
+                const unsigned im = __ballot_sync(full, tv.node >= 0);
+                const int n_inner = __popc(im);
+                bool leaf_phase = false;
+                // With VKRT_FAST_INNER or more lanes at inner nodes the warp just keeps walking: one vote per round instead of
+                // four (with >= 25 the decisions below could not come out differently anyway; 20 measured best)
+                if (n_inner < (VKRT_FAST_INNER ? VKRT_FAST_INNER : 33)) {
+                    const bool trav = has && tv.node != FIN;
+                    const unsigned tm = __ballot_sync(full, trav);
+                    if (tm == 0) break;
+                    if (__popc(tm) < (int)refill_at && __any_sync(full, !drained && !trav)) break;
+                    // lanes whose next item is a scheduled leaf wait until VKRT_LEAF_BATCH of them can run the leaf test
+                    // together (or nobody has an inner node left); everybody else keeps visiting inner nodes
+                    leaf_phase = n_inner == 0 || __popc(tm) - n_inner >= VKRT_LEAF_BATCH;
+                }
+                if (leaf_phase) {
+                    if (has && tv.node < 0 && tv.node != FIN) {
 #if VKRT_COLD_SMEM
                         // the ray's origin, direction and exact slab constants are only needed here: they live in shared
                         // memory ([field][thread], conflict-free) so the node loop's registers hold nothing cold
@@ -534,9 +546,9 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
 #pragma unroll
                     for (int u = 0; u < VKRT_TRAV_UNROLL; ++u)     // the warp votes above cost ~10 instructions: amortise them
 #if VKRT_QNODES
-                        if (has && tv.node >= 0) trav_inner_step_q<STATS>(tv, qr, stack, sc, st);
+                        if (tv.node >= 0) trav_inner_step_q<STATS>(tv, qr, stack, sc, st);
 #else
-                        if (has && tv.node >= 0) trav_inner_step<STATS>(tv, stack, sc, st);
+                        if (tv.node >= 0) trav_inner_step<STATS>(tv, stack, sc, st);
 #endif
                 }
             }
