@@ -18,4 +18,4 @@ except Exception as e:
 PY
 timeout 300 vk-renderer_b200/vkrt_headless --frames 200 --res 1024 --spp 4 --depth 4 --wavefront --seed 1 > $O/${T}_headless_1.txt 2>&1
 timeout 300 vk-renderer_b200/vkrt_headless --frames 200 --res 1024 --spp 4 --depth 4 --wavefront --seed 1 --devices $(seq -s, 0 $((N-1))) > $O/${T}_headless_$N.txt 2>&1
-tail -1 $O/${T}_headless_1.txt $O/${T}_headless_$N.txt
+tail -qn1 $O/${T}_headless_1.txt $O/${T}_headless_$N.txt
