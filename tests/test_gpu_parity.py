@@ -379,6 +379,32 @@ def test_wavefront_multi_wave_equals_megakernel(vk):
         assert outs[0][0][..., 3].max() == 3 * n_expect
 
 
+def test_pixel_major_groups_of_more_than_32_samples(vk, monkeypatch):
+    """Depth 0 hands every pixel one contiguous range of the depth-1 arrays for its surviving samples, 32 samples at a
+    time (a 32-bit survivor mask).  Waves normally hold <= 16 samples; the tuning knob VKRT_TUNE_WAVE_SPP makes one wave
+    hold 45, i.e. a full group and a ragged one: still bit-identical to the megakernel, same ray counts."""
+    V = vk
+    w, h = 96, 72
+    scene = V.scenes.random_spheres(200)
+    fd = V.default_frame_data(aspect_ratio=w / h, seed=0.3)
+    outs = []
+    for variant, wave in ((0, None), (1, "45"), (1, "33")):
+        if wave:
+            monkeypatch.setenv("VKRT_TUNE_WAVE_SPP", wave)
+        else:
+            monkeypatch.delenv("VKRT_TUNE_WAVE_SPP", raising=False)
+        r = V.Renderer(w, h, spp=45, max_depth=6, variant=variant, flags=V.FLAG_HIT_IDS)
+        r.set_scene(scene); r.build_bvh(); r.set_seed(9)
+        r.draw(fd); r.draw(fd)
+        c = r.counters()
+        outs.append((r.read_accum(), r.read_hit_ids(), (c.closest_rays, c.shadow_rays, c.paths)))
+        r.close()
+    for o in outs[1:]:
+        assert bits_equal(outs[0][0], o[0]), mismatch_report(outs[0][0], o[0])
+        assert np.array_equal(outs[0][1], o[1])
+        assert outs[0][2] == o[2]
+
+
 def test_serial_waves_flag_is_bit_identical(vk):
     """VKRT_FLAG_SERIAL_WAVES (bench.py's measurement aid) only changes where the waves are enqueued."""
     V = vk
