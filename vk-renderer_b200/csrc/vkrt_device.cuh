@@ -322,8 +322,8 @@ struct TravStack {
 #define VKRT_QSEL6 0         // 1: the FAR plane's selectors live in registers too (no `^ 0x22` per node and axis)
 #endif
 #ifndef VKRT_SENTINEL
-#define VKRT_SENTINEL 0      // 1: the stack's bottom entry is TRAV_DONE: a pop needs no "stack empty?" test, and the inner step
-#endif                       //    stores its far child unconditionally (the slot above the top is free) -- no branches
+#define VKRT_SENTINEL 2      // > 0: the stack's bottom entry is TRAV_DONE: a pop needs no "stack empty?" test (2, the default: 26.54 ->
+#endif                       //    26.47 ms/frame); 1: the inner step also stores its far child unconditionally -- no branches (slower)
 #ifndef VKRT_SELECT2
 #define VKRT_SELECT2 1       // 1: near/far child chosen by one predicate and two selects
 #endif
@@ -402,7 +402,11 @@ VKRT_DEV void trav_inner_step_q(Trav &tv, const QRay &q, Stack &stack, const Dev
     // the same choice as below (both: the nearer child first, ties -> child 0) from one predicate and two selects
     const bool take1 = h1 && (!h0 || tn1 < tn0);
     const int nearer = take1 ? c1 : c0, other = take1 ? c0 : c1;
-#if VKRT_SENTINEL && !VKRT_SMEM_STACK
+#if VKRT_SENTINEL == 2 && !VKRT_SMEM_STACK
+    if (h0 && h1) stack.push(tv.sp, other);
+    if (h0 || h1) tv.node = nearer;
+    else tv.node = stack.lm[--tv.sp];             // the bottom entry is TRAV_DONE: no "stack empty?" test
+#elif VKRT_SENTINEL && !VKRT_SMEM_STACK
     stack.lm[tv.sp] = other;                      // kept only if both children were hit
     tv.sp += (h0 && h1) ? 1 : 0;
     tv.node = nearer;
