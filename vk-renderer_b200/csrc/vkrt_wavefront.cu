@@ -817,12 +817,11 @@ struct LightsDeferred {
 // needed, returns that ray {P, L, t} and the accumulator for the other outcome (acc_v)
 struct ShadowOut { V3 P, L, acc_v; float t; };
 template <bool TB = true>
-VKRT_DEV void logic_compute(const DevScene &sc, const RenderParams &rp, const WaveParams &wp, V3 cam_pos, PathState &ps,
-                            const Hit &hit, bool found, uint32_t pix, uint32_t sl, Stats &st, bool &alive, bool &need_ray, ShadowOut &so)
+VKRT_DEV void logic_compute_k(const DevScene &sc, const RenderParams &rp, V3 cam_pos, PathState &ps,
+                              const Hit &hit, bool found, uint32_t skey, Stats &st, bool &alive, bool &need_ray, ShadowOut &so)
 {
     alive = false; need_ray = false;
     if (found) {
-        const uint32_t skey = sample_key(rp.fkey, pix, wp.s0 + sl);
         const V3 acc_b = ps.acc, mask_b = ps.mask;
         so.P = madd3(hit.t, ps.d, ps.o);                                                // P == surface_of's P
         V3 term = v3(0.0f), emis = v3(0.0f);
@@ -831,6 +830,12 @@ VKRT_DEV void logic_compute(const DevScene &sc, const RenderParams &rp, const Wa
         alive = path_shade(sc, cam_pos, rp.max_depth, skey, ps, hit, lights, &emis);
         if (need_ray) so.acc_v = acc_b + mask_b * (emis + (v3(0.0f) + term));
     }
+}
+template <bool TB = true>
+VKRT_DEV void logic_compute(const DevScene &sc, const RenderParams &rp, const WaveParams &wp, V3 cam_pos, PathState &ps,
+                            const Hit &hit, bool found, uint32_t pix, uint32_t sl, Stats &st, bool &alive, bool &need_ray, ShadowOut &so)
+{
+    logic_compute_k<TB>(sc, rp, cam_pos, ps, hit, found, sample_key(rp.fkey, pix, wp.s0 + sl), st, alive, need_ray, so);
 }
 VKRT_DEV void logic_path(const DevScene &sc, const RenderParams &rp, const WaveParams &wp, V3 cam_pos, uint32_t path, PathState &ps,
                          const Hit &hit, bool found, uint32_t pix, uint32_t sl, Stats &st, bool &alive, bool &need_ray)
@@ -1019,11 +1024,13 @@ VKRT_DEV uint32_t reserve_block_ranges(uint32_t *count, uint32_t c)
 // stores what logic_compute produced for one path: the next depth's ray / state at position j, the shadow record at
 // position k, or the finished radiance of (sample, slot)
 VKRT_DEV void dense_store(const WaveParams &wp, const PathState &ps, const ShadowOut &so, bool alive, bool need_ray, uint32_t j, uint32_t k,
-                          uint32_t slot, uint32_t sl)
+                          uint32_t slot, uint32_t sl, uint32_t skey)
 {
     const uint32_t rad_i = sl * wp.n_slots + slot;
     if (alive) {
-        st256(wp.n_ray + 2 * (size_t)j, make_float4(ps.o.x, ps.o.y, ps.o.z, 0.f), make_float4(ps.d.x, ps.d.y, ps.d.z, 0.f));
+        // the ray record's spare word carries the path's sample key: `logic` needs neither the pixel of the slot (two
+        // integer divisions) nor the two hashes of sample_key again
+        st256(wp.n_ray + 2 * (size_t)j, make_float4(ps.o.x, ps.o.y, ps.o.z, __uint_as_float(skey)), make_float4(ps.d.x, ps.d.y, ps.d.z, 0.f));
         st256(wp.n_st + 2 * (size_t)j, make_float4(ps.acc.x, ps.acc.y, ps.acc.z, __uint_as_float(slot)),
               make_float4(ps.mask.x, ps.mask.y, ps.mask.z, __uint_as_float((sl << 8) | ps.depth)));
     } else {
@@ -1046,7 +1053,7 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wfd_
         const uint32_t i = base + threadIdx.x;
         bool alive = false, need_ray = false;
         PathState ps; ShadowOut so;
-        uint32_t slot = 0, sl = 0;
+        uint32_t slot = 0, sl = 0, skey = 0;
         if (i < n) {
             float4 fo, fd, fa, fm;
             ld256cg(wp.x_ray + 2 * (size_t)i, fo, fd);
@@ -1056,22 +1063,20 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wfd_
             const uint32_t sd = __float_as_uint(fm.w);
             ps.depth = sd & 255u; sl = sd >> 8;
             slot = __float_as_uint(fa.w);
-            uint32_t px, py;
-            slot_to_pixel_w(rp, slot, px, py);
-            const uint32_t pix = py * rp.width + px;
+            skey = __float_as_uint(fo.w);
             const uint32_t id0 = __float_as_uint(h.y);
             Hit hit{h.x, id0 >> 28, id0 & 0x0fffffffu};
             ps.acc = clamp3(ps.acc, 0.0f, 1.0f);                                                        // :441
             float cur = hit.t;
             const bool found = trace_planes<true>(sc, ps.o, ps.d, cur, hit) || id0 != 0u;             // :414-428
             hit.t = cur;
-            logic_compute<TB>(sc, rp, wp, cam_pos, ps, hit, found, pix, sl, st, alive, need_ray, so);
+            logic_compute_k<TB>(sc, rp, cam_pos, ps, hit, found, skey, st, alive, need_ray, so);
         }
         uint32_t *const cs[2] = {wp.cnt_next + C_ACTIVE, wp.cnt + C_SHADOW};
         const bool ws[2] = {alive, need_ray};
         uint32_t pos[2];
         reserve_block<2>(cs, ws, pos);
-        if (i < n) dense_store(wp, ps, so, alive, need_ray, pos[0], pos[1], slot, sl);
+        if (i < n) dense_store(wp, ps, so, alive, need_ray, pos[0], pos[1], slot, sl, skey);
     }
     wf_flush(st, rp.counters, false);
 }
@@ -1141,15 +1146,16 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wfd_
             const uint32_t sl = g0 + k;
             bool alive = false, need_ray = false;
             PathState ps; ShadowOut so;
+            const uint32_t skey = sample_key(rp.fkey, pix, wp.s0 + sl);
             if (valid) {
                 path_begin(ps, o, d);                   // acc = 0: the firefly clamp of :441 leaves it unchanged
-                logic_compute<TB && BVH>(sc, rp, wp, cam_pos, ps, hit, found, pix, sl, st, alive, need_ray, so);
+                logic_compute_k<TB && BVH>(sc, rp, cam_pos, ps, hit, found, skey, st, alive, need_ray, so);
             }
             uint32_t *const cs[1] = {wp.cnt + C_SHADOW};
             const bool ws[1] = {need_ray};
             uint32_t pos[1];
             reserve_block<1>(cs, ws, pos);
-            if (valid) dense_store(wp, ps, so, alive, need_ray, j0 + (uint32_t)__popc(amask & ((1u << k) - 1u)), pos[0], slot, sl);
+            if (valid) dense_store(wp, ps, so, alive, need_ray, j0 + (uint32_t)__popc(amask & ((1u << k) - 1u)), pos[0], slot, sl, skey);
         }
     }
 #else
@@ -1164,7 +1170,7 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wfd_
         const bool ws[2] = {alive, need_ray};
         uint32_t pos[2];
         reserve_block<2>(cs, ws, pos);
-        if (valid) dense_store(wp, ps, so, alive, need_ray, pos[0], pos[1], slot, sl);
+        if (valid) dense_store(wp, ps, so, alive, need_ray, pos[0], pos[1], slot, sl, sample_key(rp.fkey, pix, wp.s0 + sl));
     }
 #endif
     wf_flush(st, rp.counters, STATS);
@@ -1211,6 +1217,7 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wfd_
     uint32_t px = 0, py = 0;
     const bool valid = slot < wp.n_slots && slot_to_pixel_w(rp, slot, px, py);
     bool alive = false, need_ray = false;
+    uint32_t skey = 0;
     PathState ps; ShadowOut so;
     if (valid) {
         V3 o, d;
@@ -1219,7 +1226,8 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wfd_
         const uint32_t id = __float_as_uint(ph.y);
         const Hit hit{ph.x, id >> 28, id & 0x0fffffffu};
         path_begin(ps, o, d);                   // acc = 0: the firefly clamp of :441 leaves it unchanged
-        logic_compute(sc, rp, wp, cam_pos, ps, hit, id != 0u, py * rp.width + px, sl, st, alive, need_ray, so);
+        skey = sample_key(rp.fkey, py * rp.width + px, wp.s0 + sl);
+        logic_compute_k(sc, rp, cam_pos, ps, hit, id != 0u, skey, st, alive, need_ray, so);
         ++st.closest; ++st.paths;
         if (sl != 0u || wp.prim_mode == 2u) ++st.shared;      // every sample but the frame's first reuses the pixel's one query
     }
@@ -1227,7 +1235,7 @@ __global__ void __launch_bounds__(VKRT_SHADE_BLOCK, VKRT_LOGIC_MINBLOCKS) k_wfd_
     const bool ws[2] = {alive, need_ray};
     uint32_t pos[2];
     reserve_block<2>(cs, ws, pos);
-    if (valid) dense_store(wp, ps, so, alive, need_ray, pos[0], pos[1], slot, sl);
+    if (valid) dense_store(wp, ps, so, alive, need_ray, pos[0], pos[1], slot, sl, skey);
     wf_flush(st, rp.counters, false);
 }
 
