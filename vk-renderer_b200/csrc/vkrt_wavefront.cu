@@ -33,6 +33,9 @@
 #ifndef VKRT_FETCH_CHUNK
 #define VKRT_FETCH_CHUNK 64   // ray indices a warp reserves per atomicAdd on the queue head
 #endif
+#ifndef VKRT_NESTED_STEPS
+#define VKRT_NESTED_STEPS 1   // the round's inner steps form ONE divergent region (no reconvergence point per step): 26.41 -> 26.01 ms/frame;
+#endif                        // steps per round 2 .. 12 measured: 3, 6 and 9 are equal (25.9 - 26.0), the others 0.4 - 1.2 ms slower
 #ifndef VKRT_TRAV_UNROLL
 #define VKRT_TRAV_UNROLL 3
 #endif
@@ -325,6 +328,16 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ Dev
 // one warp may hold either kind, the traversal is the same code.
 // MODE 3 (dense fused pipeline): like MODE 2, but item i IS ray i of the depth's dense ray array and shadow item k is
 //                   shadow record k -- no queues; the nearest hit goes to hit[i]
+#if VKRT_QNODES
+template <int N, bool STATS, class Stack>
+VKRT_DEV void nested_inner_steps(Trav &tv, const QRay &qr, Stack &stack, const DevScene &sc, Stats &st)
+{
+    if (tv.node >= 0) {
+        trav_inner_step_q<STATS>(tv, qr, stack, sc, st);
+        if (N > 1) nested_inner_steps<(N > 1 ? N - 1 : 1), STATS>(tv, qr, stack, sc, st);
+    }
+}
+#endif
 enum { TRACE_EXTEND = 0, TRACE_SHADOW = 1, TRACE_MIXED = 2, TRACE_DENSE = 3 };
 template <int MODE, bool BVH, bool STATS, bool TB = true>
 __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_trace(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
@@ -543,12 +556,18 @@ __global__ void __launch_bounds__(VKRT_TRACE_BLOCK, VKRT_TRACE_MINBLOCKS) k_wf_t
 #endif
                     }
                 } else {
+#if VKRT_NESTED_STEPS && VKRT_QNODES
+                    // ONE divergent region for the round's steps: a lane that runs out of inner nodes leaves it for good
+                    // (no reconvergence point per step)
+                    nested_inner_steps<VKRT_TRAV_UNROLL, STATS>(tv, qr, stack, sc, st);
+#else
 #pragma unroll
                     for (int u = 0; u < VKRT_TRAV_UNROLL; ++u)     // the warp votes above cost ~10 instructions: amortise them
 #if VKRT_QNODES
                         if (tv.node >= 0) trav_inner_step_q<STATS>(tv, qr, stack, sc, st);
 #else
                         if (tv.node >= 0) trav_inner_step<STATS>(tv, stack, sc, st);
+#endif
 #endif
                 }
             }
