@@ -466,7 +466,8 @@ class Bench:
                 "bounding_unit": ev.get("limiters"),
                 "note": "bound/frac are the contract's HBM figure: algorithmic bytes / kernel time against the measured copy bandwidth. "
                         "The tree (%.1f MB) is L1/L2-resident, so DRAM carries only the ray records (`traffic`); the units that actually "
-                        "bound the kernel are listed in `bounding_unit` (from the committed ncu capture) and `l2`" % (bvh.n_nodes * node_bytes / 1e6)}
+                        "bound the kernel are listed in `bounding_unit` (from the committed ncu capture) and `l2`; that is also why "
+                        "`frac` can exceed 1: the node bytes come out of L1 / L2, not HBM" % (bvh.n_nodes * node_bytes / 1e6)}
             if rank == 0:
                 l2_peak = V.measure_l2_bandwidth(local)
                 out["roofline"]["l2"] = {"achieved": achieved, "peak": l2_peak, "unit": "GB/s", "frac": achieved / l2_peak,
