@@ -326,10 +326,18 @@ typedef struct vkrt_bvh_info {
     uint32_t n_tri_nodes;
     uint32_t tri_depth;
     float    tri_build_ms;
+    uint32_t traversal_depth;    /* the tree the wavefront's 32-byte traversal nodes are made from: the same leaves and exact
+                                    union boxes as the LBVH (so rule S's answer is the same), splits chosen top-down by a binned
+                                    surface-area heuristic on the device; its depth, whether it is that tree (1) or the LBVH
+                                    itself (0), and its share of build_ms */
+    uint32_t traversal_is_sah;
+    float    traversal_build_ms;
 } vkrt_bvh_info;
 VKRT_API vkrt_error vkrt_get_bvh_info(vkrt_ctx *ctx, vkrt_bvh_info *out);
 /* Copies the packed nodes (n_nodes * 16 floats) to the host. */
 VKRT_API vkrt_error vkrt_read_bvh_nodes(vkrt_ctx *ctx, float *host, size_t bytes);
+/* The same layout for the traversal tree (n_nodes * 16 floats, root = node 0, breadth-first ids). */
+VKRT_API vkrt_error vkrt_read_bvh_traversal_nodes(vkrt_ctx *ctx, float *host, size_t bytes);
 /* Copies the 32-byte traversal nodes (n_nodes * 8 uint32: two child records {x: lo | hi << 16, y, z, ref}, ref =
  * inner node index or ~sphere) and their 16-bit grid (scale[3], offset[3]: the coordinate of code q is
  * (2^23 + q) * scale + offset) to the host.  Introspection for the containment tests. */

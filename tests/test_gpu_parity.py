@@ -157,7 +157,7 @@ def test_bvh_quantised_nodes_enclose_exact_nodes(vk, n):
     r = V.Renderer(64, 64)
     r.set_scene(scene)
     r.build_bvh()
-    exact = r.bvh_nodes().reshape(-1, 2, 8)                 # [node][child] {lo.xyz hi.x | hi.yz index kind}
+    exact = r.bvh_traversal_nodes().reshape(-1, 2, 8)       # [node][child] {lo.xyz hi.x | hi.yz index kind}: the tree the codes are made from
     qn, grid = r.bvh_qnodes()
     qn = qn.reshape(-1, 2, 4)
     r.close()
@@ -188,6 +188,60 @@ def test_bvh_quantised_nodes_enclose_exact_nodes(vk, n):
     ci = idx[inner]
     plo, phi = qlo[inner], qhi[inner]
     assert np.all(plo[:, None, :] <= qlo[ci]) and np.all(phi[:, None, :] >= qhi[ci])
+
+
+@pytest.mark.parametrize("case", ["2", "3", "17", "1024", "grid20k", "coincident"])
+def test_traversal_tree_is_a_hierarchy_of_exact_unions_over_the_same_leaves(vk, case):
+    """The wavefront's traversal nodes come from a tree of its own (top-down binned SAH, built on the device).  Rule S only
+    needs: every sphere is exactly one leaf whose box is the sphere's own padded box, and every inner box is
+    the exact min / max union of its two children.  Checked on the bits; also: breadth-first node ids, the reported depth,
+    and that the build is deterministic."""
+    V = vk
+    if case == "grid20k":
+        scene = V.scenes.grid_spheres(nx=30, ny=25, nz=27)
+    elif case == "coincident":
+        scene = V.scenes.random_spheres(64)
+        scene.spheres = np.repeat(scene.spheres[:1], 5000, axis=0).copy()
+        scene.spheres[:, 3] = np.linspace(0.5, 3.0, 5000, dtype=np.float32)
+        scene.sphere_mat = np.full(5000, 8, dtype=np.uint32)
+    else:
+        scene = V.scenes.random_spheres(int(case))
+        scene.spheres, scene.sphere_mat = scene.spheres[1:], scene.sphere_mat[1:]
+    n = scene.spheres.shape[0]
+    r = V.Renderer(64, 64)
+    r.set_scene(scene)
+    info = r.build_bvh()
+    t = r.bvh_traversal_nodes()
+    r.build_bvh()
+    assert bits_equal(t, r.bvh_traversal_nodes())                    # deterministic
+    r.close()
+    assert info.traversal_is_sah == 1 and t.shape[0] == n - 1
+    t = t.reshape(-1, 2, 8)
+    lo = t[:, :, 0:3]
+    hi = np.stack([t[:, :, 3], t[:, :, 4], t[:, :, 5]], axis=-1)
+    idx = np.ascontiguousarray(t[:, :, 6]).view(np.int32)
+    kind = np.ascontiguousarray(t[:, :, 7]).view(np.int32)
+    assert set(np.unique(kind)) <= {0, 1}
+    # leaves: every sphere once, with its own padded box (the same float32 operations as the device)
+    leaf = kind == 1
+    assert np.array_equal(np.sort(idx[leaf]), np.arange(n))
+    sp = scene.spheres.astype(np.float32)
+    rp = (sp[:, 3] * np.float32(1.001) + np.float32(0.001)).astype(np.float32)
+    assert bits_equal(lo[leaf], (sp[idx[leaf], 0:3] - rp[idx[leaf], None]).astype(np.float32))
+    assert bits_equal(hi[leaf], (sp[idx[leaf], 0:3] + rp[idx[leaf], None]).astype(np.float32))
+    # inner children: every node but the root once; box = exact union of that node's two child boxes
+    inner = kind == 0
+    ci = idx[inner]
+    assert np.array_equal(np.sort(ci), np.arange(1, n - 1))
+    assert bits_equal(lo[inner], lo[ci].min(axis=1)) and bits_equal(hi[inner], hi[ci].max(axis=1))
+    # breadth-first ids: a child's id is larger than its parent's; depth = longest chain of inner nodes
+    parent = np.repeat(np.arange(n - 1), 2).reshape(-1, 2)[inner]
+    assert np.all(ci > parent)
+    depth = np.ones(n - 1, dtype=np.int64)
+    order = np.argsort(ci)                                            # children in id order: parents are final before them
+    for c_, p_ in zip(ci[order], parent[order]):
+        depth[c_] = depth[p_] + 1
+    assert depth.max() == info.traversal_depth <= 126
 
 
 def test_bvh_duplicate_centres(vk, oracle):

@@ -1,6 +1,6 @@
 // Design experiment (test infrastructure, CPU only): counts node visits / box tests / leaf tests of candidate
 // traversal schemes on the oracle's LBVH, for synthetic secondary and shadow rays of the cfg4 scene.
-//   usage: trav_sim spheres.bin nodes.bin n_rays [sah | p<radius>]
+//   usage: trav_sim spheres.bin nodes.bin n_rays [sah | b<bins> | p<radius>]
 // The optional fourth argument replaces the LBVH by another hierarchy over the same spheres before the walks are
 // counted: `sah` = top-down full-sweep SAH, `p16` = PLOC (locally-ordered clustering along the Morton order, search
 // radius 16).  Any hierarchy with exact union boxes gives rule S's answer; the question is how many visits it costs.
@@ -122,6 +122,49 @@ static int sah_build(std::vector<int> &ids, int b, int e, Box &out)
     sahn.emplace_back();
     Box b0, b1;
     const int r0 = sah_build(ids, b, bsplit, b0), r1 = sah_build(ids, bsplit, e, b1);
+    sahn[id] = make_node(b0, r0, b1, r1);
+    out = uni(b0, b1);
+    return id;
+}
+// (1b) top-down binned SAH (NB bins per axis over the centroid bounds), what a level-synchronous device builder does
+static int binned_build(std::vector<int> &ids, int b, int e, Box &out, int NB)
+{
+    if (e - b == 1) { out = leafbox(ids[b]); return ~ids[b]; }
+    const int n = e - b;
+    float clo[3] = {1e30f, 1e30f, 1e30f}, chi[3] = {-1e30f, -1e30f, -1e30f};
+    for (int i = b; i < e; ++i) for (int k = 0; k < 3; ++k) { const float c = (&sph[ids[i]].cx)[k]; clo[k] = std::min(clo[k], c); chi[k] = std::max(chi[k], c); }
+    float bestc = 1e30f; int bax = -1, bbin = 0;
+    for (int ax = 0; ax < 3; ++ax) {
+        if (!(chi[ax] > clo[ax])) continue;
+        std::vector<Box> bb(NB, Box{{1e30f, 1e30f, 1e30f}, {-1e30f, -1e30f, -1e30f}});
+        std::vector<int> bc(NB, 0);
+        const float sc = NB / (chi[ax] - clo[ax]);
+        for (int i = b; i < e; ++i) {
+            int k = (int)(((&sph[ids[i]].cx)[ax] - clo[ax]) * sc); k = std::min(std::max(k, 0), NB - 1);
+            bb[k] = uni(bb[k], leafbox(ids[i])); ++bc[k];
+        }
+        std::vector<float> la(NB); std::vector<int> lc(NB);
+        Box acc{{1e30f, 1e30f, 1e30f}, {-1e30f, -1e30f, -1e30f}}; int cnt = 0;
+        for (int k = 0; k < NB; ++k) { if (bc[k]) acc = uni(acc, bb[k]); cnt += bc[k]; la[k] = cnt ? area(acc) * cnt : 0.f; lc[k] = cnt; }
+        acc = Box{{1e30f, 1e30f, 1e30f}, {-1e30f, -1e30f, -1e30f}}; cnt = 0;
+        for (int k = NB - 1; k >= 1; --k) {
+            if (bc[k]) acc = uni(acc, bb[k]); cnt += bc[k];
+            if (cnt == 0 || lc[k - 1] == 0) continue;
+            const float c = la[k - 1] + area(acc) * cnt;
+            if (c < bestc) { bestc = c; bax = ax; bbin = k; }
+        }
+    }
+    int mid;
+    if (bax < 0) mid = b + n / 2;            // all centroids equal: split the index range
+    else {
+        const float sc = NB / (chi[bax] - clo[bax]);
+        mid = (int)(std::stable_partition(ids.begin() + b, ids.begin() + e, [&](int x) {
+            int k = (int)(((&sph[x].cx)[bax] - clo[bax]) * sc); k = std::min(std::max(k, 0), NB - 1); return k < bbin; }) - ids.begin());
+    }
+    const int id = (int)sahn.size();
+    sahn.emplace_back();
+    Box b0, b1;
+    const int r0 = binned_build(ids, b, mid, b0, NB), r1 = binned_build(ids, mid, e, b1, NB);
     sahn[id] = make_node(b0, r0, b1, r1);
     out = uni(b0, b1);
     return id;
@@ -305,6 +348,13 @@ int main(int argc, char **argv)
     if (argc > 4 && argv[4][0] == 'p') {
         ploc_build(atoi(argv[4] + 1));
         printf("PLOC radius %d: %zu nodes, sum of child box areas %.4g\n", atoi(argv[4] + 1), nodes.size(), sum_child_area(nodes));
+    } else if (argc > 4 && argv[4][0] == 'b') {
+        std::vector<int> ids(sph.size());
+        for (size_t i = 0; i < ids.size(); ++i) ids[i] = (int)i;
+        Box rb;
+        binned_build(ids, 0, (int)ids.size(), rb, atoi(argv[4] + 1));
+        nodes = sahn;
+        printf("binned SAH, %d bins: %zu nodes, sum of child box areas %.4g\n", atoi(argv[4] + 1), nodes.size(), sum_child_area(nodes));
     } else if (argc > 4) {
         std::vector<int> ids(sph.size());
         for (size_t i = 0; i < ids.size(); ++i) ids[i] = (int)i;

@@ -68,7 +68,8 @@ class Counters(C.Structure):
 class BvhInfo(C.Structure):
     _fields_ = [("n_spheres", C.c_uint32), ("n_nodes", C.c_uint32), ("node_bytes", C.c_uint32),
                 ("build_ms", C.c_float), ("build_launches", C.c_uint32), ("depth", C.c_uint32),
-                ("n_triangles", C.c_uint32), ("n_tri_nodes", C.c_uint32), ("tri_depth", C.c_uint32), ("tri_build_ms", C.c_float)]
+                ("n_triangles", C.c_uint32), ("n_tri_nodes", C.c_uint32), ("tri_depth", C.c_uint32), ("tri_build_ms", C.c_float),
+                ("traversal_depth", C.c_uint32), ("traversal_is_sah", C.c_uint32), ("traversal_build_ms", C.c_float)]
 
 
 class ExternalImage(C.Structure):  # include/vkrt.h: one exported traced image (ref: Source/GraphicsDevice.cpp:664-699)
@@ -127,6 +128,7 @@ SIGNATURES = {
     "vkrt_debug_dump_timeline": ([_vp, C.c_char_p], C.c_int8),
     "vkrt_get_bvh_info": ([_vp, _P(BvhInfo)], C.c_int8),
     "vkrt_read_bvh_nodes": ([_vp, _vp, _sz], C.c_int8),
+    "vkrt_read_bvh_traversal_nodes": ([_vp, _vp, _sz], C.c_int8),
     "vkrt_read_bvh_qnodes": ([_vp, _vp, _sz, _P(C.c_float)], C.c_int8),
     "vkrt_pack_shard": ([_vp, _P(_vp), _P(_sz)], C.c_int8),
     "vkrt_pack_shard_into": ([_vp, _vp, _sz], C.c_int8),

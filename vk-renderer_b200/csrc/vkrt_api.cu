@@ -438,7 +438,7 @@ VKRT_API vkrt_error vkrt_destroy(vkrt_ctx *c)
     if (c->xch.base) vkrt_exchange_close(c);
     cudaFree(c->d_spheres); cudaFree(c->d_sphere_mat); cudaFree(c->d_mats); cudaFree(c->d_tris); cudaFree(c->d_tri_mats);
     cudaFree(c->tbvh.nodes);
-    cudaFree(c->bvh.nodes); cudaFree(c->bvh.nodes4); cudaFree(c->bvh.qnodes); cudaFree(c->d_accum); cudaFree(c->d_hit_ids);
+    cudaFree(c->bvh.nodes); cudaFree(c->bvh.nodes4); cudaFree(c->bvh.qnodes); cudaFree(c->bvh.tnodes); cudaFree(c->d_accum); cudaFree(c->d_hit_ids);
     for (auto p : c->d_rgba) cudaFree(p);
     for (auto &e : c->ext) { ext_release_target(e); ext_release_semaphores(e); }
     cudaFree(c->d_counters); cudaFree(c->d_work_head); cudaFree(c->d_packed); cudaFree(c->d_present);
@@ -593,6 +593,9 @@ VKRT_API vkrt_error vkrt_build_bvh(vkrt_ctx *c)
     // per tree level; the LBVH cannot be deeper than 64 levels, and this is where that is enforced
     if (c->bvh.depth + 2 > (int)BVH_STACK)
         return fail(c, VKRT_BAD_ARG, "the LBVH is " + std::to_string(c->bvh.depth) + " levels deep: deeper than the traversal stack");
+    // (the traversal tree splits index ranges in the middle from level 48 on: at most 48 + 32 levels)
+    if (c->bvh.tdepth + 2 > (int)BVH_STACK)
+        return fail(c, VKRT_BAD_ARG, "the traversal tree is " + std::to_string(c->bvh.tdepth) + " levels deep: deeper than the traversal stack");
     // triangles get a tree of their own (rule T); a scene without triangles keeps none
     CU(c, build_tri_lbvh(c->d_tris, (uint32_t)c->tris.size(), c->tbvh, c->stream));
     if (c->tbvh.depth + 2 > (int)BVH_STACK)
@@ -622,6 +625,9 @@ VKRT_API vkrt_error vkrt_get_bvh_info(vkrt_ctx *c, vkrt_bvh_info *out)
     out->n_tri_nodes = c->use_bvh ? c->tbvh.n_nodes : 0;
     out->tri_depth = c->use_bvh ? (uint32_t)c->tbvh.depth : 0;
     out->tri_build_ms = c->use_bvh ? c->tbvh.build_ms : 0.f;
+    out->traversal_depth = c->use_bvh ? (uint32_t)c->bvh.tdepth : 0;
+    out->traversal_is_sah = (c->use_bvh && c->bvh.tnodes) ? 1u : 0u;
+    out->traversal_build_ms = c->use_bvh ? c->bvh.sah_ms : 0.f;
     return VKRT_SUCCESS;
 }
 VKRT_API vkrt_error vkrt_read_bvh_nodes(vkrt_ctx *c, float *host, size_t bytes)
@@ -632,6 +638,17 @@ VKRT_API vkrt_error vkrt_read_bvh_nodes(vkrt_ctx *c, float *host, size_t bytes)
     DeviceGuard g(c->info.device_id);
     CU(c, cudaStreamSynchronize(c->stream));
     CU(c, cudaMemcpy(host, c->bvh.nodes, (size_t)c->bvh.n_nodes * 64, cudaMemcpyDeviceToHost));
+    return VKRT_SUCCESS;
+}
+
+VKRT_API vkrt_error vkrt_read_bvh_traversal_nodes(vkrt_ctx *c, float *host, size_t bytes)
+{
+    if (!c || !host) return VKRT_BAD_ARG;
+    if (!c->use_bvh) return fail(c, VKRT_BAD_ARG, "no BVH built");
+    if (bytes < (size_t)c->bvh.n_nodes * 64) return fail(c, VKRT_BAD_ARG, "buffer too small");
+    DeviceGuard g(c->info.device_id);
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaMemcpy(host, c->bvh.tnodes ? c->bvh.tnodes : c->bvh.nodes, (size_t)c->bvh.n_nodes * 64, cudaMemcpyDeviceToHost));
     return VKRT_SUCCESS;
 }
 

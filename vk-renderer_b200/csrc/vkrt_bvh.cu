@@ -9,6 +9,13 @@
 #include "vkrt_device.cuh"
 #include "vkrt_internal.h"
 
+#ifndef VKRT_SAH_TREE
+#define VKRT_SAH_TREE 1           // the wavefront's traversal nodes come from a binned-SAH tree (0: from the LBVH itself)
+#endif
+#ifndef VKRT_SAH_MIN_PRIMS
+#define VKRT_SAH_MIN_PRIMS 2
+#endif
+
 namespace vkrt {
 
 // The builder works on any primitive list that can name a centroid (Morton code) and a padded leaf box (refit):
@@ -436,17 +443,266 @@ done:
     return err;
 }
 
+
+// ---- the traversal tree: top-down binned SAH over the same primitives ---------------------------------------
+// The LBVH above is a pure function of the Morton order; on the large scenes the wavefront's traversal kernel walks a
+// tree of better quality instead: the same leaves (one primitive each, its own padded box), inner boxes = exact min / max
+// unions -- so rule S / rule T return the identical answer (DESIGN.md "Rule S": ANY such hierarchy does) -- but the
+// splits minimise the surface-area heuristic over SAH_BINS centroid bins per axis (CPU simulation on the cfg4 scene,
+// tests/tools/trav_sim.py b16: 9-10 % fewer node visits, 15 % fewer stack pushes than the LBVH).
+// Device build, level-synchronous and deterministic: per level one warp per node (1) bins the node's primitives
+// (shared-memory atomicMin / atomicMax on order-preserving integers: order-independent) and picks the cheapest of the
+// 3 x (SAH_BINS - 1) planes, (2) a one-block scan numbers the next level's nodes, (3) the warp partitions its index
+// range stably and writes the node's two child records.  Node ids are breadth-first (a level's nodes are consecutive).
+enum { SAH_BINS = 16, SAH_WARPS = 8, SAH_MEDIAN_FROM_LEVEL = 48 };
+struct SahSplit { int axis, bin; float clo, scale; uint32_t n_left; };      // axis < 0: split the index range in the middle
+
+__device__ __forceinline__ float half_area(const float *lo, const float *hi)
+{
+    const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    return dx * dy + dy * dz + dz * dx;
+}
+__device__ __forceinline__ int sah_bin(float c, float clo, float scale)
+{
+    const int b = (int)((c - clo) * scale);
+    return min(max(b, 0), SAH_BINS - 1);
+}
+
+template <class P>
+__global__ void __launch_bounds__(32 * SAH_WARPS) k_sah_split(const P prim, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ first,
+                                                               const uint32_t *__restrict__ count, uint32_t m, int force_median,
+                                                               SahSplit *__restrict__ split)
+{
+    __shared__ int s_bins[SAH_WARPS][3][SAH_BINS][7];       // per warp, axis, bin: box as 6 ordered ints, count
+    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t j = blockIdx.x * SAH_WARPS + warp;
+    if (j >= m) return;                                      // whole warps leave: only __syncwarp below
+    const uint32_t f = first[j], c = count[j];
+    const float INF = __int_as_float(0x7f800000);
+    float clo[3] = {INF, INF, INF}, chi[3] = {-INF, -INF, -INF};
+    for (uint32_t i = lane; i < c; i += 32u) {
+        float ce[3];
+        prim.centroid(idx[f + i], ce);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { clo[k] = fminf(clo[k], ce[k]); chi[k] = fmaxf(chi[k], ce[k]); }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            clo[k] = fminf(clo[k], __shfl_xor_sync(full, clo[k], o));
+            chi[k] = fmaxf(chi[k], __shfl_xor_sync(full, chi[k], o));
+        }
+    float scale[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) scale[k] = chi[k] > clo[k] ? (float)SAH_BINS / (chi[k] - clo[k]) : 0.0f;
+    int (*bins)[SAH_BINS][7] = s_bins[warp];
+    for (uint32_t t = lane; t < 3u * SAH_BINS; t += 32u) {
+        int *b = bins[t / SAH_BINS][t % SAH_BINS];
+        b[0] = b[1] = b[2] = f2ord(INF); b[3] = b[4] = b[5] = f2ord(-INF); b[6] = 0;
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < c; i += 32u) {
+        const uint32_t p = idx[f + i];
+        float ce[3], lo[3], hi[3];
+        prim.centroid(p, ce);
+        prim.box(p, lo, hi);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (!(scale[k] > 0.0f)) continue;
+            int *b = bins[k][sah_bin(ce[k], clo[k], scale[k])];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { atomicMin(b + a, f2ord(lo[a])); atomicMax(b + 3 + a, f2ord(hi[a])); }
+            atomicAdd(b + 6, 1);
+        }
+    }
+    __syncwarp();
+    // candidate t = axis * (SAH_BINS - 1) + (s - 1): bins [0, s) go left, [s, SAH_BINS) right
+    float best_cost = INF;
+    uint32_t best_t = 0xffffffffu, best_nl = 0;
+    for (uint32_t t = lane; t < 3u * (SAH_BINS - 1); t += 32u) {
+        const int k = (int)(t / (SAH_BINS - 1)), sp = (int)(t % (SAH_BINS - 1)) + 1;
+        if (!(scale[k] > 0.0f)) continue;
+        float llo[3] = {INF, INF, INF}, lhi[3] = {-INF, -INF, -INF}, rlo[3] = {INF, INF, INF}, rhi[3] = {-INF, -INF, -INF};
+        uint32_t nl = 0, nr = 0;
+        for (int b = 0; b < SAH_BINS; ++b) {
+            const int *bb = bins[k][b];
+            if (bb[6] == 0) continue;
+            if (b < sp) { nl += (uint32_t)bb[6]; for (int a = 0; a < 3; ++a) { llo[a] = fminf(llo[a], ord2f(bb[a])); lhi[a] = fmaxf(lhi[a], ord2f(bb[3 + a])); } }
+            else        { nr += (uint32_t)bb[6]; for (int a = 0; a < 3; ++a) { rlo[a] = fminf(rlo[a], ord2f(bb[a])); rhi[a] = fmaxf(rhi[a], ord2f(bb[3 + a])); } }
+        }
+        if (nl == 0 || nr == 0) continue;
+        const float cost = half_area(llo, lhi) * (float)nl + half_area(rlo, rhi) * (float)nr;
+        if (cost < best_cost || (cost == best_cost && t < best_t)) { best_cost = cost; best_t = t; best_nl = nl; }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const float oc = __shfl_xor_sync(full, best_cost, o);
+        const uint32_t ot = __shfl_xor_sync(full, best_t, o), on = __shfl_xor_sync(full, best_nl, o);
+        if (ot != 0xffffffffu && (best_t == 0xffffffffu || oc < best_cost || (oc == best_cost && ot < best_t))) { best_cost = oc; best_t = ot; best_nl = on; }
+    }
+    if (lane == 0) {
+        SahSplit r;
+        if (best_t == 0xffffffffu || force_median) { r.axis = -1; r.bin = 0; r.clo = 0.f; r.scale = 0.f; r.n_left = c / 2u; }
+        else {
+            r.axis = (int)(best_t / (SAH_BINS - 1)); r.bin = (int)(best_t % (SAH_BINS - 1)) + 1;
+            r.clo = r.axis == 0 ? clo[0] : r.axis == 1 ? clo[1] : clo[2];
+            r.scale = r.axis == 0 ? scale[0] : r.axis == 1 ? scale[1] : scale[2];
+            r.n_left = best_nl;
+        }
+        split[j] = r;
+    }
+}
+
+__device__ __forceinline__ uint32_t sah_inner_children(const SahSplit &s, uint32_t c) { return (s.n_left >= 2u ? 1u : 0u) + (c - s.n_left >= 2u ? 1u : 0u); }
+__global__ void __launch_bounds__(1024) k_sah_scan(const SahSplit *__restrict__ split, const uint32_t *__restrict__ count, uint32_t m,
+                                                    uint32_t *__restrict__ off, uint32_t *__restrict__ m_next)
+{
+    __shared__ uint32_t s_sum[1024];
+    const uint32_t chunk = (m + 1023u) / 1024u, b = threadIdx.x * chunk, e = min(b + chunk, m);
+    uint32_t sum = 0;
+    for (uint32_t j = b; j < e; ++j) sum += sah_inner_children(split[j], count[j]);
+    s_sum[threadIdx.x] = sum;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024u; o <<= 1) {
+        const uint32_t v = threadIdx.x >= o ? s_sum[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s_sum[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = s_sum[threadIdx.x] - sum;
+    for (uint32_t j = b; j < e; ++j) { off[j] = run; run += sah_inner_children(split[j], count[j]); }
+    if (threadIdx.x == 1023u) *m_next = s_sum[1023];
+}
+
+template <class P>
+__global__ void __launch_bounds__(32 * SAH_WARPS) k_sah_partition(const P prim, const uint32_t *__restrict__ idx_in, uint32_t *__restrict__ idx_out,
+                                                                   const uint32_t *__restrict__ first, const uint32_t *__restrict__ count, uint32_t m,
+                                                                   const SahSplit *__restrict__ split, const uint32_t *__restrict__ off,
+                                                                   uint32_t base, uint32_t next_base, uint32_t *__restrict__ next_first,
+                                                                   uint32_t *__restrict__ next_count, float4 *__restrict__ nodes)
+{
+    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t j = blockIdx.x * SAH_WARPS + warp;
+    if (j >= m) return;
+    const uint32_t f = first[j], c = count[j];
+    const SahSplit sp = split[j];
+    const uint32_t nl = sp.n_left;
+    const float INF = __int_as_float(0x7f800000);
+    float blo[2][3] = {{INF, INF, INF}, {INF, INF, INF}}, bhi[2][3] = {{-INF, -INF, -INF}, {-INF, -INF, -INF}};
+    uint32_t wl = 0, wr = 0;
+    for (uint32_t base_i = 0; base_i < c; base_i += 32u) {
+        const uint32_t i = base_i + lane;
+        const bool valid = i < c;
+        uint32_t p = 0;
+        bool left = false;
+        if (valid) {
+            p = idx_in[f + i];
+            if (sp.axis < 0) left = i < nl;
+            else {
+                float ce[3];
+                prim.centroid(p, ce);
+                const float cx = sp.axis == 0 ? ce[0] : sp.axis == 1 ? ce[1] : ce[2];
+                left = sah_bin(cx, sp.clo, sp.scale) < sp.bin;
+            }
+            float lo[3], hi[3];
+            prim.box(p, lo, hi);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                if (left) { blo[0][a] = fminf(blo[0][a], lo[a]); bhi[0][a] = fmaxf(bhi[0][a], hi[a]); }
+                else      { blo[1][a] = fminf(blo[1][a], lo[a]); bhi[1][a] = fmaxf(bhi[1][a], hi[a]); }
+            }
+        }
+        const unsigned ml = __ballot_sync(full, valid && left), mr = __ballot_sync(full, valid && !left);
+        const unsigned lt = (1u << lane) - 1u;
+        if (valid) idx_out[left ? f + wl + (uint32_t)__popc(ml & lt) : f + nl + wr + (uint32_t)__popc(mr & lt)] = p;
+        wl += (uint32_t)__popc(ml); wr += (uint32_t)__popc(mr);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1)
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                blo[s][a] = fminf(blo[s][a], __shfl_xor_sync(full, blo[s][a], o));
+                bhi[s][a] = fmaxf(bhi[s][a], __shfl_xor_sync(full, bhi[s][a], o));
+            }
+    __syncwarp();
+    if (lane == 0) {
+        float4 *node = nodes + 4 * (size_t)(base + j);
+        uint32_t q = off[j];
+        const uint32_t cnt[2] = {nl, c - nl}, fst[2] = {f, f + nl};
+        for (int s = 0; s < 2; ++s) {
+            if (cnt[s] == 1u) write_child(node, s, true, (int)idx_out[fst[s]], blo[s], bhi[s]);
+            else {
+                write_child(node, s, false, (int)(next_base + q), blo[s], bhi[s]);
+                next_first[q] = fst[s]; next_count[q] = cnt[s];
+                ++q;
+            }
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_iota(uint32_t *p, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+// `nodes`: n - 1 exact 64-byte nodes (caller-allocated), root = node 0.  n >= 2.
+template <class P>
+static cudaError_t build_sah_tree(const P prim, uint32_t n, float4 *nodes, int *depth_out, uint32_t *launches_out, cudaStream_t st)
+{
+    cudaError_t err = cudaSuccess;
+    uint32_t *idx[2] = {nullptr, nullptr}, *first[2] = {nullptr, nullptr}, *count[2] = {nullptr, nullptr}, *off = nullptr, *d_mnext = nullptr;
+    SahSplit *split = nullptr;
+    uint32_t launches = 0, m = 1, base = 0;
+    int level = 0, cur = 0;
+    const uint32_t root[2] = {0u, n};
+    for (int k = 0; k < 2; ++k) {
+        CK(cudaMalloc(&idx[k], (size_t)n * sizeof(uint32_t)));
+        CK(cudaMalloc(&first[k], (size_t)n * sizeof(uint32_t)));
+        CK(cudaMalloc(&count[k], (size_t)n * sizeof(uint32_t)));
+    }
+    CK(cudaMalloc(&off, (size_t)n * sizeof(uint32_t)));
+    CK(cudaMalloc(&split, (size_t)n * sizeof(SahSplit)));
+    CK(cudaMalloc(&d_mnext, sizeof(uint32_t)));
+    k_iota<<<(n + 255u) / 256u, 256, 0, st>>>(idx[0], n); ++launches;
+    CK(cudaMemcpyAsync(first[0], &root[0], sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(count[0], &root[1], sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    while (m > 0) {
+        const unsigned grid = (m + SAH_WARPS - 1u) / SAH_WARPS;
+        uint32_t m_next = 0;
+        k_sah_split<P><<<grid, 32 * SAH_WARPS, 0, st>>>(prim, idx[cur], first[cur], count[cur], m, level >= SAH_MEDIAN_FROM_LEVEL ? 1 : 0, split); ++launches;
+        k_sah_scan<<<1, 1024, 0, st>>>(split, count[cur], m, off, d_mnext); ++launches;
+        k_sah_partition<P><<<grid, 32 * SAH_WARPS, 0, st>>>(prim, idx[cur], idx[cur ^ 1], first[cur], count[cur], m, split, off, base, base + m,
+                                                          first[cur ^ 1], count[cur ^ 1], nodes); ++launches;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&m_next, d_mnext, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        base += m; m = m_next; cur ^= 1; ++level;
+        if (level > 120) { err = cudaErrorUnknown; goto done; }      // cannot happen: median splits from level 48 on
+    }
+    if (base != n - 1u) { err = cudaErrorUnknown; goto done; }
+    *depth_out = level;
+    *launches_out += launches;
+done:
+    for (int k = 0; k < 2; ++k) { cudaFree(idx[k]); cudaFree(first[k]); cudaFree(count[k]); }
+    cudaFree(off); cudaFree(split); cudaFree(d_mnext);
+    return err;
+}
+
 cudaError_t build_lbvh(const float4 *d_spheres, uint32_t n, BvhBuild &out, cudaStream_t st)
 {
     cudaError_t err = cudaSuccess;
     if (out.nodes) { cudaFree(out.nodes); out.nodes = nullptr; }
     if (out.nodes4) { cudaFree(out.nodes4); out.nodes4 = nullptr; }
     if (out.qnodes) { cudaFree(out.qnodes); out.qnodes = nullptr; }
+    if (out.tnodes) { cudaFree(out.tnodes); out.tnodes = nullptr; }
     float *grid = nullptr;
-    out.n_nodes = 0; out.build_ms = 0.f; out.launches = 0; out.depth = 0;
+    out.n_nodes = 0; out.build_ms = 0.f; out.launches = 0; out.depth = 0; out.tdepth = 0; out.sah_ms = 0.f;
     if (n == 0) return cudaSuccess;
 
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
     const uint32_t n_inner = n > 1 ? n - 1 : 1;
     uint32_t launches = 0;
 
@@ -459,20 +715,38 @@ cudaError_t build_lbvh(const float4 *d_spheres, uint32_t n, BvhBuild &out, cudaS
     CK(build_tree(PrimSpheres{d_spheres}, n, out.nodes, &out.depth, &launches, st));
     k_collapse4<<<(n_inner + 255u) / 256u, 256, 0, st>>>(out.nodes, n_inner, out.nodes4); ++launches;
     CK(cudaGetLastError());
-    k_qgrid<<<1, 32, 0, st>>>(out.nodes, grid); ++launches;
-    k_quantize<<<(n_inner + 255u) / 256u, 256, 0, st>>>(out.nodes, n_inner, grid, out.qnodes); ++launches;
+    // the traversal tree of the 32-byte coded nodes: the SAH tree for scenes of VKRT_SAH_MIN_PRIMS primitives or more
+    // (below that the LBVH itself; rule S's answer does not depend on the choice)
+    {
+        const float4 *src = out.nodes;
+        out.tdepth = out.depth;
+        if (VKRT_SAH_TREE && n >= (uint32_t)VKRT_SAH_MIN_PRIMS) {
+            CK(cudaEventCreate(&e2));
+            CK(cudaMalloc(&out.tnodes, (size_t)n_inner * 64));
+            CK(cudaEventRecord(e2, st));
+            CK(build_sah_tree(PrimSpheres{d_spheres}, n, out.tnodes, &out.tdepth, &launches, st));
+            src = out.tnodes;
+        }
+        k_qgrid<<<1, 32, 0, st>>>(src, grid); ++launches;
+        k_quantize<<<(n_inner + 255u) / 256u, 256, 0, st>>>(src, n_inner, grid, out.qnodes); ++launches;
+    }
     CK(cudaGetLastError());
     CK(cudaEventRecord(e1, st));
     CK(cudaMemcpyAsync(out.qgrid, grid, 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&out.build_ms, e0, e1));
+    if (e2) CK(cudaEventElapsedTime(&out.sah_ms, e2, e1));
     out.n_nodes = n_inner;
     out.launches = launches;
 done:
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
+    if (e2) cudaEventDestroy(e2);
     cudaFree(grid);
-    if (err != cudaSuccess) { cudaFree(out.nodes); cudaFree(out.nodes4); cudaFree(out.qnodes); out.nodes = nullptr; out.nodes4 = nullptr; out.qnodes = nullptr; }
+    if (err != cudaSuccess) {
+        cudaFree(out.nodes); cudaFree(out.nodes4); cudaFree(out.qnodes); cudaFree(out.tnodes);
+        out.nodes = nullptr; out.nodes4 = nullptr; out.qnodes = nullptr; out.tnodes = nullptr;
+    }
     return err;
 }
 

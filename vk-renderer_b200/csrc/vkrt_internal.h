@@ -99,6 +99,9 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
 struct BvhBuild {
     float4 *nodes = nullptr;      // binary nodes: 4 float4 (two child records) per inner node
     float4 *nodes4 = nullptr;     // 4-wide traversal nodes: 8 float4 (four child records) per binary node id
+    float4 *tnodes = nullptr;     // exact nodes of the traversal tree (binned SAH, same leaves) the coded nodes are made from; null: `nodes`
+    int tdepth = 0;               // its depth
+    float sah_ms = 0.f;           // device time of its build (part of build_ms)
     uint4 *qnodes = nullptr;      // 32-byte traversal nodes: two 16-byte child records on the 16-bit grid below
     float qgrid[6] = {0, 0, 0, 0, 0, 0};   // per axis: scale s[3], offset b2[3]; coordinate of code q = (2^23 + q) * s + b2
     uint32_t n_nodes = 0;

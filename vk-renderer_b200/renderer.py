@@ -121,6 +121,14 @@ class Renderer:
             self._ck(self.lib.vkrt_read_bvh_nodes(self.ctx, _ptr(out), out.nbytes))
         return out
 
+    def bvh_traversal_nodes(self):
+        """The exact nodes of the tree the 32-byte traversal nodes are made from (binned SAH; same layout as bvh_nodes)."""
+        n = self.bvh_info().n_nodes
+        out = np.zeros((n, 16), dtype=np.float32)
+        if n:
+            self._ck(self.lib.vkrt_read_bvh_traversal_nodes(self.ctx, _ptr(out), out.nbytes))
+        return out
+
     def bvh_qnodes(self):
         """-> ((n, 8) uint32 traversal nodes, grid[6] float32): two child records {x: lo | hi << 16, y, z, ref}."""
         n = self.bvh_info().n_nodes
