@@ -387,7 +387,10 @@ class Bench:
                "scaling": "weak" if weak else "strong", "n_gpus": world,
                "exchange": ("peer stores over NVLink (csrc/vkrt_exchange.cu)" if peer else "NCCL gather") if world > 1 else None,
                "config": config_for(name, wl, variant, scene.digest(), world, n_sample_shards, spp, weak),
-               "bvh": {"nodes": bvh.n_nodes, "build_ms": bvh.build_ms} if use_bvh else None,
+               "bvh": {"nodes": bvh.n_nodes, "build_ms": bvh.build_ms, "lbvh_depth": bvh.depth,
+                       "traversal_tree": "binned SAH, built on the device from the same leaves (exact union boxes)" if bvh.traversal_is_sah else "the LBVH",
+                       "traversal_depth": bvh.traversal_depth, "traversal_build_ms": bvh.traversal_build_ms,
+                       "note": "one-off per static scene, outside the timed region"} if use_bvh else None,
                "rays_per_frame": total_rays / steps, "closest_rays": rays[1] / steps, "shadow_rays": rays[2] / steps,
                "paths_per_frame": rays[3] / steps, "shared_primary_rays": rays[4] / steps,
                "zero_term_shadow_rays": rays[5] / steps, "traversed_rays_per_frame": traversed / steps,

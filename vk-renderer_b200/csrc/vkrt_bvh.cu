@@ -454,7 +454,10 @@ done:
 // (shared-memory atomicMin / atomicMax on order-preserving integers: order-independent) and picks the cheapest of the
 // 3 x (SAH_BINS - 1) planes, (2) a one-block scan numbers the next level's nodes, (3) the warp partitions its index
 // range stably and writes the node's two child records.  Node ids are breadth-first (a level's nodes are consecutive).
-enum { SAH_BINS = 16, SAH_WARPS = 8, SAH_MEDIAN_FROM_LEVEL = 48 };
+#ifndef VKRT_SAH_BINS
+#define VKRT_SAH_BINS 16
+#endif
+enum { SAH_BINS = VKRT_SAH_BINS, SAH_WARPS = 8, SAH_MEDIAN_FROM_LEVEL = 48 };
 struct SahSplit { int axis, bin; float clo, scale; uint32_t n_left; };      // axis < 0: split the index range in the middle
 
 __device__ __forceinline__ float half_area(const float *lo, const float *hi)
