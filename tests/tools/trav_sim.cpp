@@ -169,6 +169,36 @@ static int binned_build(std::vector<int> &ids, int b, int e, Box &out, int NB)
     out = uni(b0, b1);
     return id;
 }
+// (1c) tree rotations on top of any tree in `t` (Kensler 2008): swap a child with a grandchild under the sibling when
+// that lowers the sum of box areas; a few bottom-up passes
+static Box child_box(const Node &n, int j) { Box b; memcpy(b.lo, n.c[j].lo, 12); memcpy(b.hi, n.c[j].hi, 12); return b; }
+static void set_child(Node &n, int j, const Box &b, int kind, int index) { memcpy(n.c[j].lo, b.lo, 12); memcpy(n.c[j].hi, b.hi, 12); n.c[j].kind = kind; n.c[j].index = index; }
+static int rotate_pass(std::vector<Node> &t)
+{
+    int done = 0;
+    // children have larger ids than parents in the trees built here (sahn: preorder), so a reverse sweep is bottom-up
+    for (int v = (int)t.size() - 1; v >= 0; --v) {
+        for (int side = 0; side < 2; ++side) {
+            Node &n = t[v];
+            if (n.c[side].kind) continue;                    // the child to open must be an inner node
+            const int w = n.c[side].index;
+            const int other = 1 - side;
+            float best = area(child_box(n, side));           // only the opened child's box changes
+            int pick = -1;
+            for (int g = 0; g < 2; ++g) {                    // swap n.c[other] with t[w].c[g]
+                const Box nb = uni(child_box(n, other), child_box(t[w], 1 - g));
+                if (area(nb) < best) { best = area(nb); pick = g; }
+            }
+            if (pick < 0) continue;
+            Child a = n.c[other], b = t[w].c[pick];
+            n.c[other] = b; t[w].c[pick] = a;
+            const Box nb = uni(child_box(t[w], 0), child_box(t[w], 1));
+            set_child(n, side, nb, 0, w);
+            ++done;
+        }
+    }
+    return done;
+}
 // (2) PLOC: clusters in the LBVH's leaf (Morton) order; every cluster looks `R` neighbours to each side for the partner
 // with the smallest merged box, mutual choices merge, repeat until one cluster is left
 static void leaf_order(int n, std::vector<int> &out)
@@ -355,6 +385,7 @@ int main(int argc, char **argv)
         binned_build(ids, 0, (int)ids.size(), rb, atoi(argv[4] + 1));
         nodes = sahn;
         printf("binned SAH, %d bins: %zu nodes, sum of child box areas %.4g\n", atoi(argv[4] + 1), nodes.size(), sum_child_area(nodes));
+        if (argc > 5) for (int pass = 0; pass < atoi(argv[5]); ++pass) { const int r = rotate_pass(nodes); printf("rotation pass %d: %d rotations, sum of child box areas %.4g\n", pass, r, sum_child_area(nodes)); }
     } else if (argc > 4) {
         std::vector<int> ids(sph.size());
         for (size_t i = 0; i < ids.size(); ++i) ids[i] = (int)i;
