@@ -1424,7 +1424,7 @@ cudaError_t launch_path_wavefront(const DevScene &sc, const RenderParams &rp, Wa
     if (occ_s > VKRT_TRACE_RESIDENT) occ_s = VKRT_TRACE_RESIDENT;
 #endif
     const unsigned grid_e = (unsigned)(sm_count * (occ_e > 0 ? occ_e : 1)), grid_s = (unsigned)(sm_count * (occ_s > 0 ? occ_s : 1));
-    const unsigned grid_shade = (unsigned)sm_count * 8u * (256u / VKRT_SHADE_BLOCK);
+    const unsigned grid_shade = (unsigned)sm_count * (2048u / VKRT_SHADE_BLOCK);
 
     // with lanes the waves never wait for `st` as a whole (that would serialise consecutive frames): see ev_consumed
     const bool fork = n_lanes > 1;
