@@ -37,7 +37,7 @@
 #define VKRT_NESTED_STEPS 1   // the round's inner steps form ONE divergent region (no reconvergence point per step): 26.41 -> 26.01 ms/frame;
 #endif                        // steps per round 2 .. 12 measured: 3, 6 and 9 are equal (25.9 - 26.0), the others 0.4 - 1.2 ms slower
 #ifndef VKRT_TRAV_UNROLL
-#define VKRT_TRAV_UNROLL 3
+#define VKRT_TRAV_UNROLL 6    // inner steps per node-loop round (one nested region, one vote): 3, 6 and 9 are the good values, 6 is 0.5 % ahead of 3
 #endif
 #ifndef VKRT_LEAF_BATCH
 #define VKRT_LEAF_BATCH 8    // run a leaf phase once this many lanes wait at a leaf (0: leaf tests inside the node step)
