@@ -12,6 +12,9 @@
 #ifndef VKRT_SAH_TREE
 #define VKRT_SAH_TREE 1           // the wavefront's traversal nodes come from a binned-SAH tree (0: from the LBVH itself)
 #endif
+#ifndef VKRT_SAH_BLOCK_LEVELS
+#define VKRT_SAH_BLOCK_LEVELS 1   // the top levels of its build give every node a block instead of a warp (0: warps only; same tree)
+#endif
 #ifndef VKRT_SAH_MIN_PRIMS
 #define VKRT_SAH_MIN_PRIMS 2
 #endif
@@ -471,6 +474,74 @@ __device__ __forceinline__ int sah_bin(float c, float clo, float scale)
     return min(max(b, 0), SAH_BINS - 1);
 }
 
+// One warp evaluates the 3 x (SAH_BINS - 1) planes of a node from its bins and writes the split (lane 0).
+// candidate t = axis * (SAH_BINS - 1) + (s - 1): bins [0, s) go left, [s, SAH_BINS) right
+__device__ __forceinline__ void sah_pick_plane(const int (*bins)[SAH_BINS][7], const float *clo, const float *scale, uint32_t c, int force_median,
+                                               unsigned lane, SahSplit *out)
+{
+    const unsigned full = 0xffffffffu;
+    const float INF = __int_as_float(0x7f800000);
+    float best_cost = INF;
+    uint32_t best_t = 0xffffffffu, best_nl = 0;
+    for (uint32_t t = lane; t < 3u * (SAH_BINS - 1); t += 32u) {
+        const int k = (int)(t / (SAH_BINS - 1)), sp = (int)(t % (SAH_BINS - 1)) + 1;
+        if (!(scale[k] > 0.0f)) continue;
+        float llo[3] = {INF, INF, INF}, lhi[3] = {-INF, -INF, -INF}, rlo[3] = {INF, INF, INF}, rhi[3] = {-INF, -INF, -INF};
+        uint32_t nl = 0, nr = 0;
+        for (int b = 0; b < SAH_BINS; ++b) {
+            const int *bb = bins[k][b];
+            if (bb[6] == 0) continue;
+            if (b < sp) { nl += (uint32_t)bb[6]; for (int a = 0; a < 3; ++a) { llo[a] = fminf(llo[a], ord2f(bb[a])); lhi[a] = fmaxf(lhi[a], ord2f(bb[3 + a])); } }
+            else        { nr += (uint32_t)bb[6]; for (int a = 0; a < 3; ++a) { rlo[a] = fminf(rlo[a], ord2f(bb[a])); rhi[a] = fmaxf(rhi[a], ord2f(bb[3 + a])); } }
+        }
+        if (nl == 0 || nr == 0) continue;
+        const float cost = half_area(llo, lhi) * (float)nl + half_area(rlo, rhi) * (float)nr;
+        if (cost < best_cost || (cost == best_cost && t < best_t)) { best_cost = cost; best_t = t; best_nl = nl; }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const float oc = __shfl_xor_sync(full, best_cost, o);
+        const uint32_t ot = __shfl_xor_sync(full, best_t, o), on = __shfl_xor_sync(full, best_nl, o);
+        if (ot != 0xffffffffu && (best_t == 0xffffffffu || oc < best_cost || (oc == best_cost && ot < best_t))) { best_cost = oc; best_t = ot; best_nl = on; }
+    }
+    if (lane == 0) {
+        SahSplit r;
+        if (best_t == 0xffffffffu || force_median) { r.axis = -1; r.bin = 0; r.clo = 0.f; r.scale = 0.f; r.n_left = c / 2u; }
+        else {
+            r.axis = (int)(best_t / (SAH_BINS - 1)); r.bin = (int)(best_t % (SAH_BINS - 1)) + 1;
+            r.clo = r.axis == 0 ? clo[0] : r.axis == 1 ? clo[1] : clo[2];
+            r.scale = r.axis == 0 ? scale[0] : r.axis == 1 ? scale[1] : scale[2];
+            r.n_left = best_nl;
+        }
+        *out = r;
+    }
+}
+// which side primitive p (position i of the node's range) goes to
+template <class P>
+__device__ __forceinline__ bool sah_goes_left(const P &prim, uint32_t p, uint32_t i, const SahSplit &sp)
+{
+    if (sp.axis < 0) return i < sp.n_left;
+    float ce[3];
+    prim.centroid(p, ce);
+    const float cx = sp.axis == 0 ? ce[0] : sp.axis == 1 ? ce[1] : ce[2];
+    return sah_bin(cx, sp.clo, sp.scale) < sp.bin;
+}
+// the node's two child records and the next level's descriptors of its inner children
+__device__ __forceinline__ void sah_write_node(float4 *nodes, uint32_t id, uint32_t q, uint32_t next_base, uint32_t nl, uint32_t c, uint32_t f,
+                                               const uint32_t *idx_out, float (*blo)[3], float (*bhi)[3], uint32_t *next_first, uint32_t *next_count)
+{
+    float4 *node = nodes + 4 * (size_t)id;
+    const uint32_t cnt[2] = {nl, c - nl}, fst[2] = {f, f + nl};
+    for (int s = 0; s < 2; ++s) {
+        if (cnt[s] == 1u) write_child(node, s, true, (int)idx_out[fst[s]], blo[s], bhi[s]);
+        else {
+            write_child(node, s, false, (int)(next_base + q), blo[s], bhi[s]);
+            next_first[q] = fst[s]; next_count[q] = cnt[s];
+            ++q;
+        }
+    }
+}
+
 template <class P>
 __global__ void __launch_bounds__(32 * SAH_WARPS) k_sah_split(const P prim, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ first,
                                                                const uint32_t *__restrict__ count, uint32_t m, int force_median,
@@ -520,41 +591,7 @@ __global__ void __launch_bounds__(32 * SAH_WARPS) k_sah_split(const P prim, cons
         }
     }
     __syncwarp();
-    // candidate t = axis * (SAH_BINS - 1) + (s - 1): bins [0, s) go left, [s, SAH_BINS) right
-    float best_cost = INF;
-    uint32_t best_t = 0xffffffffu, best_nl = 0;
-    for (uint32_t t = lane; t < 3u * (SAH_BINS - 1); t += 32u) {
-        const int k = (int)(t / (SAH_BINS - 1)), sp = (int)(t % (SAH_BINS - 1)) + 1;
-        if (!(scale[k] > 0.0f)) continue;
-        float llo[3] = {INF, INF, INF}, lhi[3] = {-INF, -INF, -INF}, rlo[3] = {INF, INF, INF}, rhi[3] = {-INF, -INF, -INF};
-        uint32_t nl = 0, nr = 0;
-        for (int b = 0; b < SAH_BINS; ++b) {
-            const int *bb = bins[k][b];
-            if (bb[6] == 0) continue;
-            if (b < sp) { nl += (uint32_t)bb[6]; for (int a = 0; a < 3; ++a) { llo[a] = fminf(llo[a], ord2f(bb[a])); lhi[a] = fmaxf(lhi[a], ord2f(bb[3 + a])); } }
-            else        { nr += (uint32_t)bb[6]; for (int a = 0; a < 3; ++a) { rlo[a] = fminf(rlo[a], ord2f(bb[a])); rhi[a] = fmaxf(rhi[a], ord2f(bb[3 + a])); } }
-        }
-        if (nl == 0 || nr == 0) continue;
-        const float cost = half_area(llo, lhi) * (float)nl + half_area(rlo, rhi) * (float)nr;
-        if (cost < best_cost || (cost == best_cost && t < best_t)) { best_cost = cost; best_t = t; best_nl = nl; }
-    }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-        const float oc = __shfl_xor_sync(full, best_cost, o);
-        const uint32_t ot = __shfl_xor_sync(full, best_t, o), on = __shfl_xor_sync(full, best_nl, o);
-        if (ot != 0xffffffffu && (best_t == 0xffffffffu || oc < best_cost || (oc == best_cost && ot < best_t))) { best_cost = oc; best_t = ot; best_nl = on; }
-    }
-    if (lane == 0) {
-        SahSplit r;
-        if (best_t == 0xffffffffu || force_median) { r.axis = -1; r.bin = 0; r.clo = 0.f; r.scale = 0.f; r.n_left = c / 2u; }
-        else {
-            r.axis = (int)(best_t / (SAH_BINS - 1)); r.bin = (int)(best_t % (SAH_BINS - 1)) + 1;
-            r.clo = r.axis == 0 ? clo[0] : r.axis == 1 ? clo[1] : clo[2];
-            r.scale = r.axis == 0 ? scale[0] : r.axis == 1 ? scale[1] : scale[2];
-            r.n_left = best_nl;
-        }
-        split[j] = r;
-    }
+    sah_pick_plane(bins, clo, scale, c, force_median, lane, split + j);
 }
 
 __device__ __forceinline__ uint32_t sah_inner_children(const SahSplit &s, uint32_t c) { return (s.n_left >= 2u ? 1u : 0u) + (c - s.n_left >= 2u ? 1u : 0u); }
@@ -601,13 +638,7 @@ __global__ void __launch_bounds__(32 * SAH_WARPS) k_sah_partition(const P prim, 
         bool left = false;
         if (valid) {
             p = idx_in[f + i];
-            if (sp.axis < 0) left = i < nl;
-            else {
-                float ce[3];
-                prim.centroid(p, ce);
-                const float cx = sp.axis == 0 ? ce[0] : sp.axis == 1 ? ce[1] : ce[2];
-                left = sah_bin(cx, sp.clo, sp.scale) < sp.bin;
-            }
+            left = sah_goes_left(prim, p, i, sp);
             float lo[3], hi[3];
             prim.box(p, lo, hi);
 #pragma unroll
@@ -631,18 +662,136 @@ __global__ void __launch_bounds__(32 * SAH_WARPS) k_sah_partition(const P prim, 
                 bhi[s][a] = fmaxf(bhi[s][a], __shfl_xor_sync(full, bhi[s][a], o));
             }
     __syncwarp();
-    if (lane == 0) {
-        float4 *node = nodes + 4 * (size_t)(base + j);
-        uint32_t q = off[j];
-        const uint32_t cnt[2] = {nl, c - nl}, fst[2] = {f, f + nl};
-        for (int s = 0; s < 2; ++s) {
-            if (cnt[s] == 1u) write_child(node, s, true, (int)idx_out[fst[s]], blo[s], bhi[s]);
-            else {
-                write_child(node, s, false, (int)(next_base + q), blo[s], bhi[s]);
-                next_first[q] = fst[s]; next_count[q] = cnt[s];
-                ++q;
+    if (lane == 0) sah_write_node(nodes, base + j, off[j], next_base, nl, c, f, idx_out, blo, bhi, next_first, next_count);
+}
+
+// The same two steps with one BLOCK per node, for the few large nodes of the top levels (one warp per node would leave
+// the GPU idle there).  Bins and boxes are order-independent, the partition is stable: the tree is bit-identical.
+template <class P>
+__global__ void __launch_bounds__(32 * SAH_WARPS) k_sah_split_block(const P prim, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ first,
+                                                                     const uint32_t *__restrict__ count, uint32_t m, int force_median,
+                                                                     SahSplit *__restrict__ split)
+{
+    __shared__ int s_bins[3][SAH_BINS][7];
+    __shared__ float s_red[SAH_WARPS][6];
+    __shared__ float s_c[6];
+    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t j = blockIdx.x;
+    const uint32_t f = first[j], c = count[j];
+    const float INF = __int_as_float(0x7f800000);
+    float clo[3] = {INF, INF, INF}, chi[3] = {-INF, -INF, -INF};
+    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
+        float ce[3];
+        prim.centroid(idx[f + i], ce);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { clo[k] = fminf(clo[k], ce[k]); chi[k] = fmaxf(chi[k], ce[k]); }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            clo[k] = fminf(clo[k], __shfl_xor_sync(full, clo[k], o));
+            chi[k] = fmaxf(chi[k], __shfl_xor_sync(full, chi[k], o));
+        }
+    if (lane == 0) for (int k = 0; k < 3; ++k) { s_red[warp][k] = clo[k]; s_red[warp][3 + k] = chi[k]; }
+    for (uint32_t t = threadIdx.x; t < 3u * SAH_BINS; t += blockDim.x) {
+        int *b = s_bins[t / SAH_BINS][t % SAH_BINS];
+        b[0] = b[1] = b[2] = f2ord(INF); b[3] = b[4] = b[5] = f2ord(-INF); b[6] = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6u) {
+        float v = s_red[0][threadIdx.x];
+        for (int w = 1; w < SAH_WARPS; ++w) v = threadIdx.x < 3u ? fminf(v, s_red[w][threadIdx.x]) : fmaxf(v, s_red[w][threadIdx.x]);
+        s_c[threadIdx.x] = v;
+    }
+    __syncthreads();
+    float scale[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { clo[k] = s_c[k]; chi[k] = s_c[3 + k]; scale[k] = chi[k] > clo[k] ? (float)SAH_BINS / (chi[k] - clo[k]) : 0.0f; }
+    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
+        const uint32_t p = idx[f + i];
+        float ce[3], lo[3], hi[3];
+        prim.centroid(p, ce);
+        prim.box(p, lo, hi);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (!(scale[k] > 0.0f)) continue;
+            int *b = s_bins[k][sah_bin(ce[k], clo[k], scale[k])];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { atomicMin(b + a, f2ord(lo[a])); atomicMax(b + 3 + a, f2ord(hi[a])); }
+            atomicAdd(b + 6, 1);
+        }
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    sah_pick_plane(s_bins, clo, scale, c, force_median, lane, split + j);
+}
+
+template <class P>
+__global__ void __launch_bounds__(32 * SAH_WARPS) k_sah_partition_block(const P prim, const uint32_t *__restrict__ idx_in, uint32_t *__restrict__ idx_out,
+                                                                         const uint32_t *__restrict__ first, const uint32_t *__restrict__ count, uint32_t m,
+                                                                         const SahSplit *__restrict__ split, const uint32_t *__restrict__ off,
+                                                                         uint32_t base, uint32_t next_base, uint32_t *__restrict__ next_first,
+                                                                         uint32_t *__restrict__ next_count, float4 *__restrict__ nodes)
+{
+    __shared__ uint32_t s_cnt[SAH_WARPS][2];
+    __shared__ float s_box[SAH_WARPS][12];
+    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t j = blockIdx.x;
+    const uint32_t f = first[j], c = count[j];
+    const SahSplit sp = split[j];
+    const uint32_t nl = sp.n_left;
+    const float INF = __int_as_float(0x7f800000);
+    float blo[2][3] = {{INF, INF, INF}, {INF, INF, INF}}, bhi[2][3] = {{-INF, -INF, -INF}, {-INF, -INF, -INF}};
+    uint32_t wl = 0, wr = 0;
+    for (uint32_t base_i = 0; base_i < c; base_i += blockDim.x) {
+        const uint32_t i = base_i + threadIdx.x;
+        const bool valid = i < c;
+        uint32_t p = 0;
+        bool left = false;
+        if (valid) {
+            p = idx_in[f + i];
+            left = sah_goes_left(prim, p, i, sp);
+            float lo[3], hi[3];
+            prim.box(p, lo, hi);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                if (left) { blo[0][a] = fminf(blo[0][a], lo[a]); bhi[0][a] = fmaxf(bhi[0][a], hi[a]); }
+                else      { blo[1][a] = fminf(blo[1][a], lo[a]); bhi[1][a] = fmaxf(bhi[1][a], hi[a]); }
             }
         }
+        const unsigned ml = __ballot_sync(full, valid && left), mr = __ballot_sync(full, valid && !left);
+        if (lane == 0) { s_cnt[warp][0] = (uint32_t)__popc(ml); s_cnt[warp][1] = (uint32_t)__popc(mr); }
+        __syncthreads();
+        uint32_t pl = 0, pr = 0, tl = 0, tr = 0;
+#pragma unroll
+        for (int w = 0; w < SAH_WARPS; ++w) {
+            if (w < (int)warp) { pl += s_cnt[w][0]; pr += s_cnt[w][1]; }
+            tl += s_cnt[w][0]; tr += s_cnt[w][1];
+        }
+        const unsigned lt = (1u << lane) - 1u;
+        if (valid) idx_out[left ? f + wl + pl + (uint32_t)__popc(ml & lt) : f + nl + wr + pr + (uint32_t)__popc(mr & lt)] = p;
+        wl += tl; wr += tr;
+        __syncthreads();
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1)
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                blo[s][a] = fminf(blo[s][a], __shfl_xor_sync(full, blo[s][a], o));
+                bhi[s][a] = fmaxf(bhi[s][a], __shfl_xor_sync(full, bhi[s][a], o));
+            }
+    if (lane == 0)
+        for (int s = 0; s < 2; ++s)
+            for (int a = 0; a < 3; ++a) { s_box[warp][s * 6 + a] = blo[s][a]; s_box[warp][s * 6 + 3 + a] = bhi[s][a]; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < SAH_WARPS; ++w)
+            for (int s = 0; s < 2; ++s)
+                for (int a = 0; a < 3; ++a) { blo[s][a] = fminf(blo[s][a], s_box[w][s * 6 + a]); bhi[s][a] = fmaxf(bhi[s][a], s_box[w][s * 6 + 3 + a]); }
+        sah_write_node(nodes, base + j, off[j], next_base, nl, c, f, idx_out, blo, bhi, next_first, next_count);
     }
 }
 __global__ void __launch_bounds__(256) k_iota(uint32_t *p, uint32_t n)
@@ -675,10 +824,18 @@ static cudaError_t build_sah_tree(const P prim, uint32_t n, float4 *nodes, int *
     while (m > 0) {
         const unsigned grid = (m + SAH_WARPS - 1u) / SAH_WARPS;
         uint32_t m_next = 0;
-        k_sah_split<P><<<grid, 32 * SAH_WARPS, 0, st>>>(prim, idx[cur], first[cur], count[cur], m, level >= SAH_MEDIAN_FROM_LEVEL ? 1 : 0, split); ++launches;
+        // a level whose nodes hold 1024 primitives or more on average (the top levels) gives every node a block
+        const bool by_block = VKRT_SAH_BLOCK_LEVELS && (uint64_t)m * 1024u <= n;
+        const int fm = level >= SAH_MEDIAN_FROM_LEVEL ? 1 : 0;
+        if (by_block) k_sah_split_block<P><<<m, 32 * SAH_WARPS, 0, st>>>(prim, idx[cur], first[cur], count[cur], m, fm, split);
+        else k_sah_split<P><<<grid, 32 * SAH_WARPS, 0, st>>>(prim, idx[cur], first[cur], count[cur], m, fm, split);
+        ++launches;
         k_sah_scan<<<1, 1024, 0, st>>>(split, count[cur], m, off, d_mnext); ++launches;
-        k_sah_partition<P><<<grid, 32 * SAH_WARPS, 0, st>>>(prim, idx[cur], idx[cur ^ 1], first[cur], count[cur], m, split, off, base, base + m,
-                                                          first[cur ^ 1], count[cur ^ 1], nodes); ++launches;
+        if (by_block) k_sah_partition_block<P><<<m, 32 * SAH_WARPS, 0, st>>>(prim, idx[cur], idx[cur ^ 1], first[cur], count[cur], m, split, off, base, base + m,
+                                                                             first[cur ^ 1], count[cur ^ 1], nodes);
+        else k_sah_partition<P><<<grid, 32 * SAH_WARPS, 0, st>>>(prim, idx[cur], idx[cur ^ 1], first[cur], count[cur], m, split, off, base, base + m,
+                                                                 first[cur ^ 1], count[cur ^ 1], nodes);
+        ++launches;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(&m_next, d_mnext, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
