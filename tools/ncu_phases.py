@@ -87,6 +87,7 @@ def main():
     dev = function_spans(os.path.join(CSRC, "vkrt_device.cuh"))
     ari = function_spans(os.path.join(CSRC, "vkrt_arith.cuh"))
     wfs = trace_sections(os.path.join(CSRC, "vkrt_wavefront.cu"))
+    wff = function_spans(os.path.join(CSRC, "vkrt_wavefront.cu"))
     agg = defaultdict(lambda: [0, 0, 0])
     tot = [0, 0, 0]
     for r in body:
@@ -99,7 +100,7 @@ def main():
             elif f == "vkrt_arith.cuh":
                 phase = "IEEE division / sqrt, vector helpers (set-up and leaf)"
             elif f == "vkrt_wavefront.cu":
-                phase = wfs.get(l) or "ray set-up"
+                phase = wfs.get(l) or ("loop control + votes" if wff.get(l) == "nested_inner_steps" else "ray set-up")
             else:
                 phase = "loop control + votes" if "intrinsics" in f else "other (%s)" % f
         ie = int(float(r[col["Instructions Executed"]] or 0))
