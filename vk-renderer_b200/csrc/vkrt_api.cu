@@ -590,7 +590,7 @@ VKRT_API vkrt_error vkrt_build_bvh(vkrt_ctx *c)
     if (r != VKRT_SUCCESS) return r;
     CU(c, build_lbvh(c->d_spheres, (uint32_t)c->spheres.size(), c->bvh, c->stream));
     // the traversal stacks (BVH_STACK entries of thread-local memory, unchecked in the kernels) hold at most one entry
-    // per tree level; the LBVH cannot be deeper than 64 levels, and this is where that is enforced
+    // per tree level; the LBVH cannot be deeper than 64 levels, and this is where the bound is enforced for both trees
     if (c->bvh.depth + 2 > (int)BVH_STACK)
         return fail(c, VKRT_BAD_ARG, "the LBVH is " + std::to_string(c->bvh.depth) + " levels deep: deeper than the traversal stack");
     // (the traversal tree splits index ranges in the middle from level 48 on: at most 48 + 32 levels)

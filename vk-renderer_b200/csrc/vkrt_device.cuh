@@ -13,8 +13,9 @@
 namespace vkrt {
 
 // BVH_STACK: entries of the per-thread traversal stacks.  The near-first binary walk holds at most one entry per tree
-// level and the LBVH has at most 64 levels (vkrt_bvh.cu::k_tree_depth; vkrt_build_bvh refuses a deeper tree), so the
-// kernels push without a bound check.
+// level (+ the sentinel of the wavefront's stacks); the LBVH has at most 64 levels (vkrt_bvh.cu::k_tree_depth), the SAH
+// traversal tree at most 48 + 32 (median index splits from level 48 on), and vkrt_build_bvh refuses a tree with
+// depth + 2 > BVH_STACK, so the kernels push without a bound check.
 enum { MAX_PLANES = 16, BVH_STACK = 128 };
 enum { KIND_TRI = 1, KIND_SPHERE = 2, KIND_PLANE = 3 };
 
