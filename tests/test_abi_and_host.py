@@ -31,6 +31,30 @@ def test_library_exports_every_declared_symbol(vk):
     assert vk._lib.load().vkrt_version().startswith(b"libvkrt_cuda")
 
 
+def test_python_mirror_of_the_public_structs_matches_the_header(vk, tmp_path):
+    """The ctypes structures of vk-renderer_b200/_lib.py are a hand-written mirror of include/vkrt.h: a C program
+    compiled against the header prints every public struct's size and field offsets, and they must agree."""
+    L = vk._lib
+    pairs = {"vkrt_camera_data": L.CameraData, "vkrt_frame_data": L.FrameData, "vkrt_triangle": L.Triangle,
+             "vkrt_material": L.Material, "vkrt_create_info": L.CreateInfo, "vkrt_counters": L.Counters,
+             "vkrt_bvh_info": L.BvhInfo, "vkrt_external_image": L.ExternalImage, "vkrt_exchange_handle": L.ExchangeHandle}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "vkrt.h"', "int main(void) {"]
+    for cname, cls in pairs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ["return 0; }"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(ln.split() for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in pairs.items():
+        assert int(out[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, "%s.%s" % (cname, fname)
+
+
 def test_library_is_sm100a_only(vk):
     out = subprocess.run(["cuobjdump", "-lelf", vk._lib.LIB_PATH], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_\d+a?", out))
