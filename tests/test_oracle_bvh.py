@@ -120,3 +120,29 @@ def test_cfg4_primary_id_fixture_is_the_oracles(vk, oracle):
     _, ids, _, _ = sc.render(fd, w, h, spp=1, max_depth=1, sphere_mode=oracle.S_BVH, seed=2026, rect=rect)
     x0, y0, x1, y1 = rect
     assert np.array_equal(ids[y0:y1, x0:x1], z["ids"][y0:y1, x0:x1])
+
+
+def test_traversal_design_simulator_agrees_with_itself(tmp_path):
+    """tests/tools/trav_sim.cpp backs DESIGN.md section 4 (wide nodes, entry distances on the stack, tree quality).  Every scheme
+    it replays must return the binary walk's answer for every nearest-hit ray (it prints MISMATCH otherwise), on the
+    oracle's LBVH and on the binned-SAH tree the device builder mirrors; the SAH tree must not cost more visits."""
+    import subprocess
+    import oracle as O
+    import vk_renderer_b200.scenes as scenes
+    from helpers import apply_scene
+    from conftest import ROOT
+    import os
+    sc = scenes.grid_spheres(nx=12, ny=10, nz=12)
+    o = apply_scene(O, sc, fast=True).build_bvh()
+    sc.spheres.astype(np.float32).tofile(str(tmp_path / "spheres.bin"))
+    np.ascontiguousarray(o.bvh_nodes()).tofile(str(tmp_path / "nodes.bin"))
+    exe = str(tmp_path / "trav_sim")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "tools", "trav_sim.cpp")], check=True)
+    visits = {}
+    for tree in ([], ["b16"]):
+        out = subprocess.run([exe, str(tmp_path / "spheres.bin"), str(tmp_path / "nodes.bin"), "20000"] + tree,
+                             capture_output=True, text=True, check=True).stdout
+        assert "MISMATCH" not in out, out
+        line = [ln for ln in out.splitlines() if ln.startswith("binary (shipping)") and "nearest" in ln][0]
+        visits[bool(tree)] = float(line.split("visits")[1].split()[0])
+    assert visits[True] <= visits[False], visits
