@@ -63,6 +63,7 @@ def _load(fast):
     lib.orc_scene_set_triangle_materials.argtypes = [vp, vp, C.c_uint32]
     lib.orc_scene_use_default.argtypes = [vp, C.c_uint32]
     lib.orc_scene_build_bvh.argtypes = [vp]
+    lib.orc_scene_set_bvh.argtypes = [vp, vp, C.c_uint32]
     lib.orc_scene_bvh_nodes.argtypes = [vp]
     lib.orc_scene_bvh_nodes.restype = C.c_uint32
     lib.orc_scene_read_bvh.argtypes = [vp, vp, C.c_size_t]
@@ -153,6 +154,12 @@ class Scene:
 
     def build_bvh(self):
         assert self.l.orc_scene_build_bvh(self.h) == 0
+        return self
+
+    def set_bvh(self, nodes):
+        """Test hook: walk this hierarchy ((n, 16) float32, bvh_nodes' layout, root = node 0) instead of the oracle's own LBVH."""
+        a = np.ascontiguousarray(nodes, dtype=np.float32).reshape(-1, 16)
+        assert self.l.orc_scene_set_bvh(self.h, _ptr(a), a.shape[0]) == 0
         return self
 
     def bvh_nodes(self):

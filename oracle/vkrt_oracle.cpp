@@ -893,6 +893,17 @@ int orc_scene_build_bvh(orc_scene *s)
         }
     return 0;
 }
+// Test hook: the oracle walks ANY hierarchy handed to it in the node layout of orc_scene_read_bvh (root = node 0).  Rule S
+//  claims the answer does not depend on the hierarchy as long as leaves carry the spheres' own padded boxes and
+// inner boxes are exact unions; tests feed random trees and the device's SAH traversal tree through this.
+int orc_scene_set_bvh(orc_scene *s, const float *nodes, uint32_t n_nodes)
+{
+    if (!nodes && n_nodes) return 6;
+    s->bvh.resize(n_nodes);
+    if (n_nodes) std::memcpy(s->bvh.data(), nodes, (size_t)n_nodes * sizeof(BvhNode));
+    s->has_bvh = true;
+    return 0;
+}
 uint32_t orc_scene_bvh_nodes(const orc_scene *s) { return (uint32_t)s->bvh.size(); }
 int orc_scene_read_bvh(const orc_scene *s, float *out, size_t bytes)
 {

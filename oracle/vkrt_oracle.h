@@ -82,6 +82,8 @@ int  orc_scene_set_triangles(orc_scene *, const orc_triangle *, uint32_t n, uint
 int  orc_scene_set_triangle_materials(orc_scene *, const uint32_t *mat_ids, uint32_t n);
 int  orc_scene_use_default(orc_scene *, uint32_t which /* 0 Tracer.comp, 1 Raytracer.comp */);
 int  orc_scene_build_bvh(orc_scene *);          /* CPU LBVH (Morton / sort / Karras / refit) */
+/* test hook: replace the hierarchy by any tree in orc_scene_read_bvh's layout (rule S must not depend on it) */
+int  orc_scene_set_bvh(orc_scene *, const float *nodes, uint32_t n_nodes);
 uint32_t orc_scene_bvh_nodes(const orc_scene *);
 /* node i: 16 floats, same logical content as the device layout (child record 0, child record 1) */
 int  orc_scene_read_bvh(const orc_scene *, float *out, size_t bytes);

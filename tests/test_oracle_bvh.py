@@ -146,3 +146,73 @@ def test_traversal_design_simulator_agrees_with_itself(tmp_path):
         line = [ln for ln in out.splitlines() if ln.startswith("binary (shipping)") and "nearest" in ln][0]
         visits[bool(tree)] = float(line.split("visits")[1].split()[0])
     assert visits[True] <= visits[False], visits
+
+
+def _random_hierarchy(spheres, rng):
+    """A random binary tree over the spheres in bvh_nodes' layout: leaves = the spheres' own padded boxes (the same float32
+    operations as the oracle and the device), inner boxes = exact min / max unions, root = node 0."""
+    sp = spheres.astype(np.float32)
+    rp = (sp[:, 3] * np.float32(1.001) + np.float32(0.001)).astype(np.float32)
+    llo = (sp[:, 0:3] - rp[:, None]).astype(np.float32)
+    lhi = (sp[:, 0:3] + rp[:, None]).astype(np.float32)
+    n = sp.shape[0]
+    nodes = np.zeros((max(n - 1, 1), 2, 8), dtype=np.float32)
+    ints = nodes.view(np.int32)
+    order = rng.permutation(n)
+    next_id = [1]
+
+    def put(node, k, lo, hi, index, kind):
+        nodes[node, k, 0:3] = lo; nodes[node, k, 3] = hi[0]; nodes[node, k, 4:6] = hi[1:3]
+        ints[node, k, 6] = index; ints[node, k, 7] = kind
+
+    def build(ids, node):                      # fills `node`, returns its box
+        cut = int(rng.integers(1, len(ids)))   # any split, however lopsided
+        boxes = []
+        for k, part in enumerate((ids[:cut], ids[cut:])):
+            if len(part) == 1:
+                lo, hi = llo[part[0]], lhi[part[0]]
+                put(node, k, lo, hi, int(part[0]), 1)
+            else:
+                child = next_id[0]; next_id[0] += 1
+                lo, hi = build(part, child)
+                put(node, k, lo, hi, child, 0)
+            boxes.append((lo, hi))
+        return np.minimum(boxes[0][0], boxes[1][0]), np.maximum(boxes[0][1], boxes[1][1])
+
+    if n == 1:
+        put(0, 0, llo[0], lhi[0], 0, 1); put(0, 1, llo[0], lhi[0], 0, 1)
+    else:
+        build(list(order), 0)
+    return nodes.reshape(-1, 16)
+
+
+@pytest.mark.parametrize("n,seed", [(2, 1), (9, 2), (150, 3)])
+def test_rule_s_does_not_depend_on_the_hierarchy(vk, oracle, n, seed):
+    """DESIGN.md "Rule S": ANY hierarchy whose leaves carry the spheres' own padded boxes and whose inner boxes are exact
+    unions returns the linear scan's answer -- which is what lets the wavefront walk a SAH tree while the megakernel and the
+    oracle walk the LBVH.  Random trees (random permutation, random lopsided splits, up to 90 levels deep) through the
+    oracle's traversal: frames identical to the linear scan, bit for bit."""
+    import sys
+    sys.setrecursionlimit(10000)
+    scene = vk.scenes.random_spheres(n, seed=seed)
+    sc = apply_scene(oracle, scene)
+    w, h = 64, 48
+    fd = vk.default_frame_data(aspect_ratio=w / h, seed=0.2 * seed)
+    b, ib, _, cb = sc.render(fd, w, h, spp=2, max_depth=6, sphere_mode=oracle.S_LINEAR, seed=seed)
+    rng = np.random.default_rng(100 + seed)
+    for trial in range(3):
+        while True:
+            nodes = _random_hierarchy(scene.spheres, rng)
+            # the oracle's traversal stack holds 96 entries: keep the random tree's depth below that
+            ints = nodes.reshape(-1, 2, 8).view(np.int32)
+            depth = np.ones(nodes.shape[0], dtype=np.int64)
+            for v in range(nodes.shape[0]):               # children have larger ids than their parents
+                for k in range(2):
+                    if ints[v, k, 7] == 0:
+                        depth[ints[v, k, 6]] = depth[v] + 1
+            if depth.max() <= 90:
+                break
+        sc.set_bvh(nodes)
+        a, ia, _, ca = sc.render(fd, w, h, spp=2, max_depth=6, sphere_mode=oracle.S_BVH, seed=seed)
+        assert np.array_equal(ia, ib) and bits_equal(a, b)
+        assert (ca.closest_rays, ca.shadow_rays) == (cb.closest_rays, cb.shadow_rays)
