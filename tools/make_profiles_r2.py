@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turns one tools/evidence_r2.sh run (gpurun_out/<tag>_*) into the committed round evidence under profiles/.
 
-  python tools/make_profiles_r2.py <tag> [round-prefix, default r02]
+  python tools/make_profiles_r2.py <tag> [round-prefix, default r02] [commit the run was taken at, default HEAD]
 """
 import collections
 import csv
@@ -19,6 +19,8 @@ P = lambda name: os.path.join(ROOT, "profiles", "%s_%s" % (rnd, name))
 
 
 def head():
+    if len(sys.argv) > 3:            # the commit the evidence run was taken at, when it is not the current one
+        return sys.argv[3]
     try:
         return subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], stdout=subprocess.PIPE, text=True).stdout.strip()
     except Exception:
@@ -218,4 +220,24 @@ with open(P("SUMMARY.md"), "w") as f:
         f.write("* %s = %.1f\n" % (k, L[k]))
     f.write("* local / global load-store instruction counts: see the full captures (`%s_ncu_full_*.txt`, sass__inst_executed_*)\n" % rnd)
     f.write("* dram bytes per traversal launch: %.1f MB\n" % (ev["cfg4_wavefront"]["dram_bytes_per_launch"] / 1e6))
+    # ---- multi-GPU lines (tools/r2_mgpu.sh, copied next to this file) and the other evidence of the round
+    f.write("\n## Multi-GPU (`%s_bench_n*.json`: `torchrun ... bench.py --gpus N --steps 20 --warmup 5`; `%s_pytest_multi_gpu_N.log`)\n\n" % (rnd, rnd))
+    try:
+        one = json.loads(open(P("bench.json")).read())
+        f.write("| N | scaling | ms/step | Mrays/s | vs N x one GPU | weak Mrays/s | cfg5 ms/frame | NCCL-gather ms/step |\n|---|---|---|---|---|---|---|---|\n")
+        for n in (2, 4, 8):
+            if not os.path.exists(P("bench_n%d.json" % n)):
+                continue
+            d = json.loads(open(P("bench_n%d.json" % n)).read())
+            f.write("| %d | %s | %.3f | %.1f | %.3f | %.1f | %.1f | %.3f |\n" % (n, d["scaling"], d["ms_per_step"], d["value"], d["value"] / (n * one["value"]),
+                    d["weak"]["value"], d["cfg5"]["ms_per_step"], d["nccl_gather"]["ms_per_step"]))
+    except Exception as e:
+        f.write("(multi-GPU lines missing: %s)\n" % e)
+    f.write("\n## Other evidence in this directory\n\n"
+            "* `%s_trace_phases.txt`: issue slots, stall samples and active lanes per phase of the traversal kernel (tools/ncu_phases.py)\n"
+            "* `%s_sweeps.txt`: every tuning variant measured this round, taken or not\n"
+            "* `%s_traversal_design_sim.txt`: CPU simulation of traversal schemes and tree builders (tests/tools/trav_sim.py)\n"
+            "* `%s_sanitizer_*.txt`: compute-sanitizer memcheck / racecheck / synccheck (tools/sanitize.sh)\n"
+            "* `%s_pytest_gpu.log`, `%s_pytest_multi_gpu_*.log`: the GPU test runs; `peaks_micro.json`, `ncu_limiters.json`: what bench.py reads\n"
+            % ((rnd,) * 6))
 print(open(P("SUMMARY.md")).read())
